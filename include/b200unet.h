@@ -1,0 +1,212 @@
+/* libb200unet -- C-ABI of the B200-native U-Net train/infer hot path.
+ *
+ * The reference (deadskull7/One-Stop-for-COVID-19-...) has no FFI of its own: its runners call Keras
+ * objects.  Every entry point below therefore cites the Keras call it replaces
+ * (paths relative to /root/reference/Scripts; T1H = task1_preprocessing_plus_unet_with_comments.py,
+ * UPP = task1_unet_plus_plus.py, T2 = task2_covid19_classifcation.py).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; b2u_last_error() gives the message
+ *     (thread-local).  Nothing throws, nothing calls exit().
+ *   - all pointers are DEVICE pointers unless the name starts with h_; the caller owns all memory
+ *     (the library never allocates on the hot path); all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*) and is asynchronous.
+ *   - activations are NHWC "views": base pointer + `ld` = element stride between consecutive pixels
+ *     (ld >= C), so that a channel slice of a wider concat buffer is addressable in place
+ *     (keras `concatenate`, T1H:887 -- zero-copy).
+ *   - dt selects the storage type of activations/activation-gradients: B2U_F32 (exact mode, CUDA-core
+ *     kernels) or B2U_F16 (tensor mode: tcgen05 kernels, fp32 accumulation).  Parameters, parameter
+ *     gradients, optimizer state, BN statistics and the loss are always fp32/fp64.
+ *   - weights stay in Keras layout: Conv2D (kh,kw,Cin,Cout); Conv2DTranspose (kh,kw,Cout,Cin);
+ *     Dense (in,out).
+ *   - ws / ws_bytes: scratch the op may use (b2u_ws_bytes() gives a safe upper bound).
+ */
+#ifndef B200UNET_H
+#define B200UNET_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2U_VERSION 100
+
+enum { B2U_OK = 0, B2U_ERR_ARG = -1, B2U_ERR_CUDA = -2, B2U_ERR_UNSUPPORTED = -3, B2U_ERR_NCCL = -4 };
+enum { B2U_F32 = 0, B2U_F16 = 1 };
+enum { B2U_ACT_NONE = 0, B2U_ACT_RELU = 1, B2U_ACT_ELU = 2, B2U_ACT_SIGMOID = 3 };
+
+/* Device-resident per-step scalars, read by dropout / Adam / loss kernels so that a captured CUDA
+ * graph never bakes them in (lr is set per epoch by CosineAnnealingScheduler, T1H:980-982). */
+typedef struct b2u_step_state {
+  uint64_t seed;        /* dropout stream key                                  */
+  uint64_t step;        /* global step counter (dropout counter word 1)        */
+  float lr;             /* Adam learning rate (T1H:1053 lr=0.0005)             */
+  float beta1, beta2, eps;
+  float beta1_pow;      /* beta1^t, beta2^t for the CURRENT step t (>=1)       */
+  float beta2_pow;
+  float loss_scale;     /* gradients are multiplied by this in the loss backward (fp16 range) */
+  float grad_div;       /* Adam divides gradients by loss_scale*grad_div (grad_div = world size) */
+  uint32_t overflow;    /* set !=0 by Adam if a non-finite gradient was seen (step skipped)   */
+  uint32_t pad_;
+} b2u_step_state;
+
+int b2u_version(void);
+const char* b2u_last_error(void);
+size_t b2u_ws_bytes(void);
+/* 1 if the tcgen05 tensor path is compiled in and the current device is sm_100 */
+int b2u_tensor_path_available(void);
+
+/* ---- step state ---------------------------------------------------------------------------- */
+/* step += 1; beta_pows *= beta (device-side, graph-capturable) */
+int b2u_state_advance(b2u_step_state* d_state, void* stream);
+
+/* ---- Conv2D 3x3 'same' (T1H:859 ... :911; UPP:878; T2:748) ---------------------------------- */
+/* y = act(x (*) w + bias); optionally accumulates per-channel sum / sum-of-squares of y into
+ * stats[2*cout] (double) for the BatchNormalization that follows (T1H:861). */
+int b2u_conv3x3_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, int act,
+                    void* y, int ldy, int cout, double* stats, int n, int h, int wd,
+                    void* ws, size_t ws_bytes, void* stream);
+/* dx = dgrad(dy, w) [* act'(mask)] ; mask is the (post-activation) tensor whose producer's
+ * pre-activation gradient is wanted (NULL: none). accumulate!=0: dx += ... */
+int b2u_conv3x3_dgrad(int dt, const void* dy, int lddy, int cout, const float* w,
+                      void* dx, int lddx, int cin, const void* mask, int ldmask, int mask_act,
+                      int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+/* dw += x^T (*) dy ; db += sum(dy)   (fp32, Keras layout) */
+int b2u_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, int lddy, int cout,
+                      float* dw, float* db, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Conv2DTranspose 2x2 stride 2 (T1H:886, 893, 900, 907; UPP:890 ...) --------------------- */
+/* y[n,2i+a,2j+b,co] = sum_ci x[n,i,j,ci] * w[a,b,co,ci] + bias[co]; (h,wd) are INPUT dims */
+int b2u_convt2x2_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias,
+                     void* y, int ldy, int cout, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+int b2u_convt2x2_dgrad(int dt, const void* dy, int lddy, int cout, const float* w,
+                       void* dx, int lddx, int cin, const void* mask, int ldmask, int mask_act,
+                       int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+int b2u_convt2x2_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, int lddy, int cout,
+                       float* dw, float* db, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- BatchNormalization (T1H:861, 888 ...; momentum .99, eps 1e-3) --------------------------- */
+int b2u_bn_stats(int dt, const void* x, int ldx, int c, long long npix, double* sums, void* stream);
+/* training: batch stats from sums -> scale/shift, save_mean/save_invstd, moving-stat update.
+ * inference: scale/shift from the moving statistics. */
+int b2u_bn_finalize(const double* sums, long long count, const float* gamma, const float* beta,
+                    float* moving_mean, float* moving_var, float momentum, float eps, int training,
+                    float* scale, float* shift, float* save_mean, float* save_invstd, int c, void* stream);
+int b2u_bn_apply(int dt, const void* x, int ldx, void* y, int ldy, int c, long long npix,
+                 const float* scale, const float* shift, void* stream);
+/* sums[0:c] += sum(dy), sums[c:2c] += sum(dy * xhat) */
+int b2u_bn_bwd_reduce(int dt, const void* dy, int lddy, const void* x, int ldx, int c, long long npix,
+                      const float* save_mean, const float* save_invstd, double* sums, void* stream);
+/* dx = gamma*invstd*(dy - sum_dy/count - xhat*sum_dyxhat/count) [* act'(mask)]; dgamma += ..; dbeta += ..
+ * (count == npix on one GPU; the global pixel count when the sums were all-reduced) */
+int b2u_bn_bwd_apply(int dt, const void* dy, int lddy, const void* x, int ldx, void* dx, int lddx,
+                     int c, long long npix, long long count, const float* gamma, const float* save_mean,
+                     const float* save_invstd, const double* sums, float* dgamma, float* dbeta,
+                     const void* mask, int ldmask, int mask_act, void* stream);
+
+/* ---- MaxPooling2D((2,2)) [+ Dropout(p)] (T1H:862-863) ---------------------------------------- */
+/* (h,wd) are INPUT dims. p_drop==0 -> plain pooling. */
+int b2u_maxpool_fwd(int dt, const void* x, int ldx, void* y, int ldy, int c, int n, int h, int wd,
+                    float p_drop, int op_id, const b2u_step_state* d_state, void* stream);
+/* dx[first arg-max of each window] (+)= dy*keep/(1-p), other window elements (+)= 0 */
+int b2u_maxpool_bwd(int dt, const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int c,
+                    int n, int h, int wd, float p_drop, int op_id, const b2u_step_state* d_state,
+                    int accumulate, void* stream);
+/* ---- Dropout(p) (UPP:864, 879; T2:777) -------------------------------------------------------- */
+int b2u_dropout_fwd(int dt, const void* x, int ldx, void* y, int ldy, int c, long long npix, float p,
+                    int op_id, const b2u_step_state* d_state, void* stream);
+int b2u_dropout_bwd(int dt, const void* dy, int lddy, void* dx, int lddx, int c, long long npix, float p,
+                    int op_id, const b2u_step_state* d_state, const void* mask, int ldmask, int mask_act,
+                    void* stream);
+/* ---- concatenate helpers (UPP:905: one tensor feeding several concats) ------------------------ */
+int b2u_copy_slice(int dt, const void* src, int ldsrc, void* dst, int lddst, int c, long long npix,
+                   int accumulate, void* stream);
+
+/* ---- output head: Conv2D(1,(1,1),activation='sigmoid') (T1H:913) + bce_dice_loss (T1H:784-799) - */
+int b2u_head_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias,
+                 float* prob, long long npix, void* stream);
+/* sums[0..3] += sum(t*p), sum(t), sum(p), sum(bce) */
+int b2u_bce_dice_sums(const float* prob, const float* target, long long count, double* sums, void* stream);
+/* out[0] = 0.5*bce_mean + 0.5*(1-dice), out[1] = dice */
+int b2u_bce_dice_finalize(const double* sums, long long count, float* out, void* stream);
+/* dlogit = loss_scale * dL/dp * p(1-p); dx = dlogit * w [* act'(x)]; dw += sum dlogit*x; db += sum dlogit.
+ * global_count/global sums allow a data-parallel batch to use whole-batch Dice statistics. */
+int b2u_head_bwd(int dt, const float* prob, const float* target, const double* sums, long long count,
+                 const b2u_step_state* d_state, const void* x, int ldx, int cin, const float* w,
+                 void* dx, int lddx, int x_act, float* dw, float* db, long long npix, void* stream);
+
+/* ---- Dense (T2:776-778) ------------------------------------------------------------------------ */
+/* x (n,k) of storage type dt -> y (n,m) ALWAYS fp32 (dense outputs / their gradients are tiny) */
+int b2u_dense_fwd(int dt, const void* x, int k, const float* w, const float* bias, int act,
+                  void* y, int m, int n, void* stream);
+int b2u_dense_bwd(int dt, const void* x, int k, const float* w, const void* y, int act, const void* dy,
+                  void* dx, const void* mask, int mask_act, float* dw, float* db, int m, int n, void* stream);
+/* weighted binary cross-entropy on (n,1) probabilities (T2:828, class_weight T2:836) */
+int b2u_bce_fwd(const float* prob, const float* target, const float* sample_w, int n, float* out, void* stream);
+/* dlogit for a sigmoid unit, written as storage type dt: dy[i] = loss_scale * w_i (p-t)/n (clip-aware) */
+int b2u_bce_sigmoid_bwd(int dt, const float* prob, const float* target, const float* sample_w, int n,
+                        const b2u_step_state* d_state, void* dlogit, void* stream);
+
+/* ---- Adam (T1H:1053) --------------------------------------------------------------------------- */
+int b2u_adam(float* params, const float* grads, float* m, float* v, long long n,
+             b2u_step_state* d_state, void* stream);
+
+/* ---- host-array ingest: fit/predict batches (T1H:1059 model.fit(x_train, ...)) ----------------- */
+/* dst[b, :] = (T) src[idx[b], :]  (src fp32, device-resident dataset; idx int32 device) */
+int b2u_gather_batch(int dt, const float* src, const int* idx, void* dst, long long per_sample, int nb,
+                     void* stream);
+
+/* ---- sm.metrics threshold sweep (T1H:1206-1211) ------------------------------------------------ */
+/* for each threshold k: tp[k] += sum(t * (p > thr[k])), sum_pr[k] += sum(p > thr[k]); sum_gt += sum(t) */
+int b2u_threshold_counts(const float* prob, const float* target, long long count, const float* thresholds,
+                         int nthr, double* tp, double* sum_pr, double* sum_gt, void* stream);
+
+/* ---- preprocessing (T1H:163-194 clahe_enhancer, T1H:211-273 cropper, T1H:485-488 resize) ------- */
+/* cv2.createCLAHE(clipLimit, (tiles,tiles)).apply on n uint8 images (h % tiles == 0, w % tiles == 0) */
+int b2u_clahe_u8(const uint8_t* in, uint8_t* out, int n, int h, int wd, float clip_limit, int tiles,
+                 void* ws, size_t ws_bytes, void* stream);
+/* per image: crop two boxes (x,y,w,h int32 x8), cv2.resize INTER_AREA to (half_w x out_h) each, hconcat,
+ * cv2.resize INTER_LINEAR (u8 fixed point) to final x final, /255 -> float32 (n,final,final) */
+int b2u_crop_resize(const uint8_t* in, int n, int h, int wd, const int* boxes, int half_w, int out_h,
+                    int final_dim, uint8_t* mid_u8, float* out, void* stream);
+
+/* ---- plan executor: a whole forward / train step as one array of op records ------------------- */
+enum {
+  B2U_OP_CONV3X3_FWD = 1, B2U_OP_CONV3X3_DGRAD, B2U_OP_CONV3X3_WGRAD,
+  B2U_OP_CONVT_FWD, B2U_OP_CONVT_DGRAD, B2U_OP_CONVT_WGRAD,
+  B2U_OP_BN_STATS, B2U_OP_BN_FINALIZE, B2U_OP_BN_APPLY, B2U_OP_BN_BWD_REDUCE, B2U_OP_BN_BWD_APPLY,
+  B2U_OP_MAXPOOL_FWD, B2U_OP_MAXPOOL_BWD, B2U_OP_DROPOUT_FWD, B2U_OP_DROPOUT_BWD, B2U_OP_COPY_SLICE,
+  B2U_OP_HEAD_FWD, B2U_OP_BCE_DICE_SUMS, B2U_OP_BCE_DICE_FINALIZE, B2U_OP_HEAD_BWD,
+  B2U_OP_DENSE_FWD, B2U_OP_DENSE_BWD, B2U_OP_BCE_FWD, B2U_OP_BCE_SIGMOID_BWD,
+  B2U_OP_ADAM, B2U_OP_MEMSET, B2U_OP_ALLREDUCE_F32, B2U_OP_ALLREDUCE_F64, B2U_OP_STATE_ADVANCE,
+  B2U_OP_GATHER_BATCH
+};
+/* one record; the meaning of p[]/i[]/f[] per kind is the argument order of the function above
+ * (pointers in order into p[], ints/long longs into i[], floats into f[]). */
+typedef struct b2u_op {
+  int32_t kind;
+  int32_t dt;
+  void* p[12];
+  int64_t i[12];
+  float f[4];
+} b2u_op;
+int b2u_run_ops(const b2u_op* h_ops, int n_ops, void* ws, size_t ws_bytes, void* comm, void* stream);
+/* CUDA-graph capture of an op list (launch-bound inner loop -> one graph launch per step) */
+int b2u_graph_create(const b2u_op* h_ops, int n_ops, void* ws, size_t ws_bytes, void* comm, void* stream,
+                     void** out_graph);
+int b2u_graph_launch(void* graph, void* stream);
+int b2u_graph_destroy(void* graph);
+/* number of kernels launched by this library since process start (bench.py's gpu_launches) */
+long long b2u_launch_count(void);
+
+/* ---- data-parallel gradient exchange (no reference counterpart: the reference is single-device) - */
+int b2u_comm_unique_id(void* h_out_128B);
+int b2u_comm_create(const void* h_id_128B, int rank, int world, void** out_comm);
+int b2u_comm_destroy(void* comm);
+int b2u_allreduce(void* comm, void* buf, long long count, int is_double, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,328 @@
+// C-ABI glue: error string, conv dispatch (tcgen05 tensor path vs exact CUDA-core path), the op-list
+// executor with CUDA-graph capture, and the NCCL gradient exchange.
+#include <dlfcn.h>
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+#include "launch.cuh"
+#include "internal.h"
+
+unsigned long long g_b2u_launches = 0;
+
+static thread_local char g_err[1024] = "";
+
+void b2u_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int b2u_version(void) { return B2U_VERSION; }
+extern "C" const char* b2u_last_error(void) { return g_err; }
+extern "C" size_t b2u_ws_bytes(void) { return (size_t)64 << 20; }
+extern "C" long long b2u_launch_count(void) { return (long long)__atomic_load_n(&g_b2u_launches, __ATOMIC_RELAXED); }
+
+static int g_tc_state = -1;   // -1 unknown, 0 off, 1 on
+extern "C" int b2u_tensor_path_available(void) {
+  if (g_tc_state < 0) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    const char* env = getenv("B2U_DISABLE_TC");
+    if (env != nullptr && env[0] == '1') g_tc_state = 0;
+    else if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) g_tc_state = 0;
+    else g_tc_state = (prop.major == 10 && b2u_tc_compiled()) ? 1 : 0;
+  }
+  return g_tc_state;
+}
+
+// ------------------------------------------------------------------------------------------
+// conv dispatch
+// ------------------------------------------------------------------------------------------
+extern "C" int b2u_conv3x3_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, int act,
+                               void* y, int ldy, int cout, double* stats, int n, int h, int wd, void* ws,
+                               size_t ws_bytes, void* stream) {
+  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy))
+    return b2u_tc_conv3x3(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, 0, 0, 0, n, h, wd, ws, ws_bytes,
+                          stream);
+  return b2u_direct_conv3x3(dt, x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, 0, 0, 0, n, h, wd, stream);
+}
+
+extern "C" int b2u_conv3x3_dgrad(int dt, const void* dy, int lddy, int cout, const float* w, void* dx, int lddx,
+                                 int cin, const void* mask, int ldmask, int mask_act, int accumulate, int n, int h,
+                                 int wd, void* ws, size_t ws_bytes, void* stream) {
+  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cout, cin, lddy, lddx))
+    return b2u_tc_conv3x3(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, mask, ldmask, mask_act,
+                          accumulate, n, h, wd, ws, ws_bytes, stream);
+  return b2u_direct_conv3x3(dt, dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, mask, ldmask,
+                            mask_act, accumulate, n, h, wd, stream);
+}
+
+extern "C" int b2u_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, int lddy, int cout,
+                                 float* dw, float* db, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_wgrad_ok(cin, cout, ldx, lddy))
+    return b2u_tc_conv3x3_wgrad(x, ldx, cin, dy, lddy, cout, dw, db, n, h, wd, ws, ws_bytes, stream);
+  return b2u_direct_conv3x3_wgrad(dt, x, ldx, cin, dy, lddy, cout, dw, db, n, h, wd, stream);
+}
+
+extern "C" int b2u_convt2x2_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, void* y,
+                                int ldy, int cout, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_convt_ok(cin, cout, ldx, ldy))
+    return b2u_tc_convt_fwd(x, ldx, cin, w, bias, y, ldy, cout, n, h, wd, ws, ws_bytes, stream);
+  return b2u_direct_convt_fwd(dt, x, ldx, cin, w, bias, y, ldy, cout, n, h, wd, stream);
+}
+
+extern "C" int b2u_convt2x2_dgrad(int dt, const void* dy, int lddy, int cout, const float* w, void* dx, int lddx,
+                                  int cin, const void* mask, int ldmask, int mask_act, int accumulate, int n, int h,
+                                  int wd, void* ws, size_t ws_bytes, void* stream) {
+  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_convt_ok(cin, cout, lddx, lddy))
+    return b2u_tc_convt_dgrad(dy, lddy, cout, w, dx, lddx, cin, mask, ldmask, mask_act, accumulate, n, h, wd, ws,
+                              ws_bytes, stream);
+  return b2u_direct_convt_dgrad(dt, dy, lddy, cout, w, dx, lddx, cin, mask, ldmask, mask_act, accumulate, n, h, wd,
+                                stream);
+}
+
+extern "C" int b2u_convt2x2_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, int lddy, int cout,
+                                  float* dw, float* db, int n, int h, int wd, void* ws, size_t ws_bytes,
+                                  void* stream) {
+  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_convt_ok(cin, cout, ldx, lddy))
+    return b2u_tc_convt_wgrad(x, ldx, cin, dy, lddy, cout, dw, db, n, h, wd, ws, ws_bytes, stream);
+  return b2u_direct_convt_wgrad(dt, x, ldx, cin, dy, lddy, cout, dw, db, n, h, wd, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// op-list executor
+// ------------------------------------------------------------------------------------------
+static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
+  void* const* p = o.p;
+  const int64_t* i = o.i;
+  const float* f = o.f;
+  const int dt = o.dt;
+#define I(k) ((int)i[k])
+  switch (o.kind) {
+    case B2U_OP_CONV3X3_FWD:
+      return b2u_conv3x3_fwd(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], I(2), p[3], I(3), I(4),
+                             (double*)p[4], I(5), I(6), I(7), ws, wsb, s);
+    case B2U_OP_CONV3X3_DGRAD:
+      return b2u_conv3x3_dgrad(dt, p[0], I(0), I(1), (const float*)p[1], p[2], I(2), I(3), p[3], I(4), I(5), I(6), I(7),
+                               I(8), I(9), ws, wsb, s);
+    case B2U_OP_CONV3X3_WGRAD:
+      return b2u_conv3x3_wgrad(dt, p[0], I(0), I(1), p[1], I(2), I(3), (float*)p[2], (float*)p[3], I(4), I(5), I(6), ws,
+                               wsb, s);
+    case B2U_OP_CONVT_FWD:
+      return b2u_convt2x2_fwd(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], p[3], I(2), I(3), I(4), I(5),
+                              I(6), ws, wsb, s);
+    case B2U_OP_CONVT_DGRAD:
+      return b2u_convt2x2_dgrad(dt, p[0], I(0), I(1), (const float*)p[1], p[2], I(2), I(3), p[3], I(4), I(5), I(6), I(7),
+                                I(8), I(9), ws, wsb, s);
+    case B2U_OP_CONVT_WGRAD:
+      return b2u_convt2x2_wgrad(dt, p[0], I(0), I(1), p[1], I(2), I(3), (float*)p[2], (float*)p[3], I(4), I(5), I(6), ws,
+                                wsb, s);
+    case B2U_OP_BN_STATS:
+      return b2u_bn_stats(dt, p[0], I(0), I(1), i[2], (double*)p[1], s);
+    case B2U_OP_BN_FINALIZE:
+      return b2u_bn_finalize((const double*)p[0], i[0], (const float*)p[1], (const float*)p[2], (float*)p[3],
+                             (float*)p[4], f[0], f[1], I(1), (float*)p[5], (float*)p[6], (float*)p[7], (float*)p[8], I(2),
+                             s);
+    case B2U_OP_BN_APPLY:
+      return b2u_bn_apply(dt, p[0], I(0), p[1], I(1), I(2), i[3], (const float*)p[2], (const float*)p[3], s);
+    case B2U_OP_BN_BWD_REDUCE:
+      return b2u_bn_bwd_reduce(dt, p[0], I(0), p[1], I(1), I(2), i[3], (const float*)p[2], (const float*)p[3],
+                               (double*)p[4], s);
+    case B2U_OP_BN_BWD_APPLY:
+      return b2u_bn_bwd_apply(dt, p[0], I(0), p[1], I(1), p[2], I(2), I(3), i[4], i[7], (const float*)p[3],
+                              (const float*)p[4], (const float*)p[5], (const double*)p[6], (float*)p[7], (float*)p[8],
+                              p[9], I(5), I(6), s);
+    case B2U_OP_MAXPOOL_FWD:
+      return b2u_maxpool_fwd(dt, p[0], I(0), p[1], I(1), I(2), I(3), I(4), I(5), f[0], I(6),
+                             (const b2u_step_state*)p[2], s);
+    case B2U_OP_MAXPOOL_BWD:
+      return b2u_maxpool_bwd(dt, p[0], I(0), p[1], I(1), p[2], I(2), I(3), I(4), I(5), I(6), f[0], I(7),
+                             (const b2u_step_state*)p[3], I(8), s);
+    case B2U_OP_DROPOUT_FWD:
+      return b2u_dropout_fwd(dt, p[0], I(0), p[1], I(1), I(2), i[3], f[0], I(4), (const b2u_step_state*)p[2], s);
+    case B2U_OP_DROPOUT_BWD:
+      return b2u_dropout_bwd(dt, p[0], I(0), p[1], I(1), I(2), i[3], f[0], I(4), (const b2u_step_state*)p[2], p[3], I(5),
+                             I(6), s);
+    case B2U_OP_COPY_SLICE:
+      return b2u_copy_slice(dt, p[0], I(0), p[1], I(1), I(2), i[3], I(4), s);
+    case B2U_OP_HEAD_FWD:
+      return b2u_head_fwd(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], (float*)p[3], i[2], s);
+    case B2U_OP_BCE_DICE_SUMS:
+      return b2u_bce_dice_sums((const float*)p[0], (const float*)p[1], i[0], (double*)p[2], s);
+    case B2U_OP_BCE_DICE_FINALIZE:
+      return b2u_bce_dice_finalize((const double*)p[0], i[0], (float*)p[1], s);
+    case B2U_OP_HEAD_BWD:
+      return b2u_head_bwd(dt, (const float*)p[0], (const float*)p[1], (const double*)p[2], i[0],
+                          (const b2u_step_state*)p[3], p[4], I(1), I(2), (const float*)p[5], p[6], I(3), I(4),
+                          (float*)p[7], (float*)p[8], i[5], s);
+    case B2U_OP_DENSE_FWD:
+      return b2u_dense_fwd(dt, p[0], I(0), (const float*)p[1], (const float*)p[2], I(1), p[3], I(2), I(3), s);
+    case B2U_OP_DENSE_BWD:
+      return b2u_dense_bwd(dt, p[0], I(0), (const float*)p[1], p[2], I(1), p[3], p[4], p[5], I(2), (float*)p[6],
+                           (float*)p[7], I(3), I(4), s);
+    case B2U_OP_BCE_FWD:
+      return b2u_bce_fwd((const float*)p[0], (const float*)p[1], (const float*)p[2], I(0), (float*)p[3], s);
+    case B2U_OP_BCE_SIGMOID_BWD:
+      return b2u_bce_sigmoid_bwd(dt, (const float*)p[0], (const float*)p[1], (const float*)p[2], I(0),
+                                 (const b2u_step_state*)p[3], p[4], s);
+    case B2U_OP_ADAM:
+      return b2u_adam((float*)p[0], (const float*)p[1], (float*)p[2], (float*)p[3], i[0], (b2u_step_state*)p[4], s);
+    case B2U_OP_MEMSET:
+      B2U_CHECK_CUDA(cudaMemsetAsync(p[0], 0, (size_t)i[0], (cudaStream_t)s));
+      return B2U_OK;
+    case B2U_OP_ALLREDUCE_F32:
+      return b2u_allreduce(comm, p[0], i[0], 0, s);
+    case B2U_OP_ALLREDUCE_F64:
+      return b2u_allreduce(comm, p[0], i[0], 1, s);
+    case B2U_OP_STATE_ADVANCE:
+      return b2u_state_advance((b2u_step_state*)p[0], s);
+    case B2U_OP_GATHER_BATCH:
+      return b2u_gather_batch(dt, (const float*)p[0], (const int*)p[1], p[2], i[0], I(1), s);
+    default:
+      b2u_set_error("run_ops: unknown op kind %d", o.kind);
+      return B2U_ERR_ARG;
+  }
+#undef I
+}
+
+extern "C" int b2u_run_ops(const b2u_op* h_ops, int n_ops, void* ws, size_t ws_bytes, void* comm, void* stream) {
+  B2U_REQUIRE(h_ops != nullptr || n_ops == 0, "run_ops: null op list");
+  for (int k = 0; k < n_ops; ++k) {
+    int rc = run_one(h_ops[k], ws, ws_bytes, comm, stream);
+    if (rc != B2U_OK) {
+      char tmp[900];
+      strncpy(tmp, g_err, sizeof(tmp) - 1);
+      tmp[sizeof(tmp) - 1] = 0;
+      b2u_set_error("op %d (kind %d): %s", k, h_ops[k].kind, tmp);
+      return rc;
+    }
+  }
+  return B2U_OK;
+}
+
+struct b2u_graph {
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+};
+
+extern "C" int b2u_graph_create(const b2u_op* h_ops, int n_ops, void* ws, size_t ws_bytes, void* comm, void* stream,
+                                void** out_graph) {
+  B2U_REQUIRE(out_graph != nullptr, "graph_create: null out pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  B2U_REQUIRE(s != nullptr, "graph_create: capture needs a non-default stream");
+  B2U_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int rc = b2u_run_ops(h_ops, n_ops, ws, ws_bytes, comm, stream);
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(s, &g);
+  if (rc != B2U_OK) {
+    if (g) cudaGraphDestroy(g);
+    return rc;
+  }
+  B2U_CHECK_CUDA(e);
+  cudaGraphExec_t ex = nullptr;
+  B2U_CHECK_CUDA(cudaGraphInstantiate(&ex, g, 0));
+  b2u_graph* h = new b2u_graph{g, ex};
+  *out_graph = h;
+  return B2U_OK;
+}
+
+extern "C" int b2u_graph_launch(void* graph, void* stream) {
+  B2U_REQUIRE(graph != nullptr, "graph_launch: null graph");
+  B2U_CHECK_CUDA(cudaGraphLaunch(((b2u_graph*)graph)->exec, (cudaStream_t)stream));
+  return B2U_OK;
+}
+
+extern "C" int b2u_graph_destroy(void* graph) {
+  if (graph == nullptr) return B2U_OK;
+  b2u_graph* h = (b2u_graph*)graph;
+  cudaGraphExecDestroy(h->exec);
+  cudaGraphDestroy(h->graph);
+  delete h;
+  return B2U_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// NCCL (dlopen'ed so that the library loads on a box without it; torch ships libnccl.so.2)
+// ------------------------------------------------------------------------------------------
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm_t;
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(nccl_uid*) = nullptr;
+  int (*CommInitRank)(nccl_comm_t*, int, nccl_uid, int) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+  if (g_nccl.handle != nullptr) return B2U_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  const char* env = getenv("B2U_NCCL_LIB");
+  if (env != nullptr) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+  for (int k = 0; h == nullptr && k < 2; ++k) h = dlopen(names[k], RTLD_NOW | RTLD_GLOBAL);
+  if (h == nullptr) {
+    b2u_set_error("cannot dlopen libnccl.so.2 (set B2U_NCCL_LIB): %s", dlerror());
+    return B2U_ERR_NCCL;
+  }
+  g_nccl.GetUniqueId = (int (*)(nccl_uid*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(nccl_comm_t*, int, nccl_uid, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.CommDestroy = (int (*)(nccl_comm_t))dlsym(h, "ncclCommDestroy");
+  g_nccl.AllReduce =
+      (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) {
+    b2u_set_error("libnccl is missing a required symbol");
+    return B2U_ERR_NCCL;
+  }
+  g_nccl.handle = h;
+  return B2U_OK;
+}
+#define B2U_CHECK_NCCL(expr)                                                                          \
+  do {                                                                                                \
+    int _r = (expr);                                                                                  \
+    if (_r != 0) {                                                                                    \
+      b2u_set_error("NCCL error %d: %s", _r, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
+      return B2U_ERR_NCCL;                                                                            \
+    }                                                                                                 \
+  } while (0)
+}  // namespace
+
+extern "C" int b2u_comm_unique_id(void* h_out_128B) {
+  int rc = nccl_load();
+  if (rc != B2U_OK) return rc;
+  nccl_uid id;
+  B2U_CHECK_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(h_out_128B, &id, 128);
+  return B2U_OK;
+}
+
+extern "C" int b2u_comm_create(const void* h_id_128B, int rank, int world, void** out_comm) {
+  int rc = nccl_load();
+  if (rc != B2U_OK) return rc;
+  nccl_uid id;
+  memcpy(&id, h_id_128B, 128);
+  nccl_comm_t c = nullptr;
+  B2U_CHECK_NCCL(g_nccl.CommInitRank(&c, world, id, rank));
+  *out_comm = c;
+  return B2U_OK;
+}
+
+extern "C" int b2u_comm_destroy(void* comm) {
+  if (comm == nullptr) return B2U_OK;
+  B2U_CHECK_NCCL(g_nccl.CommDestroy((nccl_comm_t)comm));
+  return B2U_OK;
+}
+
+extern "C" int b2u_allreduce(void* comm, void* buf, long long count, int is_double, void* stream) {
+  B2U_REQUIRE(comm != nullptr, "allreduce: no communicator (single-GPU plans must not contain ALLREDUCE ops)");
+  // ncclFloat32 = 7, ncclFloat64 = 8, ncclSum = 0
+  B2U_CHECK_NCCL(g_nccl.AllReduce(buf, buf, (size_t)count, is_double ? 8 : 7, 0, (nccl_comm_t)comm,
+                                  (cudaStream_t)stream));
+  __atomic_fetch_add(&g_b2u_launches, 1ULL, __ATOMIC_RELAXED);
+  return B2U_OK;
+}

@@ -1,0 +1,836 @@
+// HBM-bound kernels of the U-Net step: BatchNorm statistics/apply/backward, 2x2 max-pool (+dropout),
+// dropout, concat slice copies, the 1x1+sigmoid head with the BCE+Dice loss, Adam, batch gather.
+// All are coalesced 8-channel-vector streaming kernels with grids sized in multiples of the SM count.
+#include "common.cuh"
+#include "launch.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__host__ int stream_grid(long long work_items, int per_block = kThreads, int waves = 8) {
+  long long b = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)B2U_NUM_SMS * waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm statistics: sums[c] += sum x, sums[C + c] += sum x^2   (double accumulators)
+// ------------------------------------------------------------------------------------------
+template <typename T, bool kBwd>
+__global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const T* __restrict__ a, int lda,
+                                                             const T* __restrict__ x, int ldx, int C,
+                                                             long long npix, const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd,
+                                                             double* __restrict__ sums) {
+  // kBwd == false: a = x (stats of a).  kBwd == true: a = dy, x = bn input; sums of dy and dy*xhat.
+  extern __shared__ double sacc[];   // [2*C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.0;
+  __syncthreads();
+  const int cg = C >> 3;
+  const int lanes = kThreads / cg;              // pixel lanes per block
+  const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+  if (lane < lanes) {
+    float s1[8], s2[8], mu[8], is[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; mu[i] = 0.f; is[i] = 1.f; }
+    if (kBwd) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { mu[i] = mean[g * 8 + i]; is[i] = invstd[g * 8 + i]; }
+    }
+    for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
+      float v[8];
+      load8<T>(a + p * lda + g * 8, v);
+      if (kBwd) {
+        float xv[8];
+        load8<T>(x + p * ldx + g * 8, xv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1[i] += v[i]; s2[i] += v[i] * ((xv[i] - mu[i]) * is[i]); }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1[i] += v[i]; s2[i] += v[i] * v[i]; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sacc[g * 8 + i], (double)s1[i]);
+      atomicAdd(&sacc[C + g * 8 + i], (double)s2[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], sacc[i]);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ mmean, float* __restrict__ mvar, float momentum,
+                                   float eps, int training, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ save_mean,
+                                   float* __restrict__ save_invstd, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    double m = sums[c] / (double)count;
+    double v = sums[C + c] / (double)count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    // Keras 2.3 normalization.py: sample variance n/(n-(1+eps)) feeds the moving average
+    double unb = v * ((double)count / ((double)count - (1.0 + (double)eps)));
+    mmean[c] = momentum * mmean[c] + (1.f - momentum) * mean;
+    mvar[c] = momentum * mvar[c] + (1.f - momentum) * (float)unb;
+  } else {
+    mean = mmean[c];
+    var = mvar[c];
+  }
+  float is = rsqrtf(var + eps);
+  is = is * (1.5f - 0.5f * (var + eps) * is * is);   // one Newton step: full fp32 accuracy
+  float sc = gamma[c] * is;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  if (save_mean) save_mean[c] = mean;
+  if (save_invstd) save_invstd[c] = is;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y,
+                                                            int ldy, int C, long long npix,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift) {
+  const int cg = C >> 3;
+  const long long total = npix * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long p = i / cg;
+    int g = (int)(i - p * cg);
+    float v[8];
+    load8<T>(x + p * ldx + g * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], __ldg(scale + g * 8 + k), __ldg(shift + g * 8 + k));
+    store8<T>(y + p * ldy + g * 8, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
+    const T* __restrict__ dy, int lddy, const T* __restrict__ x, int ldx, T* __restrict__ dx, int lddx, int C,
+    long long npix, long long count, const float* __restrict__ gamma, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const double* __restrict__ sums, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, const T* __restrict__ mask, int ldmask, int mask_act) {
+  const int cg = C >> 3;
+  const long long total = npix * cg;
+  const float inv_n = 1.f / (float)count;
+  if (blockIdx.x == 0 && dgamma != nullptr) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dbeta[c] += (float)sums[c];
+      dgamma[c] += (float)sums[C + c];
+    }
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long p = i / cg;
+    int g = (int)(i - p * cg);
+    float d[8], xv[8], o[8];
+    load8<T>(dy + p * lddy + g * 8, d);
+    load8<T>(x + p * ldx + g * 8, xv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int c = g * 8 + k;
+      float is = __ldg(invstd + c);
+      float xh = (xv[k] - __ldg(mean + c)) * is;
+      float s1 = (float)sums[c] * inv_n, s2 = (float)sums[C + c] * inv_n;
+      o[k] = __ldg(gamma + c) * is * (d[k] - s1 - xh * s2);
+    }
+    if (mask != nullptr) {
+      float mv[8];
+      load8<T>(mask + p * ldmask + g * 8, mv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] *= act_bwd_from_y(mv[k], mask_act);
+    }
+    store8<T>(dx + p * lddx + g * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2x2 max-pool (+ optional dropout on the pooled output)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void keep_factors(float p, uint64_t e0, const b2u_step_state* st, int op_id,
+                                             float f[8]) {
+  // e0 is the logical index of the first of 8 consecutive elements (multiple of 8)
+  const uint32_t thr = dropout_threshold(p);
+  const float sc = 1.f / (1.f - p);
+  uint4 a = dropout_words(e0 >> 2, st->seed, st->step, (uint32_t)op_id);
+  uint4 b = dropout_words((e0 >> 2) + 1, st->seed, st->step, (uint32_t)op_id);
+  f[0] = a.x >= thr ? sc : 0.f; f[1] = a.y >= thr ? sc : 0.f; f[2] = a.z >= thr ? sc : 0.f; f[3] = a.w >= thr ? sc : 0.f;
+  f[4] = b.x >= thr ? sc : 0.f; f[5] = b.y >= thr ? sc : 0.f; f[6] = b.z >= thr ? sc : 0.f; f[7] = b.w >= thr ? sc : 0.f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y,
+                                                               int ldy, int C, int N, int H, int W, float p_drop,
+                                                               int op_id, const b2u_step_state* __restrict__ st) {
+  const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)N * Ho * Wo * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long op = i / cg;
+    int g = (int)(i - op * cg);
+    int wo = (int)(op % Wo);
+    long long t = op / Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    const T* base = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * ldx + g * 8;
+    float a[8], b[8], c[8], d[8], m[8];
+    load8<T>(base, a);
+    load8<T>(base + ldx, b);
+    load8<T>(base + (long long)W * ldx, c);
+    load8<T>(base + (long long)W * ldx + ldx, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = fmaxf(fmaxf(a[k], b[k]), fmaxf(c[k], d[k]));
+    if (p_drop > 0.f) {
+      float f[8];
+      keep_factors(p_drop, (uint64_t)op * C + g * 8, st, op_id, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] *= f[k];
+    }
+    store8<T>(y + op * ldy + g * 8, m);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const T* __restrict__ x, int ldx,
+                                                               const T* __restrict__ dy, int lddy,
+                                                               T* __restrict__ dx, int lddx, int C, int N, int H,
+                                                               int W, float p_drop, int op_id,
+                                                               const b2u_step_state* __restrict__ st,
+                                                               int accumulate) {
+  const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)N * Ho * Wo * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long op = i / cg;
+    int g = (int)(i - op * cg);
+    int wo = (int)(op % Wo);
+    long long t = op / Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    long long ip = ((long long)n * H + 2 * ho) * W + 2 * wo;
+    const T* base = x + ip * ldx + g * 8;
+    float a[8], b[8], c[8], d[8], gy[8];
+    load8<T>(base, a);
+    load8<T>(base + ldx, b);
+    load8<T>(base + (long long)W * ldx, c);
+    load8<T>(base + (long long)W * ldx + ldx, d);
+    load8<T>(dy + op * lddy + g * 8, gy);
+    if (p_drop > 0.f) {
+      float f[8];
+      keep_factors(p_drop, (uint64_t)op * C + g * 8, st, op_id, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gy[k] *= f[k];
+    }
+    float oa[8], ob[8], oc[8], od[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      // first maximum in window order (0,0),(0,1),(1,0),(1,1) takes the gradient (TF/torch tie rule)
+      float m = fmaxf(fmaxf(a[k], b[k]), fmaxf(c[k], d[k]));
+      int sel = (a[k] == m) ? 0 : (b[k] == m) ? 1 : (c[k] == m) ? 2 : 3;
+      oa[k] = sel == 0 ? gy[k] : 0.f;
+      ob[k] = sel == 1 ? gy[k] : 0.f;
+      oc[k] = sel == 2 ? gy[k] : 0.f;
+      od[k] = sel == 3 ? gy[k] : 0.f;
+    }
+    T* ob_ = dx + ip * lddx + g * 8;
+    if (accumulate) {
+      float e[8];
+      load8<T>(ob_, e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) oa[k] += e[k];
+      load8<T>(ob_ + lddx, e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ob[k] += e[k];
+      load8<T>(ob_ + (long long)W * lddx, e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) oc[k] += e[k];
+      load8<T>(ob_ + (long long)W * lddx + lddx, e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) od[k] += e[k];
+    }
+    store8<T>(ob_, oa);
+    store8<T>(ob_ + lddx, ob);
+    store8<T>(ob_ + (long long)W * lddx, oc);
+    store8<T>(ob_ + (long long)W * lddx + lddx, od);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) dropout_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y,
+                                                           int ldy, int C, long long npix, float p, int op_id,
+                                                           const b2u_step_state* __restrict__ st,
+                                                           const T* __restrict__ mask, int ldmask, int mask_act) {
+  const int cg = C >> 3;
+  const long long total = npix * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long px = i / cg;
+    int g = (int)(i - px * cg);
+    float v[8], f[8];
+    load8<T>(x + px * ldx + g * 8, v);
+    keep_factors(p, (uint64_t)px * C + g * 8, st, op_id, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= f[k];
+    if (mask != nullptr) {
+      float mv[8];
+      load8<T>(mask + px * ldmask + g * 8, mv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= act_bwd_from_y(mv[k], mask_act);
+    }
+    store8<T>(y + px * ldy + g * 8, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) copy_slice_kernel(const T* __restrict__ s, int lds, T* __restrict__ d,
+                                                              int ldd, int C, long long npix, int accumulate) {
+  const int cg = C >> 3;
+  const long long total = npix * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long px = i / cg;
+    int g = (int)(i - px * cg);
+    float v[8];
+    load8<T>(s + px * lds + g * 8, v);
+    if (accumulate) {
+      float e[8];
+      load8<T>(d + px * ldd + g * 8, e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += e[k];
+    }
+    store8<T>(d + px * ldd + g * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// output head: 1x1 conv (Cin -> 1) + sigmoid, BCE+Dice sums, and their backward
+// ------------------------------------------------------------------------------------------
+template <typename T, int CIN>
+__global__ void __launch_bounds__(kThreads) head_fwd_kernel(const T* __restrict__ x, int ldx,
+                                                            const float* __restrict__ w,
+                                                            const float* __restrict__ bias,
+                                                            float* __restrict__ prob, long long npix) {
+  float wr[CIN];
+#pragma unroll
+  for (int k = 0; k < CIN; ++k) wr[k] = __ldg(w + k);
+  const float b = __ldg(bias);
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
+       p += (long long)gridDim.x * blockDim.x) {
+    float acc = b;
+#pragma unroll
+    for (int g = 0; g < CIN / 8; ++g) {
+      float v[8];
+      load8<T>(x + p * ldx + g * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = fmaf(v[k], wr[g * 8 + k], acc);
+    }
+    prob[p] = 1.f / (1.f + expf(-acc));
+  }
+}
+
+__device__ __forceinline__ float bce_term(float t, float p) {
+  const float lo = 1e-7f, hi = 1.f - 1e-7f;    // keras.backend.epsilon() clip
+  float ph = fminf(fmaxf(p, lo), hi);
+  return -(t * logf(ph) + (1.f - t) * log1pf(-ph));
+}
+
+__global__ void __launch_bounds__(kThreads) bce_dice_sums_kernel(const float* __restrict__ prob,
+                                                                 const float* __restrict__ tgt, long long count,
+                                                                 double* __restrict__ sums) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    float p = prob[i], t = tgt[i];
+    s0 += t * p; s1 += t; s2 += p; s3 += bce_term(t, p);
+  }
+  __shared__ double sh[4];
+  if (threadIdx.x < 4) sh[threadIdx.x] = 0.0;
+  __syncthreads();
+  double d0 = warp_sum_d((double)s0), d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2),
+         d3 = warp_sum_d((double)s3);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sh[0], d0); atomicAdd(&sh[1], d1); atomicAdd(&sh[2], d2); atomicAdd(&sh[3], d3);
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) atomicAdd(&sums[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void bce_dice_finalize_kernel(const double* __restrict__ sums, long long count, float* __restrict__ out) {
+  double I = sums[0], S = sums[1] + sums[2];
+  double dice = (2.0 * I + 1.0) / (S + 1.0);
+  out[0] = (float)(0.5 * sums[3] / (double)count + 0.5 * (1.0 - dice));
+  out[1] = (float)dice;
+}
+
+template <typename T, int CIN>
+__global__ void __launch_bounds__(kThreads) head_bwd_kernel(
+    const float* __restrict__ prob, const float* __restrict__ tgt, const double* __restrict__ sums,
+    long long count, const b2u_step_state* __restrict__ st, const T* __restrict__ x, int ldx,
+    const float* __restrict__ w, T* __restrict__ dx, int lddx, int x_act, float* __restrict__ dw,
+    float* __restrict__ db, long long npix) {
+  __shared__ float sacc[CIN + 1];
+  for (int i = threadIdx.x; i < CIN + 1; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  float wr[CIN], acc[CIN];
+#pragma unroll
+  for (int k = 0; k < CIN; ++k) { wr[k] = __ldg(w + k); acc[k] = 0.f; }
+  float accb = 0.f;
+  const double I = sums[0], S = sums[1] + sums[2];
+  const float inv_s1 = (float)(1.0 / (S + 1.0));
+  const float two_i1 = (float)(2.0 * I + 1.0);
+  const float scale = st->loss_scale;
+  const float half_inv_n = 0.5f / (float)count;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
+       p += (long long)gridDim.x * blockDim.x) {
+    float pr = prob[p], t = tgt[p];
+    float g = 0.f;
+    if (pr >= 1e-7f && pr <= 1.f - 1e-7f) g = half_inv_n * (-t / pr + (1.f - t) / (1.f - pr));
+    // d(1-dice)/dp = -(2 t (S+1) - (2I+1)) / (S+1)^2
+    g -= 0.5f * (2.f * t - two_i1 * inv_s1) * inv_s1;
+    float dl = g * pr * (1.f - pr) * scale;
+    accb += dl;
+#pragma unroll
+    for (int gq = 0; gq < CIN / 8; ++gq) {
+      float v[8], o[8];
+      load8<T>(x + p * ldx + gq * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc[gq * 8 + k] = fmaf(dl, v[k], acc[gq * 8 + k]);
+        o[k] = dl * wr[gq * 8 + k] * act_bwd_from_y(v[k], x_act);
+      }
+      store8<T>(dx + p * lddx + gq * 8, o);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < CIN; ++k) {
+    float s = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[k], s);
+  }
+  float sb = warp_sum(accb);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[CIN], sb);
+  __syncthreads();
+  for (int i = threadIdx.x; i < CIN; i += blockDim.x) atomicAdd(&dw[i], sacc[i]);
+  if (threadIdx.x == 0) atomicAdd(db, sacc[CIN]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam over the flat parameter buffer; step-state bookkeeping; batch gather
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, long long n,
+                                                        b2u_step_state* __restrict__ st) {
+  const float b1 = st->beta1, b2 = st->beta2, eps = st->eps;
+  const float lr_t = st->lr * sqrtf(1.f - st->beta2_pow) / (1.f - st->beta1_pow);
+  const float gs = 1.f / (st->loss_scale * st->grad_div);
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gs;
+    if (!isfinite(gi)) { bad = true; continue; }
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+  if (bad) atomicOr(&st->overflow, 1u);
+}
+
+__global__ void state_advance_kernel(b2u_step_state* st) {
+  st->step += 1;
+  st->beta1_pow *= st->beta1;
+  st->beta2_pow *= st->beta2;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) gather_batch_kernel(const float* __restrict__ src,
+                                                                const int* __restrict__ idx, T* __restrict__ dst,
+                                                                long long per_sample, int nb) {
+  const long long total = (long long)nb * per_sample;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long b = i / per_sample;
+    long long e = i - b * per_sample;
+    long long s = idx ? (long long)idx[b] : b;
+    stf<T>(dst + i, src[s * per_sample + e]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// sm.metrics threshold sweep: one pass over (p, t) for all thresholds
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) threshold_counts_kernel(const float* __restrict__ prob,
+                                                                    const float* __restrict__ tgt, long long count,
+                                                                    const float* __restrict__ thr, int nthr,
+                                                                    double* __restrict__ tp, double* __restrict__ spr,
+                                                                    double* __restrict__ sgt) {
+  extern __shared__ float sh[];   // [nthr] tp, [nthr] cnt, [1] gt
+  for (int i = threadIdx.x; i < 2 * nthr + 1; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float gt = 0.f;
+  const long long start = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // all lanes of a warp iterate together (count is padded by predication)
+  for (long long i0 = start - (threadIdx.x & 31); i0 < count; i0 += stride) {
+    long long i = i0 + (threadIdx.x & 31);
+    bool ok = i < count;
+    float p = ok ? prob[i] : -1.f, t = ok ? tgt[i] : 0.f;
+    gt += t;
+    for (int k = 0; k < nthr; ++k) {
+      bool pr = ok && (p > __ldg(thr + k));
+      unsigned b = __ballot_sync(0xffffffffu, pr);
+      if (b == 0u) continue;
+      float s = warp_sum(pr ? t : 0.f);
+      if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[k], s); atomicAdd(&sh[nthr + k], (float)__popc(b)); }
+    }
+  }
+  gt = warp_sum(gt);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sh[2 * nthr], gt);
+  __syncthreads();
+  for (int k = threadIdx.x; k < nthr; k += blockDim.x) {
+    atomicAdd(&tp[k], (double)sh[k]);
+    atomicAdd(&spr[k], (double)sh[nthr + k]);
+  }
+  if (threadIdx.x == 0) atomicAdd(sgt, (double)sh[2 * nthr]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Dense + classifier loss (Task-2 head; small, HBM-bound)
+// ------------------------------------------------------------------------------------------
+template <typename T, int M>
+__global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const T* __restrict__ x, int K,
+                                                             const float* __restrict__ w,
+                                                             const float* __restrict__ bias, int act,
+                                                             float* __restrict__ y) {
+  // one block per sample; threads split K; each keeps M partial outputs (y is always fp32)
+  __shared__ float sacc[M];
+  for (int i = threadIdx.x; i < M; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.x;
+  float acc[M];
+#pragma unroll
+  for (int j = 0; j < M; ++j) acc[j] = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float xv = ldf<T>(x + (long long)n * K + k);
+#pragma unroll
+    for (int j = 0; j < M; ++j) acc[j] = fmaf(xv, __ldg(w + (long long)k * M + j), acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    float s = warp_sum(acc[j]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[j], s);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    float v = sacc[j] + bias[j];
+    if (act == B2U_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+    else v = act_fwd(v, act);
+    y[(long long)n * M + j] = v;
+  }
+}
+
+// dpre[n][j] = dy[n][j] * act'(y[n][j])   (sigmoid handled by the loss kernel: act NONE there)
+template <typename T, int M>
+__global__ void __launch_bounds__(kThreads) dense_bwd_kernel(const T* __restrict__ x, int K,
+                                                             const float* __restrict__ w, const float* __restrict__ y,
+                                                             int act, const float* __restrict__ dy, T* __restrict__ dx,
+                                                             const T* __restrict__ mask, int mask_act,
+                                                             float* __restrict__ dw, float* __restrict__ db, int N) {
+  // grid over K chunks: each thread owns one k and loops over samples (N small) -> dw row + dx column
+  extern __shared__ float dpre[];   // [N][M]
+  for (int i = threadIdx.x; i < N * M; i += blockDim.x) {
+    dpre[i] = dy[i] * act_bwd_from_y(y[i], act);
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+      float s = 0.f;
+      for (int n = 0; n < N; ++n) s += dpre[n * M + j];
+      db[j] += s;
+    }
+  }
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float wr[M], gw[M];
+#pragma unroll
+  for (int j = 0; j < M; ++j) { wr[j] = w[(long long)k * M + j]; gw[j] = 0.f; }
+  for (int n = 0; n < N; ++n) {
+    float xv = ldf<T>(x + (long long)n * K + k);
+    float d = 0.f;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      float dp = dpre[n * M + j];
+      gw[j] = fmaf(xv, dp, gw[j]);
+      d = fmaf(dp, wr[j], d);
+    }
+    if (dx != nullptr) {
+      if (mask != nullptr) d *= act_bwd_from_y(ldf<T>(mask + (long long)n * K + k), mask_act);
+      stf<T>(dx + (long long)n * K + k, d);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < M; ++j) dw[(long long)k * M + j] += gw[j];
+}
+
+__global__ void bce_fwd_kernel(const float* __restrict__ prob, const float* __restrict__ tgt,
+                               const float* __restrict__ sw, int n, float* __restrict__ out) {
+  // single block; keras: mean over batch of w_i * bce_i
+  __shared__ float sh;
+  if (threadIdx.x == 0) sh = 0.f;
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (sw ? sw[i] : 1.f) * bce_term(tgt[i], prob[i]);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sh, s);
+  __syncthreads();
+  if (threadIdx.x == 0) out[0] = sh / (float)n;
+}
+
+template <typename T>
+__global__ void bce_sigmoid_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ tgt,
+                                       const float* __restrict__ sw, int n, const b2u_step_state* __restrict__ st,
+                                       T* __restrict__ dlogit) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float p = prob[i], t = tgt[i], g = 0.f;
+  if (p >= 1e-7f && p <= 1.f - 1e-7f) g = (-t / p + (1.f - t) / (1.f - p)) * p * (1.f - p);
+  stf<T>(dlogit + i, g * (sw ? sw[i] : 1.f) / (float)n * st->loss_scale);
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C-ABI wrappers
+// ==========================================================================================
+#define DISPATCH_T(dt, ...)                                              \
+  if ((dt) == B2U_F32) { using T = float; __VA_ARGS__; }                 \
+  else if ((dt) == B2U_F16) { using T = __half; __VA_ARGS__; }           \
+  else { b2u_set_error("bad dtype %d", (int)(dt)); return B2U_ERR_ARG; }
+
+#define REQ_VEC8(c, ...)                                                                           \
+  B2U_REQUIRE((c) > 0 && (c) % 8 == 0, "%s: channel count %d must be a positive multiple of 8", __func__, (int)(c))
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" int b2u_state_advance(b2u_step_state* d_state, void* stream) {
+  B2U_LAUNCH(state_advance_kernel, 1, 1, 0, stream, d_state);
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_stats(int dt, const void* x, int ldx, int c, long long npix, double* sums, void* stream) {
+  REQ_VEC8(c);
+  B2U_REQUIRE(c <= 2048 && ldx % 8 == 0 && aligned16(x), "bn_stats: c<=2048, ld%%8==0, 16B-aligned base required");
+  int lanes = kThreads / (c / 8);
+  int grid = stream_grid(npix, lanes, 4);
+  size_t smem = 2 * (size_t)c * sizeof(double);
+  DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, false>), grid, kThreads, smem, stream, (const T*)x, ldx,
+                            (const T*)nullptr, 0, c, npix, (const float*)nullptr, (const float*)nullptr, sums));
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_finalize(const double* sums, long long count, const float* gamma, const float* beta,
+                               float* moving_mean, float* moving_var, float momentum, float eps, int training,
+                               float* scale, float* shift, float* save_mean, float* save_invstd, int c,
+                               void* stream) {
+  B2U_REQUIRE(c > 0, "bn_finalize: c must be > 0");
+  B2U_LAUNCH(bn_finalize_kernel, b2u_cdiv(c, 128), 128, 0, stream, sums, count, gamma, beta, moving_mean,
+             moving_var, momentum, eps, training, scale, shift, save_mean, save_invstd, c);
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_apply(int dt, const void* x, int ldx, void* y, int ldy, int c, long long npix,
+                            const float* scale, const float* shift, void* stream) {
+  REQ_VEC8(c);
+  B2U_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "bn_apply: alignment");
+  int grid = stream_grid(npix * (c / 8));
+  DISPATCH_T(dt, B2U_LAUNCH(bn_apply_kernel<T>, grid, kThreads, 0, stream, (const T*)x, ldx, (T*)y, ldy, c, npix,
+                            scale, shift));
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_bwd_reduce(int dt, const void* dy, int lddy, const void* x, int ldx, int c, long long npix,
+                                 const float* save_mean, const float* save_invstd, double* sums, void* stream) {
+  REQ_VEC8(c);
+  B2U_REQUIRE(c <= 2048 && ldx % 8 == 0 && lddy % 8 == 0 && aligned16(x) && aligned16(dy), "bn_bwd_reduce: alignment");
+  int lanes = kThreads / (c / 8);
+  int grid = stream_grid(npix, lanes, 4);
+  size_t smem = 2 * (size_t)c * sizeof(double);
+  DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, true>), grid, kThreads, smem, stream, (const T*)dy, lddy,
+                            (const T*)x, ldx, c, npix, save_mean, save_invstd, sums));
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_bwd_apply(int dt, const void* dy, int lddy, const void* x, int ldx, void* dx, int lddx, int c,
+                                long long npix, long long count, const float* gamma, const float* save_mean,
+                                const float* save_invstd, const double* sums, float* dgamma, float* dbeta,
+                                const void* mask, int ldmask, int mask_act, void* stream) {
+  REQ_VEC8(c);
+  B2U_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && (mask == nullptr || ldmask % 8 == 0),
+              "bn_bwd_apply: alignment");
+  int grid = stream_grid(npix * (c / 8));
+  DISPATCH_T(dt, B2U_LAUNCH(bn_bwd_apply_kernel<T>, grid, kThreads, 0, stream, (const T*)dy, lddy, (const T*)x, ldx,
+                            (T*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums, dgamma, dbeta,
+                            (const T*)mask, ldmask, mask_act));
+  return B2U_OK;
+}
+
+extern "C" int b2u_maxpool_fwd(int dt, const void* x, int ldx, void* y, int ldy, int c, int n, int h, int wd,
+                               float p_drop, int op_id, const b2u_step_state* d_state, void* stream) {
+  REQ_VEC8(c);
+  B2U_REQUIRE(h % 2 == 0 && wd % 2 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "maxpool_fwd: even H,W and ld%%8==0");
+  B2U_REQUIRE(p_drop == 0.f || d_state != nullptr, "maxpool_fwd: dropout needs a step state");
+  B2U_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "maxpool_fwd: bad dropout rate");
+  int grid = stream_grid((long long)n * (h / 2) * (wd / 2) * (c / 8));
+  DISPATCH_T(dt, B2U_LAUNCH(maxpool_fwd_kernel<T>, grid, kThreads, 0, stream, (const T*)x, ldx, (T*)y, ldy, c, n, h,
+                            wd, p_drop, op_id, d_state));
+  return B2U_OK;
+}
+
+extern "C" int b2u_maxpool_bwd(int dt, const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int c,
+                               int n, int h, int wd, float p_drop, int op_id, const b2u_step_state* d_state,
+                               int accumulate, void* stream) {
+  REQ_VEC8(c);
+  B2U_REQUIRE(h % 2 == 0 && wd % 2 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0, "maxpool_bwd: shape");
+  B2U_REQUIRE(p_drop == 0.f || d_state != nullptr, "maxpool_bwd: dropout needs a step state");
+  int grid = stream_grid((long long)n * (h / 2) * (wd / 2) * (c / 8));
+  DISPATCH_T(dt, B2U_LAUNCH(maxpool_bwd_kernel<T>, grid, kThreads, 0, stream, (const T*)x, ldx, (const T*)dy, lddy,
+                            (T*)dx, lddx, c, n, h, wd, p_drop, op_id, d_state, accumulate));
+  return B2U_OK;
+}
+
+extern "C" int b2u_dropout_fwd(int dt, const void* x, int ldx, void* y, int ldy, int c, long long npix, float p,
+                               int op_id, const b2u_step_state* d_state, void* stream) {
+  REQ_VEC8(c);
+  B2U_REQUIRE(p >= 0.f && p < 1.f && d_state != nullptr && ldx % 8 == 0 && ldy % 8 == 0, "dropout_fwd: args");
+  int grid = stream_grid(npix * (c / 8));
+  DISPATCH_T(dt, B2U_LAUNCH(dropout_kernel<T>, grid, kThreads, 0, stream, (const T*)x, ldx, (T*)y, ldy, c, npix, p,
+                            op_id, d_state, (const T*)nullptr, 0, 0));
+  return B2U_OK;
+}
+
+extern "C" int b2u_dropout_bwd(int dt, const void* dy, int lddy, void* dx, int lddx, int c, long long npix, float p,
+                               int op_id, const b2u_step_state* d_state, const void* mask, int ldmask, int mask_act,
+                               void* stream) {
+  REQ_VEC8(c);
+  B2U_REQUIRE(p >= 0.f && p < 1.f && d_state != nullptr && lddy % 8 == 0 && lddx % 8 == 0, "dropout_bwd: args");
+  int grid = stream_grid(npix * (c / 8));
+  DISPATCH_T(dt, B2U_LAUNCH(dropout_kernel<T>, grid, kThreads, 0, stream, (const T*)dy, lddy, (T*)dx, lddx, c, npix,
+                            p, op_id, d_state, (const T*)mask, ldmask, mask_act));
+  return B2U_OK;
+}
+
+extern "C" int b2u_copy_slice(int dt, const void* src, int ldsrc, void* dst, int lddst, int c, long long npix,
+                              int accumulate, void* stream) {
+  REQ_VEC8(c);
+  B2U_REQUIRE(ldsrc % 8 == 0 && lddst % 8 == 0, "copy_slice: ld%%8==0 required");
+  int grid = stream_grid(npix * (c / 8));
+  DISPATCH_T(dt, B2U_LAUNCH(copy_slice_kernel<T>, grid, kThreads, 0, stream, (const T*)src, ldsrc, (T*)dst, lddst, c,
+                            npix, accumulate));
+  return B2U_OK;
+}
+
+extern "C" int b2u_head_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, float* prob,
+                            long long npix, void* stream) {
+  B2U_REQUIRE(cin == 32 || cin == 16 || cin == 64, "head_fwd: cin must be 16, 32 or 64 (got %d)", cin);
+  B2U_REQUIRE(ldx % 8 == 0, "head_fwd: ld%%8==0 required");
+  int grid = stream_grid(npix);
+#define HEAD_FWD(CI) DISPATCH_T(dt, B2U_LAUNCH((head_fwd_kernel<T, CI>), grid, kThreads, 0, stream, (const T*)x, ldx, w, bias, prob, npix))
+  if (cin == 32) { HEAD_FWD(32); } else if (cin == 16) { HEAD_FWD(16); } else { HEAD_FWD(64); }
+#undef HEAD_FWD
+  return B2U_OK;
+}
+
+extern "C" int b2u_bce_dice_sums(const float* prob, const float* target, long long count, double* sums,
+                                 void* stream) {
+  int grid = stream_grid(count, kThreads, 4);
+  B2U_LAUNCH(bce_dice_sums_kernel, grid, kThreads, 0, stream, prob, target, count, sums);
+  return B2U_OK;
+}
+
+extern "C" int b2u_bce_dice_finalize(const double* sums, long long count, float* out, void* stream) {
+  B2U_LAUNCH(bce_dice_finalize_kernel, 1, 1, 0, stream, sums, count, out);
+  return B2U_OK;
+}
+
+extern "C" int b2u_head_bwd(int dt, const float* prob, const float* target, const double* sums, long long count,
+                            const b2u_step_state* d_state, const void* x, int ldx, int cin, const float* w,
+                            void* dx, int lddx, int x_act, float* dw, float* db, long long npix, void* stream) {
+  B2U_REQUIRE(cin == 32 || cin == 16 || cin == 64, "head_bwd: cin must be 16, 32 or 64 (got %d)", cin);
+  B2U_REQUIRE(ldx % 8 == 0 && lddx % 8 == 0 && d_state != nullptr, "head_bwd: args");
+  int grid = stream_grid(npix, kThreads, 4);
+#define HEAD_BWD(CI) DISPATCH_T(dt, B2U_LAUNCH((head_bwd_kernel<T, CI>), grid, kThreads, 0, stream, prob, target, sums, count, d_state, (const T*)x, ldx, w, (T*)dx, lddx, x_act, dw, db, npix))
+  if (cin == 32) { HEAD_BWD(32); } else if (cin == 16) { HEAD_BWD(16); } else { HEAD_BWD(64); }
+#undef HEAD_BWD
+  return B2U_OK;
+}
+
+extern "C" int b2u_adam(float* params, const float* grads, float* m, float* v, long long n, b2u_step_state* d_state,
+                        void* stream) {
+  B2U_REQUIRE(n >= 0 && d_state != nullptr, "adam: args");
+  if (n == 0) return B2U_OK;
+  B2U_LAUNCH(adam_kernel, stream_grid(n), kThreads, 0, stream, params, grads, m, v, n, d_state);
+  return B2U_OK;
+}
+
+extern "C" int b2u_gather_batch(int dt, const float* src, const int* idx, void* dst, long long per_sample, int nb,
+                                void* stream) {
+  B2U_REQUIRE(nb > 0 && per_sample > 0, "gather_batch: empty batch");
+  int grid = stream_grid((long long)nb * per_sample);
+  DISPATCH_T(dt, B2U_LAUNCH(gather_batch_kernel<T>, grid, kThreads, 0, stream, src, idx, (T*)dst, per_sample, nb));
+  return B2U_OK;
+}
+
+extern "C" int b2u_threshold_counts(const float* prob, const float* target, long long count,
+                                    const float* thresholds, int nthr, double* tp, double* sum_pr, double* sum_gt,
+                                    void* stream) {
+  B2U_REQUIRE(nthr > 0 && nthr <= 4096, "threshold_counts: 1..4096 thresholds");
+  if (count == 0) return B2U_OK;
+  int grid = stream_grid(count, kThreads, 4);
+  size_t smem = (2 * (size_t)nthr + 1) * sizeof(float);
+  B2U_LAUNCH(threshold_counts_kernel, grid, kThreads, smem, stream, prob, target, count, thresholds, nthr, tp,
+             sum_pr, sum_gt);
+  return B2U_OK;
+}
+
+extern "C" int b2u_dense_fwd(int dt, const void* x, int k, const float* w, const float* bias, int act, void* y,
+                             int m, int n, void* stream) {
+  B2U_REQUIRE(m == 32 || m == 1, "dense_fwd: units must be 32 or 1 (got %d)", m);
+  if (m == 32) { DISPATCH_T(dt, B2U_LAUNCH((dense_fwd_kernel<T, 32>), n, kThreads, 0, stream, (const T*)x, k, w, bias, act, (float*)y)); }
+  else { DISPATCH_T(dt, B2U_LAUNCH((dense_fwd_kernel<T, 1>), n, kThreads, 0, stream, (const T*)x, k, w, bias, act, (float*)y)); }
+  return B2U_OK;
+}
+
+extern "C" int b2u_dense_bwd(int dt, const void* x, int k, const float* w, const void* y, int act, const void* dy,
+                             void* dx, const void* mask, int mask_act, float* dw, float* db, int m, int n,
+                             void* stream) {
+  B2U_REQUIRE(m == 32 || m == 1, "dense_bwd: units must be 32 or 1 (got %d)", m);
+  B2U_REQUIRE((size_t)n * m * sizeof(float) <= 48 * 1024, "dense_bwd: batch too large for one pass");
+  size_t smem = (size_t)n * m * sizeof(float);
+  int grid = b2u_cdiv(k, kThreads);
+  if (m == 32) { DISPATCH_T(dt, B2U_LAUNCH((dense_bwd_kernel<T, 32>), grid, kThreads, smem, stream, (const T*)x, k, w, (const float*)y, act, (const float*)dy, (T*)dx, (const T*)mask, mask_act, dw, db, n)); }
+  else { DISPATCH_T(dt, B2U_LAUNCH((dense_bwd_kernel<T, 1>), grid, kThreads, smem, stream, (const T*)x, k, w, (const float*)y, act, (const float*)dy, (T*)dx, (const T*)mask, mask_act, dw, db, n)); }
+  return B2U_OK;
+}
+
+extern "C" int b2u_bce_fwd(const float* prob, const float* target, const float* sample_w, int n, float* out,
+                           void* stream) {
+  B2U_LAUNCH(bce_fwd_kernel, 1, kThreads, 0, stream, prob, target, sample_w, n, out);
+  return B2U_OK;
+}
+
+extern "C" int b2u_bce_sigmoid_bwd(int dt, const float* prob, const float* target, const float* sample_w, int n,
+                                   const b2u_step_state* d_state, void* dlogit, void* stream) {
+  DISPATCH_T(dt, B2U_LAUNCH(bce_sigmoid_bwd_kernel<T>, b2u_cdiv(n, 128), 128, 0, stream, prob, target, sample_w, n,
+                            d_state, (T*)dlogit));
+  return B2U_OK;
+}

@@ -1,0 +1,35 @@
+// Internal (non-ABI) entry points shared between translation units.
+#pragma once
+#include <stddef.h>
+
+// exact CUDA-core path (conv_direct.cu)
+int b2u_direct_conv3x3(int dt, const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act,
+                       void* y, int ldy, int J, double* stats, const void* mask, int ldmask, int mask_act,
+                       int accumulate, int n, int h, int wd, void* stream);
+int b2u_direct_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw,
+                             float* db, int n, int h, int wd, void* stream);
+int b2u_direct_convt_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, void* y, int ldy,
+                         int cout, int n, int h, int wd, void* stream);
+int b2u_direct_convt_dgrad(int dt, const void* dy, int lddy, int cout, const float* w, void* dx, int lddx, int cin,
+                           const void* mask, int ldmask, int mask_act, int accumulate, int n, int h, int wd,
+                           void* stream);
+int b2u_direct_convt_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw,
+                           float* db, int n, int h, int wd, void* stream);
+
+// tcgen05 tensor path (conv_tc.cu); fp16 storage, fp32 accumulation in TMEM
+int b2u_tc_compiled(void);
+int b2u_tc_conv3x3_ok(int k, int j, int ld_in, int ld_out);
+int b2u_tc_wgrad_ok(int cin, int cout, int ldx, int lddy);
+int b2u_tc_convt_ok(int cin, int cout, int ld_small, int ld_big);
+int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
+                   int ldy, int J, double* stats, const void* mask, int ldmask, int mask_act, int accumulate, int n,
+                   int h, int wd, void* ws, size_t ws_bytes, void* stream);
+int b2u_tc_conv3x3_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* db,
+                         int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+int b2u_tc_convt_fwd(const void* x, int ldx, int cin, const float* w, const float* bias, void* y, int ldy, int cout,
+                     int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+int b2u_tc_convt_dgrad(const void* dy, int lddy, int cout, const float* w, void* dx, int lddx, int cin,
+                       const void* mask, int ldmask, int mask_act, int accumulate, int n, int h, int wd, void* ws,
+                       size_t ws_bytes, void* stream);
+int b2u_tc_convt_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* db,
+                       int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);

@@ -1,0 +1,513 @@
+"""Lowers a layers.Graph to the flat device op lists libb200unet.so executes (b2u_run_ops).
+
+This is the host-side "compiler" of the engine: it decides the HBM layout (one activation arena with
+zero-copy concat buffers, flat fp32 parameter / gradient / Adam buffers in Keras weight order), the
+fusions (BN statistics in the conv epilogue, max-pool + dropout in one pass, activation-derivative
+masks folded into whichever backward kernel produces a gradient) and the backward schedule.  It is pure
+Python with no CUDA dependency, so the schedule is testable on a CPU box (tests/emulator.py interprets
+the same op list with numpy).
+
+Replaces what `model.compile(...)` + the Keras/TF graph builder did for the reference
+(/root/reference/Scripts/task1_preprocessing_plus_unet_with_comments.py:1053-1061).
+"""
+from collections import OrderedDict
+import math
+
+from . import layers as L
+
+# ---- enums mirrored from include/b200unet.h ------------------------------------------------------
+F32, F16 = 0, 1
+ACT = {None: 0, "linear": 0, "relu": 1, "elu": 2, "sigmoid": 3}
+(OP_CONV3X3_FWD, OP_CONV3X3_DGRAD, OP_CONV3X3_WGRAD, OP_CONVT_FWD, OP_CONVT_DGRAD, OP_CONVT_WGRAD,
+ OP_BN_STATS, OP_BN_FINALIZE, OP_BN_APPLY, OP_BN_BWD_REDUCE, OP_BN_BWD_APPLY, OP_MAXPOOL_FWD, OP_MAXPOOL_BWD,
+ OP_DROPOUT_FWD, OP_DROPOUT_BWD, OP_COPY_SLICE, OP_HEAD_FWD, OP_BCE_DICE_SUMS, OP_BCE_DICE_FINALIZE, OP_HEAD_BWD,
+ OP_DENSE_FWD, OP_DENSE_BWD, OP_BCE_FWD, OP_BCE_SIGMOID_BWD, OP_ADAM, OP_MEMSET, OP_ALLREDUCE_F32,
+ OP_ALLREDUCE_F64, OP_STATE_ADVANCE, OP_GATHER_BATCH) = range(1, 31)
+OP_NAMES = {v: k for k, v in list(globals().items()) if k.startswith("OP_")}
+
+ELEM = {F32: 4, F16: 2}
+STEP_STATE_BYTES = 64
+
+
+class Ref:
+    """A location inside a named arena (resolved to a device pointer at bind time)."""
+    __slots__ = ("arena", "off")
+
+    def __init__(self, arena, off):
+        self.arena, self.off = arena, int(off)
+
+    def __add__(self, nbytes):
+        return Ref(self.arena, self.off + int(nbytes))
+
+    def __repr__(self):
+        return "%s+%d" % (self.arena, self.off)
+
+
+class View:
+    """NHWC activation view: base ref, ld (elements between pixels), c channels, dt storage type.
+    Flat (n,k) tensors use h = w = 1, c = ld = k."""
+    __slots__ = ("ref", "ld", "c", "h", "w", "dt")
+
+    def __init__(self, ref, ld, c, h, w, dt):
+        self.ref, self.ld, self.c, self.h, self.w, self.dt = ref, int(ld), int(c), int(h), int(w), dt
+
+    def slice(self, c0, c):
+        return View(self.ref + c0 * ELEM[self.dt], self.ld, c, self.h, self.w, self.dt)
+
+
+class Op:
+    __slots__ = ("kind", "dt", "p", "i", "f", "tag")
+
+    def __init__(self, kind, dt, p=(), i=(), f=(), tag=""):
+        self.kind, self.dt, self.p, self.i, self.f, self.tag = kind, dt, list(p), [int(v) for v in i], \
+            [float(v) for v in f], tag
+        assert len(self.p) <= 12 and len(self.i) <= 12 and len(self.f) <= 4
+
+    def __repr__(self):
+        return "%s[%s] p=%s i=%s f=%s" % (OP_NAMES[self.kind], self.tag, self.p, self.i, self.f)
+
+
+class Arena:
+    def __init__(self, name):
+        self.name, self.size = name, 0
+
+    def alloc(self, nbytes, align=256):
+        off = (self.size + align - 1) // align * align
+        self.size = off + int(nbytes)
+        return Ref(self.name, off)
+
+
+class ParamLayout:
+    """Flat fp32 buffers in Keras weight order: `params` (trainable: kernels, biases, gamma, beta) and
+    `state` (BatchNormalization moving statistics).  grads / adam_m / adam_v mirror `params`."""
+
+    def __init__(self, graph):
+        self.specs = graph.weight_specs()
+        self.offsets = OrderedDict()     # name -> (arena, element offset, shape)
+        np_, ns = 0, 0
+        for name, shape, init, trainable in self.specs:
+            n = int(math.prod(shape))
+            if trainable:
+                self.offsets[name] = ("params", np_, shape)
+                np_ += (n + 3) // 4 * 4          # keep every tensor 16-byte aligned
+            else:
+                self.offsets[name] = ("state", ns, shape)
+                ns += (n + 3) // 4 * 4
+        self.n_params, self.n_state = np_, ns
+
+    def ref(self, name, arena=None):
+        a, off, _ = self.offsets[name]
+        return Ref(arena or a, off * 4)
+
+    def pack(self, weights):
+        """name -> ndarray dict (Keras layouts)  ->  (flat params fp32, flat state fp32)."""
+        import numpy as np
+        flat = {"params": np.zeros(self.n_params, np.float32), "state": np.zeros(max(self.n_state, 1), np.float32)}
+        for name, (arena, off, shape) in self.offsets.items():
+            a = np.asarray(weights[name], np.float32)
+            if tuple(a.shape) != tuple(shape):
+                raise ValueError("weight %s: expected shape %s, got %s" % (name, shape, a.shape))
+            flat[arena][off:off + a.size] = a.reshape(-1)
+        return flat["params"], flat["state"]
+
+    def unpack(self, params, state, arena_for_trainable="params"):
+        """inverse of pack(); `params` may also be a gradient / Adam buffer with the same layout."""
+        import numpy as np
+        out = OrderedDict()
+        for name, (arena, off, shape) in self.offsets.items():
+            n = int(math.prod(shape))
+            src = params if arena == "params" else state
+            if src is None:
+                continue
+            out[name] = np.array(src[off:off + n], np.float32).reshape(shape)
+        return out
+
+
+class Plan:
+    """Op lists + arena sizes for one (graph, batch size, storage type, mode) combination."""
+
+    def __init__(self, graph, n, dt=F32, training=True, dropout=True, loss="bce_dice", world=1,
+                 sync_stats=False, layout=None, rank=0):
+        self.graph, self.n, self.dt, self.training = graph, int(n), dt, training
+        self.dropout = dropout and training
+        self.loss, self.world, self.sync_stats = loss, int(world), bool(sync_stats) and world > 1
+        self.rank = int(rank)
+        self.layout = layout or ParamLayout(graph)
+        self.act, self.f32, self.zero = Arena("act"), Arena("f32"), Arena("zero")
+        self.fwd, self.bwd, self.opt = [], [], []
+        self.views, self.gviews = {}, {}         # id(SymTensor) -> View
+        self.layer_out = OrderedDict()           # layer name -> View (model.get_layer(name).output)
+        self.n_dropout_ops = 0
+        self._lower()
+
+    # ---------------------------------------------------------------------------------------
+    # helpers
+    # ---------------------------------------------------------------------------------------
+    def _npix(self, v):
+        return self.n * v.h * v.w
+
+    def _alloc_view(self, shape, dt, arena=None):
+        if len(shape) == 3:
+            h, w, c = shape
+        else:
+            h, w, c = 1, 1, shape[0]
+        arena = arena or self.act
+        ref = arena.alloc(self.n * h * w * c * ELEM[dt])
+        return View(ref, c, c, h, w, dt)
+
+    def _w(self, layer, short, arena=None):
+        return self.layout.ref("%s/%s" % (layer.name, short), arena)
+
+    @staticmethod
+    def _act_of(t):
+        l = t.producer
+        a = getattr(l, "activation", None)
+        return a if a in ("relu", "elu") else None
+
+    def _mask_for(self, t):
+        """(mask view, act code) if the gradient written for tensor t must be multiplied by its
+        producer's activation derivative, else (None, 0)."""
+        # look through identity dropouts (inference / dropout disabled / folded into the max-pool)
+        while t.producer.kind == "dropout" and self.views[id(t)] is self.views[id(t.producer.inputs[0])]:
+            t = t.producer.inputs[0]
+        a = self._act_of(t)
+        if a is None:
+            return None, 0
+        if len(t.consumers) != 1:
+            raise NotImplementedError("activated tensor %r with %d consumers" % (t, len(t.consumers)))
+        return self.views[id(t)], ACT[a]
+
+    # ---------------------------------------------------------------------------------------
+    # lowering
+    # ---------------------------------------------------------------------------------------
+    def _lower(self):
+        g, n, dt = self.graph, self.n, self.dt
+        layers = g.layers
+        # ---- placement: a tensor consumed by concatenate lives inside its LAST concat's buffer ----
+        home = {}        # id(tensor) -> (concat layer, channel offset)
+        for l in layers:
+            if l.kind == "concatenate":
+                off = 0
+                for t in l.inputs:
+                    if t.producer.kind in ("concatenate", "flatten", "input"):
+                        raise NotImplementedError("concatenate of %s outputs" % t.producer.kind)
+                    home[id(t)] = (l, off)       # later concats overwrite earlier ones: last wins
+                    off += t.channels
+        concat_buf, concat_gbuf = {}, {}
+        for l in layers:
+            if l.kind == "concatenate":
+                concat_buf[id(l)] = self._alloc_view(l.output.shape, dt)
+                if self.training:
+                    concat_gbuf[id(l)] = self._alloc_view(l.output.shape, dt)
+
+        def place(t, tdt):
+            if id(t) in home:
+                cl, off = home[id(t)]
+                self.views[id(t)] = concat_buf[id(cl)].slice(off, t.channels)
+                if self.training:
+                    self.gviews[id(t)] = concat_gbuf[id(cl)].slice(off, t.channels)
+            else:
+                self.views[id(t)] = self._alloc_view(t.shape, tdt)
+                if self.training:
+                    self.gviews[id(t)] = self._alloc_view(t.shape, tdt)
+
+        self.step_ref = Ref("step", 0)
+        self.x_view = None
+        drop_index = {}
+        k = 0
+        for l in layers:
+            if l.kind == "dropout":
+                drop_index[id(l)] = k
+                k += 1
+        self.n_dropout_ops = k
+        fused_drop = set()       # dropout layers folded into the preceding max-pool
+        bn_aux = {}              # id(bn layer) -> dict of small buffers
+        written = set()          # id(tensor) whose gradient view has been written (backward)
+
+        # ======================================= forward ==========================================
+        for l in layers:
+            t = l.output
+            if l.kind == "input":
+                self.views[id(t)] = self._alloc_view(t.shape, dt)
+                self.x_view = self.views[id(t)]
+                self.layer_out[l.name] = self.x_view
+                continue
+            x = l.inputs[0]
+            xv = self.views[id(x)]
+            if l.kind == "conv2d" and l.kernel_size == (3, 3):
+                place(t, dt)
+                yv = self.views[id(t)]
+                stats = None
+                cons = t.consumers
+                if self.training and len(cons) == 1 and cons[0].kind == "batch_normalization":
+                    stats = self.zero.alloc(2 * t.channels * 8)
+                    bn_aux[id(cons[0])] = {"sums": stats, "fused": True}
+                self.fwd.append(Op(OP_CONV3X3_FWD, dt, [xv.ref, self._w(l, "kernel"), self._w(l, "bias"), yv.ref, stats],
+                                   [xv.ld, xv.c, ACT[l.activation], yv.ld, yv.c, n, xv.h, xv.w], tag=l.name))
+            elif l.kind == "conv2d":      # 1x1 output head
+                if l.activation != "sigmoid" or l.filters != 1 or t is not g.output:
+                    raise NotImplementedError("1x1 conv is supported as the sigmoid output head only")
+                self.prob = self.f32.alloc(self._npix(xv) * 4)
+                self.prob_shape = (n, xv.h, xv.w, 1)
+                self.views[id(t)] = View(self.prob, 1, 1, xv.h, xv.w, F32)
+                self.fwd.append(Op(OP_HEAD_FWD, dt, [xv.ref, self._w(l, "kernel"), self._w(l, "bias"), self.prob],
+                                   [xv.ld, xv.c, self._npix(xv)], tag=l.name))
+            elif l.kind == "conv2d_transpose":
+                place(t, dt)
+                yv = self.views[id(t)]
+                self.fwd.append(Op(OP_CONVT_FWD, dt, [xv.ref, self._w(l, "kernel"), self._w(l, "bias"), yv.ref],
+                                   [xv.ld, xv.c, yv.ld, yv.c, n, xv.h, xv.w], tag=l.name))
+            elif l.kind == "batch_normalization":
+                place(t, xv.dt)
+                yv = self.views[id(t)]
+                c = xv.c
+                aux = bn_aux.setdefault(id(l), {})
+                for nm in ("scale", "shift", "mean", "invstd"):
+                    aux[nm] = self.f32.alloc(c * 4)
+                count = self._npix(xv)
+                if self.training:
+                    if "sums" not in aux:
+                        aux["sums"] = self.zero.alloc(2 * c * 8)
+                        self.fwd.append(Op(OP_BN_STATS, xv.dt, [xv.ref, aux["sums"]], [xv.ld, c, count], tag=l.name))
+                    if self.sync_stats:
+                        self.fwd.append(Op(OP_ALLREDUCE_F64, 0, [aux["sums"]], [2 * c], tag=l.name))
+                        count *= self.world
+                aux["count"] = count
+                self.fwd.append(Op(OP_BN_FINALIZE, 0,
+                                   [aux.get("sums"), self._w(l, "gamma"), self._w(l, "beta"), self._w(l, "moving_mean"),
+                                    self._w(l, "moving_variance"), aux["scale"], aux["shift"], aux["mean"], aux["invstd"]],
+                                   [count, 1 if self.training else 0, c], [l.momentum, l.epsilon], tag=l.name))
+                self.fwd.append(Op(OP_BN_APPLY, xv.dt, [xv.ref, yv.ref, aux["scale"], aux["shift"]],
+                                   [xv.ld, yv.ld, c, self._npix(xv)], tag=l.name))
+            elif l.kind == "max_pooling2d":
+                place(t, xv.dt)
+                yv = self.views[id(t)]
+                p_drop, op_id = 0.0, 0
+                cons = t.consumers
+                if len(cons) == 1 and cons[0].kind == "dropout" and id(t) not in home:
+                    fused_drop.add(id(cons[0]))
+                    if self.dropout:
+                        p_drop, op_id = cons[0].rate, drop_index[id(cons[0])]
+                l._pool_drop = (p_drop, op_id)
+                self.fwd.append(Op(OP_MAXPOOL_FWD, xv.dt, [xv.ref, yv.ref, self.step_ref if p_drop > 0 else None],
+                                   [xv.ld, yv.ld, xv.c, n, xv.h, xv.w, op_id], [p_drop], tag=l.name))
+            elif l.kind == "dropout":
+                if id(l) in fused_drop or not self.dropout:
+                    if id(t) in home:
+                        raise NotImplementedError("identity dropout feeding a concatenate")
+                    self.views[id(t)] = xv                     # alias: identity (fused or inference)
+                    if self.training:
+                        self.gviews[id(t)] = self.gviews[id(x)]
+                else:
+                    place(t, xv.dt)
+                    yv = self.views[id(t)]
+                    self.fwd.append(Op(OP_DROPOUT_FWD, xv.dt, [xv.ref, yv.ref, self.step_ref],
+                                       [xv.ld, yv.ld, xv.c, self._npix(xv), drop_index[id(l)]], [l.rate], tag=l.name))
+            elif l.kind == "concatenate":
+                buf = concat_buf[id(l)]
+                self.views[id(t)] = buf
+                if self.training:
+                    self.gviews[id(t)] = concat_gbuf[id(l)]
+                off = 0
+                for ti in l.inputs:
+                    if home[id(ti)][0] is not l:               # lives in a later concat: copy in
+                        sv = self.views[id(ti)]
+                        dv = buf.slice(off, ti.channels)
+                        self.fwd.append(Op(OP_COPY_SLICE, dt, [sv.ref, dv.ref], [sv.ld, dv.ld, sv.c, self._npix(sv), 0],
+                                           tag=l.name))
+                    off += ti.channels
+            elif l.kind == "flatten":
+                if xv.ld != xv.c:
+                    raise NotImplementedError("flatten of a strided view")
+                kf = xv.h * xv.w * xv.c
+                self.views[id(t)] = View(xv.ref, kf, kf, 1, 1, xv.dt)
+                if self.training:
+                    gx = self.gviews[id(x)]
+                    self.gviews[id(t)] = View(gx.ref, kf, kf, 1, 1, gx.dt)
+            elif l.kind == "dense":
+                yv = self._alloc_view((l.units,), F32, self.f32)
+                self.views[id(t)] = yv
+                if self.training:
+                    self.gviews[id(t)] = self._alloc_view((l.units,), F32, self.f32)
+                if t is g.output:
+                    if l.activation != "sigmoid" or l.units != 1:
+                        raise NotImplementedError("dense output head must be Dense(1, sigmoid)")
+                    self.prob, self.prob_shape = yv.ref, (n, 1)
+                self.fwd.append(Op(OP_DENSE_FWD, xv.dt, [xv.ref, self._w(l, "kernel"), self._w(l, "bias"), yv.ref],
+                                   [xv.c, ACT[l.activation], l.units, n], tag=l.name))
+            else:
+                raise NotImplementedError(l.kind)
+            self.layer_out[l.name] = self.views[id(t)]
+
+        # ---- loss / metric ------------------------------------------------------------------------
+        out_elems = int(math.prod(self.prob_shape))
+        self.target = self.f32.alloc(out_elems * 4)
+        self.sample_w = self.f32.alloc(n * 4)
+        self.loss_out = self.f32.alloc(16)
+        self.loss_ops = []
+        count = out_elems
+        if self.loss == "bce_dice":
+            self.loss_sums = self.zero.alloc(4 * 8)
+            self.loss_ops.append(Op(OP_BCE_DICE_SUMS, 0, [self.prob, self.target, self.loss_sums], [out_elems], tag="loss"))
+            if self.sync_stats:
+                self.loss_ops.append(Op(OP_ALLREDUCE_F64, 0, [self.loss_sums], [4], tag="loss"))
+                count *= self.world
+            self.loss_ops.append(Op(OP_BCE_DICE_FINALIZE, 0, [self.loss_sums, self.loss_out], [count], tag="loss"))
+        elif self.loss == "bce":
+            self.loss_ops.append(Op(OP_BCE_FWD, 0, [self.prob, self.target, self.sample_w, self.loss_out], [n], tag="loss"))
+        else:
+            raise NotImplementedError(self.loss)
+        self.loss_count = count
+        if not self.training:
+            return
+
+        # ======================================= backward =========================================
+        grads = lambda l, s: self._w(l, s, "grads")
+        for l in reversed(layers):
+            t = l.output
+            if l.kind == "input":
+                continue
+            x = l.inputs[0]
+            xv = self.views[id(x)]
+            x_is_input = x.producer.kind == "input"
+            if l.kind == "conv2d" and l.kernel_size == (1, 1):
+                gx = self.gviews[id(x)]
+                mv, ma = self._mask_for(x)
+                self.bwd.append(Op(OP_HEAD_BWD, dt, [self.prob, self.target, self.loss_sums, self.step_ref, xv.ref,
+                                                     self._w(l, "kernel"), gx.ref, grads(l, "kernel"), grads(l, "bias")],
+                                   [self.loss_count, xv.ld, xv.c, gx.ld, ma, self._npix(xv)], tag=l.name))
+                written.add(id(x))
+                continue
+            if l.kind == "dense" and t is g.output:
+                gy = self.gviews[id(t)]
+                self.bwd.append(Op(OP_BCE_SIGMOID_BWD, F32, [self.prob, self.target, self.sample_w, self.step_ref, gy.ref],
+                                   [n], tag=l.name))
+                written.add(id(t))
+            if id(t) not in written:
+                if l.kind in ("max_pooling2d",) and not t.consumers:
+                    continue                                    # dead branch (UPP:912 p4)
+                raise RuntimeError("no gradient reached %s" % l.name)
+            gy = self.gviews[id(t)]
+            if l.kind == "conv2d":
+                self.bwd.append(Op(OP_CONV3X3_WGRAD, dt, [xv.ref, gy.ref, grads(l, "kernel"), grads(l, "bias")],
+                                   [xv.ld, xv.c, gy.ld, gy.c, n, xv.h, xv.w], tag=l.name))
+                if not x_is_input:
+                    gx = self.gviews[id(x)]
+                    mv, ma = self._mask_for(x)
+                    self.bwd.append(Op(OP_CONV3X3_DGRAD, dt, [gy.ref, self._w(l, "kernel"), gx.ref, mv.ref if mv else None],
+                                       [gy.ld, gy.c, gx.ld, gx.c, mv.ld if mv else 0, ma, 1 if id(x) in written else 0,
+                                        n, xv.h, xv.w], tag=l.name))
+                    written.add(id(x))
+            elif l.kind == "conv2d_transpose":
+                self.bwd.append(Op(OP_CONVT_WGRAD, dt, [xv.ref, gy.ref, grads(l, "kernel"), grads(l, "bias")],
+                                   [xv.ld, xv.c, gy.ld, gy.c, n, xv.h, xv.w], tag=l.name))
+                gx = self.gviews[id(x)]
+                mv, ma = self._mask_for(x)
+                self.bwd.append(Op(OP_CONVT_DGRAD, dt, [gy.ref, self._w(l, "kernel"), gx.ref, mv.ref if mv else None],
+                                   [gy.ld, gy.c, gx.ld, gx.c, mv.ld if mv else 0, ma, 1 if id(x) in written else 0,
+                                    n, xv.h, xv.w], tag=l.name))
+                written.add(id(x))
+            elif l.kind == "batch_normalization":
+                aux = bn_aux[id(l)]
+                c = xv.c
+                bsums = self.zero.alloc(2 * c * 8)
+                if id(x) in written:
+                    raise NotImplementedError("BN backward accumulate")
+                gx = self.gviews[id(x)]
+                mv, ma = self._mask_for(x)
+                self.bwd.append(Op(OP_BN_BWD_REDUCE, xv.dt, [gy.ref, xv.ref, aux["mean"], aux["invstd"], bsums],
+                                   [gy.ld, xv.ld, c, self._npix(xv)], tag=l.name))
+                if self.sync_stats:
+                    self.bwd.append(Op(OP_ALLREDUCE_F64, 0, [bsums], [2 * c], tag=l.name))
+                # npix is the LOCAL pixel count; the divisor (count) is the global one under sync_stats,
+                # where the all-reduced sums must enter dgamma/dbeta on one rank only (grads are summed)
+                own = (not self.sync_stats) or self.rank == 0
+                self.bwd.append(Op(OP_BN_BWD_APPLY, xv.dt,
+                                   [gy.ref, xv.ref, gx.ref, self._w(l, "gamma"), aux["mean"], aux["invstd"], bsums,
+                                    grads(l, "gamma") if own else None, grads(l, "beta") if own else None,
+                                    mv.ref if mv else None],
+                                   [gy.ld, xv.ld, gx.ld, c, self._npix(xv), mv.ld if mv else 0, ma, aux["count"]],
+                                   tag=l.name))
+                written.add(id(x))
+            elif l.kind == "max_pooling2d":
+                gx = self.gviews[id(x)]
+                p_drop, op_id = l._pool_drop
+                if self._act_of(x) is not None:
+                    raise NotImplementedError("max-pool directly after an activated conv")
+                self.bwd.append(Op(OP_MAXPOOL_BWD, xv.dt, [xv.ref, gy.ref, gx.ref, self.step_ref if p_drop > 0 else None],
+                                   [xv.ld, gy.ld, gx.ld, xv.c, n, xv.h, xv.w, op_id, 1 if id(x) in written else 0],
+                                   [p_drop], tag=l.name))
+                written.add(id(x))
+            elif l.kind == "dropout":
+                if self.views[id(t)] is xv:                     # identity alias
+                    written.add(id(x))
+                    continue
+                if id(x) in written:
+                    raise NotImplementedError("dropout backward accumulate")
+                gx = self.gviews[id(x)]
+                mv, ma = self._mask_for(x)
+                self.bwd.append(Op(OP_DROPOUT_BWD, xv.dt, [gy.ref, gx.ref, self.step_ref, mv.ref if mv else None],
+                                   [gy.ld, gx.ld, xv.c, self._npix(xv), drop_index[id(l)], mv.ld if mv else 0, ma],
+                                   [l.rate], tag=l.name))
+                written.add(id(x))
+            elif l.kind == "concatenate":
+                off = 0
+                for ti in l.inputs:
+                    if home[id(ti)][0] is l:
+                        if id(ti) in written:
+                            raise RuntimeError("home concat must be the last consumer of %r" % ti)
+                        written.add(id(ti))                     # gradient slice already in place
+                    else:
+                        sv = gy.slice(off, ti.channels)
+                        dv = self.gviews[id(ti)]
+                        if id(ti) not in written:
+                            raise RuntimeError("copy-concat gradient before home concat for %r" % ti)
+                        if self._act_of(ti) is not None:
+                            raise NotImplementedError("activated tensor feeding several concats")
+                        self.bwd.append(Op(OP_COPY_SLICE, dt, [sv.ref, dv.ref], [sv.ld, dv.ld, sv.c, self._npix(sv), 1],
+                                           tag=l.name))
+                    off += ti.channels
+            elif l.kind == "flatten":
+                written.add(id(x))
+            elif l.kind == "dense":
+                gx = self.gviews[id(x)]
+                mv, ma = self._mask_for(x)
+                if id(x) in written:
+                    raise NotImplementedError("dense backward accumulate")
+                yv = self.views[id(t)]
+                # gy already holds the pre-activation gradient (mask applied by the consumer / loss)
+                self.bwd.append(Op(OP_DENSE_BWD, xv.dt, [xv.ref, self._w(l, "kernel"), yv.ref, gy.ref, gx.ref,
+                                                         mv.ref if mv else None, grads(l, "kernel"), grads(l, "bias")],
+                                   [xv.c, 0, ma, l.units, n], tag=l.name))
+                written.add(id(x))
+            else:
+                raise NotImplementedError(l.kind)
+
+        # ======================================= optimizer ========================================
+        npar = self.layout.n_params
+        if self.world > 1:
+            self.opt.append(Op(OP_ALLREDUCE_F32, 0, [Ref("grads", 0)], [npar], tag="allreduce"))
+        self.opt.append(Op(OP_ADAM, 0, [Ref("params", 0), Ref("grads", 0), Ref("adam_m", 0), Ref("adam_v", 0), self.step_ref],
+                           [npar], tag="adam"))
+        self.opt.append(Op(OP_STATE_ADVANCE, 0, [self.step_ref], tag="advance"))
+
+    # ---------------------------------------------------------------------------------------
+    def prologue(self):
+        """ops that must run before every step: clear the statistics arena (and gradients)."""
+        ops = []
+        if self.zero.size:
+            ops.append(Op(OP_MEMSET, 0, [Ref("zero", 0)], [self.zero.size], tag="zero-sums"))
+        if self.training:
+            ops.append(Op(OP_MEMSET, 0, [Ref("grads", 0)], [self.layout.n_params * 4], tag="zero-grads"))
+        return ops
+
+    def train_ops(self):
+        return self.prologue() + self.fwd + self.loss_ops + self.bwd + self.opt
+
+    def forward_ops(self, with_loss=False):
+        return self.prologue() + self.fwd + (self.loss_ops if with_loss else [])
+
+    def arena_sizes(self):
+        return {"act": self.act.size, "f32": self.f32.size, "zero": max(self.zero.size, 8),
+                "params": self.layout.n_params * 4, "state": max(self.layout.n_state * 4, 4),
+                "step": STEP_STATE_BYTES}
