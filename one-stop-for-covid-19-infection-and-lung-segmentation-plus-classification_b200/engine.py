@@ -1,0 +1,373 @@
+"""Device-side runtime of the engine: owns the HBM buffers (torch tensors as storage only), binds
+plan.py op lists to them and launches them through libb200unet.so -- eagerly or as a CUDA graph.
+
+This is the part of `model.fit / evaluate / predict`
+(/root/reference/Scripts/task1_preprocessing_plus_unet_with_comments.py:1059, 1101, 1137) that ran
+inside Keras/TensorFlow for the reference.  There is no CPU fallback: everything here needs the CUDA
+library and a B200.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import plan as P
+
+
+# --------------------------------------------------------------------------------------------
+# initialisers (Keras VarianceScaling semantics: he_normal = truncated normal, glorot_uniform)
+# --------------------------------------------------------------------------------------------
+def init_weights(graph, seed=42):
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape, init, _tr in graph.weight_specs():
+        kind = init[0]
+        if kind == "zeros":
+            w = np.zeros(shape, np.float32)
+        elif kind == "ones":
+            w = np.ones(shape, np.float32)
+        elif kind == "he_normal":
+            std = math.sqrt(2.0 / init[1]) / 0.87962566103423978
+            w = rng.standard_normal(shape)
+            bad = np.abs(w) > 2.0
+            while bad.any():
+                w[bad] = rng.standard_normal(int(bad.sum()))
+                bad = np.abs(w) > 2.0
+            w = (w * std).astype(np.float32)
+        elif kind == "glorot_uniform":
+            lim = math.sqrt(6.0 / (init[1] + init[2]))
+            w = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+        else:
+            raise ValueError("unknown initializer %r" % (kind,))
+        out[name] = w
+    return out
+
+
+class Comm:
+    """NCCL communicator for the data-parallel gradient all-reduce (one process per GPU).  The unique id
+    is created on rank 0 and broadcast through torch.distributed (any backend)."""
+
+    def __init__(self, rank, world):
+        import torch.distributed as dist
+        self.rank, self.world = rank, world
+        l = _lib.lib()
+        idbuf = (C.c_char * 128)()
+        if rank == 0:
+            _lib.check(l.b2u_comm_unique_id(idbuf), "comm_unique_id")
+        t = torch.frombuffer(bytearray(bytes(idbuf)), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().numpy().tobytes())
+        self.handle = C.c_void_p()
+        _lib.check(l.b2u_comm_create(C.c_char_p(raw), rank, world, C.byref(self.handle)), "comm_create")
+
+    def close(self):
+        if self.handle:
+            _lib.lib().b2u_comm_destroy(self.handle)
+            self.handle = None
+
+
+class _Bound:
+    """A plan bound to device addresses, with its ctypes op arrays and (optionally) a captured graph."""
+
+    def __init__(self, plan):
+        self.plan = plan
+        self.ops = {}          # name -> (ctypes array, n)
+        self.graphs = {}       # name -> graph handle
+
+
+class Engine:
+    def __init__(self, graph, precision="float16", device=None, seed=42, loss="bce_dice", comm=None,
+                 sync_stats=False, use_graph=True, dropout_seed=7, loss_scale=None):
+        if not torch.cuda.is_available():
+            raise _lib.B2UError("the b200unet engine needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.lib()
+        self.graph = graph
+        self.dt = P.F16 if precision in ("float16", "fp16", "half", "mixed") else P.F32
+        if precision not in ("float16", "fp16", "half", "mixed", "float32", "fp32"):
+            raise ValueError("precision must be float16 or float32")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.loss = loss
+        self.comm = comm
+        self.world = comm.world if comm is not None else 1
+        self.rank = comm.rank if comm is not None else 0
+        self.sync_stats = bool(sync_stats) and self.world > 1
+        self.use_graph = use_graph
+        self.layout = P.ParamLayout(graph)
+        self.user_loss_scale = loss_scale
+        npar = self.layout.n_params
+        dev = self.device
+        with torch.cuda.stream(self.stream):
+            self.params = torch.zeros(npar, dtype=torch.float32, device=dev)
+            self.state = torch.zeros(max(self.layout.n_state, 1), dtype=torch.float32, device=dev)
+            self.grads = torch.zeros(npar, dtype=torch.float32, device=dev)
+            self.adam_m = torch.zeros(npar, dtype=torch.float32, device=dev)
+            self.adam_v = torch.zeros(npar, dtype=torch.float32, device=dev)
+            self.step_dev = torch.zeros(P.STEP_STATE_BYTES, dtype=torch.uint8, device=dev)
+            self.ws = torch.empty(int(self.lib.b2u_ws_bytes()), dtype=torch.uint8, device=dev)
+        self.host_state = _lib.StepState(seed=dropout_seed, step=0, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-7,
+                                         beta1_pow=0.9, beta2_pow=0.999, loss_scale=1.0,
+                                         grad_div=1.0 if self.sync_stats else float(self.world), overflow=0, pad_=0)
+        self._arenas = {}        # name -> torch uint8 tensor (grown on demand, shared between plans)
+        self._bound = {}         # (n, training, dropout, loss) -> _Bound
+        self._push_state()
+        self.set_weights(init_weights(graph, seed))
+        if self.comm is not None:
+            self.broadcast_weights()
+
+    # ---------------------------------------------------------------------------------------
+    # step state
+    # ---------------------------------------------------------------------------------------
+    def _push_state(self):
+        """host -> device copy of the whole step state (blocking; only on (re)configuration)."""
+        raw = np.frombuffer(bytes(self.host_state), dtype=np.uint8).copy()
+        self.stream.synchronize()
+        with torch.cuda.stream(self.stream):
+            self.step_dev[:raw.size].copy_(torch.from_numpy(raw))
+        self.stream.synchronize()
+
+    def _pull_state(self):
+        self.stream.synchronize()
+        raw = self.step_dev.cpu().numpy().tobytes()
+        C.memmove(C.addressof(self.host_state), raw, C.sizeof(_lib.StepState))
+        return self.host_state
+
+    def _set_fields(self, **kw):
+        st = self._pull_state()
+        changed = False
+        for k, v in kw.items():
+            if getattr(st, k) != v:
+                setattr(st, k, v)
+                changed = True
+        if changed:
+            self._push_state()
+
+    def reset_optimizer(self, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-7):
+        """model.compile(optimizer=Adam(lr)) -- fresh optimizer state, weights kept (CV4:1062-1083)."""
+        self.stream.synchronize()
+        with torch.cuda.stream(self.stream):
+            self.adam_m.zero_()
+            self.adam_v.zero_()
+        st = self._pull_state()
+        st.lr, st.beta1, st.beta2, st.eps = lr, beta1, beta2, eps
+        st.beta1_pow, st.beta2_pow, st.overflow = beta1, beta2, 0
+        self._push_state()
+
+    @property
+    def lr(self):
+        return float(self._pull_state().lr)
+
+    @lr.setter
+    def lr(self, v):
+        self._set_fields(lr=float(np.float32(v)))
+
+    def overflowed(self):
+        return bool(self._pull_state().overflow)
+
+    # ---------------------------------------------------------------------------------------
+    # weights
+    # ---------------------------------------------------------------------------------------
+    def set_weights(self, weights):
+        fp, fs = self.layout.pack(weights)
+        self.stream.synchronize()
+        with torch.cuda.stream(self.stream):
+            self.params.copy_(torch.from_numpy(fp))
+            self.state[:fs.size].copy_(torch.from_numpy(fs))
+        self.stream.synchronize()
+
+    def get_weights(self):
+        self.stream.synchronize()
+        return self.layout.unpack(self.params.cpu().numpy(), self.state.cpu().numpy())
+
+    def get_grads(self):
+        self.stream.synchronize()
+        return self.layout.unpack(self.grads.cpu().numpy(), None)
+
+    def broadcast_weights(self):
+        """make every rank start from rank 0's weights"""
+        import torch.distributed as dist
+        for t in (self.params, self.state):
+            if dist.get_backend() == "nccl":
+                dist.broadcast(t, src=0)
+            else:
+                h = t.cpu()
+                dist.broadcast(h, src=0)
+                t.copy_(h)
+        torch.cuda.synchronize(self.device)
+
+    # ---------------------------------------------------------------------------------------
+    # plans
+    # ---------------------------------------------------------------------------------------
+    def _arena(self, name, nbytes):
+        t = self._arenas.get(name)
+        if t is None or t.numel() < nbytes:
+            self.stream.synchronize()
+            for b in self._bound.values():        # addresses change: drop bound op arrays / graphs
+                for g in b.graphs.values():
+                    self.lib.b2u_graph_destroy(g)
+                b.ops.clear()
+                b.graphs.clear()
+            with torch.cuda.stream(self.stream):
+                t = torch.zeros(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+            self._arenas[name] = t
+        return t
+
+    def _get_bound(self, n, training, dropout=True, loss=None):
+        key = (int(n), bool(training), bool(dropout), loss or self.loss)
+        b = self._bound.get(key)
+        if b is None:
+            pl = P.Plan(self.graph, n, dt=self.dt, training=training, dropout=dropout, loss=loss or self.loss,
+                        world=self.world, sync_stats=self.sync_stats, layout=self.layout, rank=self.rank)
+            b = _Bound(pl)
+            self._bound[key] = b
+        sizes = b.plan.arena_sizes()
+        for name in ("act", "f32", "zero"):
+            self._arena(name, sizes[name])
+        return b
+
+    def _resolve(self, ref):
+        a = ref.arena
+        if a in self._arenas:
+            base = self._arenas[a].data_ptr()
+        elif a == "params":
+            base = self.params.data_ptr()
+        elif a == "state":
+            base = self.state.data_ptr()
+        elif a == "grads":
+            base = self.grads.data_ptr()
+        elif a == "adam_m":
+            base = self.adam_m.data_ptr()
+        elif a == "adam_v":
+            base = self.adam_v.data_ptr()
+        elif a == "step":
+            base = self.step_dev.data_ptr()
+        else:
+            raise KeyError(a)
+        return base + ref.off
+
+    def _ops(self, b, name):
+        if name not in b.ops:
+            pl = b.plan
+            lst = {"train": pl.train_ops, "forward": pl.forward_ops,
+                   "forward_loss": lambda: pl.forward_ops(with_loss=True)}[name]()
+            b.ops[name] = (_lib.make_ops(lst, self._resolve), len(lst))
+        return b.ops[name]
+
+    def _run(self, b, name):
+        arr, n = self._ops(b, name)
+        comm = self.comm.handle if self.comm is not None else None
+        s = C.c_void_p(self.stream.cuda_stream)
+        if self.use_graph:
+            g = b.graphs.get(name)
+            if g is None:
+                h = C.c_void_p()
+                _lib.check(self.lib.b2u_graph_create(arr, n, C.c_void_p(self.ws.data_ptr()), self.ws.numel(), comm, s,
+                                                     C.byref(h)), "graph_create(%s)" % name)
+                b.graphs[name] = g = h
+            _lib.check(self.lib.b2u_graph_launch(g, s), "graph_launch(%s)" % name)
+        else:
+            _lib.check(self.lib.b2u_run_ops(arr, n, C.c_void_p(self.ws.data_ptr()), self.ws.numel(), comm, s),
+                       "run_ops(%s)" % name)
+
+    def _gather(self, dt, src, idx, dst_ptr, per_sample, nb):
+        _lib.check(self.lib.b2u_gather_batch(dt, C.c_void_p(src.data_ptr()),
+                                             C.c_void_p(idx.data_ptr()) if idx is not None else None,
+                                             C.c_void_p(dst_ptr), per_sample, nb, C.c_void_p(self.stream.cuda_stream)),
+                   "gather_batch")
+
+    def _load_inputs(self, b, x_src, idx, n, t_src=None, sw_src=None):
+        pl = b.plan
+        xv = pl.x_view
+        per = xv.h * xv.w * xv.c
+        assert x_src.dtype == torch.float32 and x_src.is_contiguous()
+        self._gather(self.dt, x_src, idx, self._resolve(xv.ref), per, n)
+        if t_src is not None:
+            per_t = int(math.prod(pl.prob_shape[1:]))
+            assert t_src.dtype == torch.float32 and t_src.is_contiguous()
+            self._gather(P.F32, t_src, idx, self._resolve(pl.target), per_t, n)
+            if pl.loss == "bce":
+                if sw_src is None:
+                    raise ValueError("the weighted-BCE plan needs per-sample weights")
+                self._gather(P.F32, sw_src, idx, self._resolve(pl.sample_w), 1, n)
+
+    def _loss_scale_for(self, pl):
+        if self.user_loss_scale is not None:
+            return float(self.user_loss_scale)
+        if self.dt == P.F32:
+            return 1.0
+        nel = int(math.prod(pl.prob_shape)) * (self.world if self.sync_stats else 1)
+        s = 2.0 ** math.floor(math.log2(max(nel / 64.0, 1.0)))
+        return float(min(max(s, 1.0), 32768.0))
+
+    # ---------------------------------------------------------------------------------------
+    # public device API (all asynchronous on self.stream unless they return host data)
+    # ---------------------------------------------------------------------------------------
+    def train_batch(self, x_src, t_src, idx, n, dropout=True, sw_src=None):
+        """one optimisation step on samples x_src[idx] (device-resident fp32, NHWC)."""
+        b = self._get_bound(n, True, dropout)
+        ls = self._loss_scale_for(b.plan)
+        if getattr(self, "_cur_ls", None) != ls:
+            self._set_fields(loss_scale=ls)
+            self._cur_ls = ls
+        self._load_inputs(b, x_src, idx, n, t_src, sw_src)
+        self._run(b, "train")
+        return b
+
+    def forward_batch(self, x_src, idx, n, t_src=None, sw_src=None, training=False):
+        """inference-mode forward (BN moving statistics, no dropout); with t_src also the loss."""
+        b = self._get_bound(n, training, False)
+        self._load_inputs(b, x_src, idx, n, t_src, sw_src)
+        self._run(b, "forward_loss" if t_src is not None else "forward")
+        return b
+
+    def probs(self, b):
+        """device view of the last forward's sigmoid outputs, shape plan.prob_shape (fp32)."""
+        pl = b.plan
+        nel = int(math.prod(pl.prob_shape))
+        a = self._arenas["f32"]
+        return a[pl.prob.off:pl.prob.off + nel * 4].view(torch.float32).view(*pl.prob_shape)
+
+    def targets(self, b):
+        pl = b.plan
+        nel = int(math.prod(pl.prob_shape))
+        a = self._arenas["f32"]
+        return a[pl.target.off:pl.target.off + nel * 4].view(torch.float32).view(*pl.prob_shape)
+
+    def loss_dev(self, b):
+        """device view: [loss, metric] of the last step (fp32)."""
+        a = self._arenas["f32"]
+        off = b.plan.loss_out.off
+        return a[off:off + 8].view(torch.float32)
+
+    def layer_output(self, b, name):
+        """host copy of an intermediate activation (Model(inputs, get_layer(name).output), T1H:1386)."""
+        v = b.plan.layer_out[name]
+        self.stream.synchronize()
+        a = self._arenas[v.ref.arena]
+        es = P.ELEM[v.dt]
+        npix = b.plan.n * v.h * v.w
+        tdt = torch.float16 if v.dt == P.F16 else torch.float32
+        raw = a[v.ref.off:v.ref.off + ((npix - 1) * v.ld + v.c) * es].view(tdt)
+        out = torch.as_strided(raw, (npix, v.c), (v.ld, 1)).float().cpu().numpy()
+        return out.reshape(b.plan.n, v.h, v.w, v.c)
+
+    def threshold_counts(self, b, thresholds_dev, tp, spr, sgt):
+        pl = b.plan
+        nel = int(math.prod(pl.prob_shape))
+        _lib.check(self.lib.b2u_threshold_counts(C.c_void_p(self._resolve(pl.prob)), C.c_void_p(self._resolve(pl.target)),
+                                                 nel, C.c_void_p(thresholds_dev.data_ptr()), thresholds_dev.numel(),
+                                                 C.c_void_p(tp.data_ptr()), C.c_void_p(spr.data_ptr()),
+                                                 C.c_void_p(sgt.data_ptr()), C.c_void_p(self.stream.cuda_stream)),
+                   "threshold_counts")
+
+    def close(self):
+        self.stream.synchronize()
+        for b in self._bound.values():
+            for g in b.graphs.values():
+                self.lib.b2u_graph_destroy(g)
+            b.graphs.clear()

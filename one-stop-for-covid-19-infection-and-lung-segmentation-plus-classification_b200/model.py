@@ -1,0 +1,491 @@
+"""Keras-shaped facade: the subset of `keras.models.Model` the reference runners call.
+
+  compile / fit / evaluate / predict / predict_proba / save_weights / load_weights / to_json /
+  summary / get_layer / optimizer.lr / callbacks (on_epoch_begin, on_epoch_end)
+
+Call sites replaced: /root/reference/Scripts/task1_preprocessing_plus_unet_with_comments.py:1053
+(compile), :1059-1061 (fit), :1101 (evaluate), :1137 (predict), :1073-1093 (weights / json),
+:1196-1343 (threshold sweeps); task2_covid19_classifcation.py:726-728 (predict_proba), :828-836.
+
+Inputs are host numpy arrays (NHWC, float64/float32 in [0,1]) exactly as the reference passes them;
+outputs are fresh host arrays.  All arithmetic runs in libb200unet.so on the GPU.
+"""
+import json
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import engine as E
+from . import layers as L
+from . import losses as LS
+from . import plan as P
+
+
+class Adam:
+    """keras.optimizers.Adam(lr=...) -- T1H:1053"""
+
+    def __init__(self, lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, learning_rate=None, **kw):
+        self.lr = float(learning_rate if learning_rate is not None else lr)
+        self.beta_1, self.beta_2, self.epsilon = beta_1, beta_2, epsilon
+
+
+class _OptimizerHandle:
+    """`model.optimizer.lr` get/set (K.set_value / K.get_value in the reference, T1H:982-990)."""
+
+    def __init__(self, eng):
+        self._eng = eng
+
+    @property
+    def lr(self):
+        return self._eng.lr
+
+    @lr.setter
+    def lr(self, v):
+        self._eng.lr = v
+
+
+class History:
+    def __init__(self):
+        self.history = {}
+        self.epoch = []
+
+
+class Callback:
+    def set_model(self, model):
+        self.model = model
+
+    def on_train_begin(self, logs=None):
+        pass
+
+    def on_train_end(self, logs=None):
+        pass
+
+    def on_epoch_begin(self, epoch, logs=None):
+        pass
+
+    def on_epoch_end(self, epoch, logs=None):
+        pass
+
+
+class CosineAnnealingScheduler(Callback):
+    """T1H:970-990: lr(e) = eta_min + (eta_max - eta_min) * (1 + cos(pi * e / T_max)) / 2 at epoch begin."""
+
+    def __init__(self, T_max, eta_max, eta_min=0, verbose=1):
+        self.T_max, self.eta_max, self.eta_min, self.verbose = T_max, eta_max, eta_min, verbose
+
+    def on_epoch_begin(self, epoch, logs=None):
+        lr = self.eta_min + (self.eta_max - self.eta_min) * (1 + math.cos(math.pi * epoch / self.T_max)) / 2
+        self.model.optimizer.lr = lr
+        if self.verbose > 0:
+            print('\nEpoch %05d: CosineAnnealingScheduler setting learning rate to %s.' % (epoch + 1, lr))
+
+    def on_epoch_end(self, epoch, logs=None):
+        if logs is not None:
+            logs['lr'] = self.model.optimizer.lr
+
+
+class ModelCheckpoint(Callback):
+    """keras ModelCheckpoint(filepath, monitor, save_best_only, mode) -- T1H:1044-1047 (weights as .npz)."""
+
+    def __init__(self, filepath, monitor='val_loss', verbose=0, save_best_only=False, mode='auto', **kw):
+        self.filepath, self.monitor, self.verbose, self.save_best_only = filepath, monitor, verbose, save_best_only
+        if mode == 'auto':
+            mode = 'max' if ('acc' in monitor or 'dice' in monitor or 'auc' in monitor or monitor.startswith('val_f')) else 'min'
+        self.mode = mode
+        self.best = -np.inf if mode == 'max' else np.inf
+
+    def on_epoch_end(self, epoch, logs=None):
+        cur = (logs or {}).get(self.monitor)
+        if not self.save_best_only:
+            self.model.save_weights(self.filepath)
+            return
+        if cur is None:
+            return
+        better = cur > self.best if self.mode == 'max' else cur < self.best
+        if better:
+            if self.verbose:
+                print('Epoch %05d: %s improved from %0.5f to %0.5f, saving model to %s'
+                      % (epoch + 1, self.monitor, self.best, cur, self.filepath))
+            self.best = cur
+            self.model.save_weights(self.filepath)
+
+
+class RocCallback(Callback):
+    """T2:706-741: ROC-AUC on train and validation after every epoch; saves weights on best val AUC."""
+
+    def __init__(self, training_data, validation_data, filepath=None):
+        self.x, self.y = training_data
+        self.x_val, self.y_val = validation_data
+        self.filepath = filepath
+        self.best = -1.0
+
+    def on_epoch_end(self, epoch, logs=None):
+        from sklearn.metrics import roc_auc_score
+        roc = roc_auc_score(self.y, self.model.predict_proba(self.x))
+        roc_val = roc_auc_score(self.y_val, self.model.predict_proba(self.x_val))
+        if logs is not None:
+            logs['roc_auc'], logs['val_roc_auc'] = roc, roc_val
+        print('\rroc-auc: %s - roc-auc_val: %s' % (str(round(roc, 5)), str(round(roc_val, 5))), end=100 * ' ' + '\n')
+        if roc_val > self.best and self.filepath:
+            self.best = roc_val
+            self.model.save_weights(self.filepath)
+
+
+def _metric_name(m):
+    return m if isinstance(m, str) else getattr(m, "__name__", m.__class__.__name__)
+
+
+class Model:
+    """`Model(inputs=[inputs], outputs=[outputs])` (T1H:915) over a layers.Graph."""
+
+    def __init__(self, inputs=None, outputs=None, graph=None, precision="float16", seed=42, comm=None,
+                 sync_stats=False, use_graph=True, device=None, dropout_seed=7, loss_scale=None):
+        self.graph = graph if graph is not None else L.Graph(inputs, outputs)
+        self._eng_kw = dict(precision=precision, seed=seed, comm=comm, sync_stats=sync_stats, use_graph=use_graph,
+                            device=device, dropout_seed=dropout_seed, loss_scale=loss_scale)
+        self._eng = None
+        self.loss_kind = "bce_dice" if len(self.graph.output.shape) == 3 else "bce"
+        self.metrics = []
+        self.metrics_names = ["loss"]
+        self.stop_training = False
+        self._shuffle_rng = np.random.RandomState(1234)
+
+    # ---- structure --------------------------------------------------------------------------
+    @property
+    def layers(self):
+        return self.graph.layers
+
+    @property
+    def input(self):
+        return self.graph.input
+
+    def get_layer(self, name):
+        return self.graph.get_layer(name)
+
+    def count_params(self):
+        return self.graph.count_params()[0]
+
+    def summary(self, print_fn=print):
+        print_fn('Model: "model"')
+        print_fn("_" * 98)
+        print_fn("%-32s %-26s %-10s %s" % ("Layer (type)", "Output Shape", "Param #", "Connected to"))
+        print_fn("=" * 98)
+        for l in self.graph.layers:
+            shp = "(None, " + ", ".join(str(s) for s in l.output.shape) + ")"
+            conn = ", ".join(t.producer.name for t in l.inputs)
+            print_fn("%-32s %-26s %-10d %s" % ("%s (%s)" % (l.name, type(l).__name__), shp, l.count_params(), conn))
+        tot, tr, ntr = self.graph.count_params()
+        print_fn("=" * 98)
+        print_fn("Total params: {:,}".format(tot))
+        print_fn("Trainable params: {:,}".format(tr))
+        print_fn("Non-trainable params: {:,}".format(ntr))
+
+    def to_json(self):
+        cfg = []
+        for l in self.graph.layers:
+            d = {"class_name": type(l).__name__, "name": l.name, "inbound": [t.producer.name for t in l.inputs],
+                 "output_shape": list(l.output.shape)}
+            for k in ("filters", "kernel_size", "activation", "rate", "units", "kernel_initializer", "momentum", "epsilon"):
+                if hasattr(l, k):
+                    d[k] = getattr(l, k)
+            cfg.append(d)
+        return json.dumps({"class_name": "Model", "config": {"layers": cfg}, "backend": "b200unet"})
+
+    # ---- engine ------------------------------------------------------------------------------
+    @property
+    def engine(self):
+        if self._eng is None:
+            self._eng = E.Engine(self.graph, loss=self.loss_kind, **self._eng_kw)
+        return self._eng
+
+    @property
+    def optimizer(self):
+        return _OptimizerHandle(self.engine)
+
+    def compile(self, optimizer=None, loss=None, metrics=None, **kw):
+        """Fresh optimizer state, weights kept (the reference re-compiles per fold / per threshold)."""
+        name = _metric_name(loss) if loss is not None else None
+        if name in ("bce_dice_loss",):
+            kind = "bce_dice"
+        elif name in ("binary_crossentropy",):
+            kind = "bce" if len(self.graph.output.shape) == 1 else "bce_dice_unsupported"
+        elif name is None:
+            kind = self.loss_kind
+        else:
+            raise ValueError("unsupported loss %r (engine implements bce_dice_loss and binary_crossentropy)" % name)
+        if kind == "bce_dice_unsupported":
+            raise ValueError("binary_crossentropy alone is implemented for the Dense(1) classifier head only")
+        if self._eng is not None and kind != self.loss_kind:
+            self._eng.loss = kind
+        self.loss_kind = kind
+        self.metrics = list(metrics or [])
+        self.metrics_names = ["loss"] + [_metric_name(m) for m in self.metrics]
+        opt = optimizer if optimizer is not None else Adam()
+        if isinstance(opt, str):
+            opt = Adam()
+        self.engine.reset_optimizer(lr=opt.lr, beta1=opt.beta_1, beta2=opt.beta_2, eps=opt.epsilon)
+
+    # ---- weights -----------------------------------------------------------------------------
+    def get_weights(self):
+        return list(self.engine.get_weights().values())
+
+    def set_weights(self, ws):
+        names = [n for n, _, _, _ in self.graph.weight_specs()]
+        self.engine.set_weights(dict(zip(names, ws)))
+
+    def get_weights_dict(self):
+        return self.engine.get_weights()
+
+    def set_weights_dict(self, d):
+        self.engine.set_weights(d)
+
+    def save_weights(self, path):
+        d = self.engine.get_weights()
+        with open(path, "wb") as f:
+            np.savez(f, **{k.replace("/", "__"): v for k, v in d.items()})
+
+    def load_weights(self, path):
+        with np.load(path) as z:
+            self.engine.set_weights({k.replace("__", "/"): z[k] for k in z.files})
+
+    # ---- data --------------------------------------------------------------------------------
+    def _to_dev(self, a, flat_out=False):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+        eng = self.engine
+        with torch.cuda.stream(eng.stream):
+            return torch.from_numpy(a).to(eng.device, non_blocking=False)
+
+    def _check_x(self, x):
+        x = np.asarray(x)
+        if tuple(x.shape[1:]) != tuple(self.graph.input.shape):
+            raise ValueError("expected input of shape (N,%s), got %s" % (",".join(map(str, self.graph.input.shape)), x.shape))
+        return x
+
+    def _sample_weights(self, y, class_weight):
+        if class_weight is None:
+            return np.ones(len(y), np.float32)
+        yl = np.asarray(y).reshape(len(y), -1)[:, 0]
+        if isinstance(class_weight, dict):
+            return np.asarray([class_weight[int(round(v))] for v in yl], np.float32)
+        cw = np.asarray(class_weight, np.float32)           # the reference passes an ndarray (T2:801-803, 836)
+        return cw[np.rint(yl).astype(np.int64)]
+
+    # ---- metric plumbing -----------------------------------------------------------------------
+    def _host_metrics(self, metrics, t, p):
+        out = []
+        for m in metrics:
+            if isinstance(m, str):
+                if m in ("accuracy", "acc"):
+                    out.append(float((np.rint(p) == np.rint(t)).mean()))
+                else:
+                    raise ValueError("unknown metric %r" % m)
+            else:
+                out.append(float(m(t, p)))
+        return out
+
+    def _run_eval(self, x, y, batch_size, metrics, class_weight=None):
+        """forward (inference mode) over x in batches; returns [loss, metrics...] with Keras'
+        batch-size-weighted averaging of per-batch values."""
+        eng = self.engine
+        x = self._check_x(x)
+        n_tot = len(x)
+        xd, yd = self._to_dev(x), self._to_dev(np.asarray(y).reshape(n_tot, -1))
+        swd = self._to_dev(self._sample_weights(y, class_weight)) if self.loss_kind == "bce" else None
+        sm = [m for m in metrics if isinstance(m, LS._SMMetric)]
+        dice_idx = [k for k, m in enumerate(metrics) if _metric_name(m) == "dice_coeff"]
+        host_ms = [m for m in metrics if not isinstance(m, LS._SMMetric) and _metric_name(m) != "dice_coeff"]
+        nb = (n_tot + batch_size - 1) // batch_size
+        with torch.cuda.stream(eng.stream):
+            lossbuf = torch.zeros(nb, 2, dtype=torch.float32, device=eng.device)
+            thr = torch.tensor([m.threshold for m in sm] or [0.5], dtype=torch.float32, device=eng.device)
+            tp = torch.zeros(nb, thr.numel(), dtype=torch.float64, device=eng.device)
+            spr = torch.zeros_like(tp)
+            sgt = torch.zeros(nb, dtype=torch.float64, device=eng.device)
+            probs_all = torch.empty((n_tot,) + tuple(self.graph.output.shape), dtype=torch.float32,
+                                    device=eng.device) if host_ms else None
+            sizes = []
+            for bi in range(nb):
+                lo = bi * batch_size
+                n = min(batch_size, n_tot - lo)
+                sizes.append(n)
+                b = eng.forward_batch(xd[lo:lo + n], None, n, t_src=yd[lo:lo + n],
+                                      sw_src=swd[lo:lo + n] if swd is not None else None)
+                lossbuf[bi].copy_(eng.loss_dev(b))
+                if sm:
+                    eng.threshold_counts(b, thr, tp[bi], spr[bi], sgt[bi:bi + 1])
+                if probs_all is not None:
+                    probs_all[lo:lo + n].copy_(eng.probs(b))
+        eng.stream.synchronize()
+        w = np.asarray(sizes, np.float64)
+        lb = lossbuf.cpu().numpy().astype(np.float64)
+        res = {"loss": float((lb[:, 0] * w).sum() / w.sum())}
+        vals = []
+        tpn, sprn, sgtn = tp.cpu().numpy(), spr.cpu().numpy(), sgt.cpu().numpy()
+        hm = None
+        if host_ms:
+            pa = probs_all.cpu().numpy()
+            ya = np.asarray(y, np.float64).reshape(pa.shape)
+            hm = np.zeros((nb, len(host_ms)))
+            for bi in range(nb):
+                lo = bi * batch_size
+                hm[bi] = self._host_metrics(host_ms, ya[lo:lo + sizes[bi]], pa[lo:lo + sizes[bi]])
+        ks = kh = 0
+        for k, m in enumerate(metrics):
+            if k in dice_idx:
+                vals.append(float((lb[:, 1] * w).sum() / w.sum()))
+            elif isinstance(m, LS._SMMetric):
+                per = np.array([m.from_counts(tpn[bi, ks], sprn[bi, ks], sgtn[bi]) for bi in range(nb)])
+                vals.append(float((per * w).sum() / w.sum()))
+                ks += 1
+            else:
+                vals.append(float((hm[:, kh] * w).sum() / w.sum()))
+                kh += 1
+        return [res["loss"]] + vals
+
+    # ---- public API ----------------------------------------------------------------------------
+    def evaluate(self, x, y, batch_size=32, verbose=0, **kw):
+        out = self._run_eval(x, y, batch_size, self.metrics)
+        return out if len(out) > 1 else out[0]
+
+    def predict(self, x, batch_size=32, verbose=0, **kw):
+        eng = self.engine
+        x = self._check_x(x)
+        n_tot = len(x)
+        xd = self._to_dev(x)
+        with torch.cuda.stream(eng.stream):
+            out = torch.empty((n_tot,) + tuple(self.graph.output.shape), dtype=torch.float32, device=eng.device)
+            for lo in range(0, n_tot, batch_size):
+                n = min(batch_size, n_tot - lo)
+                b = eng.forward_batch(xd[lo:lo + n], None, n)
+                out[lo:lo + n].copy_(eng.probs(b))
+        eng.stream.synchronize()
+        return out.cpu().numpy()
+
+    def predict_proba(self, x, batch_size=32, verbose=0):
+        return self.predict(x, batch_size=batch_size)
+
+    def intermediate(self, x, layer_name):
+        """Model(inputs=model.input, outputs=model.get_layer(name).output).predict(x) -- T1H:1386-1405"""
+        eng = self.engine
+        x = self._check_x(x)
+        outs = []
+        xd = self._to_dev(x)
+        for lo in range(0, len(x), 32):
+            n = min(32, len(x) - lo)
+            b = eng.forward_batch(xd[lo:lo + n], None, n)
+            outs.append(eng.layer_output(b, layer_name))
+        return np.concatenate(outs, 0)
+
+    def threshold_sweep(self, x, y, thresholds, batch_size=32):
+        """All thresholds x {F1, IoU, precision, recall} from ONE forward pass (replaces the reference's
+        re-compile + evaluate loop, T1H:1196-1343).  Values are Keras-style batch-weighted means."""
+        ms = []
+        for t in thresholds:
+            ms += [LS.FScore(threshold=t), LS.IOUScore(threshold=t), LS.Precision(threshold=t), LS.Recall(threshold=t)]
+        # one device threshold per metric object is wasteful but tiny; counts are shared by value
+        vals = self._run_eval(x, y, batch_size, ms)[1:]
+        v = np.asarray(vals).reshape(len(thresholds), 4)
+        return {"threshold": np.asarray(thresholds), "f1": v[:, 0], "iou": v[:, 1], "precision": v[:, 2], "recall": v[:, 3]}
+
+    def fit(self, x, y, batch_size=32, epochs=1, validation_data=None, callbacks=None, class_weight=None,
+            shuffle=True, verbose=1, initial_epoch=0, dropout=True, **kw):
+        eng = self.engine
+        x = self._check_x(x)
+        n_tot = len(x)
+        world, rank = eng.world, eng.rank
+        xd, yd = self._to_dev(x), self._to_dev(np.asarray(y).reshape(n_tot, -1))
+        swd = self._to_dev(self._sample_weights(y, class_weight)) if self.loss_kind == "bce" else None
+        hist = History()
+        cbs = list(callbacks or [])
+        for cb in cbs:
+            cb.set_model(self)
+            cb.on_train_begin({})
+        metric_names = [_metric_name(m) for m in self.metrics]
+        if verbose:
+            if validation_data is not None:
+                print("Train on %d samples, validate on %d samples" % (n_tot, len(validation_data[0])))
+            else:
+                print("Train on %d samples" % n_tot)
+        for epoch in range(initial_epoch, epochs):
+            if self.stop_training:
+                break
+            logs = {}
+            for cb in cbs:
+                cb.on_epoch_begin(epoch, logs)
+            t0 = time.time()
+            perm = self._shuffle_rng.permutation(n_tot) if shuffle else np.arange(n_tot)
+            starts = list(range(0, n_tot, batch_size))
+            with torch.cuda.stream(eng.stream):
+                perm_d = torch.from_numpy(perm.astype(np.int32)).to(eng.device)
+                lossbuf = torch.zeros(len(starts), 2, dtype=torch.float32, device=eng.device)
+                sizes = []
+                for bi, lo in enumerate(starts):
+                    n = min(batch_size, n_tot - lo)
+                    sizes.append(n)
+                    b = eng.train_batch(xd, yd, perm_d[lo:lo + n], n, dropout=dropout, sw_src=swd)
+                    lossbuf[bi].copy_(eng.loss_dev(b))
+            eng.stream.synchronize()
+            if eng.overflowed():
+                print("warning: non-finite gradients were skipped this epoch (loss scale %g)" % eng._cur_ls)
+                eng._set_fields(overflow=0)
+            w = np.asarray(sizes, np.float64)
+            lb = lossbuf.cpu().numpy().astype(np.float64)
+            logs["loss"] = float((lb[:, 0] * w).sum() / w.sum())
+            if "dice_coeff" in metric_names:
+                logs["dice_coeff"] = float((lb[:, 1] * w).sum() / w.sum())
+            if validation_data is not None:
+                xv, yv = validation_data[0], validation_data[1]
+                vals = self._run_eval(xv, yv, batch_size, self.metrics)
+                logs["val_loss"] = vals[0]
+                for nm, v in zip(metric_names, vals[1:]):
+                    logs["val_" + nm] = v
+            dt_ = time.time() - t0
+            for cb in cbs:
+                cb.on_epoch_end(epoch, logs)
+            hist.epoch.append(epoch)
+            for k, v in logs.items():
+                hist.history.setdefault(k, []).append(v)
+            if verbose:
+                msg = " - ".join("%s: %.4f" % (k, v) for k, v in logs.items())
+                print("Epoch %d/%d\n%d/%d - %ds %dms/sample - %s" % (epoch + 1, epochs, n_tot, n_tot, int(dt_),
+                                                                      int(1000 * dt_ / max(n_tot, 1)), msg))
+        for cb in cbs:
+            cb.on_train_end({})
+        self.history = hist
+        return hist
+
+
+class Sequential(Model):
+    """keras.models.Sequential: model.add(layer) chains (T2:747-778)."""
+
+    def __init__(self, **kw):
+        self._seq_layers, self._seq_out, self._kw = [], None, kw
+        self._built = False
+
+    def add(self, layer):
+        if self._seq_out is None:
+            shape = getattr(layer, "input_shape", None)
+            if shape is None:
+                raise ValueError("the first layer of a Sequential model needs input_shape=")
+            L.reset_names()
+            self._seq_in = L.Input(shape)
+            self._seq_out = layer(self._seq_in)
+        else:
+            self._seq_out = layer(self._seq_out)
+        self._built = False
+
+    def _ensure(self):
+        if not self._built:
+            Model.__init__(self, inputs=[self._seq_in], outputs=[self._seq_out], **self._kw)
+            self._built = True
+
+    def __getattr__(self, name):
+        # first access to any Model attribute after add() finalises the graph
+        if name in ("_seq_layers", "_seq_out", "_kw", "_built", "_seq_in"):
+            raise AttributeError(name)
+        if not self.__dict__.get("_built", False) and self.__dict__.get("_seq_out") is not None:
+            self._ensure()
+            return getattr(self, name)
+        raise AttributeError(name)

@@ -1,0 +1,49 @@
+"""Shared helpers for the plan/emulator (CPU) and CUDA (GPU) parity tests."""
+import importlib
+
+import numpy as np
+import torch
+
+from oracle import keras_ref as K
+
+PKG = "one-stop-for-covid-19-infection-and-lung-segmentation-plus-classification_b200"
+P = importlib.import_module(PKG + ".plan")
+G = importlib.import_module(PKG + ".graphs")
+
+
+def perturbed_params(gname, hw, cin=1, seed=3):
+    """oracle init with non-trivial biases / BN affine parameters (fresh init has b=0, gamma=1, beta=0)."""
+    params, _ = K.init_params(gname, (hw, hw, cin), seed=seed)
+    rng = np.random.default_rng(seed + 100)
+    for k in params:
+        if k.endswith("bias") or k.endswith("beta"):
+            params[k] = (rng.standard_normal(params[k].shape) * 0.1).astype(np.float32)
+        if k.endswith("gamma"):
+            params[k] = (1 + rng.standard_normal(params[k].shape) * 0.1).astype(np.float32)
+        if k.endswith("moving_mean"):
+            params[k] = (rng.standard_normal(params[k].shape) * 0.1).astype(np.float32)
+        if k.endswith("moving_variance"):
+            params[k] = (1 + rng.random(params[k].shape)).astype(np.float32)
+    return params
+
+
+def synth_batch(n, hw, cin=1, seg=True, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, hw, hw, cin)).astype(np.float32)
+    if seg:
+        t = np.clip(rng.random((n, hw, hw, 1)) * 1.4 - 0.2, 0, 1).astype(np.float32)   # soft targets (T1H:488)
+    else:
+        t = (rng.random((n, 1)) > 0.4).astype(np.float32)
+    return x, t
+
+
+def grad_errors(got, want, skip_zero_bias=True):
+    """max over tensors of max|got-want| / max|want|; convT biases feeding a BN are analytically zero."""
+    worst, who = 0.0, None
+    for k, v in want.items():
+        if skip_zero_bias and "conv2d_transpose" in k and k.endswith("bias"):
+            continue
+        d = float(np.abs(got[k] - v).max() / (np.abs(v).max() + 1e-12))
+        if d > worst:
+            worst, who = d, k
+    return worst, who

@@ -1,0 +1,212 @@
+"""Whole-path parity on the GPU: the engine (planner + CUDA kernels through the C-ABI) against the
+oracle and the committed golden vectors -- training step (loss, Dice, probabilities, every parameter
+gradient, Adam update, BN moving statistics), inference forward at the reference's real size (224) and
+at BASELINE.json's 512, CUDA-graph replay, and a short training run (Dice parity).
+
+Tolerances (stated by BASELINE.json north_star: 1e-3 max-abs on the sigmoid outputs):
+  exact mode (fp32 storage)  : 2e-5 on probabilities, 2e-3 relative on gradients
+  tensor mode (fp16 storage) : 1e-3 on probabilities, 5e-2 relative on gradients (per tensor, vs max|g|)
+"""
+import glob
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG, ROOT
+from helpers import G, K, P, grad_errors, perturbed_params, synth_batch
+
+pytestmark = pytest.mark.gpu
+
+E = importlib.import_module(PKG + ".engine")
+PTOL = {"float32": 2e-5, "float16": 1e-3}
+GTOL = {"float32": 2e-3, "float16": 5e-2}
+
+
+def engine_for(gname, hw, precision, params, cin=1, use_graph=False, **kw):
+    loss = "bce" if gname == "classifier" else "bce_dice"
+    eng = E.Engine(G.GRAPHS[gname](hw, cin), precision=precision, use_graph=use_graph, loss=loss, dropout_seed=7, **kw)
+    eng.set_weights(params)
+    return eng
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a.reshape(len(a), -1), dtype=np.float32)).cuda()
+
+
+@pytest.mark.parametrize("precision", ["float32", "float16"])
+@pytest.mark.parametrize("gname,hw,n", [("unet", 32, 2), ("unet", 48, 3), ("unetpp", 32, 2), ("classifier", 32, 4)])
+def test_train_step_vs_oracle(gname, hw, n, precision):
+    seg = gname != "classifier"
+    loss = "bce_dice" if seg else "bce"
+    params = perturbed_params(gname, hw)
+    x, t = synth_batch(n, hw, seg=seg)
+    eng = engine_for(gname, hw, precision, params)
+    eng._set_fields(step=5)
+    sw = torch.ones(n, device="cuda")
+    b = eng.train_batch(dev(x).view(n, hw, hw, 1), dev(t), None, n, sw_src=sw)
+    eng.stream.synchronize()
+    r = K.loss_and_grads(gname, params, x, t, dtype=torch.float64, dropout=dict(seed=7, step=5), loss=loss)
+    lo = eng.loss_dev(b).cpu().numpy()
+    probs = eng.probs(b).cpu().numpy().reshape(r["probs"].shape)
+    assert np.abs(probs - r["probs"]).max() < PTOL[precision] * (3 if not seg else 1)
+    assert lo[0] == pytest.approx(r["loss"], abs=20 * PTOL[precision])
+    if seg:
+        assert lo[1] == pytest.approx(r["metric"], abs=5 * PTOL[precision])
+    ls = eng._cur_ls
+    grads = {k: v / ls for k, v in eng.get_grads().items()}
+    worst, who = grad_errors(grads, r["grads"])
+    assert worst < GTOL[precision], (who, worst)
+    assert not eng.overflowed()
+    if precision == "float32":
+        want = {k: v.copy() for k, v in params.items()}
+        K.Adam().step(want, r["grads"])
+        want.update(r["new_moving"])
+        new = eng.get_weights()
+        for k in want:
+            if "conv2d_transpose" in k and k.endswith("bias"):
+                continue
+            assert np.abs(new[k] - want[k]).max() < 5e-5, k
+    assert eng._pull_state().step == 6
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", ["float32", "float16"])
+@pytest.mark.parametrize("gname,hw,n", [("unet", 224, 2), ("unet", 512, 1), ("unetpp", 224, 1), ("classifier", 224, 4)])
+def test_inference_forward_vs_oracle(gname, hw, n, precision):
+    """model.predict parity at the reference's real size (224) and BASELINE's 512."""
+    params = perturbed_params(gname, hw)
+    S = importlib.import_module(PKG + ".synthetic")
+    x, _ = S.make_slices(n, hw, seed=3)
+    want, _ = K.forward(gname, params, x, training=False, dtype=torch.float32)
+    eng = engine_for(gname, hw, precision, params)
+    b = eng.forward_batch(dev(x).view(n, hw, hw, 1), None, n)
+    eng.stream.synchronize()
+    got = eng.probs(b).cpu().numpy().reshape(want.shape)
+    err = np.abs(got - want).max()
+    print("%s %d %s: max|dp| = %.3e" % (gname, hw, precision, err))
+    assert err < PTOL[precision]
+    eng.close()
+
+
+FILES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("precision", ["float32", "float16"])
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+def test_against_golden_vectors(path, precision):
+    with np.load(path) as z:
+        gold = {k.replace("__", "/"): z[k] for k in z.files}
+    gname, hw, n = os.path.basename(path)[:-4].split("_")
+    hw, n = int(hw), int(n[1:])
+    params = perturbed_params(gname, hw, seed=11)
+    assert np.allclose([float(np.asarray(v, np.float64).sum()) for v in params.values()], gold["weight_checksum"])
+    x, t = gold["x"], gold["t"]
+    eng = engine_for(gname, hw, precision, params)
+    b = eng.forward_batch(dev(x).view(n, hw, hw, 1), None, n)
+    eng.stream.synchronize()
+    assert np.abs(eng.probs(b).cpu().numpy().reshape(gold["probs_infer"].shape) - gold["probs_infer"]).max() < PTOL[precision] * 3
+    eng._set_fields(step=2)
+    b = eng.train_batch(dev(x).view(n, hw, hw, 1), dev(t), None, n, sw_src=torch.ones(n, device="cuda"))
+    eng.stream.synchronize()
+    assert np.abs(eng.probs(b).cpu().numpy().reshape(gold["probs_train"].shape) - gold["probs_train"]).max() < PTOL[precision] * 3
+    assert eng.loss_dev(b).cpu().numpy()[0] == pytest.approx(float(gold["loss"]), abs=20 * PTOL[precision])
+    ls = eng._cur_ls
+    for k, g in eng.get_grads().items():
+        if "conv2d_transpose" in k and k.endswith("bias"):
+            continue
+        g = g / ls
+        scale = float(gold["gabs/" + k]) / g.size + 1e-12
+        assert np.abs(g.reshape(-1)[:8] - gold["ghead/" + k]).max() < GTOL[precision] * 40 * scale + 1e-7, k
+        assert abs(float(g.astype(np.float64).sum()) - float(gold["gsum/" + k])) < GTOL[precision] * float(gold["gabs/" + k]) + 1e-7, k
+    new = eng.get_weights()
+    for k in gold:
+        if k.startswith("moving/"):
+            assert np.abs(new[k[7:]] - gold[k]).max() < (1e-5 if precision == "float32" else 2e-3), k
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", ["float32", "float16"])
+def test_graph_replay_matches_eager_training(precision):
+    hw, n = 32, 4
+    params = perturbed_params("unet", hw)
+    x, t = synth_batch(3 * n, hw)
+    outs = []
+    for use_graph in (False, True):
+        eng = engine_for("unet", hw, precision, params, use_graph=use_graph)
+        xd, td = dev(x).view(3 * n, hw, hw, 1), dev(t)
+        losses = []
+        for s in range(3):
+            idx = torch.arange(s * n, (s + 1) * n, dtype=torch.int32, device="cuda")
+            b = eng.train_batch(xd, td, idx, n)
+            eng.stream.synchronize()
+            losses.append(eng.loss_dev(b).cpu().numpy().copy())
+        outs.append((np.array(losses), eng.get_weights()))
+        eng.close()
+    # atomics make the reduction order run-dependent: compare with a tolerance, not bit-for-bit
+    assert np.allclose(outs[0][0], outs[1][0], rtol=2e-3 if precision == "float16" else 1e-4)
+    for k in outs[0][1]:
+        assert np.abs(outs[0][1][k] - outs[1][1][k]).max() < (2e-3 if precision == "float16" else 2e-4), k
+
+
+def test_partial_batch_and_odd_sizes():
+    """last batch of an epoch is partial (1129 mod 32 = 9, SURVEY hard part 5); W != H."""
+    hw = 32
+    params = perturbed_params("unet", hw)
+    eng = engine_for("unet", hw, "float32", params)
+    for n in (1, 3):
+        x, t = synth_batch(n, hw, seed=n)
+        b = eng.forward_batch(dev(x).view(n, hw, hw, 1), None, n)
+        eng.stream.synchronize()
+        want, _ = K.forward("unet", params, x, training=False, dtype=torch.float32)
+        assert np.abs(eng.probs(b).cpu().numpy() - want).max() < 2e-5
+    eng.close()
+
+
+def test_model_facade_fit_matches_oracle_training():
+    """BASELINE config 1 in miniature: 16 synthetic slices, train_test_split 70/30 seed 42 (T1H:762),
+    one epoch, batch 8 -> steps of 8 and 3; Dice parity with the oracle trained on the same batches."""
+    from sklearn.model_selection import train_test_split
+    M = importlib.import_module(PKG + ".model")
+    LS = importlib.import_module(PKG + ".losses")
+    S = importlib.import_module(PKG + ".synthetic")
+    hw = 64
+    x, t = S.make_slices(16, hw, seed=1234)
+    xtr, xva, ttr, tva = train_test_split(x, t, test_size=0.3, random_state=42)
+    assert len(xtr) == 11 and len(xva) == 5
+    params, _ = K.init_params("unet", (hw, hw, 1), seed=42)
+    m = M.Model(graph=G.unet(hw, 1), precision="float32", dropout_seed=7)
+    m.set_weights_dict(params)
+    m.compile(optimizer=M.Adam(lr=0.0005), loss=LS.bce_dice_loss, metrics=[LS.dice_coeff])
+    h = m.fit(xtr, ttr, batch_size=8, epochs=2, validation_data=(xva, tva), shuffle=False, verbose=0)
+    # oracle: same batches, same dropout stream, fp32
+    opt = K.Adam(lr=0.0005)
+    p = {k: v.copy() for k, v in params.items()}
+    step, logs = 0, []
+    for ep in range(2):
+        ls = []
+        for lo in (0, 8):
+            l, d = K.train_step("unet", p, opt, xtr[lo:lo + 8], ttr[lo:lo + 8], dtype=torch.float32,
+                                dropout=dict(seed=7, step=step))
+            ls.append((l, d, len(xtr[lo:lo + 8])))
+            step += 1
+        w = np.array([a[2] for a in ls], float)
+        logs.append((float((np.array([a[0] for a in ls]) * w).sum() / w.sum()),
+                     float((np.array([a[1] for a in ls]) * w).sum() / w.sum())))
+    pv, _ = K.forward("unet", p, xva, training=False, dtype=torch.float32)
+    val_dice = float(K.dice_coeff(torch.from_numpy(tva).double(), torch.from_numpy(pv).double()))
+    assert h.history["loss"][0] == pytest.approx(logs[0][0], rel=1e-3)
+    assert h.history["loss"][1] == pytest.approx(logs[1][0], rel=2e-2)
+    assert h.history["dice_coeff"][1] == pytest.approx(logs[1][1], abs=5e-3)       # +-0.5 pt
+    assert h.history["val_dice_coeff"][1] == pytest.approx(val_dice, abs=5e-3)
+    # evaluate / predict / threshold sweep surface
+    ev = m.evaluate(xva, tva, batch_size=8)
+    assert ev[1] == pytest.approx(h.history["val_dice_coeff"][1], rel=1e-5)
+    pr = m.predict(xva)
+    assert pr.shape == (5, hw, hw, 1) and np.abs(pr - pv).max() < 5e-3
+    sw = m.threshold_sweep(xva, tva, [0.3, 0.5, 0.7], batch_size=8)
+    for k, th in enumerate([0.3, 0.5, 0.7]):
+        want = K.sm_threshold_metrics(tva, pr, th)
+        assert sw["f1"][k] == pytest.approx(want["f1"], rel=1e-4) and sw["iou"][k] == pytest.approx(want["iou"], rel=1e-4)

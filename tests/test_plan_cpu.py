@@ -1,0 +1,107 @@
+"""The planner's schedule (fusions, zero-copy concat, gradient routing) interpreted on the CPU by
+tests/emulator.py must reproduce the oracle's autograd for all three reference graphs."""
+import numpy as np
+import pytest
+import torch
+
+import emulator as E
+from helpers import G, K, P, grad_errors, perturbed_params, synth_batch
+
+
+def _load(em, plan, params, x, t):
+    fp, fs = plan.layout.pack(params)
+    em.f32(P.Ref("params", 0), fp.size)[:] = fp
+    em.f32(P.Ref("state", 0), fs.size)[:] = fs
+    xv = plan.x_view
+    em.view(xv.ref, xv.ld, xv.c, x.shape[0] * xv.h * xv.w, xv.dt)[:] = x.reshape(-1, xv.c).astype(E.NPDT[xv.dt])
+    em.f32(plan.target, t.size)[:] = t.reshape(-1)
+    em.f32(plan.sample_w, x.shape[0])[:] = 1.0
+    return fp, fs
+
+
+@pytest.mark.parametrize("gname,hw,n,loss", [("unet", 32, 2, "bce_dice"), ("unetpp", 16, 2, "bce_dice"),
+                                             ("classifier", 32, 4, "bce")])
+def test_train_step_matches_oracle(gname, hw, n, loss):
+    g = G.GRAPHS[gname](hw, 1)
+    plan = P.Plan(g, n, dt=P.F32, training=True, dropout=True, loss=loss)
+    params = perturbed_params(gname, hw)
+    x, t = synth_batch(n, hw, seg=(loss == "bce_dice"))
+    em = E.Emulator(plan.arena_sizes())
+    em.state.update(seed=7, step=5)
+    fp, fs = _load(em, plan, params, x, t)
+    em.run(plan.train_ops())
+    r = K.loss_and_grads(gname, params, x, t, dtype=torch.float64, dropout=dict(seed=7, step=5), loss=loss)
+    lo = em.f32(plan.loss_out, 2)
+    assert lo[0] == pytest.approx(r["loss"], rel=1e-5)
+    if loss == "bce_dice":
+        assert lo[1] == pytest.approx(r["metric"], rel=1e-5)
+    probs = em.f32(plan.prob, t.size).reshape(t.shape)
+    assert np.abs(probs - r["probs"]).max() < 2e-5
+    grads = plan.layout.unpack(em.f32(P.Ref("grads", 0), fp.size), None)
+    worst, who = grad_errors(grads, r["grads"])
+    assert worst < 1e-3, (who, worst)
+    # Adam + BN moving statistics
+    want = {k: v.copy() for k, v in params.items()}
+    K.Adam().step(want, r["grads"])
+    want.update(r["new_moving"])
+    new = plan.layout.unpack(em.f32(P.Ref("params", 0), fp.size), em.f32(P.Ref("state", 0), fs.size))
+    for k in want:
+        if "conv2d_transpose" in k and k.endswith("bias"):
+            continue
+        assert np.abs(new[k] - want[k]).max() < 2e-5, k
+    assert em.state["step"] == 6
+
+
+@pytest.mark.parametrize("gname,hw,n", [("unet", 32, 3), ("unetpp", 16, 2), ("classifier", 32, 5)])
+def test_inference_forward_matches_oracle(gname, hw, n):
+    g = G.GRAPHS[gname](hw, 1)
+    loss = "bce" if gname == "classifier" else "bce_dice"
+    plan = P.Plan(g, n, dt=P.F32, training=False, loss=loss)
+    params = perturbed_params(gname, hw)
+    x, t = synth_batch(n, hw, seg=(loss == "bce_dice"))
+    em = E.Emulator(plan.arena_sizes())
+    _load(em, plan, params, x, t)
+    em.run(plan.forward_ops(with_loss=True))
+    want, _ = K.forward(gname, params, x, training=False, dtype=torch.float64)
+    probs = em.f32(plan.prob, t.size).reshape(t.shape)
+    assert np.abs(probs - want).max() < 2e-5
+    assert not plan.bwd and not plan.opt
+
+
+def test_unet_concat_is_zero_copy_and_fused():
+    plan = P.Plan(G.unet(32, 1), 2, dt=P.F16, training=True)
+    kinds = [o.kind for o in plan.train_ops()]
+    assert P.OP_COPY_SLICE not in kinds                  # skips + upsampled halves are written in place
+    assert P.OP_DROPOUT_FWD not in kinds                 # dropout folded into the max-pool pass
+    assert kinds.count(P.OP_BN_STATS) == 4               # only the 4 concat BNs need a separate statistics pass
+    assert kinds.count(P.OP_CONV3X3_FWD) == 18 and kinds.count(P.OP_CONVT_FWD) == 4
+
+
+def test_unetpp_home_is_last_concat():
+    plan = P.Plan(G.unetpp(16, 1), 1, dt=P.F32, training=True)
+    # c1 feeds three concats (2 copies), conv1_2 two (1 copy), c2 two (1 copy); everything else is in place
+    assert sum(1 for o in plan.fwd if o.kind == P.OP_COPY_SLICE) == 2 + 1 + 1
+    assert sum(1 for o in plan.bwd if o.kind == P.OP_COPY_SLICE) == 2 + 1 + 1
+    assert all(o.i[4] == 1 for o in plan.bwd if o.kind == P.OP_COPY_SLICE)
+
+
+def test_param_layout_roundtrip_and_counts():
+    for gname, want in (("unet", 7762401), ("unetpp", 2207329), ("classifier", 1677937)):
+        g = G.GRAPHS[gname](224, 1)
+        lay = P.ParamLayout(g)
+        tr = sum(int(np.prod(s)) for _, s, _, t in g.weight_specs() if t)
+        assert tr == want
+        assert lay.n_params >= tr and lay.n_params - tr < 4 * len(lay.specs)
+    params = perturbed_params("unet", 32)
+    lay = P.ParamLayout(G.unet(32, 1))
+    fp, fs = lay.pack(params)
+    back = lay.unpack(fp, fs)
+    assert all(np.array_equal(back[k], params[k]) for k in params)
+    with pytest.raises(ValueError):
+        bad = dict(params); bad["conv2d_1/kernel"] = np.zeros((3, 3, 2, 32), np.float32)
+        lay.pack(bad)
+
+
+def test_shape_validation():
+    with pytest.raises(ValueError):
+        G.unet(30, 1)          # 30 is not divisible by 16: the 2nd pool would see an odd size
