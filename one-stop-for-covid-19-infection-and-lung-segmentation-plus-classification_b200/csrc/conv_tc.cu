@@ -1,13 +1,476 @@
-// placeholder until the tcgen05 kernels land
+// tcgen05 implicit-GEMM convolution for sm_100a (fp16 operands, fp32 accumulation in TMEM).
+//
+//   out[p][j] = epilogue( sum_t sum_k  A_t[p + off_t][k] * Wp[t][j][k] )
+//
+// with p a pixel of an NHWC activation tensor, k the reduction channels, j the output channels and
+// t the filter taps.  One kernel serves
+//   * Conv2D 3x3 'same' forward        (9 taps, offsets -1..1, A = x,  Wp[t][co][ci] = w[t][ci][co])
+//   * its data gradient                (9 taps, offsets -1..1, A = dy, Wp[t][ci][co] = w[8-t][ci][co])
+//   * Conv2DTranspose 2x2/s2 forward   (1 tap, A = x, J = 4*Cout, scatter epilogue)
+//   * its data gradient                (4 taps = the 2x2 sub-grids of dy, each its own tensor map)
+//
+// Structure (one CTA per SM, persistent over output tiles of 128 pixels x JT channels):
+//   warp 0      TMA producer: per (tap, 64-channel K slab) one 4-D box load of the activations
+//               (8x16 pixel patch x KS channels, out-of-image rows/cols zero-filled by TMA = the conv
+//               padding) and one 3-D box load of the packed fp16 weights, into a 4-stage smem ring with
+//               128B/64B/32B swizzle
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=JT, K=16) per 16 channels, accumulators
+//               double-buffered in TMEM (2 x JT columns); tcgen05.commit releases smem stages / publishes
+//               the accumulator
+//   warps 2-5   epilogue: tcgen05.ld -> bias / ReLU / ELU / activation-derivative mask / accumulate ->
+//               fp16 NHWC stores (strided: writes straight into concat-buffer channel slices) and the
+//               per-channel sum / sum-of-squares for the following BatchNorm (warp-shuffle transpose
+//               reduction -> smem -> one fp64 atomic per channel per CTA)
+#include <cuda.h>
 #include "common.cuh"
 #include "internal.h"
-int b2u_tc_compiled(void) { return 0; }
-int b2u_tc_conv3x3_ok(int, int, int, int) { return 0; }
+#include "launch.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kTileH = 8, kTileW = 16, kTileM = 128;       // 8 x 16 output pixels per tile
+constexpr int kThreadsTc = 192;                            // 6 warps
+constexpr int kMaxTaps = 9;
+
+struct TcParams {
+  int N, H, W;            // output-pixel grid of the GEMM (for convT fwd: the INPUT grid)
+  int K, J;               // reduction channels, output columns
+  int KS, JT;             // K slab (64/32/16) and N tile
+  int ntaps;
+  int tap_dh[kMaxTaps], tap_dw[kMaxTaps], tap_map[kMaxTaps];   // pixel offset and tensor-map index per tap
+  int mode;               // 0: plain NHWC store, 1: convT scatter (column = (a*2+b)*Cout + co)
+  int cout;               // mode 1: Cout
+  __half* y; int ldy;
+  const float* bias;      // [J] (mode 1: [Cout]) or null
+  int act;
+  const __half* mask; int ldmask; int mask_act;
+  int accumulate;
+  double* stats;          // [2*J] or null
+};
+
+struct TcMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) { return act_fwd(v, act); }
+
+// lane j ends with sum over lanes of v[j] (32 values per lane), 31 shuffles
+__device__ __forceinline__ float transpose_reduce16(float v[16], int lane) {
+  // 16 columns x 32 lanes: first fold lanes 16 apart (values stay 16 wide), then transpose-reduce
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      float a = v[i], b = v[i + s];
+      bool up = (lane & s) != 0;
+      float send = up ? a : b, keep = up ? b : a;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];      // lane (l & 15) owns column (l & 15); both half-warps hold the same totals
+}
+
+__global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_constant__ TcMaps maps,
+                                                                 const __grid_constant__ TcParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A tile 128 x KS halves][B tile JT x KS halves] | barriers | tmem ptr | bias | stats
+  const int KS = prm.KS, JT = prm.JT;
+  const uint32_t a_bytes = kTileM * KS * 2, b_bytes = JT * KS * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;          // both multiples of 1024 (KS>=16, JT>=16 -> b>=512!)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t b_stride = (b_bytes + 1023) & ~1023u;
+  const uint32_t stage_stride = a_bytes + b_stride;
+  uint8_t* tail = smem + kStages * stage_stride;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);
+  float* s_stats = s_bias + prm.J;                         // [2*J]
+  (void)stage_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_w = (prm.W + kTileW - 1) / kTileW, tiles_h = (prm.H + kTileH - 1) / kTileH;
+  const int nj = prm.J / JT;
+  const long long ntiles = (long long)prm.N * tiles_h * tiles_w * nj;
+  const int kslabs = prm.K / KS;
+  const int ksteps = prm.ntaps * kslabs;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * JT)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull_bar[s], 1); tc::mbar_init(&tempty_bar[s], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
+  for (int i = threadIdx.x; i < prm.J; i += kThreadsTc) {
+    float b = 0.f;
+    if (prm.bias != nullptr) b = prm.bias[prm.mode == 1 ? (i % prm.cout) : i];
+    s_bias[i] = b;
+  }
+  for (int i = threadIdx.x; i < 2 * prm.J; i += kThreadsTc) s_stats[i] = 0.f;
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =========================================
+    if (lane == 0) {
+      tc::prefetch_tmap(&maps.b);
+      tc::prefetch_tmap(&maps.a[0]);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int jt = (int)(tile % nj);
+        long long pt = tile / nj;
+        int tw = (int)(pt % tiles_w);
+        long long r = pt / tiles_w;
+        int th = (int)(r % tiles_h);
+        int n = (int)(r / tiles_h);
+        for (int t = 0; t < prm.ntaps; ++t) {
+          const CUtensorMap* am = &maps.a[prm.tap_map[t]];
+          for (int ks = 0; ks < kslabs; ++ks) {
+            tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * stage_stride;
+            uint8_t* sb = sa + a_bytes;
+            tc::mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+            tc::tma_load_4d(sa, am, &full_bar[stage], ks * KS, tw * kTileW + prm.tap_dw[t], th * kTileH + prm.tap_dh[t], n);
+            tc::tma_load_3d(sb, &maps.b, &full_bar[stage], ks * KS, jt * JT, t);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ============================================
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_f16(kTileM, JT, 0, 0);
+      const uint64_t layout = KS == 64 ? tc::SWZ_128B : (KS == 32 ? tc::SWZ_64B : tc::SWZ_32B);
+      const uint32_t sbo = 8 * KS * 2;                     // 8 rows of KS halves
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * JT;
+        for (int k = 0; k < ksteps; ++k) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(smem + stage * stage_stride);
+          const uint32_t sb = sa + a_bytes;
+          for (int kk = 0; kk < KS / 16; ++kk) {
+            uint64_t ad = tc::smem_desc(sa + kk * 32, 16, sbo, layout);
+            uint64_t bd = tc::smem_desc(sb + kk * 32, 16, sbo, layout);
+            tc::mma_f16_ss(d_tmem, ad, bd, idesc, (k | kk) != 0);
+          }
+          tc::mma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc::mma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue ==============================================
+    const int lg = warp & 3;                               // TMEM lane group this warp may access
+    const int row = lg * 32 + lane;                        // tile row = pixel (row / 16, row % 16)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int jt = (int)(tile % nj);
+      long long pt = tile / nj;
+      int tw = (int)(pt % tiles_w);
+      long long r = pt / tiles_w;
+      int th = (int)(r % tiles_h);
+      int n = (int)(r / tiles_h);
+      const int h = th * kTileH + row / kTileW, w = tw * kTileW + row % kTileW;
+      const bool valid = h < prm.H && w < prm.W;
+      const long long pix = ((long long)n * prm.H + h) * prm.W + w;
+      tc::mbar_wait(&tfull_bar[acc], acc_phase);
+      tc::fence_after_sync();
+      for (int c0 = 0; c0 < JT; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * JT + c0, v);
+        const int j0 = jt * JT + c0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i] + s_bias[j0 + i], prm.act);
+        __half* dst;
+        if (prm.mode == 1) {
+          int ab = j0 / prm.cout, co = j0 - ab * prm.cout;
+          long long op = (((long long)n * 2 * prm.H + 2 * h + (ab >> 1)) * (2LL * prm.W) + 2 * w + (ab & 1));
+          dst = prm.y + op * prm.ldy + co;
+        } else {
+          dst = prm.y + pix * prm.ldy + j0;
+        }
+        if (valid) {
+          if (prm.mask != nullptr) {
+            float m[8];
+            load8<__half>(prm.mask + pix * prm.ldmask + j0, m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= act_bwd_from_y(m[i], prm.mask_act);
+            load8<__half>(prm.mask + pix * prm.ldmask + j0 + 8, m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 + i] *= act_bwd_from_y(m[i], prm.mask_act);
+          }
+          if (prm.accumulate) {
+            float e[8];
+            load8<__half>(dst, e);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += e[i];
+            load8<__half>(dst + 8, e);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 + i] += e[i];
+          }
+          store8<__half>(dst, v);
+          store8<__half>(dst + 8, v + 8);
+        }
+        if (prm.stats != nullptr) {
+          float q[16], sq[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float rv = valid ? __half2float(__float2half_rn(v[i])) : 0.f;   // statistics of the stored value
+            q[i] = rv;
+            sq[i] = rv * rv;
+          }
+          float s1 = transpose_reduce16(q, lane);
+          float s2 = transpose_reduce16(sq, lane);
+          if (lane < 16) {
+            atomicAdd(&s_stats[j0 + lane], s1);
+            atomicAdd(&s_stats[prm.J + j0 + lane], s2);
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (prm.stats != nullptr) {
+    for (int i = threadIdx.x; i < 2 * prm.J; i += kThreadsTc) {
+      float s = s_stats[i];
+      if (s != 0.f) atomicAdd(&prm.stats[i], (double)s);
+    }
+  }
+  if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---- weight packing: fp32 Keras layouts -> fp16 [tap][j][k] ---------------------------------------
+// mode 0 (conv fwd)   : Wp[t][co][ci] = w[t][ci][co]
+// mode 1 (conv dgrad) : Wp[t][ci][co] = w[8-t][ci][co]
+// mode 2 (convT fwd)  : Wp[0][q][ci]  = w[q][ci]                 (q = (a*2+b)*Cout + co)
+// mode 3 (convT dgrad): Wp[ab][ci][co] = w[ab][co][ci]
+__global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ wp, int mode, int taps, int J,
+                                    int K) {
+  long long total = (long long)taps * J * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i % K);
+    long long r = i / K;
+    int j = (int)(r % J);
+    int t = (int)(r / J);
+    float v;
+    if (mode == 0) v = w[((long long)t * K + k) * J + j];
+    else if (mode == 1) v = w[((long long)(8 - t) * J + j) * K + k];
+    else if (mode == 2) v = w[(long long)j * K + k];
+    else v = w[((long long)t * K + k) * J + j];
+    wp[i] = __float2half_rn(v);
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int get_encode() {
+  if (g_encode != nullptr) return B2U_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  B2U_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    b2u_set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return B2U_ERR_CUDA;
+  }
+  g_encode = (EncodeTiledFn)fn;
+  return B2U_OK;
+}
+
+CUtensorMapSwizzle swizzle_for(int ks) {
+  return ks == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (ks == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// activation map: dims (C, W, H, N), element strides given in elements of the underlying fp16 buffer
+int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sW, long long sH,
+                 long long sN, int KS) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
+  cuuint32_t box[4] = {(cuuint32_t)KS, (cuuint32_t)kTileW, (cuuint32_t)kTileH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KS), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    b2u_set_error("cuTensorMapEncodeTiled(activations C=%d W=%d H=%d N=%d sW=%lld KS=%d) failed: %d", C, W, H, N, sW, KS,
+                  (int)r);
+    return B2U_ERR_CUDA;
+  }
+  return B2U_OK;
+}
+
+int make_w_map(CUtensorMap* m, const void* base, int K, int J, int taps, int KS, int JT) {
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)J, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * J * 2};
+  cuuint32_t box[3] = {(cuuint32_t)KS, (cuuint32_t)JT, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KS), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    b2u_set_error("cuTensorMapEncodeTiled(weights K=%d J=%d taps=%d KS=%d JT=%d) failed: %d", K, J, taps, KS, JT, (int)r);
+    return B2U_ERR_CUDA;
+  }
+  return B2U_OK;
+}
+
+int pick_ks(int K) { return K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : (K % 16 == 0 ? 16 : 0)); }
+int pick_jt(int J) {
+  if (J <= 256) return J;
+  for (int jt = 256; jt >= 16; jt -= 16)
+    if (J % jt == 0) return jt;
+  return 0;
+}
+
+size_t smem_bytes_for(int KS, int JT, int J) {
+  size_t a = (size_t)kTileM * KS * 2, b = ((size_t)JT * KS * 2 + 1023) & ~(size_t)1023;
+  return 1024 + kStages * (a + b) + (2 * kStages + 4) * 8 + 16 + (size_t)3 * J * 4 + 64;
+}
+
+bool g_attr_set = false;
+
+int launch_tc(const TcMaps& maps, const TcParams& prm, void* stream) {
+  size_t smem = smem_bytes_for(prm.KS, prm.JT, prm.J);
+  B2U_REQUIRE(smem <= 227 * 1024, "tc_conv: shared memory %zu exceeds 227 KB", smem);
+  if (!g_attr_set) {
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    g_attr_set = true;
+  }
+  long long tiles = (long long)prm.N * b2u_cdiv(prm.H, kTileH) * b2u_cdiv(prm.W, kTileW) * (prm.J / prm.JT);
+  int grid = (int)(tiles < B2U_NUM_SMS ? tiles : B2U_NUM_SMS);
+  B2U_LAUNCH(tc_conv_kernel, grid, kThreadsTc, smem, stream, maps, prm);
+  return B2U_OK;
+}
+
+int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int J, int K, void* stream) {
+  size_t need = (size_t)taps * J * K * 2;
+  B2U_REQUIRE(ws != nullptr && need <= ws_bytes, "tc_conv: workspace too small (%zu > %zu)", need, ws_bytes);
+  long long total = (long long)taps * J * K;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 8 * B2U_NUM_SMS) grid = 8 * B2U_NUM_SMS;
+  B2U_LAUNCH(pack_weights_kernel, grid, 256, 0, stream, w, (__half*)ws, mode, taps, J, K);
+  return B2U_OK;
+}
+
+}  // namespace
+
+int b2u_tc_compiled(void) { return 1; }
+
+int b2u_tc_conv3x3_ok(int k, int j, int ld_in, int ld_out) {
+  return pick_ks(k) != 0 && j % 16 == 0 && pick_jt(j) != 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && j <= 1024;
+}
+int b2u_tc_convt_ok(int cin, int cout, int ld_small, int ld_big) {
+  return pick_ks(cin) != 0 && pick_ks(cout) != 0 && cout % 16 == 0 && cin % 16 == 0 && pick_jt(4 * cout) != 0 &&
+         ld_small % 8 == 0 && ld_big % 8 == 0 && 4 * cout <= 1024 && cin <= 1024;
+}
 int b2u_tc_wgrad_ok(int, int, int, int) { return 0; }
-int b2u_tc_convt_ok(int, int, int, int) { return 0; }
-#define NOTC b2u_set_error("tensor path not compiled"); return B2U_ERR_UNSUPPORTED
-int b2u_tc_conv3x3(const void*, int, int, const float*, int, const float*, int, void*, int, int, double*, const void*, int, int, int, int, int, int, void*, size_t, void*) { NOTC; }
-int b2u_tc_conv3x3_wgrad(const void*, int, int, const void*, int, int, float*, float*, int, int, int, void*, size_t, void*) { NOTC; }
-int b2u_tc_convt_fwd(const void*, int, int, const float*, const float*, void*, int, int, int, int, int, void*, size_t, void*) { NOTC; }
-int b2u_tc_convt_dgrad(const void*, int, int, const float*, void*, int, int, const void*, int, int, int, int, int, int, void*, size_t, void*) { NOTC; }
-int b2u_tc_convt_wgrad(const void*, int, int, const void*, int, int, float*, float*, int, int, int, void*, size_t, void*) { NOTC; }
+
+int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
+                   int ldy, int J, double* stats, const void* mask, int ldmask, int mask_act, int accumulate, int n,
+                   int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+  int rc = get_encode();
+  if (rc != B2U_OK) return rc;
+  TcParams p{};
+  p.N = n; p.H = h; p.W = wd; p.K = K; p.J = J; p.KS = pick_ks(K); p.JT = pick_jt(J); p.ntaps = 9;
+  for (int t = 0; t < 9; ++t) { p.tap_dh[t] = t / 3 - 1; p.tap_dw[t] = t % 3 - 1; p.tap_map[t] = 0; }
+  p.mode = 0; p.cout = J; p.y = (__half*)y; p.ldy = ldy; p.bias = bias; p.act = act;
+  p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate; p.stats = stats;
+  rc = pack(w, ws, ws_bytes, dgrad ? 1 : 0, 9, J, K, stream);
+  if (rc != B2U_OK) return rc;
+  TcMaps maps;
+  rc = make_act_map(&maps.a[0], x, K, wd, h, n, ldx, (long long)wd * ldx, (long long)h * wd * ldx, p.KS);
+  if (rc != B2U_OK) return rc;
+  for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+  rc = make_w_map(&maps.b, ws, K, J, 9, p.KS, p.JT);
+  if (rc != B2U_OK) return rc;
+  return launch_tc(maps, p, stream);
+}
+
+int b2u_tc_convt_fwd(const void* x, int ldx, int cin, const float* w, const float* bias, void* y, int ldy, int cout,
+                     int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+  int rc = get_encode();
+  if (rc != B2U_OK) return rc;
+  TcParams p{};
+  p.N = n; p.H = h; p.W = wd; p.K = cin; p.J = 4 * cout; p.KS = pick_ks(cin); p.JT = pick_jt(4 * cout);
+  if (p.JT > cout && p.JT % cout != 0) p.JT = cout;       // a 16-column chunk must not straddle two (a,b) groups
+  p.ntaps = 1; p.tap_dh[0] = 0; p.tap_dw[0] = 0; p.tap_map[0] = 0;
+  p.mode = 1; p.cout = cout; p.y = (__half*)y; p.ldy = ldy; p.bias = bias; p.act = B2U_ACT_NONE;
+  rc = pack(w, ws, ws_bytes, 2, 1, 4 * cout, cin, stream);
+  if (rc != B2U_OK) return rc;
+  TcMaps maps;
+  rc = make_act_map(&maps.a[0], x, cin, wd, h, n, ldx, (long long)wd * ldx, (long long)h * wd * ldx, p.KS);
+  if (rc != B2U_OK) return rc;
+  for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+  rc = make_w_map(&maps.b, ws, cin, 4 * cout, 1, p.KS, p.JT);
+  if (rc != B2U_OK) return rc;
+  return launch_tc(maps, p, stream);
+}
+
+int b2u_tc_convt_dgrad(const void* dy, int lddy, int cout, const float* w, void* dx, int lddx, int cin,
+                       const void* mask, int ldmask, int mask_act, int accumulate, int n, int h, int wd, void* ws,
+                       size_t ws_bytes, void* stream) {
+  int rc = get_encode();
+  if (rc != B2U_OK) return rc;
+  TcParams p{};
+  p.N = n; p.H = h; p.W = wd; p.K = cout; p.J = cin; p.KS = pick_ks(cout); p.JT = pick_jt(cin); p.ntaps = 4;
+  for (int t = 0; t < 4; ++t) { p.tap_dh[t] = 0; p.tap_dw[t] = 0; p.tap_map[t] = t; }
+  p.mode = 0; p.cout = cin; p.y = (__half*)dx; p.ldy = lddx; p.bias = nullptr; p.act = B2U_ACT_NONE;
+  p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate;
+  rc = pack(w, ws, ws_bytes, 3, 4, cin, cout, stream);
+  if (rc != B2U_OK) return rc;
+  TcMaps maps;
+  // tap (a,b): the sub-grid dy[n, 2i+a, 2j+b, :] seen as an (N,H,W,C) tensor with doubled pixel strides
+  for (int t = 0; t < 4; ++t) {
+    const __half* base = (const __half*)dy + ((long long)(t >> 1) * (2 * wd) + (t & 1)) * lddy;
+    rc = make_act_map(&maps.a[t], base, cout, wd, h, n, 2LL * lddy, 4LL * wd * lddy, 4LL * h * wd * lddy, p.KS);
+    if (rc != B2U_OK) return rc;
+  }
+  rc = make_w_map(&maps.b, ws, cout, cin, 4, p.KS, p.JT);
+  if (rc != B2U_OK) return rc;
+  return launch_tc(maps, p, stream);
+}
+
+int b2u_tc_conv3x3_wgrad(const void*, int, int, const void*, int, int, float*, float*, int, int, int, void*, size_t,
+                         void*) {
+  b2u_set_error("tc wgrad not built yet");
+  return B2U_ERR_UNSUPPORTED;
+}
+int b2u_tc_convt_wgrad(const void*, int, int, const void*, int, int, float*, float*, int, int, int, void*, size_t,
+                       void*) {
+  b2u_set_error("tc convT wgrad not built yet");
+  return B2U_ERR_UNSUPPORTED;
+}

@@ -37,13 +37,17 @@ def synth_batch(n, hw, cin=1, seg=True, seed=0):
     return x, t
 
 
-def grad_errors(got, want, skip_zero_bias=True):
-    """max over tensors of max|got-want| / max|want|; convT biases feeding a BN are analytically zero."""
+def grad_errors(got, want, skip_zero_bias=True, norm="max"):
+    """worst tensor of max|got-want| / max|want| (norm="max") or ||got-want||_2 / ||want||_2 (norm="l2");
+    convT biases feeding a BN are analytically zero and skipped."""
     worst, who = 0.0, None
     for k, v in want.items():
         if skip_zero_bias and "conv2d_transpose" in k and k.endswith("bias"):
             continue
-        d = float(np.abs(got[k] - v).max() / (np.abs(v).max() + 1e-12))
+        if norm == "l2":
+            d = float(np.linalg.norm((got[k] - v).ravel()) / (np.linalg.norm(np.ravel(v)) + 1e-12))
+        else:
+            d = float(np.abs(got[k] - v).max() / (np.abs(v).max() + 1e-12))
         if d > worst:
             worst, who = d, k
     return worst, who

@@ -1,0 +1,82 @@
+"""tcgen05 implicit-GEMM kernels (csrc/conv_tc.cu) against tests/emulator.py on U-Net-shaped problems:
+all K-slab widths (16/32/64 channels -> 32B/64B/128B swizzle), several N tiles (J = 512), ragged
+image sizes (tiles clipped by TMA zero-fill), concat-slice strides, mask / accumulate / BN-statistics
+epilogues, and the transposed-conv scatter / sub-grid gather variants."""
+import importlib
+
+import numpy as np
+import pytest
+
+import emulator as E
+from conftest import PKG
+from helpers import P
+from test_gpu_ops import Img, compare
+
+pytestmark = pytest.mark.gpu
+dt = P.F16
+
+
+def test_tensor_path_is_live():
+    lib = importlib.import_module(PKG + "._lib")
+    assert lib.lib().b2u_tensor_path_available() == 1, "tcgen05 path not compiled in / not an sm_100 device"
+
+
+TC_CONV = [  # n, h, w, cin, cout
+    (1, 16, 16, 64, 64), (2, 32, 32, 32, 32), (1, 32, 32, 256, 512), (1, 16, 16, 512, 256), (2, 24, 40, 128, 128),
+    (1, 14, 14, 256, 512), (1, 28, 28, 96, 32), (1, 56, 56, 16, 16), (3, 8, 8, 192, 64), (1, 64, 64, 64, 32),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", TC_CONV)
+def test_tc_conv3x3_fwd(n, h, w, cin, cout):
+    img = Img(21)
+    x = img.view(n, h, w, cin, dt, ld=2 * cin, c0=cin, fill="uniform")          # right half of a concat buffer
+    y = img.view(n, h, w, cout, dt, ld=cout + 16, c0=8, fill=None)
+    wt = img.farr(img.par, 9 * cin * cout, scale=(2.0 / (9 * cin)) ** 0.5)
+    b = img.farr(img.par, cout, scale=0.1)
+    stats = img.zero.alloc(2 * cout * 8)
+    for act in (1, 2):
+        ops = [P.Op(P.OP_CONV3X3_FWD, dt, [x.ref, wt, b, y.ref, stats], [x.ld, cin, act, y.ld, cout, n, h, w])]
+        compare(ops, img, dt, tol=3e-3)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", TC_CONV)
+def test_tc_conv3x3_dgrad(n, h, w, cin, cout):
+    img = Img(22)
+    dy = img.view(n, h, w, cout, dt, ld=cout + 8, scale=0.5)
+    dx = img.view(n, h, w, cin, dt, ld=2 * cin, c0=0, scale=0.3)
+    mask = img.view(n, h, w, cin, dt)
+    wt = img.farr(img.par, 9 * cin * cout, scale=(2.0 / (9 * cin)) ** 0.5)
+    for acc, mact in ((0, 1), (1, 2), (0, 0)):
+        ops = [P.Op(P.OP_CONV3X3_DGRAD, dt, [dy.ref, wt, dx.ref, mask.ref if mact else None],
+                    [dy.ld, cout, dx.ld, cin, mask.ld, mact, acc, n, h, w])]
+        compare(ops, img, dt, tol=4e-3)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 8, 8, 64, 32), (1, 5, 7, 32, 16), (1, 4, 4, 512, 256), (1, 32, 32, 128, 64),
+                                            (2, 16, 16, 256, 128)])
+def test_tc_convt(n, h, w, cin, cout):
+    img = Img(23)
+    x = img.view(n, h, w, cin, dt, fill="uniform")
+    y = img.view(n, 2 * h, 2 * w, cout, dt, ld=2 * cout, c0=0, fill=None)
+    dy = img.view(n, 2 * h, 2 * w, cout, dt, ld=2 * cout, c0=cout, scale=0.5)
+    dx = img.view(n, h, w, cin, dt, scale=0.2)
+    wt = img.farr(img.par, 4 * cout * cin, scale=(1.0 / cin) ** 0.5)
+    b = img.farr(img.par, cout, scale=0.1)
+    for acc in (0, 1):
+        ops = [P.Op(P.OP_CONVT_FWD, dt, [x.ref, wt, b, y.ref], [x.ld, cin, y.ld, cout, n, h, w]),
+               P.Op(P.OP_CONVT_DGRAD, dt, [dy.ref, wt, dx.ref, x.ref], [dy.ld, cout, dx.ld, cin, x.ld, 1, acc, n, h, w])]
+        compare(ops, img, dt, tol=4e-3)
+
+
+def test_tc_large_layer_many_tiles():
+    """more tiles than SMs: exercises the persistent loop, the smem ring wrap-around and both TMEM stages"""
+    n, h, w, cin, cout = 2, 128, 128, 32, 32
+    img = Img(24)
+    x = img.view(n, h, w, cin, dt, fill="uniform")
+    y = img.view(n, h, w, cout, dt, fill=None)
+    wt = img.farr(img.par, 9 * cin * cout, scale=(2.0 / (9 * cin)) ** 0.5)
+    b = img.farr(img.par, cout, scale=0.1)
+    stats = img.zero.alloc(2 * cout * 8)
+    ops = [P.Op(P.OP_CONV3X3_FWD, dt, [x.ref, wt, b, y.ref, stats], [x.ld, cin, 1, y.ld, cout, n, h, w])]
+    compare(ops, img, dt, tol=3e-3)
