@@ -192,6 +192,10 @@ typedef struct b2u_op {
   float f[4];
 } b2u_op;
 int b2u_run_ops(const b2u_op* h_ops, int n_ops, void* ws, size_t ws_bytes, void* comm, void* stream);
+/* b2u_run_ops with a CUDA event between consecutive ops; h_ms_out[k] = device milliseconds of op k.
+ * Synchronises the stream before returning (profiling aid for bench.py's roofline numbers). */
+int b2u_run_ops_timed(const b2u_op* h_ops, int n_ops, void* ws, size_t ws_bytes, void* comm, void* stream,
+                      float* h_ms_out);
 /* CUDA-graph capture of an op list (launch-bound inner loop -> one graph launch per step) */
 int b2u_graph_create(const b2u_op* h_ops, int n_ops, void* ws, size_t ws_bytes, void* comm, void* stream,
                      void** out_graph);

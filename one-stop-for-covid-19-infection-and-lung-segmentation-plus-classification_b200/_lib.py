@@ -37,7 +37,7 @@ SYMBOLS = [
     "b2u_bn_bwd_apply", "b2u_maxpool_fwd", "b2u_maxpool_bwd", "b2u_dropout_fwd", "b2u_dropout_bwd",
     "b2u_copy_slice", "b2u_head_fwd", "b2u_bce_dice_sums", "b2u_bce_dice_finalize", "b2u_head_bwd",
     "b2u_dense_fwd", "b2u_dense_bwd", "b2u_bce_fwd", "b2u_bce_sigmoid_bwd", "b2u_adam", "b2u_gather_batch",
-    "b2u_threshold_counts", "b2u_clahe_u8", "b2u_crop_resize", "b2u_run_ops", "b2u_graph_create",
+    "b2u_threshold_counts", "b2u_clahe_u8", "b2u_crop_resize", "b2u_run_ops", "b2u_run_ops_timed", "b2u_graph_create",
     "b2u_graph_launch", "b2u_graph_destroy", "b2u_launch_count", "b2u_comm_unique_id", "b2u_comm_create",
     "b2u_comm_destroy", "b2u_allreduce",
 ]
@@ -59,6 +59,7 @@ def lib():
     l.b2u_launch_count.restype = i64
     l.b2u_tensor_path_available.restype = C.c_int
     l.b2u_run_ops.argtypes = [C.POINTER(Op), i32, vp, sz, vp, vp]
+    l.b2u_run_ops_timed.argtypes = [C.POINTER(Op), i32, vp, sz, vp, vp, C.POINTER(C.c_float)]
     l.b2u_graph_create.argtypes = [C.POINTER(Op), i32, vp, sz, vp, vp, C.POINTER(vp)]
     l.b2u_graph_launch.argtypes = [vp, vp]
     l.b2u_graph_destroy.argtypes = [vp]

@@ -85,7 +85,7 @@ extern "C" int b2u_convt2x2_dgrad(int dt, const void* dy, int lddy, int cout, co
 extern "C" int b2u_convt2x2_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, int lddy, int cout,
                                   float* dw, float* db, int n, int h, int wd, void* ws, size_t ws_bytes,
                                   void* stream) {
-  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_convt_ok(cin, cout, ldx, lddy))
+  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_convt_wgrad_ok(cin, cout, ldx, lddy))
     return b2u_tc_convt_wgrad(x, ldx, cin, dy, lddy, cout, dw, db, n, h, wd, ws, ws_bytes, stream);
   return b2u_direct_convt_wgrad(dt, x, ldx, cin, dy, lddy, cout, dw, db, n, h, wd, stream);
 }
@@ -198,6 +198,31 @@ extern "C" int b2u_run_ops(const b2u_op* h_ops, int n_ops, void* ws, size_t ws_b
       return rc;
     }
   }
+  return B2U_OK;
+}
+
+// same as b2u_run_ops, with a CUDA event between consecutive ops on the launching stream:
+// h_ms_out[k] = device time of op k in milliseconds (bench.py's live per-kernel roofline numbers)
+extern "C" int b2u_run_ops_timed(const b2u_op* h_ops, int n_ops, void* ws, size_t ws_bytes, void* comm, void* stream,
+                                 float* h_ms_out) {
+  B2U_REQUIRE(h_ops != nullptr && h_ms_out != nullptr && n_ops > 0, "run_ops_timed: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaEvent_t* ev = new cudaEvent_t[n_ops + 1];
+  for (int k = 0; k <= n_ops; ++k) cudaEventCreate(&ev[k]);
+  int rc = B2U_OK;
+  cudaEventRecord(ev[0], s);
+  for (int k = 0; k < n_ops && rc == B2U_OK; ++k) {
+    rc = run_one(h_ops[k], ws, ws_bytes, comm, stream);
+    cudaEventRecord(ev[k + 1], s);
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (rc == B2U_OK && e == cudaSuccess) {
+    for (int k = 0; k < n_ops; ++k) cudaEventElapsedTime(&h_ms_out[k], ev[k], ev[k + 1]);
+  }
+  for (int k = 0; k <= n_ops; ++k) cudaEventDestroy(ev[k]);
+  delete[] ev;
+  if (rc != B2U_OK) return rc;
+  B2U_CHECK_CUDA(e);
   return B2U_OK;
 }
 

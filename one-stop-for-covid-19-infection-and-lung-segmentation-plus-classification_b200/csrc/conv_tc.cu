@@ -398,6 +398,7 @@ int b2u_tc_convt_ok(int cin, int cout, int ld_small, int ld_big) {
          ld_small % 8 == 0 && ld_big % 8 == 0 && 4 * cout <= 1024 && cin <= 1024;
 }
 int b2u_tc_wgrad_ok(int, int, int, int) { return 0; }
+int b2u_tc_convt_wgrad_ok(int, int, int, int) { return 0; }
 
 int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                    int ldy, int J, double* stats, const void* mask, int ldmask, int mask_act, int accumulate, int n,

@@ -365,6 +365,17 @@ class Engine:
                                                  C.c_void_p(sgt.data_ptr()), C.c_void_p(self.stream.cuda_stream)),
                    "threshold_counts")
 
+    def profile_train_ops(self, n, dropout=True):
+        """One eager training step with a CUDA event between ops (b2u_run_ops_timed): returns
+        [(plan.Op, milliseconds)].  Inputs must already be in place (call train_batch once before)."""
+        b = self._get_bound(n, True, dropout)
+        arr, cnt = self._ops(b, "train")
+        ms = (C.c_float * cnt)()
+        comm = self.comm.handle if self.comm is not None else None
+        _lib.check(self.lib.b2u_run_ops_timed(arr, cnt, C.c_void_p(self.ws.data_ptr()), self.ws.numel(), comm,
+                                              C.c_void_p(self.stream.cuda_stream), ms), "run_ops_timed")
+        return list(zip(b.plan.train_ops(), [float(v) for v in ms]))
+
     def close(self):
         self.stream.synchronize()
         for b in self._bound.values():

@@ -389,6 +389,34 @@ class Model:
         v = np.asarray(vals).reshape(len(thresholds), 4)
         return {"threshold": np.asarray(thresholds), "f1": v[:, 0], "iou": v[:, 1], "precision": v[:, 2], "recall": v[:, 3]}
 
+    def train_on_batch(self, x, y, sample_weight=None, dropout=True):
+        """keras Model.train_on_batch: one optimisation step on a HOST batch; returns [loss, metric].
+        The host->device copy of the batch and the device->host read of the loss are part of the call
+        (this is the end-to-end path bench.py times).  x / y may be numpy arrays or pinned torch tensors."""
+        eng = self.engine
+        n = len(x)
+        xt = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        yt = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32))
+        key = (n, tuple(xt.shape[1:]))
+        st = getattr(self, "_stage", None)
+        if st is None or st[0] != key:
+            with torch.cuda.stream(eng.stream):
+                st = (key, torch.empty(xt.shape, dtype=torch.float32, device=eng.device),
+                      torch.empty((n, int(yt.numel() // n)), dtype=torch.float32, device=eng.device),
+                      torch.ones(n, dtype=torch.float32, device=eng.device),
+                      torch.empty(2, dtype=torch.float32).pin_memory())
+            self._stage = st
+        _, xd, yd, swd, out = st
+        with torch.cuda.stream(eng.stream):
+            xd.copy_(xt, non_blocking=True)
+            yd.copy_(yt.reshape(n, -1), non_blocking=True)
+            if sample_weight is not None:
+                swd.copy_(torch.as_tensor(sample_weight, dtype=torch.float32), non_blocking=True)
+            b = eng.train_batch(xd, yd, None, n, dropout=dropout, sw_src=swd)
+            out.copy_(eng.loss_dev(b), non_blocking=True)
+        eng.stream.synchronize()
+        return [float(out[0]), float(out[1])]
+
     def fit(self, x, y, batch_size=32, epochs=1, validation_data=None, callbacks=None, class_weight=None,
             shuffle=True, verbose=1, initial_epoch=0, dropout=True, **kw):
         eng = self.engine

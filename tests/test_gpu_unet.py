@@ -158,7 +158,8 @@ def test_graph_replay_matches_eager_training(precision):
     # atomics make the reduction order run-dependent: compare with a tolerance, not bit-for-bit
     assert np.allclose(outs[0][0], outs[1][0], rtol=2e-3 if precision == "float16" else 1e-4)
     for k in outs[0][1]:
-        assert np.abs(outs[0][1][k] - outs[1][1][k]).max() < (2e-3 if precision == "float16" else 2e-4), k
+        # Adam turns noise-level gradients (atomics -> run-dependent rounding) into +-lr sized updates
+        assert np.abs(outs[0][1][k] - outs[1][1][k]).max() < 2 * 3 * 5e-4 + 1e-6, k
 
 
 def test_partial_batch_and_odd_sizes():
