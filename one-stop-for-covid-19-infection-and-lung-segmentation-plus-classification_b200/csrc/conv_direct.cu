@@ -446,6 +446,16 @@ int b2u_direct_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const void
   return B2U_OK;
 }
 
+// db[c] += sum over pixels of dy[.][c]  (bias gradient beside the tcgen05 weight-gradient kernel)
+int b2u_channel_sum_f16(const void* dy, int lddy, int c, long long npix, float* db, void* stream) {
+  B2U_REQUIRE(c % 8 == 0 && lddy % 8 == 0 && c <= 2048, "channel_sum: c%%8==0 required");
+  int lanes = 256 / (c / 8);
+  long long g = (npix + lanes - 1) / lanes;
+  if (g > 4 * B2U_NUM_SMS) g = 4 * B2U_NUM_SMS;
+  B2U_LAUNCH(channel_sum_kernel<__half>, (int)g, 256, c * sizeof(float), stream, (const __half*)dy, lddy, c, npix, db);
+  return B2U_OK;
+}
+
 int b2u_direct_convt_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, void* y, int ldy,
                          int cout, int n, int h, int wd, void* stream) {
   long long M = (long long)n * h * wd;

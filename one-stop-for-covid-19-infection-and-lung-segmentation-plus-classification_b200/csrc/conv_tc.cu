@@ -397,8 +397,6 @@ int b2u_tc_convt_ok(int cin, int cout, int ld_small, int ld_big) {
   return pick_ks(cin) != 0 && pick_ks(cout) != 0 && cout % 16 == 0 && cin % 16 == 0 && pick_jt(4 * cout) != 0 &&
          ld_small % 8 == 0 && ld_big % 8 == 0 && 4 * cout <= 1024 && cin <= 1024;
 }
-int b2u_tc_wgrad_ok(int, int, int, int) { return 0; }
-int b2u_tc_convt_wgrad_ok(int, int, int, int) { return 0; }
 
 int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                    int ldy, int J, double* stats, const void* mask, int ldmask, int mask_act, int accumulate, int n,
@@ -463,15 +461,4 @@ int b2u_tc_convt_dgrad(const void* dy, int lddy, int cout, const float* w, void*
   rc = make_w_map(&maps.b, ws, cout, cin, 4, p.KS, p.JT);
   if (rc != B2U_OK) return rc;
   return launch_tc(maps, p, stream);
-}
-
-int b2u_tc_conv3x3_wgrad(const void*, int, int, const void*, int, int, float*, float*, int, int, int, void*, size_t,
-                         void*) {
-  b2u_set_error("tc wgrad not built yet");
-  return B2U_ERR_UNSUPPORTED;
-}
-int b2u_tc_convt_wgrad(const void*, int, int, const void*, int, int, float*, float*, int, int, int, void*, size_t,
-                       void*) {
-  b2u_set_error("tc convT wgrad not built yet");
-  return B2U_ERR_UNSUPPORTED;
 }

@@ -1,0 +1,351 @@
+// tcgen05 weight-gradient kernel for sm_100a: dW = A^T * B reduced over pixels.
+//
+//   D[r][j] = sum_p  A_r[p] * B[p][j]        M = 128 accumulator rows, N = JT columns, K = pixels
+//
+// Both operands are NHWC activation tiles ([128 pixels][channels], channels contiguous), i.e. "MN-major"
+// for the tensor core: the pixel axis is the GEMM K axis, so the same TMA boxes the forward kernel uses
+// feed tcgen05.mma with a_major = b_major = MN.  The 128 accumulator rows are assembled from `nchunks`
+// activation tiles of KSA channels each (KSA * nchunks = 128): for thin layers several filter taps share
+// one MMA (4 taps x 32 channels, 2 taps x 64 channels), for wide layers a chunk is a 64-channel slab.
+//
+//   Conv2D 3x3      : A = x shifted by the tap offset (TMA zero-fill = padding), B = dy;  D -> dw[t][ci][co]
+//   Conv2DTranspose : A = the (a,b) sub-grid of dy (own tensor map),            B = x;   D -> dw[a][b][co][ci]
+//
+// One CTA per SM, persistent over tasks (row group, N tile, pixel split); split-K partial sums are
+// added to the fp32 gradient buffer with atomics.  Warp roles as in conv_tc.cu.
+#include <cuda.h>
+#include "common.cuh"
+#include "internal.h"
+#include "launch.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kThreadsW = 192;
+constexpr int kTileH = 8, kTileW = 16;        // 128 pixels per K block
+constexpr int kMaxGroups = 36, kMaxChunks = 8;
+
+struct WgParams {
+  int N, H, W;                 // pixel grid both operands are sampled on
+  int KSA, nchunks;            // A chunk width (channels) ; 128 / KSA
+  int KSB, JT, J;              // B slab width, N tile, total B channels
+  int ngroups;                 // row groups (each: nchunks chunks = 128 accumulator rows)
+  int8_t ch_map[kMaxGroups][kMaxChunks];     // tensor-map index of the chunk (-1: unused rows)
+  int8_t ch_dh[kMaxGroups][kMaxChunks], ch_dw[kMaxGroups][kMaxChunks];
+  int16_t ch_c0[kMaxGroups][kMaxChunks];     // first channel of the chunk inside its tensor
+  int out_base[kMaxGroups][kMaxChunks];      // dw element offset of the chunk's first row
+  int out_row_stride;          // elements between consecutive accumulator rows in dw
+  int nsplit;                  // pixel-block splits
+  int stages;
+  float* dw;
+};
+
+struct WgMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+__global__ void __launch_bounds__(kThreadsW, 1) tc_wgrad_kernel(const __grid_constant__ WgMaps maps,
+                                                                 const __grid_constant__ WgParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int KSA = prm.KSA, KSB = prm.KSB, JT = prm.JT, nchunks = prm.nchunks, stages = prm.stages;
+  const uint32_t a_tile = 128u * KSA * 2, b_tile = 128u * KSB * 2;
+  const int nb = JT / KSB;                                   // B slabs per N tile
+  const uint32_t a_bytes = a_tile * nchunks, b_bytes = b_tile * nb;   // 32 KB, JT * 256 B
+  const uint32_t stage_stride = a_bytes + b_bytes;           // multiples of 1024 (tiles are >= 4 KB)
+  uint8_t* tail = smem + stages * stage_stride;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tfull_bar = empty_bar + 8;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_w = (prm.W + kTileW - 1) / kTileW, tiles_h = (prm.H + kTileH - 1) / kTileH;
+  const int nblocks = prm.N * tiles_h * tiles_w;             // K blocks of 128 pixels
+  const int nj = prm.J / JT;
+  const int ntasks = prm.nsplit * prm.ngroups * nj;          // task = (split, group, jt), split-major
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * JT)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull_bar[s], 1); tc::mbar_init(&tempty_bar[s], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =========================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const int jt = task % nj, g = (task / nj) % prm.ngroups, sp = task / (nj * prm.ngroups);
+        for (int blk = sp; blk < nblocks; blk += prm.nsplit) {
+          const int tw = blk % tiles_w, th = (blk / tiles_w) % tiles_h, n = blk / (tiles_w * tiles_h);
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_stride;
+          uint8_t* sb = sa + a_bytes;
+          int live = 0;
+          for (int c = 0; c < nchunks; ++c) live += prm.ch_map[g][c] >= 0;
+          tc::mbar_expect_tx(&full_bar[stage], live * a_tile + b_bytes);
+          for (int c = 0; c < nchunks; ++c) {
+            const int m = prm.ch_map[g][c];
+            if (m < 0) continue;
+            tc::tma_load_4d(sa + c * a_tile, &maps.a[m], &full_bar[stage], prm.ch_c0[g][c],
+                            tw * kTileW + prm.ch_dw[g][c], th * kTileH + prm.ch_dh[g][c], n);
+          }
+          for (int s = 0; s < nb; ++s)
+            tc::tma_load_4d(sb + s * b_tile, &maps.b, &full_bar[stage], jt * JT + s * KSB, tw * kTileW, th * kTileH, n);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ============================================
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_f16(128, JT, 1, 1);              // both operands MN-major
+      const uint64_t la = KSA == 64 ? tc::SWZ_128B : (KSA == 32 ? tc::SWZ_64B : tc::SWZ_32B);
+      const uint64_t lb = KSB == 64 ? tc::SWZ_128B : (KSB == 32 ? tc::SWZ_64B : tc::SWZ_32B);
+      const uint32_t rowa = KSA * 2, rowb = KSB * 2;                    // bytes per pixel row of a tile
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const int sp = task / (nj * prm.ngroups);
+        tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * JT;
+        uint32_t first = 1;
+        for (int blk = sp; blk < nblocks; blk += prm.nsplit) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(smem + stage * stage_stride);
+          const uint32_t sb = sa + a_bytes;
+          for (int kk = 0; kk < 8; ++kk) {                              // 8 x 16 pixels
+            // MN-major: LBO = distance between channel chunks (tiles), SBO = 8 pixel rows
+            uint64_t ad = tc::smem_desc(sa + kk * 16 * rowa, a_tile, 8 * rowa, la);
+            uint64_t bd = tc::smem_desc(sb + kk * 16 * rowb, b_tile, 8 * rowb, lb);
+            tc::mma_f16_ss(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+            first = 0;
+          }
+          tc::mma_commit(&empty_bar[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        tc::mma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue ==============================================
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+      const int jt = task % nj, g = (task / nj) % prm.ngroups, sp = task / (nj * prm.ngroups);
+      const int c = row / KSA, rr = row % KSA;
+      const bool live = prm.ch_map[g][c] >= 0 && sp < nblocks;
+      float* out = prm.dw + (long long)prm.out_base[g][c] + (long long)rr * prm.out_row_stride + jt * JT;
+      tc::mbar_wait(&tfull_bar[acc], acc_phase);
+      tc::fence_after_sync();
+      for (int c0 = 0; c0 < JT; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * JT + c0, v);
+        if (live) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(out + c0 + i, v[i]);
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_enc = nullptr;
+
+int get_enc() {
+  if (g_enc != nullptr) return B2U_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  B2U_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    b2u_set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return B2U_ERR_CUDA;
+  }
+  g_enc = (EncodeTiledFn)fn;
+  return B2U_OK;
+}
+
+int act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sW, long long sH, long long sN,
+            int KS) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
+  cuuint32_t box[4] = {(cuuint32_t)KS, (cuuint32_t)kTileW, (cuuint32_t)kTileH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle sw = KS == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (KS == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = g_enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    b2u_set_error("cuTensorMapEncodeTiled(wgrad C=%d W=%d H=%d N=%d KS=%d) failed: %d", C, W, H, N, KS, (int)r);
+    return B2U_ERR_CUDA;
+  }
+  return B2U_OK;
+}
+
+int ks_for(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : (c % 16 == 0 ? 16 : 0)); }
+
+bool g_attr = false;
+
+int launch_wg(const WgMaps& maps, WgParams& p, void* stream) {
+  const size_t a_bytes = 128 * 128 * 2, b_bytes = (size_t)p.JT * 256;
+  p.stages = (int)((200 * 1024) / (a_bytes + b_bytes));
+  if (p.stages > 6) p.stages = 6;
+  B2U_REQUIRE(p.stages >= 2, "tc_wgrad: tile too large for a 2-stage pipeline");
+  size_t smem = 1024 + p.stages * (a_bytes + b_bytes) + 256;
+  const int nblocks = p.N * b2u_cdiv(p.H, kTileH) * b2u_cdiv(p.W, kTileW);
+  const int base = p.ngroups * (p.J / p.JT);
+  int ns = (2 * B2U_NUM_SMS + base - 1) / base;              // ~2 tasks per SM
+  if (ns > nblocks) ns = nblocks;
+  if (ns < 1) ns = 1;
+  p.nsplit = ns;
+  if (!g_attr) {
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    g_attr = true;
+  }
+  int ntasks = ns * base;
+  int grid = ntasks < B2U_NUM_SMS ? ntasks : B2U_NUM_SMS;
+  B2U_LAUNCH(tc_wgrad_kernel, grid, kThreadsW, smem, stream, maps, p);
+  return B2U_OK;
+}
+
+int pick_jt_w(int J) {            // N tile: <= 128 columns, multiple of the slab width
+  if (J <= 128) return J;
+  return J % 128 == 0 ? 128 : (J % 64 == 0 ? 64 : (J % 32 == 0 ? 32 : 16));
+}
+
+}  // namespace
+
+int b2u_channel_sum_f16(const void* dy, int lddy, int c, long long npix, float* db, void* stream);
+
+int b2u_tc_wgrad_ok(int cin, int cout, int ldx, int lddy) {
+  if (ks_for(cin) == 0 || ks_for(cout) == 0 || ldx % 8 || lddy % 8 || cout % 16) return 0;
+  const int ksa = cin >= 128 ? 64 : ks_for(cin);
+  if (cin >= 128 && cin % 128) return 0;
+  if (cin < 128 && 128 % cin) return 0;
+  const int taps_per_group = cin >= 128 ? 1 : 128 / cin;
+  const int groups = cin >= 128 ? 9 * (cin / 128) : (9 + taps_per_group - 1) / taps_per_group;
+  (void)ksa;
+  return groups <= kMaxGroups;
+}
+int b2u_tc_convt_wgrad_ok(int cin, int cout, int ldx, int lddy) {
+  if (ks_for(cin) == 0 || ks_for(cout) == 0 || ldx % 8 || lddy % 8 || cin % 16) return 0;
+  if (cout >= 128 && cout % 128) return 0;
+  if (cout < 128 && (128 % cout || 128 / cout > 4)) return 0;
+  const int groups = cout >= 128 ? 4 * (cout / 128) : (4 * cout + 127) / 128;
+  return groups <= kMaxGroups;
+}
+
+// dw[t][ci][co] += sum_p x[p + off_t][ci] * dy[p][co];  db[co] += sum_p dy[p][co]
+int b2u_tc_conv3x3_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* db,
+                         int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+  (void)ws; (void)ws_bytes;
+  int rc = get_enc();
+  if (rc != B2U_OK) return rc;
+  WgParams p{};
+  p.N = n; p.H = h; p.W = wd;
+  p.KSA = cin >= 128 ? 64 : ks_for(cin);
+  if (cin < 128 && p.KSA != cin) p.KSA = ks_for(cin);        // e.g. cin = 96 -> 32-wide chunks
+  p.nchunks = 128 / p.KSA;
+  p.KSB = ks_for(cout); p.J = cout; p.JT = pick_jt_w(cout);
+  if (p.JT % p.KSB) p.KSB = ks_for(p.JT);
+  p.out_row_stride = cout; p.dw = dw;
+  // row groups: each chunk is (tap, channel slab); rows of a chunk are consecutive input channels
+  const int slabs = cin / p.KSA;                              // chunks per tap
+  int g = 0, c = 0;
+  for (int t = 0; t < 9; ++t) {
+    for (int s = 0; s < slabs; ++s) {
+      B2U_REQUIRE(g < kMaxGroups, "tc_wgrad: too many row groups (cin=%d)", cin);
+      p.ch_map[g][c] = 0; p.ch_dh[g][c] = (int8_t)(t / 3 - 1); p.ch_dw[g][c] = (int8_t)(t % 3 - 1);
+      p.ch_c0[g][c] = (int16_t)(s * p.KSA);
+      p.out_base[g][c] = (t * cin + s * p.KSA) * cout;
+      if (++c == p.nchunks) { c = 0; ++g; }
+    }
+  }
+  if (c != 0) {
+    for (; c < p.nchunks; ++c) p.ch_map[g][c] = -1;
+    ++g;
+  }
+  p.ngroups = g;
+  WgMaps maps;
+  rc = act_map(&maps.a[0], x, cin, wd, h, n, ldx, (long long)wd * ldx, (long long)h * wd * ldx, p.KSA);
+  if (rc != B2U_OK) return rc;
+  for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+  rc = act_map(&maps.b, dy, cout, wd, h, n, lddy, (long long)wd * lddy, (long long)h * wd * lddy, p.KSB);
+  if (rc != B2U_OK) return rc;
+  rc = launch_wg(maps, p, stream);
+  if (rc != B2U_OK) return rc;
+  if (db != nullptr) return b2u_channel_sum_f16(dy, lddy, cout, (long long)n * h * wd, db, stream);
+  return B2U_OK;
+}
+
+// dw[ab][co][ci] += sum_p dy[n,2i+a,2j+b,co] * x[n,i,j,ci];  db[co] += sum over all output pixels of dy
+int b2u_tc_convt_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* db, int n,
+                       int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+  (void)ws; (void)ws_bytes;
+  int rc = get_enc();
+  if (rc != B2U_OK) return rc;
+  WgParams p{};
+  p.N = n; p.H = h; p.W = wd;
+  p.KSA = cout >= 128 ? 64 : ks_for(cout);
+  p.nchunks = 128 / p.KSA;
+  p.KSB = ks_for(cin); p.J = cin; p.JT = pick_jt_w(cin);
+  if (p.JT % p.KSB) p.KSB = ks_for(p.JT);
+  p.out_row_stride = cin; p.dw = dw;
+  const int slabs = cout / p.KSA;
+  int g = 0, c = 0;
+  for (int ab = 0; ab < 4; ++ab) {
+    for (int s = 0; s < slabs; ++s) {
+      B2U_REQUIRE(g < kMaxGroups, "tc_convt_wgrad: too many row groups (cout=%d)", cout);
+      p.ch_map[g][c] = (int8_t)ab; p.ch_dh[g][c] = 0; p.ch_dw[g][c] = 0;
+      p.ch_c0[g][c] = (int16_t)(s * p.KSA);
+      p.out_base[g][c] = (ab * cout + s * p.KSA) * cin;
+      if (++c == p.nchunks) { c = 0; ++g; }
+    }
+  }
+  if (c != 0) {
+    for (; c < p.nchunks; ++c) p.ch_map[g][c] = -1;
+    ++g;
+  }
+  p.ngroups = g;
+  WgMaps maps;
+  for (int ab = 0; ab < 4; ++ab) {
+    const __half* base = (const __half*)dy + ((long long)(ab >> 1) * (2 * wd) + (ab & 1)) * lddy;
+    rc = act_map(&maps.a[ab], base, cout, wd, h, n, 2LL * lddy, 4LL * wd * lddy, 4LL * h * wd * lddy, p.KSA);
+    if (rc != B2U_OK) return rc;
+  }
+  rc = act_map(&maps.b, x, cin, wd, h, n, ldx, (long long)wd * ldx, (long long)h * wd * ldx, p.KSB);
+  if (rc != B2U_OK) return rc;
+  rc = launch_wg(maps, p, stream);
+  if (rc != B2U_OK) return rc;
+  if (db != nullptr) return b2u_channel_sum_f16(dy, lddy, cout, 4LL * n * h * wd, db, stream);
+  return B2U_OK;
+}

@@ -80,3 +80,33 @@ def test_tc_large_layer_many_tiles():
     stats = img.zero.alloc(2 * cout * 8)
     ops = [P.Op(P.OP_CONV3X3_FWD, dt, [x.ref, wt, b, y.ref, stats], [x.ld, cin, 1, y.ld, cout, n, h, w])]
     compare(ops, img, dt, tol=3e-3)
+
+
+TC_WGRAD = [  # n, h, w, cin, cout
+    (2, 16, 16, 32, 32), (1, 32, 32, 64, 64), (2, 16, 32, 64, 128), (1, 16, 16, 128, 128), (1, 24, 40, 128, 256),
+    (1, 8, 8, 512, 512), (1, 16, 16, 512, 256), (1, 20, 12, 32, 64), (2, 40, 24, 16, 16), (1, 14, 14, 256, 512),
+    (2, 64, 64, 32, 32),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", TC_WGRAD)
+def test_tc_conv3x3_wgrad(n, h, w, cin, cout):
+    img = Img(31)
+    x = img.view(n, h, w, cin, dt, ld=2 * cin, c0=cin, fill="uniform")
+    dy = img.view(n, h, w, cout, dt, ld=cout + 8, scale=0.5)
+    dw = img.farr(img.gr, 9 * cin * cout, scale=0.01)
+    db = img.farr(img.gr, cout, scale=0.01)
+    ops = [P.Op(P.OP_CONV3X3_WGRAD, dt, [x.ref, dy.ref, dw, db], [x.ld, cin, dy.ld, cout, n, h, w])]
+    compare(ops, img, dt, tol=3e-3)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 8, 8, 64, 32), (1, 16, 16, 128, 64), (1, 4, 4, 512, 256), (1, 32, 32, 256, 128),
+                                            (2, 10, 6, 64, 32)])
+def test_tc_convt_wgrad(n, h, w, cin, cout):
+    img = Img(32)
+    x = img.view(n, h, w, cin, dt, fill="uniform")
+    dy = img.view(n, 2 * h, 2 * w, cout, dt, ld=2 * cout, c0=0, scale=0.5)
+    dw = img.farr(img.gr, 4 * cout * cin, scale=0.01)
+    db = img.farr(img.gr, cout, scale=0.01)
+    ops = [P.Op(P.OP_CONVT_WGRAD, dt, [x.ref, dy.ref, dw, db], [x.ld, cin, dy.ld, cout, n, h, w])]
+    compare(ops, img, dt, tol=3e-3)
