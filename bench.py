@@ -280,6 +280,14 @@ def run_engine(args):
                     "peak_source": peaks["src"]}
         breakdown = {k: {"ms": round(v[0], 4), "launches": v[1], "tflops": round(v[2] / (v[0] / 1000.0) / 1e12, 2) if v[2] and v[0] > 0 else None}
                      for k, v in sorted(kinds.items(), key=lambda kv: -kv[1][0])}
+        breakdown["_step_ms_eager_timed"] = round(step_ms, 4)
+        if args.per_op:
+            rows = []
+            for op, ms in prof:
+                fl = conv_flops(op, P)
+                rows.append({"op": P.OP_NAMES[op.kind][3:].lower(), "layer": op.tag, "ms": round(ms, 4),
+                             "tflops": round(fl / (ms / 1000.0) / 1e12, 1) if fl and ms > 0 else None, "i": op.i[:10]})
+            breakdown["_per_op"] = rows
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
@@ -322,6 +330,7 @@ def main():
     ap.add_argument("--precision", default="float16", choices=["float16", "float32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--per-op", action="store_true", help="add per-op device times to op_breakdown_ms")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -8,6 +8,26 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// Thread mapping shared by the streaming kernels: a thread owns one 8-channel group `g` (fixed for its
+// lifetime, so per-channel constants live in registers) and walks pixels `p` with a grid stride --
+// no integer division in the loop, 16-byte (fp16) / 32-byte (fp32) accesses, consecutive threads on
+// consecutive addresses.
+#define PIXEL_LANE_LOOP(C, npix)                                                          \
+  const int cg = (C) >> 3;                                                                \
+  const int lanes = kThreads / cg;                                                        \
+  const int g = threadIdx.x % cg, lane_ = threadIdx.x / cg;                               \
+  if (lane_ < lanes)                                                                      \
+    for (long long p = (long long)blockIdx.x * lanes + lane_; p < (npix); p += (long long)gridDim.x * lanes)
+
+__host__ int lane_grid(long long npix, int c, int waves = 8) {
+  int lanes = kThreads / (c >> 3);
+  long long b = (npix + lanes - 1) / lanes;
+  long long cap = (long long)B2U_NUM_SMS * waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
 __host__ int stream_grid(long long work_items, int per_block = kThreads, int waves = 8) {
   long long b = (work_items + per_block - 1) / per_block;
   long long cap = (long long)B2U_NUM_SMS * waves;
@@ -100,16 +120,17 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
                                                             int ldy, int C, long long npix,
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift) {
-  const int cg = C >> 3;
-  const long long total = npix * cg;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long p = i / cg;
-    int g = (int)(i - p * cg);
+  float sc[8], sh[8];
+  {
+    const int g0 = (threadIdx.x % (C >> 3)) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = scale[g0 + k]; sh[k] = shift[g0 + k]; }
+  }
+  PIXEL_LANE_LOOP(C, npix) {
     float v[8];
     load8<T>(x + p * ldx + g * 8, v);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], __ldg(scale + g * 8 + k), __ldg(shift + g * 8 + k));
+    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
     store8<T>(y + p * ldy + g * 8, v);
   }
 }
@@ -120,8 +141,6 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
     long long npix, long long count, const float* __restrict__ gamma, const float* __restrict__ mean,
     const float* __restrict__ invstd, const double* __restrict__ sums, float* __restrict__ dgamma,
     float* __restrict__ dbeta, const T* __restrict__ mask, int ldmask, int mask_act) {
-  const int cg = C >> 3;
-  const long long total = npix * cg;
   const float inv_n = 1.f / (float)count;
   if (blockIdx.x == 0 && dgamma != nullptr) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -129,21 +148,28 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
       dgamma[c] += (float)sums[C + c];
     }
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long p = i / cg;
-    int g = (int)(i - p * cg);
+  // per-channel constants in registers: dx = a*dy + b*x + c0  with
+  //   a = gamma*invstd, b = -a*invstd*s2, c0 = -a*s1 + a*invstd*mean*s2
+  float ca[8], cb[8], cc[8];
+  {
+    const int g0 = (threadIdx.x % (C >> 3)) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = g0 + k;
+      const float is = invstd[c], mu = mean[c];
+      const float s1 = (float)(sums[c] * (double)inv_n), s2 = (float)(sums[C + c] * (double)inv_n);
+      const float a = gamma[c] * is;
+      ca[k] = a;
+      cb[k] = -a * is * s2;
+      cc[k] = -a * s1 + a * is * mu * s2;
+    }
+  }
+  PIXEL_LANE_LOOP(C, npix) {
     float d[8], xv[8], o[8];
     load8<T>(dy + p * lddy + g * 8, d);
     load8<T>(x + p * ldx + g * 8, xv);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      int c = g * 8 + k;
-      float is = __ldg(invstd + c);
-      float xh = (xv[k] - __ldg(mean + c)) * is;
-      float s1 = (float)sums[c] * inv_n, s2 = (float)sums[C + c] * inv_n;
-      o[k] = __ldg(gamma + c) * is * (d[k] - s1 - xh * s2);
-    }
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(ca[k], d[k], fmaf(cb[k], xv[k], cc[k]));
     if (mask != nullptr) {
       float mv[8];
       load8<T>(mask + p * ldmask + g * 8, mv);
@@ -172,16 +198,15 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y,
                                                                int ldy, int C, int N, int H, int W, float p_drop,
                                                                int op_id, const b2u_step_state* __restrict__ st) {
-  const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
-  const long long total = (long long)N * Ho * Wo * cg;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long op = i / cg;
-    int g = (int)(i - op * cg);
-    int wo = (int)(op % Wo);
-    long long t = op / Wo;
-    int ho = (int)(t % Ho);
-    int n = (int)(t / Ho);
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long nopix = (long long)N * Ho * Wo;            // < 2^31 for any tensor that fits in HBM here
+  PIXEL_LANE_LOOP(C, nopix) {
+    const long long op = p;
+    const unsigned opu = (unsigned)p;
+    const int wo = (int)(opu % (unsigned)Wo);
+    const unsigned t = opu / (unsigned)Wo;
+    const int ho = (int)(t % (unsigned)Ho);
+    const int n = (int)(t / (unsigned)Ho);
     const T* base = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * ldx + g * 8;
     float a[8], b[8], c[8], d[8], m[8];
     load8<T>(base, a);
@@ -207,16 +232,15 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const T* __restri
                                                                int W, float p_drop, int op_id,
                                                                const b2u_step_state* __restrict__ st,
                                                                int accumulate) {
-  const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
-  const long long total = (long long)N * Ho * Wo * cg;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long op = i / cg;
-    int g = (int)(i - op * cg);
-    int wo = (int)(op % Wo);
-    long long t = op / Wo;
-    int ho = (int)(t % Ho);
-    int n = (int)(t / Ho);
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long nopix = (long long)N * Ho * Wo;            // < 2^31 for any tensor that fits in HBM here
+  PIXEL_LANE_LOOP(C, nopix) {
+    const long long op = p;
+    const unsigned opu = (unsigned)p;
+    const int wo = (int)(opu % (unsigned)Wo);
+    const unsigned t = opu / (unsigned)Wo;
+    const int ho = (int)(t % (unsigned)Ho);
+    const int n = (int)(t / (unsigned)Ho);
     long long ip = ((long long)n * H + 2 * ho) * W + 2 * wo;
     const T* base = x + ip * ldx + g * 8;
     float a[8], b[8], c[8], d[8], gy[8];
@@ -270,12 +294,8 @@ __global__ void __launch_bounds__(kThreads) dropout_kernel(const T* __restrict__
                                                            int ldy, int C, long long npix, float p, int op_id,
                                                            const b2u_step_state* __restrict__ st,
                                                            const T* __restrict__ mask, int ldmask, int mask_act) {
-  const int cg = C >> 3;
-  const long long total = npix * cg;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long px = i / cg;
-    int g = (int)(i - px * cg);
+  PIXEL_LANE_LOOP(C, npix) {
+    const long long px = p;
     float v[8], f[8];
     load8<T>(x + px * ldx + g * 8, v);
     keep_factors(p, (uint64_t)px * C + g * 8, st, op_id, f);
@@ -294,12 +314,8 @@ __global__ void __launch_bounds__(kThreads) dropout_kernel(const T* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(kThreads) copy_slice_kernel(const T* __restrict__ s, int lds, T* __restrict__ d,
                                                               int ldd, int C, long long npix, int accumulate) {
-  const int cg = C >> 3;
-  const long long total = npix * cg;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long px = i / cg;
-    int g = (int)(i - px * cg);
+  PIXEL_LANE_LOOP(C, npix) {
+    const long long px = p;
     float v[8];
     load8<T>(s + px * lds + g * 8, v);
     if (accumulate) {
@@ -652,7 +668,8 @@ extern "C" int b2u_bn_apply(int dt, const void* x, int ldx, void* y, int ldy, in
                             const float* scale, const float* shift, void* stream) {
   REQ_VEC8(c);
   B2U_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "bn_apply: alignment");
-  int grid = stream_grid(npix * (c / 8));
+  B2U_REQUIRE(c <= 2048, "bn_apply: c <= 2048");
+  int grid = lane_grid(npix, c);
   DISPATCH_T(dt, B2U_LAUNCH(bn_apply_kernel<T>, grid, kThreads, 0, stream, (const T*)x, ldx, (T*)y, ldy, c, npix,
                             scale, shift));
   return B2U_OK;
@@ -677,7 +694,8 @@ extern "C" int b2u_bn_bwd_apply(int dt, const void* dy, int lddy, const void* x,
   REQ_VEC8(c);
   B2U_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && (mask == nullptr || ldmask % 8 == 0),
               "bn_bwd_apply: alignment");
-  int grid = stream_grid(npix * (c / 8));
+  B2U_REQUIRE(c <= 2048, "bn_bwd_apply: c <= 2048");
+  int grid = lane_grid(npix, c);
   DISPATCH_T(dt, B2U_LAUNCH(bn_bwd_apply_kernel<T>, grid, kThreads, 0, stream, (const T*)dy, lddy, (const T*)x, ldx,
                             (T*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums, dgamma, dbeta,
                             (const T*)mask, ldmask, mask_act));
@@ -690,7 +708,8 @@ extern "C" int b2u_maxpool_fwd(int dt, const void* x, int ldx, void* y, int ldy,
   B2U_REQUIRE(h % 2 == 0 && wd % 2 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "maxpool_fwd: even H,W and ld%%8==0");
   B2U_REQUIRE(p_drop == 0.f || d_state != nullptr, "maxpool_fwd: dropout needs a step state");
   B2U_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "maxpool_fwd: bad dropout rate");
-  int grid = stream_grid((long long)n * (h / 2) * (wd / 2) * (c / 8));
+  B2U_REQUIRE(c <= 2048 && (long long)n * h * wd < (1LL << 31), "maxpool_fwd: tensor too large");
+  int grid = lane_grid((long long)n * (h / 2) * (wd / 2), c);
   DISPATCH_T(dt, B2U_LAUNCH(maxpool_fwd_kernel<T>, grid, kThreads, 0, stream, (const T*)x, ldx, (T*)y, ldy, c, n, h,
                             wd, p_drop, op_id, d_state));
   return B2U_OK;
@@ -702,7 +721,8 @@ extern "C" int b2u_maxpool_bwd(int dt, const void* x, int ldx, const void* dy, i
   REQ_VEC8(c);
   B2U_REQUIRE(h % 2 == 0 && wd % 2 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0, "maxpool_bwd: shape");
   B2U_REQUIRE(p_drop == 0.f || d_state != nullptr, "maxpool_bwd: dropout needs a step state");
-  int grid = stream_grid((long long)n * (h / 2) * (wd / 2) * (c / 8));
+  B2U_REQUIRE(c <= 2048 && (long long)n * h * wd < (1LL << 31), "maxpool_bwd: tensor too large");
+  int grid = lane_grid((long long)n * (h / 2) * (wd / 2), c);
   DISPATCH_T(dt, B2U_LAUNCH(maxpool_bwd_kernel<T>, grid, kThreads, 0, stream, (const T*)x, ldx, (const T*)dy, lddy,
                             (T*)dx, lddx, c, n, h, wd, p_drop, op_id, d_state, accumulate));
   return B2U_OK;
@@ -712,7 +732,8 @@ extern "C" int b2u_dropout_fwd(int dt, const void* x, int ldx, void* y, int ldy,
                                int op_id, const b2u_step_state* d_state, void* stream) {
   REQ_VEC8(c);
   B2U_REQUIRE(p >= 0.f && p < 1.f && d_state != nullptr && ldx % 8 == 0 && ldy % 8 == 0, "dropout_fwd: args");
-  int grid = stream_grid(npix * (c / 8));
+  B2U_REQUIRE(c <= 2048, "dropout: c <= 2048");
+  int grid = lane_grid(npix, c);
   DISPATCH_T(dt, B2U_LAUNCH(dropout_kernel<T>, grid, kThreads, 0, stream, (const T*)x, ldx, (T*)y, ldy, c, npix, p,
                             op_id, d_state, (const T*)nullptr, 0, 0));
   return B2U_OK;
@@ -723,7 +744,8 @@ extern "C" int b2u_dropout_bwd(int dt, const void* dy, int lddy, void* dx, int l
                                void* stream) {
   REQ_VEC8(c);
   B2U_REQUIRE(p >= 0.f && p < 1.f && d_state != nullptr && lddy % 8 == 0 && lddx % 8 == 0, "dropout_bwd: args");
-  int grid = stream_grid(npix * (c / 8));
+  B2U_REQUIRE(c <= 2048, "dropout: c <= 2048");
+  int grid = lane_grid(npix, c);
   DISPATCH_T(dt, B2U_LAUNCH(dropout_kernel<T>, grid, kThreads, 0, stream, (const T*)dy, lddy, (T*)dx, lddx, c, npix,
                             p, op_id, d_state, (const T*)mask, ldmask, mask_act));
   return B2U_OK;
@@ -733,7 +755,8 @@ extern "C" int b2u_copy_slice(int dt, const void* src, int ldsrc, void* dst, int
                               int accumulate, void* stream) {
   REQ_VEC8(c);
   B2U_REQUIRE(ldsrc % 8 == 0 && lddst % 8 == 0, "copy_slice: ld%%8==0 required");
-  int grid = stream_grid(npix * (c / 8));
+  B2U_REQUIRE(c <= 2048, "copy_slice: c <= 2048");
+  int grid = lane_grid(npix, c);
   DISPATCH_T(dt, B2U_LAUNCH(copy_slice_kernel<T>, grid, kThreads, 0, stream, (const T*)src, ldsrc, (T*)dst, lddst, c,
                             npix, accumulate));
   return B2U_OK;
