@@ -151,6 +151,109 @@ __global__ void __launch_bounds__(256) conv3x3_direct_kernel(
 }
 
 // ==========================================================================================
+// Cin == 1 first layer (T1H:859 Conv2D(32,(3,3)) on the (H,W,1) input; T2:748 with 16 filters).
+// K = 9: no tensor-core shape, pure HBM streaming (writes COUT x what it reads).  One thread per pixel,
+// 64-byte (fp16) contiguous stores; the backward accumulates the 9 x COUT weight gradient in registers.
+// ==========================================================================================
+template <typename T, int COUT>
+__global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const T* __restrict__ x, int ldx,
+                                                             const float* __restrict__ w,
+                                                             const float* __restrict__ bias, int act,
+                                                             T* __restrict__ y, int ldy, int N, int H, int W) {
+  __shared__ float xs[18][18 + 1];
+  __shared__ float ws[9][COUT];
+  __shared__ float bs[COUT];
+  const int tiles_w = (W + 15) / 16;
+  const int h0 = (blockIdx.x / tiles_w) * 16, w0 = (blockIdx.x % tiles_w) * 16, n = blockIdx.y;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 18 * 18; i += 256) {
+    int rr = i / 18, cc = i % 18, hh = h0 + rr - 1, wwp = w0 + cc - 1;
+    float v = 0.f;
+    if (hh >= 0 && hh < H && wwp >= 0 && wwp < W) v = ldf<T>(x + (((long long)n * H + hh) * W + wwp) * ldx);
+    xs[rr][cc] = v;
+  }
+  for (int i = tid; i < 9 * COUT; i += 256) ws[i / COUT][i % COUT] = w[i];
+  for (int i = tid; i < COUT; i += 256) bs[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int r = tid / 16, c = tid % 16;
+  const int hh = h0 + r, wwp = w0 + c;
+  if (hh >= H || wwp >= W) return;
+  float xv[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) xv[t] = xs[r + t / 3][c + t % 3];
+  T* dst = y + (((long long)n * H + hh) * W + wwp) * ldy;
+#pragma unroll
+  for (int g = 0; g < COUT / 8; ++g) {
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float a = bs[g * 8 + k];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) a = fmaf(xv[t], ws[t][g * 8 + k], a);
+      o[k] = act_fwd(a, act);
+    }
+    store8<T>(dst + g * 8, o);
+  }
+}
+
+template <typename T, int COUT>
+__global__ void __launch_bounds__(256) conv3x3_c1_wgrad_kernel(const T* __restrict__ x, int ldx,
+                                                               const T* __restrict__ dy, int lddy,
+                                                               float* __restrict__ dw, float* __restrict__ db, int N,
+                                                               int H, int W) {
+  // thread = (pixel lane, 8-channel group); registers: 9 taps x 8 channels + 8 bias sums
+  constexpr int CG = COUT / 8;
+  constexpr int LANES = 256 / CG;
+  __shared__ float sacc[10 * COUT];
+  for (int i = threadIdx.x; i < 10 * COUT; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  const int g = threadIdx.x % CG, lane = threadIdx.x / CG;
+  float acc[9][8], accb[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    accb[k] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t][k] = 0.f;
+  }
+  const long long npix = (long long)N * H * W;
+  for (long long p = (long long)blockIdx.x * LANES + lane; p < npix; p += (long long)gridDim.x * LANES) {
+    const int wwp = (int)(p % W);
+    const long long tq = p / W;
+    const int hh = (int)(tq % H);
+    float d[8];
+    load8<T>(dy + p * lddy + g * 8, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) accb[k] += d[k];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int dh = t / 3 - 1, dwp = t % 3 - 1;
+      float xv = 0.f;
+      if (hh + dh >= 0 && hh + dh < H && wwp + dwp >= 0 && wwp + dwp < W)
+        xv = ldf<T>(x + (p + (long long)dh * W + dwp) * ldx);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(xv, d[k], acc[t][k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    // lanes of a warp that share g: reduce across the warp first (stride CG lanes share a group)
+    float vb = accb[k];
+    for (int o = 16; o >= CG; o >>= 1) vb += __shfl_xor_sync(0xffffffffu, vb, o);
+    if ((threadIdx.x & 31) < CG) atomicAdd(&sacc[9 * COUT + g * 8 + k], vb);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float v = acc[t][k];
+      for (int o = 16; o >= CG; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) < CG) atomicAdd(&sacc[t * COUT + g * 8 + k], v);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * COUT; i += 256) atomicAdd(dw + i, sacc[i]);
+  if (db != nullptr)
+    for (int i = threadIdx.x; i < COUT; i += 256) atomicAdd(db + i, sacc[9 * COUT + i]);
+}
+
+// ==========================================================================================
 // 3x3 wgrad: dw[tap][ci][co] += sum_p x[p+tap][ci] * dy[p][co];  db[co] += sum_p dy[p][co]
 // Block owns (ci chunk of 8) x (co tile of 64) x all 9 taps and loops over its share of 8x16 pixel
 // tiles, then flushes once with atomics.  128 threads: 32 co-pairs x 4 ci-pairs.
@@ -420,6 +523,12 @@ int b2u_direct_conv3x3(int dt, const void* x, int ldx, int K, const float* w, in
   B2U_REQUIRE(n > 0 && h > 0 && wd > 0 && K > 0 && J > 0, "conv3x3: empty shape");
   B2U_REQUIRE((K % 8 != 0) || (ldx % 8 == 0), "conv3x3: ldx must be a multiple of 8 when Cin %% 8 == 0");
   int tiles = b2u_cdiv(h, TH) * b2u_cdiv(wd, TW);
+  if (K == 1 && !dgrad && stats == nullptr && mask == nullptr && !accumulate && ldy % 8 == 0 && (J == 32 || J == 16)) {
+    dim3 grid1(tiles, n);
+    if (J == 32) { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_fwd_kernel<T, 32>), grid1, 256, 0, stream, (const T*)x, ldx, w, bias, act, (T*)y, ldy, n, h, wd)); }
+    else { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_fwd_kernel<T, 16>), grid1, 256, 0, stream, (const T*)x, ldx, w, bias, act, (T*)y, ldy, n, h, wd)); }
+    return B2U_OK;
+  }
   if (J > 32) {
     dim3 grid(tiles, n, b2u_cdiv(J, 64));
     DISPATCH_T(dt, B2U_LAUNCH((conv3x3_direct_kernel<T, 64>), grid, 256, 0, stream, (const T*)x, ldx, K, w, dgrad, bias,
@@ -435,6 +544,15 @@ int b2u_direct_conv3x3(int dt, const void* x, int ldx, int K, const float* w, in
 int b2u_direct_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw,
                              float* db, int n, int h, int wd, void* stream) {
   B2U_REQUIRE(n > 0 && h > 0 && wd > 0 && cin > 0 && cout > 0, "conv3x3_wgrad: empty shape");
+  if (cin == 1 && lddy % 8 == 0 && (cout == 32 || cout == 16)) {
+    long long npix = (long long)n * h * wd;
+    int lanes = 256 / (cout / 8);
+    long long gl = (npix + lanes - 1) / lanes;
+    int grid1 = (int)(gl < 4 * B2U_NUM_SMS ? gl : 4 * B2U_NUM_SMS);
+    if (cout == 32) { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_wgrad_kernel<T, 32>), grid1, 256, 0, stream, (const T*)x, ldx, (const T*)dy, lddy, dw, db, n, h, wd)); }
+    else { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_wgrad_kernel<T, 16>), grid1, 256, 0, stream, (const T*)x, ldx, (const T*)dy, lddy, dw, db, n, h, wd)); }
+    return B2U_OK;
+  }
   int cib = b2u_cdiv(cin, WG_CI), cob = b2u_cdiv(cout, WG_CO);
   long long ntiles = (long long)n * b2u_cdiv(h, WG_TH) * b2u_cdiv(wd, WG_TW);
   long long nsplit = (4LL * B2U_NUM_SMS * 4) / ((long long)cib * cob);

@@ -29,7 +29,7 @@
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 12;
 constexpr int kTileH = 8, kTileW = 16, kTileM = 128;       // 8 x 16 output pixels per tile
 constexpr int kThreadsTc = 192;                            // 6 warps
 constexpr int kMaxTaps = 9;
@@ -38,6 +38,7 @@ struct TcParams {
   int N, H, W;            // output-pixel grid of the GEMM (for convT fwd: the INPUT grid)
   int K, J;               // reduction channels, output columns
   int KS, JT;             // K slab (64/32/16) and N tile
+  int stages;             // smem ring depth (as many as fit: small-channel layers are TMA-latency bound)
   int ntaps;
   int tap_dh[kMaxTaps], tap_dw[kMaxTaps], tap_map[kMaxTaps];   // pixel offset and tensor-map index per tap
   int mode;               // 0: plain NHWC store, 1: convT scatter (column = (a*2+b)*Cout + co)
@@ -85,10 +86,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t b_stride = (b_bytes + 1023) & ~1023u;
   const uint32_t stage_stride = a_bytes + b_stride;
+  const int kStages = prm.stages;
   uint8_t* tail = smem + kStages * stage_stride;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);
@@ -356,15 +358,24 @@ int pick_jt(int J) {
   return 0;
 }
 
-size_t smem_bytes_for(int KS, int JT, int J) {
+size_t tail_bytes_for(int J) { return (2 * kMaxStages + 4) * 8 + 16 + (size_t)3 * J * 4 + 64; }
+int stages_for(int KS, int JT, int J) {
   size_t a = (size_t)kTileM * KS * 2, b = ((size_t)JT * KS * 2 + 1023) & ~(size_t)1023;
-  return 1024 + kStages * (a + b) + (2 * kStages + 4) * 8 + 16 + (size_t)3 * J * 4 + 64;
+  long long room = 220 * 1024 - 1024 - (long long)tail_bytes_for(J);
+  int st = (int)(room / (long long)(a + b));
+  return st > kMaxStages ? kMaxStages : st;
+}
+size_t smem_bytes_for(int KS, int JT, int J, int stages) {
+  size_t a = (size_t)kTileM * KS * 2, b = ((size_t)JT * KS * 2 + 1023) & ~(size_t)1023;
+  return 1024 + stages * (a + b) + tail_bytes_for(J);
 }
 
 bool g_attr_set = false;
 
-int launch_tc(const TcMaps& maps, const TcParams& prm, void* stream) {
-  size_t smem = smem_bytes_for(prm.KS, prm.JT, prm.J);
+int launch_tc(const TcMaps& maps, TcParams& prm, void* stream) {
+  prm.stages = stages_for(prm.KS, prm.JT, prm.J);
+  B2U_REQUIRE(prm.stages >= 2, "tc_conv: tile too large for a 2-stage pipeline");
+  size_t smem = smem_bytes_for(prm.KS, prm.JT, prm.J, prm.stages);
   B2U_REQUIRE(smem <= 227 * 1024, "tc_conv: shared memory %zu exceeds 227 KB", smem);
   if (!g_attr_set) {
     B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

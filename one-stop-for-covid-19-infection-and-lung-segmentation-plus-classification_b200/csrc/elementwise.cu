@@ -291,14 +291,14 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const T* __restri
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) dropout_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y,
-                                                           int ldy, int C, long long npix, float p, int op_id,
+                                                           int ldy, int C, long long npix, float prob, int op_id,
                                                            const b2u_step_state* __restrict__ st,
                                                            const T* __restrict__ mask, int ldmask, int mask_act) {
   PIXEL_LANE_LOOP(C, npix) {
     const long long px = p;
     float v[8], f[8];
     load8<T>(x + px * ldx + g * 8, v);
-    keep_factors(p, (uint64_t)px * C + g * 8, st, op_id, f);
+    keep_factors(prob, (uint64_t)px * C + g * 8, st, op_id, f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] *= f[k];
     if (mask != nullptr) {
