@@ -56,6 +56,9 @@ const char* b2u_last_error(void);
 size_t b2u_ws_bytes(void);
 /* 1 if the tcgen05 tensor path is compiled in and the current device is sm_100 */
 int b2u_tensor_path_available(void);
+/* tuning / test switches: "tc_halo" = 0 per-tap TMA loads, 1 halo tile (default), 2 halo tile with
+ * descriptor base offsets, 3 three-box halo; "tensor_path" = 0/1.  Returns the previous value (<0: unknown). */
+int b2u_set_option(const char* name, int value);
 
 /* ---- step state ---------------------------------------------------------------------------- */
 /* step += 1; beta_pows *= beta (device-side, graph-capturable) */

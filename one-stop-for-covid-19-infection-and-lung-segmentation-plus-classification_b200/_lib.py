@@ -31,7 +31,7 @@ _lib = None
 
 # every symbol include/b200unet.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
-    "b2u_version", "b2u_last_error", "b2u_ws_bytes", "b2u_tensor_path_available", "b2u_state_advance",
+    "b2u_version", "b2u_last_error", "b2u_ws_bytes", "b2u_tensor_path_available", "b2u_set_option", "b2u_state_advance",
     "b2u_conv3x3_fwd", "b2u_conv3x3_dgrad", "b2u_conv3x3_wgrad", "b2u_convt2x2_fwd", "b2u_convt2x2_dgrad",
     "b2u_convt2x2_wgrad", "b2u_bn_stats", "b2u_bn_finalize", "b2u_bn_apply", "b2u_bn_bwd_reduce",
     "b2u_bn_bwd_apply", "b2u_maxpool_fwd", "b2u_maxpool_bwd", "b2u_dropout_fwd", "b2u_dropout_bwd",
@@ -58,6 +58,7 @@ def lib():
     l.b2u_ws_bytes.restype = sz
     l.b2u_launch_count.restype = i64
     l.b2u_tensor_path_available.restype = C.c_int
+    l.b2u_set_option.argtypes = [C.c_char_p, C.c_int]
     l.b2u_run_ops.argtypes = [C.POINTER(Op), i32, vp, sz, vp, vp]
     l.b2u_run_ops_timed.argtypes = [C.POINTER(Op), i32, vp, sz, vp, vp, C.POINTER(C.c_float)]
     l.b2u_graph_create.argtypes = [C.POINTER(Op), i32, vp, sz, vp, vp, C.POINTER(vp)]

@@ -36,6 +36,21 @@ extern "C" int b2u_tensor_path_available(void) {
   return g_tc_state;
 }
 
+extern "C" int b2u_set_option(const char* name, int value) {
+  if (name == nullptr) return -1;
+  if (strcmp(name, "tc_halo") == 0) {
+    int old = g_b2u_tc_halo;
+    g_b2u_tc_halo = value;
+    return old;
+  }
+  if (strcmp(name, "tensor_path") == 0) {
+    int old = b2u_tensor_path_available();
+    g_tc_state = value ? (b2u_tc_compiled() ? 1 : 0) : 0;
+    return old;
+  }
+  return -1;
+}
+
 // ------------------------------------------------------------------------------------------
 // conv dispatch
 // ------------------------------------------------------------------------------------------
@@ -43,8 +58,8 @@ extern "C" int b2u_conv3x3_fwd(int dt, const void* x, int ldx, int cin, const fl
                                void* y, int ldy, int cout, double* stats, int n, int h, int wd, void* ws,
                                size_t ws_bytes, void* stream) {
   if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy))
-    return b2u_tc_conv3x3(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, 0, 0, 0, n, h, wd, ws, ws_bytes,
-                          stream);
+    return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats,
+                                                                  nullptr, 0, 0, 0, n, h, wd, ws, ws_bytes, stream);
   return b2u_direct_conv3x3(dt, x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, 0, 0, 0, n, h, wd, stream);
 }
 
@@ -52,8 +67,9 @@ extern "C" int b2u_conv3x3_dgrad(int dt, const void* dy, int lddy, int cout, con
                                  int cin, const void* mask, int ldmask, int mask_act, int accumulate, int n, int h,
                                  int wd, void* ws, size_t ws_bytes, void* stream) {
   if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cout, cin, lddy, lddx))
-    return b2u_tc_conv3x3(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, mask, ldmask, mask_act,
-                          accumulate, n, h, wd, ws, ws_bytes, stream);
+    return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx,
+                                                                  cin, nullptr, mask, ldmask, mask_act, accumulate, n, h,
+                                                                  wd, ws, ws_bytes, stream);
   return b2u_direct_conv3x3(dt, dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, mask, ldmask,
                             mask_act, accumulate, n, h, wd, stream);
 }

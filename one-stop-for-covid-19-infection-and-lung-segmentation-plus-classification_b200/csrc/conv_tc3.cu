@@ -1,0 +1,448 @@
+// tcgen05 3x3 convolution with HALO-TILE reuse (forward and data gradient).
+//
+// conv_tc.cu loads one activation box per filter tap: the same pixels cross L2 -> shared memory nine
+// times, which makes the thin, full-resolution layers (32/64 channels at 512^2 / 256^2: the HBM-bound
+// half of the U-Net) L2- and TMA-latency-bound.  Here a CTA loads the (16+2) x (8+2) pixel halo patch of
+// its 16 x 8 output tile ONCE per 64-channel slab and issues the nine taps as nine tcgen05.mma groups
+// whose A descriptors start at row (dh*10 + dw) of that patch: a tile row (8 pixels) is one 8-row
+// core-matrix group, consecutive tile rows are 10 halo rows apart (SBO = 10 rows).  The 128B/64B/32B
+// swizzle applied by TMA is a function of the shared-memory address bits, so a row-shifted start stays
+// consistent (`amode` 1; `amode` 3 is the conservative variant: three boxes, one per dw, whose tap starts
+// are whole 8-row groups).  Weights of thin layers (9*K*J*2 bytes <= ~110 KB) are loaded once and stay
+// RESIDENT in shared memory for the whole persistent CTA; wide layers stream per-tap weight tiles through
+// a second ring.
+//
+// Warp roles: TMA producer, single-thread MMA issuer, 8 epilogue warps (the epilogue is instruction-latency
+// bound with 4: one warp per scheduler cannot hide its own dependent-issue latency),
+// double-buffered TMEM accumulator, bias / ReLU / ELU / mask / accumulate / BN statistics).
+#include <cuda.h>
+#include "common.cuh"
+#include "internal.h"
+#include "launch.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kTH = 16, kTW = 8;            // output tile: 16 rows x 8 columns = 128 pixels
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane group, each owning half of the columns
+constexpr int kThreads3 = 64 + 32 * kEpiWarps;
+constexpr int kMaxSA = 8, kMaxSB = 8;
+
+struct C3Params {
+  int N, H, W, K, J, KS, JT;
+  int amode;              // 1: one halo box (18 x 10), 3: three boxes (18 x 8), one per dw
+  int bo_mode;            // amode 1: 0 = descriptor base_offset 0, 1 = (start >> 7) & 7
+  int bres;               // weights resident in smem
+  int SA, SB;             // ring depths
+  uint32_t a_sub;         // bytes of one A sub-tile (1024-aligned), a_stage = a_sub * (amode == 3 ? 3 : 1)
+  __half* y; int ldy;
+  const float* bias; int act;
+  const __half* mask; int ldmask; int mask_act;
+  int accumulate;
+  double* stats;
+};
+
+struct C3Maps {
+  CUtensorMap a;          // activations, box (KS, 10 | 8, 18, 1)
+  CUtensorMap b;          // packed weights [9][J][K], box (KS, JT, 1)
+};
+
+__device__ __forceinline__ float transpose_reduce16_(float v[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      float a = v[i], b = v[i + s];
+      bool up = (lane & s) != 0;
+      float send = up ? a : b, keep = up ? b : a;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_constant__ C3Maps maps,
+                                                                 const __grid_constant__ C3Params prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int KS = prm.KS, JT = prm.JT, SA = prm.SA, SB = prm.SB;
+  const int kslabs = prm.K / KS;
+  const uint32_t rowb = KS * 2;                                   // bytes per pixel row
+  const uint32_t a_stage = prm.a_sub * (prm.amode == 3 ? 3 : 1);
+  const uint32_t b_tile = ((uint32_t)JT * rowb + 1023) & ~1023u;  // one (tap, slab) weight tile
+  // layout: [A ring][B ring or resident weights][barriers][tmem ptr][bias][stats]
+  uint8_t* a_ring = smem;
+  uint8_t* b_area = a_ring + (size_t)SA * a_stage;
+  const uint32_t b_bytes_total = prm.bres ? 9u * kslabs * b_tile : (uint32_t)SB * b_tile;
+  uint8_t* tail = b_area + b_bytes_total;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* a_empty = a_full + kMaxSA;
+  uint64_t* b_full = a_empty + kMaxSA;
+  uint64_t* b_empty = b_full + kMaxSB;
+  uint64_t* w_full = b_empty + kMaxSB;
+  uint64_t* tfull = w_full + 1;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);
+  float* s_stats = s_bias + prm.J;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_w = (prm.W + kTW - 1) / kTW, tiles_h = (prm.H + kTH - 1) / kTH;
+  const int nj = prm.J / JT;
+  const int ntiles = prm.N * tiles_h * tiles_w * nj;          // host guarantees < 2^31
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * JT)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < SB; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
+    tc::mbar_init(w_full, 1);
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], kEpiWarps); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
+  for (int i = threadIdx.x; i < prm.J; i += kThreads3) s_bias[i] = prm.bias ? prm.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 2 * prm.J; i += kThreads3) s_stats[i] = 0.f;
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =========================================
+    if (lane == 0) {
+      tc::prefetch_tmap(&maps.a);
+      tc::prefetch_tmap(&maps.b);
+      if (prm.bres) {
+        tc::mbar_expect_tx(w_full, 9u * kslabs * (uint32_t)JT * rowb);
+        for (int t = 0; t < 9; ++t)
+          for (int ks = 0; ks < kslabs; ++ks)
+            tc::tma_load_3d(b_area + (size_t)(t * kslabs + ks) * b_tile, &maps.b, w_full, ks * KS, 0, t);
+      }
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const uint32_t a_tx = (prm.amode == 3 ? 3u * 18 * 8 : 18u * 10) * rowb;
+      for (unsigned tile = blockIdx.x; tile < (unsigned)ntiles; tile += gridDim.x) {
+        const int jt = (int)(tile % (unsigned)nj);
+        const unsigned pt = tile / (unsigned)nj;
+        const int tw = (int)(pt % (unsigned)tiles_w);
+        const unsigned r = pt / (unsigned)tiles_w;
+        const int th = (int)(r % (unsigned)tiles_h), n = (int)(r / (unsigned)tiles_h);
+        for (int ks = 0; ks < kslabs; ++ks) {
+          tc::mbar_wait(&a_empty[sa], pa ^ 1);
+          uint8_t* dst = a_ring + (size_t)sa * a_stage;
+          tc::mbar_expect_tx(&a_full[sa], a_tx);
+          if (prm.amode == 3) {
+            for (int dw = 0; dw < 3; ++dw)
+              tc::tma_load_4d(dst + dw * prm.a_sub, &maps.a, &a_full[sa], ks * KS, tw * kTW - 1 + dw, th * kTH - 1, n);
+          } else {
+            tc::tma_load_4d(dst, &maps.a, &a_full[sa], ks * KS, tw * kTW - 1, th * kTH - 1, n);
+          }
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+          if (!prm.bres) {
+            for (int t = 0; t < 9; ++t) {
+              tc::mbar_wait(&b_empty[sb], pb ^ 1);
+              tc::mbar_expect_tx(&b_full[sb], (uint32_t)JT * rowb);
+              tc::tma_load_3d(b_area + (size_t)sb * b_tile, &maps.b, &b_full[sb], ks * KS, jt * JT, t);
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ============================================
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_f16(128, JT, 0, 0);
+      const uint64_t layout = KS == 64 ? tc::SWZ_128B : (KS == 32 ? tc::SWZ_64B : tc::SWZ_32B);
+      const uint32_t sbo_b = 8 * rowb;
+      const uint32_t a_rows = prm.amode == 3 ? 8 : 10;            // halo row pitch in pixels
+      const uint32_t sbo_a = a_rows * rowb;
+      if (prm.bres) { tc::mbar_wait(w_full, 0); tc::fence_after_sync(); }
+      int sa = 0, sb = 0, acc = 0;
+      uint32_t pa = 0, pb = 0, acc_phase = 0;
+      for (unsigned tile = blockIdx.x; tile < (unsigned)ntiles; tile += gridDim.x) {
+        tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * JT;
+        for (int ks = 0; ks < kslabs; ++ks) {
+          tc::mbar_wait(&a_full[sa], pa);
+          tc::fence_after_sync();
+          const uint32_t a_base = tc::smem_u32(a_ring + (size_t)sa * a_stage);
+          for (int t = 0; t < 9; ++t) {
+            const int dh = t / 3, dw = t % 3;
+            uint32_t b_base;
+            if (prm.bres) {
+              b_base = tc::smem_u32(b_area + (size_t)(t * kslabs + ks) * b_tile);
+            } else {
+              tc::mbar_wait(&b_full[sb], pb);
+              tc::fence_after_sync();
+              b_base = tc::smem_u32(b_area + (size_t)sb * b_tile);
+            }
+            const uint32_t a_start = prm.amode == 3 ? a_base + dw * prm.a_sub + (uint32_t)(dh * 8) * rowb
+                                                    : a_base + (uint32_t)(dh * 10 + dw) * rowb;
+            const uint32_t bo = (prm.amode == 1 && prm.bo_mode) ? ((a_start >> 7) & 7u) : 0u;
+            for (int kk = 0; kk < KS / 16; ++kk) {
+              uint64_t ad = tc::smem_desc(a_start + kk * 32, 16, sbo_a, layout, bo);
+              uint64_t bd = tc::smem_desc(b_base + kk * 32, 16, sbo_b, layout);
+              tc::mma_f16_ss(d_tmem, ad, bd, idesc, (ks | t | kk) != 0);
+            }
+            if (!prm.bres) {
+              tc::mma_commit(&b_empty[sb]);
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+            }
+          }
+          tc::mma_commit(&a_empty[sa]);
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+        }
+        tc::mma_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue ==============================================
+    // 8 warps: warp -> TMEM lane group (warp & 3) and column half ((warp - 2) >> 2).  A thread owns one
+    // output pixel (accumulator row) and walks its columns 16 at a time.  BatchNorm statistics of thin
+    // layers (<= 32 columns per thread) accumulate in registers across ALL tiles of the persistent CTA
+    // and are reduced once at the end; wider layers reduce per tile with a shuffle transpose.
+    const int ew = warp - 2;
+    const int lg = warp & 3;
+    const int half = ew >> 2;
+    const int row = lg * 32 + lane;
+    const int ccols = JT / 2 >= 16 ? JT / 2 : JT;                 // columns owned by this warp within a tile
+    const int cbeg = JT / 2 >= 16 ? half * ccols : 0;
+    const bool has_cols = JT / 2 >= 16 || half == 0;
+    const bool reg_stats = prm.stats != nullptr && ccols <= 32 && nj == 1;
+    float rs1[32], rs2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (unsigned tile = blockIdx.x; tile < (unsigned)ntiles; tile += gridDim.x) {
+      const int jt = (int)(tile % (unsigned)nj);
+      const unsigned pt = tile / (unsigned)nj;
+      const int tw = (int)(pt % (unsigned)tiles_w);
+      const unsigned r = pt / (unsigned)tiles_w;
+      const int th = (int)(r % (unsigned)tiles_h), n = (int)(r / (unsigned)tiles_h);
+      const int h = th * kTH + (row >> 3), w = tw * kTW + (row & 7);
+      const bool valid = h < prm.H && w < prm.W;
+      const long long pix = ((long long)n * prm.H + h) * prm.W + w;
+      __half* yrow = prm.y + pix * prm.ldy + jt * JT;
+      const __half* mrow = prm.mask != nullptr ? prm.mask + pix * prm.ldmask + jt * JT : nullptr;
+      tc::mbar_wait(&tfull[acc], acc_phase);
+      tc::fence_after_sync();
+      if (has_cols) {
+#pragma unroll 2
+        for (int cc = 0; cc < ccols; cc += 16) {
+          const int c0 = cbeg + cc;
+          float v[16];
+          tc::tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * JT + c0, v);
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + jt * JT + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b4 = bp[q];
+            v[4 * q + 0] = act_fwd(v[4 * q + 0] + b4.x, prm.act);
+            v[4 * q + 1] = act_fwd(v[4 * q + 1] + b4.y, prm.act);
+            v[4 * q + 2] = act_fwd(v[4 * q + 2] + b4.z, prm.act);
+            v[4 * q + 3] = act_fwd(v[4 * q + 3] + b4.w, prm.act);
+          }
+          if (valid) {
+            if (mrow != nullptr) {
+              float m[8];
+              load8<__half>(mrow + c0, m);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= act_bwd_from_y(m[i], prm.mask_act);
+              load8<__half>(mrow + c0 + 8, m);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 + i] *= act_bwd_from_y(m[i], prm.mask_act);
+            }
+            if (prm.accumulate) {
+              float e[8];
+              load8<__half>(yrow + c0, e);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += e[i];
+              load8<__half>(yrow + c0 + 8, e);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 + i] += e[i];
+            }
+            store8<__half>(yrow + c0, v);
+            store8<__half>(yrow + c0 + 8, v + 8);
+          }
+          if (prm.stats != nullptr) {
+            if (reg_stats) {
+              if (valid) {
+                if (cc == 0) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) { rs1[i] += v[i]; rs2[i] = fmaf(v[i], v[i], rs2[i]); }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) { rs1[16 + i] += v[i]; rs2[16 + i] = fmaf(v[i], v[i], rs2[16 + i]); }
+                }
+              }
+            } else {
+              float q[16], sq[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { q[i] = valid ? v[i] : 0.f; sq[i] = q[i] * q[i]; }
+              float s1 = transpose_reduce16_(q, lane);
+              float s2 = transpose_reduce16_(sq, lane);
+              if (lane < 16) {
+                atomicAdd(&s_stats[jt * JT + c0 + lane], s1);
+                atomicAdd(&s_stats[prm.J + jt * JT + c0 + lane], s2);
+              }
+            }
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (reg_stats && has_cols) {
+      // register statistics hold columns [cbeg, cbeg + ccols) of the (single) N tile: J == JT here
+      for (int cc = 0; cc < ccols; cc += 16) {
+        float q[16], sq[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { q[i] = cc == 0 ? rs1[i] : rs1[16 + i]; sq[i] = cc == 0 ? rs2[i] : rs2[16 + i]; }
+        float s1 = transpose_reduce16_(q, lane);
+        float s2 = transpose_reduce16_(sq, lane);
+        if (lane < 16) {
+          atomicAdd(&s_stats[cbeg + cc + lane], s1);
+          atomicAdd(&s_stats[prm.J + cbeg + cc + lane], s2);
+        }
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (prm.stats != nullptr) {
+    for (int i = threadIdx.x; i < 2 * prm.J; i += kThreads3) {
+      float s = s_stats[i];
+      if (s != 0.f) atomicAdd(&prm.stats[i], (double)s);
+    }
+  }
+  if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+__global__ void pack3_kernel(const float* __restrict__ w, __half* __restrict__ wp, int dgrad, int J, int K) {
+  // fwd: Wp[t][co][ci] = w[t][ci][co];  dgrad: Wp[t][ci][co] = w[8-t][ci][co]
+  long long total = 9LL * J * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i % K);
+    long long r = i / K;
+    int j = (int)(r % J), t = (int)(r / J);
+    float v = dgrad ? w[((long long)(8 - t) * J + j) * K + k] : w[((long long)t * K + k) * J + j];
+    wp[i] = __float2half_rn(v);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_enc3 = nullptr;
+bool g_attr3 = false;
+
+int get_enc3() {
+  if (g_enc3 != nullptr) return B2U_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  B2U_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    b2u_set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return B2U_ERR_CUDA;
+  }
+  g_enc3 = (EncodeTiledFn)fn;
+  return B2U_OK;
+}
+
+CUtensorMapSwizzle swz3(int ks) {
+  return ks == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (ks == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+}  // namespace
+
+int g_b2u_tc_halo = 1;       // 0: per-tap loads (conv_tc.cu), 1: halo box, 2: halo box + base_offset, 3: three boxes
+
+int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
+                        int ldy, int J, double* stats, const void* mask, int ldmask, int mask_act, int accumulate,
+                        int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+  int rc = get_enc3();
+  if (rc != B2U_OK) return rc;
+  C3Params p{};
+  p.N = n; p.H = h; p.W = wd; p.K = K; p.J = J;
+  p.KS = K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : 16);
+  p.JT = J <= 256 ? J : 256;
+  B2U_REQUIRE(K % 16 == 0 && J % 16 == 0 && J % p.JT == 0, "tc_conv3: unsupported channel counts K=%d J=%d", K, J);
+  p.amode = g_b2u_tc_halo == 3 ? 3 : 1;
+  p.bo_mode = g_b2u_tc_halo == 2 ? 1 : 0;
+  p.y = (__half*)y; p.ldy = ldy; p.bias = bias; p.act = act;
+  p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate; p.stats = stats;
+  const uint32_t rowb = p.KS * 2;
+  const uint32_t rows = p.amode == 3 ? 18 * 8 : 18 * 10;
+  p.a_sub = (rows * rowb + 1023) & ~1023u;
+  const size_t a_stage = (size_t)p.a_sub * (p.amode == 3 ? 3 : 1);
+  const size_t b_tile = ((size_t)p.JT * rowb + 1023) & ~(size_t)1023;
+  const int kslabs = K / p.KS;
+  const size_t tail = (2 * kMaxSA + 2 * kMaxSB + 5) * 8 + 16 + (size_t)3 * J * 4 + 64;
+  const size_t budget = 222 * 1024 - 1024 - tail;
+  const size_t wres = 9 * (size_t)kslabs * b_tile;
+  p.bres = (p.JT == J && wres + 2 * a_stage <= budget && wres <= 120 * 1024) ? 1 : 0;
+  if (p.bres) {
+    p.SB = 1;
+    p.SA = (int)((budget - wres) / a_stage);
+  } else {
+    // split the budget: at least 2 A stages, the rest to the weight ring (>= 3 tiles)
+    p.SA = 2;
+    long long room = (long long)budget - 2 * (long long)a_stage;
+    p.SB = (int)(room / (long long)b_tile);
+    if (p.SB > kMaxSB) {
+      p.SB = kMaxSB;
+      p.SA = (int)((budget - (size_t)p.SB * b_tile) / a_stage);
+    }
+  }
+  if (p.SA > kMaxSA) p.SA = kMaxSA;
+  B2U_REQUIRE(p.SA >= 2 && p.SB >= 1 && (p.bres || p.SB >= 2), "tc_conv3: tiles do not fit shared memory (K=%d J=%d)", K, J);
+  const size_t smem = 1024 + (size_t)p.SA * a_stage + (p.bres ? wres : (size_t)p.SB * b_tile) + tail;
+  B2U_REQUIRE(smem <= 227 * 1024, "tc_conv3: shared memory %zu exceeds 227 KB", smem);
+
+  // packed fp16 weights in the workspace
+  const size_t need = 9 * (size_t)J * K * 2;
+  B2U_REQUIRE(ws != nullptr && need <= ws_bytes, "tc_conv3: workspace too small");
+  {
+    long long total = 9LL * J * K;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 8 * B2U_NUM_SMS) grid = 8 * B2U_NUM_SMS;
+    B2U_LAUNCH(pack3_kernel, grid, 256, 0, stream, w, (__half*)ws, dgrad, J, K);
+  }
+  C3Maps maps;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)wd * ldx * 2, (cuuint64_t)h * wd * ldx * 2};
+    cuuint32_t box[4] = {(cuuint32_t)p.KS, (cuuint32_t)(p.amode == 3 ? 8 : 10), 18, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = g_enc3(&maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz3(p.KS), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b2u_set_error("tc_conv3: activation tensor map failed (%d)", (int)r); return B2U_ERR_CUDA; }
+    cuuint64_t bd[3] = {(cuuint64_t)K, (cuuint64_t)J, 9};
+    cuuint64_t bs[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * J * 2};
+    cuuint32_t bb[3] = {(cuuint32_t)p.KS, (cuuint32_t)p.JT, 1};
+    cuuint32_t be[3] = {1, 1, 1};
+    r = g_enc3(&maps.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ws, bd, bs, bb, be, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               swz3(p.KS), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b2u_set_error("tc_conv3: weight tensor map failed (%d)", (int)r); return B2U_ERR_CUDA; }
+  }
+  if (!g_attr3) {
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    g_attr3 = true;
+  }
+  long long tiles = (long long)n * b2u_cdiv(h, kTH) * b2u_cdiv(wd, kTW) * (J / p.JT);
+  int grid = (int)(tiles < B2U_NUM_SMS ? tiles : B2U_NUM_SMS);
+  B2U_LAUNCH(tc_conv3_kernel, grid, kThreads3, smem, stream, maps, p);
+  return B2U_OK;
+}
