@@ -31,7 +31,8 @@ namespace {
 
 constexpr int kMaxStages = 12;
 constexpr int kTileH = 8, kTileW = 16, kTileM = 128;       // 8 x 16 output pixels per tile
-constexpr int kThreadsTc = 192;                            // 6 warps
+constexpr int kEpiWarpsTc = 8;                             // two per TMEM lane group (column halves)
+constexpr int kThreadsTc = 64 + 32 * kEpiWarpsTc;
 constexpr int kMaxTaps = 9;
 
 struct TcParams {
@@ -93,14 +94,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 15) & ~(uintptr_t)15);
   float* s_stats = s_bias + prm.J;                         // [2*J]
   (void)stage_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_w = (prm.W + kTileW - 1) / kTileW, tiles_h = (prm.H + kTileH - 1) / kTileH;
   const int nj = prm.J / JT;
-  const long long ntiles = (long long)prm.N * tiles_h * tiles_w * nj;
+  const unsigned ntiles = (unsigned)(prm.N * tiles_h * tiles_w * nj);   // host guarantees < 2^31
   const int kslabs = prm.K / KS;
   const int ksteps = prm.ntaps * kslabs;
   uint32_t tmem_cols = 32;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull_bar[s], 1); tc::mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull_bar[s], 1); tc::mbar_init(&tempty_bar[s], kEpiWarpsTc); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
@@ -130,13 +131,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
       tc::prefetch_tmap(&maps.a[0]);
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int jt = (int)(tile % nj);
-        long long pt = tile / nj;
-        int tw = (int)(pt % tiles_w);
-        long long r = pt / tiles_w;
-        int th = (int)(r % tiles_h);
-        int n = (int)(r / tiles_h);
+      for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int jt = (int)(tile % (unsigned)nj);
+        const unsigned pt = tile / (unsigned)nj;
+        const int tw = (int)(pt % (unsigned)tiles_w);
+        const unsigned r = pt / (unsigned)tiles_w;
+        const int th = (int)(r % (unsigned)tiles_h);
+        const int n = (int)(r / (unsigned)tiles_h);
         for (int t = 0; t < prm.ntaps; ++t) {
           const CUtensorMap* am = &maps.a[prm.tap_map[t]];
           for (int ks = 0; ks < kslabs; ++ks) {
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * JT;
@@ -184,71 +185,82 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
     }
   } else {
     // ===================================== epilogue ==============================================
-    const int lg = warp & 3;                               // TMEM lane group this warp may access
+    // 8 warps: TMEM lane group = warp & 3, column half = (warp - 2) >> 2
+    const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = lg * 32 + lane;                        // tile row = pixel (row / 16, row % 16)
+    const int ccols = JT / 2 >= 16 ? JT / 2 : JT;
+    const int cbeg = JT / 2 >= 16 ? half * ccols : 0;
+    const bool has_cols = JT / 2 >= 16 || half == 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      int jt = (int)(tile % nj);
-      long long pt = tile / nj;
-      int tw = (int)(pt % tiles_w);
-      long long r = pt / tiles_w;
-      int th = (int)(r % tiles_h);
-      int n = (int)(r / tiles_h);
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int jt = (int)(tile % (unsigned)nj);
+      const unsigned pt = tile / (unsigned)nj;
+      const int tw = (int)(pt % (unsigned)tiles_w);
+      const unsigned r = pt / (unsigned)tiles_w;
+      const int th = (int)(r % (unsigned)tiles_h);
+      const int n = (int)(r / (unsigned)tiles_h);
       const int h = th * kTileH + row / kTileW, w = tw * kTileW + row % kTileW;
       const bool valid = h < prm.H && w < prm.W;
       const long long pix = ((long long)n * prm.H + h) * prm.W + w;
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::fence_after_sync();
-      for (int c0 = 0; c0 < JT; c0 += 16) {
-        float v[16];
-        tc::tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * JT + c0, v);
-        const int j0 = jt * JT + c0;
+      if (has_cols) {
+        for (int cc = 0; cc < ccols; cc += 16) {
+          const int c0 = cbeg + cc;
+          float v[16];
+          tc::tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * JT + c0, v);
+          const int j0 = jt * JT + c0;
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + j0);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i] + s_bias[j0 + i], prm.act);
-        __half* dst;
-        if (prm.mode == 1) {
-          int ab = j0 / prm.cout, co = j0 - ab * prm.cout;
-          long long op = (((long long)n * 2 * prm.H + 2 * h + (ab >> 1)) * (2LL * prm.W) + 2 * w + (ab & 1));
-          dst = prm.y + op * prm.ldy + co;
-        } else {
-          dst = prm.y + pix * prm.ldy + j0;
-        }
-        if (valid) {
-          if (prm.mask != nullptr) {
-            float m[8];
-            load8<__half>(prm.mask + pix * prm.ldmask + j0, m);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] *= act_bwd_from_y(m[i], prm.mask_act);
-            load8<__half>(prm.mask + pix * prm.ldmask + j0 + 8, m);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 + i] *= act_bwd_from_y(m[i], prm.mask_act);
+          for (int q = 0; q < 4; ++q) {
+            const float4 b4 = bp[q];
+            v[4 * q + 0] = apply_act(v[4 * q + 0] + b4.x, prm.act);
+            v[4 * q + 1] = apply_act(v[4 * q + 1] + b4.y, prm.act);
+            v[4 * q + 2] = apply_act(v[4 * q + 2] + b4.z, prm.act);
+            v[4 * q + 3] = apply_act(v[4 * q + 3] + b4.w, prm.act);
           }
-          if (prm.accumulate) {
-            float e[8];
-            load8<__half>(dst, e);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += e[i];
-            load8<__half>(dst + 8, e);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 + i] += e[i];
+          __half* dst;
+          if (prm.mode == 1) {
+            int ab = j0 / prm.cout, co = j0 - ab * prm.cout;
+            long long op = (((long long)n * 2 * prm.H + 2 * h + (ab >> 1)) * (2LL * prm.W) + 2 * w + (ab & 1));
+            dst = prm.y + op * prm.ldy + co;
+          } else {
+            dst = prm.y + pix * prm.ldy + j0;
           }
-          store8<__half>(dst, v);
-          store8<__half>(dst + 8, v + 8);
-        }
-        if (prm.stats != nullptr) {
-          float q[16], sq[16];
+          if (valid) {
+            if (prm.mask != nullptr) {
+              float m[8];
+              load8<__half>(prm.mask + pix * prm.ldmask + j0, m);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float rv = valid ? __half2float(__float2half_rn(v[i])) : 0.f;   // statistics of the stored value
-            q[i] = rv;
-            sq[i] = rv * rv;
+              for (int i = 0; i < 8; ++i) v[i] *= act_bwd_from_y(m[i], prm.mask_act);
+              load8<__half>(prm.mask + pix * prm.ldmask + j0 + 8, m);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 + i] *= act_bwd_from_y(m[i], prm.mask_act);
+            }
+            if (prm.accumulate) {
+              float e[8];
+              load8<__half>(dst, e);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += e[i];
+              load8<__half>(dst + 8, e);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 + i] += e[i];
+            }
+            store8<__half>(dst, v);
+            store8<__half>(dst + 8, v + 8);
           }
-          float s1 = transpose_reduce16(q, lane);
-          float s2 = transpose_reduce16(sq, lane);
-          if (lane < 16) {
-            atomicAdd(&s_stats[j0 + lane], s1);
-            atomicAdd(&s_stats[prm.J + j0 + lane], s2);
+          if (prm.stats != nullptr) {
+            float q[16], sq[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { q[i] = valid ? v[i] : 0.f; sq[i] = q[i] * q[i]; }
+            float s1 = transpose_reduce16(q, lane);
+            float s2 = transpose_reduce16(sq, lane);
+            if (lane < 16) {
+              atomicAdd(&s_stats[j0 + lane], s1);
+              atomicAdd(&s_stats[prm.J + j0 + lane], s2);
+            }
           }
         }
       }
@@ -358,7 +370,7 @@ int pick_jt(int J) {
   return 0;
 }
 
-size_t tail_bytes_for(int J) { return (2 * kMaxStages + 4) * 8 + 16 + (size_t)3 * J * 4 + 64; }
+size_t tail_bytes_for(int J) { return (2 * kMaxStages + 4) * 8 + 32 + (size_t)3 * J * 4 + 64; }
 int stages_for(int KS, int JT, int J) {
   size_t a = (size_t)kTileM * KS * 2, b = ((size_t)JT * KS * 2 + 1023) & ~(size_t)1023;
   long long room = 220 * 1024 - 1024 - (long long)tail_bytes_for(J);
@@ -382,6 +394,7 @@ int launch_tc(const TcMaps& maps, TcParams& prm, void* stream) {
     g_attr_set = true;
   }
   long long tiles = (long long)prm.N * b2u_cdiv(prm.H, kTileH) * b2u_cdiv(prm.W, kTileW) * (prm.J / prm.JT);
+  B2U_REQUIRE(tiles < (1LL << 31), "tc_conv: too many tiles");
   int grid = (int)(tiles < B2U_NUM_SMS ? tiles : B2U_NUM_SMS);
   B2U_LAUNCH(tc_conv_kernel, grid, kThreadsTc, smem, stream, maps, prm);
   return B2U_OK;

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
   uint64_t* tfull = w_full + 1;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 15) & ~(uintptr_t)15);
   float* s_stats = s_bias + prm.J;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -388,7 +388,7 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   const size_t a_stage = (size_t)p.a_sub * (p.amode == 3 ? 3 : 1);
   const size_t b_tile = ((size_t)p.JT * rowb + 1023) & ~(size_t)1023;
   const int kslabs = K / p.KS;
-  const size_t tail = (2 * kMaxSA + 2 * kMaxSB + 5) * 8 + 16 + (size_t)3 * J * 4 + 64;
+  const size_t tail = (2 * kMaxSA + 2 * kMaxSB + 5) * 8 + 32 + (size_t)3 * J * 4 + 64;
   const size_t budget = 222 * 1024 - 1024 - tail;
   const size_t wres = 9 * (size_t)kslabs * b_tile;
   p.bres = (p.JT == J && wres + 2 * a_stage <= budget && wres <= 120 * 1024) ? 1 : 0;

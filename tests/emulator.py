@@ -365,8 +365,17 @@ class Emulator:
         self.state["beta1_pow"] *= self.state["beta1"]
         self.state["beta2_pow"] *= self.state["beta2"]
 
+    def _allreduce(self, o, dtype):
+        # single-process emulation: identity; under torch.distributed (gloo): the real exchange
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            a = self.arr(o.p[0], o.i[0], dtype)
+            t = torch.from_numpy(a.copy())
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            a[:] = t.numpy()
+
     def op_allreduce_f32(self, o):
-        pass   # single-process emulation: world-size-1 semantics
+        self._allreduce(o, np.float32)
 
     def op_allreduce_f64(self, o):
-        pass
+        self._allreduce(o, np.float64)
