@@ -1,0 +1,22 @@
+"""run one tcgen05 conv forward a few times (ncu target). usage: one_conv.py N H W CIN COUT MODE"""
+import ctypes as C
+import os
+import sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from gpu_harness import LIB  # noqa: E402
+n, h, w, cin, cout, mode = [int(v) for v in sys.argv[1:7]]
+lib = LIB.lib()
+lib.b2u_set_option(b"tc_halo", mode)
+x = torch.rand(n, h, w, cin, device="cuda").half()
+y = torch.empty(n, h, w, cout, device="cuda", dtype=torch.float16)
+wt = torch.randn(3, 3, cin, cout, device="cuda") * 0.05
+b = torch.zeros(cout, device="cuda")
+ws = torch.empty(int(lib.b2u_ws_bytes()), dtype=torch.uint8, device="cuda")
+for _ in range(4):
+    LIB.check(lib.b2u_conv3x3_fwd(1, x.data_ptr(), cin, cin, wt.data_ptr(), b.data_ptr(), 1, y.data_ptr(), cout, cout,
+                                  None, n, h, w, ws.data_ptr(), ws.numel(), None))
+torch.cuda.synchronize()
+print("done")
