@@ -158,6 +158,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
       const uint32_t idesc = tc::idesc_f16(kTileM, JT, 0, 0);
       const uint64_t layout = KS == 64 ? tc::SWZ_128B : (KS == 32 ? tc::SWZ_64B : tc::SWZ_32B);
       const uint32_t sbo = 8 * KS * 2;                     // 8 rows of KS halves
+      // descriptor words hoisted out of the issue loop (single-thread dependent instruction stream)
+      const uint32_t ab_hi = (uint32_t)(tc::smem_desc(0, 16, sbo, layout) >> 32);
+      const uint32_t ab_lo0 = ((tc::smem_u32(smem) & 0x3FFFF) >> 4) | (1u << 16);
+      const uint32_t stage16 = stage_stride >> 4, a_bytes16 = a_bytes >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -169,11 +173,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
         for (int k = 0; k < ksteps; ++k) {
           tc::mbar_wait(&full_bar[stage], phase);
           tc::fence_after_sync();
-          const uint32_t sa = tc::smem_u32(smem + stage * stage_stride);
-          const uint32_t sb = sa + a_bytes;
+          const uint32_t a_lo = ab_lo0 + (uint32_t)stage * stage16;
+          const uint32_t b_lo = a_lo + a_bytes16;
           for (int kk = 0; kk < KS / 16; ++kk) {
-            uint64_t ad = tc::smem_desc(sa + kk * 32, 16, sbo, layout);
-            uint64_t bd = tc::smem_desc(sb + kk * 32, 16, sbo, layout);
+            const uint64_t ad = ((uint64_t)ab_hi << 32) | (uint64_t)(a_lo + 2 * kk);
+            const uint64_t bd = ((uint64_t)ab_hi << 32) | (uint64_t)(b_lo + 2 * kk);
             tc::mma_f16_ss(d_tmem, ad, bd, idesc, (k | kk) != 0);
           }
           tc::mma_commit(&empty_bar[stage]);

@@ -16,6 +16,7 @@
 // bound with 4: one warp per scheduler cannot hide its own dependent-issue latency),
 // double-buffered TMEM accumulator, bias / ReLU / ELU / mask / accumulate / BN statistics).
 #include <cuda.h>
+#include <type_traits>
 #include "common.cuh"
 #include "internal.h"
 #include "launch.cuh"
@@ -24,8 +25,8 @@
 namespace {
 
 constexpr int kTH = 16, kTW = 8;            // output tile: 16 rows x 8 columns = 128 pixels
-constexpr int kEpiWarps = 8;                 // two warps per TMEM lane group, each owning half of the columns
-constexpr int kThreads3 = 64 + 32 * kEpiWarps;
+constexpr int kMaxEpiWarps = 8;             // 8: two warps per TMEM lane group (column halves); 4 when two CTAs share an SM
+constexpr int kThreads3 = 64 + 32 * kMaxEpiWarps;
 constexpr int kMaxSA = 8, kMaxSB = 8;
 
 struct C3Params {
@@ -34,6 +35,7 @@ struct C3Params {
   int bo_mode;            // amode 1: 0 = descriptor base_offset 0, 1 = (start >> 7) & 7
   int bres;               // weights resident in smem
   int SA, SB;             // ring depths
+  int epi_warps;          // 4 or 8 (block = 64 + 32 * epi_warps threads)
   uint32_t a_sub;         // bytes of one A sub-tile (1024-aligned), a_stage = a_sub * (amode == 3 ? 3 : 1)
   __half* y; int ldy;
   const float* bias; int act;
@@ -99,12 +101,12 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
     for (int s = 0; s < SA; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < SB; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
     tc::mbar_init(w_full, 1);
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], prm.epi_warps); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
-  for (int i = threadIdx.x; i < prm.J; i += kThreads3) s_bias[i] = prm.bias ? prm.bias[i] : 0.f;
-  for (int i = threadIdx.x; i < 2 * prm.J; i += kThreads3) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < prm.J; i += blockDim.x) s_bias[i] = prm.bias ? prm.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 2 * prm.J; i += blockDim.x) s_stats[i] = 0.f;
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -154,15 +156,54 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ============================================
+    // One thread issues every tcgen05.mma of the CTA.  It is a single dependent instruction stream, so the
+    // descriptors are NOT rebuilt per MMA: the high words are constants, the low words (start address >> 4)
+    // advance by precomputed offsets, and the 9-tap x K-step nest is fully unrolled (issue_slab<KSTEPS>).
     if (lane == 0) {
       const uint32_t idesc = tc::idesc_f16(128, JT, 0, 0);
       const uint64_t layout = KS == 64 ? tc::SWZ_128B : (KS == 32 ? tc::SWZ_64B : tc::SWZ_32B);
-      const uint32_t sbo_b = 8 * rowb;
       const uint32_t a_rows = prm.amode == 3 ? 8 : 10;            // halo row pitch in pixels
-      const uint32_t sbo_a = a_rows * rowb;
+      // descriptor words: lo = (addr >> 4) | LBO(=1) << 16 ; hi = SBO >> 4 | version 1 << 14 | layout << 29
+      const uint32_t a_hi = (uint32_t)(tc::smem_desc(0, 16, a_rows * rowb, layout) >> 32);
+      const uint32_t b_hi = (uint32_t)(tc::smem_desc(0, 16, 8 * rowb, layout) >> 32);
+      uint32_t tap_off[9];                                        // A start offset of tap t, in 16-byte units
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int dh = t / 3, dw = t % 3;
+        tap_off[t] = prm.amode == 3 ? (dw * prm.a_sub + (uint32_t)(dh * 8) * rowb) >> 4
+                                    : ((uint32_t)(dh * 10 + dw) * rowb) >> 4;
+      }
+      const uint32_t a_ring_lo = ((tc::smem_u32(a_ring) & 0x3FFFF) >> 4) | (1u << 16);
+      const uint32_t b_area_lo = ((tc::smem_u32(b_area) & 0x3FFFF) >> 4) | (1u << 16);
+      const uint32_t a_stage16 = a_stage >> 4, b_tile16 = b_tile >> 4;
       if (prm.bres) { tc::mbar_wait(w_full, 0); tc::fence_after_sync(); }
       int sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, acc_phase = 0;
+      auto issue_slab = [&](auto ksteps_tag, uint32_t d_tmem, uint32_t a_lo, int ks) {
+        constexpr int KSTEPS = decltype(ksteps_tag)::value;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          uint32_t b_lo;
+          if (prm.bres) {
+            b_lo = b_area_lo + (uint32_t)(t * kslabs + ks) * b_tile16;
+          } else {
+            tc::mbar_wait(&b_full[sb], pb);
+            tc::fence_after_sync();
+            b_lo = b_area_lo + (uint32_t)sb * b_tile16;
+          }
+          const uint32_t at = a_lo + tap_off[t];
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk) {
+            const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(at + 2 * kk);
+            const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2 * kk);
+            tc::mma_f16_ss(d_tmem, ad, bd, idesc, (t | kk) != 0 ? 1u : (ks != 0 ? 1u : 0u));
+          }
+          if (!prm.bres) {
+            tc::mma_commit(&b_empty[sb]);
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+        }
+      };
       for (unsigned tile = blockIdx.x; tile < (unsigned)ntiles; tile += gridDim.x) {
         tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc::fence_after_sync();
@@ -170,30 +211,10 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
         for (int ks = 0; ks < kslabs; ++ks) {
           tc::mbar_wait(&a_full[sa], pa);
           tc::fence_after_sync();
-          const uint32_t a_base = tc::smem_u32(a_ring + (size_t)sa * a_stage);
-          for (int t = 0; t < 9; ++t) {
-            const int dh = t / 3, dw = t % 3;
-            uint32_t b_base;
-            if (prm.bres) {
-              b_base = tc::smem_u32(b_area + (size_t)(t * kslabs + ks) * b_tile);
-            } else {
-              tc::mbar_wait(&b_full[sb], pb);
-              tc::fence_after_sync();
-              b_base = tc::smem_u32(b_area + (size_t)sb * b_tile);
-            }
-            const uint32_t a_start = prm.amode == 3 ? a_base + dw * prm.a_sub + (uint32_t)(dh * 8) * rowb
-                                                    : a_base + (uint32_t)(dh * 10 + dw) * rowb;
-            const uint32_t bo = (prm.amode == 1 && prm.bo_mode) ? ((a_start >> 7) & 7u) : 0u;
-            for (int kk = 0; kk < KS / 16; ++kk) {
-              uint64_t ad = tc::smem_desc(a_start + kk * 32, 16, sbo_a, layout, bo);
-              uint64_t bd = tc::smem_desc(b_base + kk * 32, 16, sbo_b, layout);
-              tc::mma_f16_ss(d_tmem, ad, bd, idesc, (ks | t | kk) != 0);
-            }
-            if (!prm.bres) {
-              tc::mma_commit(&b_empty[sb]);
-              if (++sb == SB) { sb = 0; pb ^= 1; }
-            }
-          }
+          const uint32_t a_lo = a_ring_lo + (uint32_t)sa * a_stage16;
+          if (KS == 64) issue_slab(std::integral_constant<int, 4>{}, d_tmem, a_lo, ks);
+          else if (KS == 32) issue_slab(std::integral_constant<int, 2>{}, d_tmem, a_lo, ks);
+          else issue_slab(std::integral_constant<int, 1>{}, d_tmem, a_lo, ks);
           tc::mma_commit(&a_empty[sa]);
           if (++sa == SA) { sa = 0; pa ^= 1; }
         }
@@ -211,9 +232,10 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
     const int lg = warp & 3;
     const int half = ew >> 2;
     const int row = lg * 32 + lane;
-    const int ccols = JT / 2 >= 16 ? JT / 2 : JT;                 // columns owned by this warp within a tile
-    const int cbeg = JT / 2 >= 16 ? half * ccols : 0;
-    const bool has_cols = JT / 2 >= 16 || half == 0;
+    const bool split = prm.epi_warps == 8 && JT / 2 >= 16;          // two warps share a lane group's columns
+    const int ccols = split ? JT / 2 : JT;                        // columns owned by this warp within a tile
+    const int cbeg = split ? half * ccols : 0;
+    const bool has_cols = split || half == 0;
     const bool reg_stats = prm.stats != nullptr && ccols <= 32 && nj == 1;
     float rs1[32], rs2[32];
 #pragma unroll
@@ -320,7 +342,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
   __syncthreads();
   tc::fence_after_sync();
   if (prm.stats != nullptr) {
-    for (int i = threadIdx.x; i < 2 * prm.J; i += kThreads3) {
+    for (int i = threadIdx.x; i < 2 * prm.J; i += blockDim.x) {
       float s = s_stats[i];
       if (s != 0.f) atomicAdd(&prm.stats[i], (double)s);
     }
@@ -379,7 +401,7 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   p.JT = J <= 256 ? J : 256;
   B2U_REQUIRE(K % 16 == 0 && J % 16 == 0 && J % p.JT == 0, "tc_conv3: unsupported channel counts K=%d J=%d", K, J);
   p.amode = g_b2u_tc_halo == 3 ? 3 : 1;
-  p.bo_mode = g_b2u_tc_halo == 2 ? 1 : 0;
+  p.bo_mode = 0;      // descriptor base offsets are wrong for address-anchored swizzles (probed on B200): unused
   p.y = (__half*)y; p.ldy = ldy; p.bias = bias; p.act = act;
   p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate; p.stats = stats;
   const uint32_t rowb = p.KS * 2;
@@ -407,6 +429,17 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   }
   if (p.SA > kMaxSA) p.SA = kMaxSA;
   B2U_REQUIRE(p.SA >= 2 && p.SB >= 1 && (p.bres || p.SB >= 2), "tc_conv3: tiles do not fit shared memory (K=%d J=%d)", K, J);
+  // two CTAs per SM for thin resident-weight layers: cap the A ring so that one CTA stays under ~110 KB
+  bool two_per_sm = false;
+  if (p.bres && p.JT <= 64) {
+    const size_t cap = 110 * 1024;
+    if (1024 + wres + tail + 2 * a_stage <= cap) {
+      int sa2 = (int)((cap - 1024 - wres - tail) / a_stage);
+      if (sa2 > kMaxSA) sa2 = kMaxSA;
+      if (sa2 >= 2) { p.SA = sa2; two_per_sm = true; }
+    }
+  }
+  p.epi_warps = two_per_sm ? 4 : 8;
   const size_t smem = 1024 + (size_t)p.SA * a_stage + (p.bres ? wres : (size_t)p.SB * b_tile) + tail;
   B2U_REQUIRE(smem <= 227 * 1024, "tc_conv3: shared memory %zu exceeds 227 KB", smem);
 
@@ -442,7 +475,12 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
     g_attr3 = true;
   }
   long long tiles = (long long)n * b2u_cdiv(h, kTH) * b2u_cdiv(wd, kTW) * (J / p.JT);
-  int grid = (int)(tiles < B2U_NUM_SMS ? tiles : B2U_NUM_SMS);
-  B2U_LAUNCH(tc_conv3_kernel, grid, kThreads3, smem, stream, maps, p);
+  B2U_REQUIRE(tiles < (1LL << 31), "tc_conv3: too many tiles");
+  // thin layers are bound by the single MMA-issuing thread (~75 issue cycles per tcgen05.mma): run two CTAs
+  // per SM (two issuers) when shared memory and TMEM (2*JT columns each) allow it
+  int ctas = B2U_NUM_SMS;
+  if (two_per_sm && tiles >= 4 * B2U_NUM_SMS) ctas = 2 * B2U_NUM_SMS;
+  int grid = (int)(tiles < ctas ? tiles : ctas);
+  B2U_LAUNCH(tc_conv3_kernel, grid, 64 + 32 * p.epi_warps, smem, stream, maps, p);
   return B2U_OK;
 }

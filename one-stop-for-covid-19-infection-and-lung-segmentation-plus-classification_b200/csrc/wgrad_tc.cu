@@ -114,6 +114,12 @@ __global__ void __launch_bounds__(kThreadsW, 1) tc_wgrad_kernel(const __grid_con
       const uint64_t la = KSA == 64 ? tc::SWZ_128B : (KSA == 32 ? tc::SWZ_64B : tc::SWZ_32B);
       const uint64_t lb = KSB == 64 ? tc::SWZ_128B : (KSB == 32 ? tc::SWZ_64B : tc::SWZ_32B);
       const uint32_t rowa = KSA * 2, rowb = KSB * 2;                    // bytes per pixel row of a tile
+      const uint32_t a_hi = (uint32_t)(tc::smem_desc(0, a_tile, 8 * rowa, la) >> 32);
+      const uint32_t b_hi = (uint32_t)(tc::smem_desc(0, b_tile, 8 * rowb, lb) >> 32);
+      const uint32_t a_lbo16 = ((a_tile >> 4) & 0x3FFF) << 16, b_lbo16 = ((b_tile >> 4) & 0x3FFF) << 16;
+      const uint32_t a_lo0 = ((tc::smem_u32(smem) & 0x3FFFF) >> 4) | a_lbo16;
+      const uint32_t stage16 = stage_stride >> 4, a_bytes16 = a_bytes >> 4;
+      const uint32_t ka16 = (16 * rowa) >> 4, kb16 = (16 * rowb) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -127,15 +133,17 @@ __global__ void __launch_bounds__(kThreadsW, 1) tc_wgrad_kernel(const __grid_con
         for (int blk = sp; blk < nblocks; blk += prm.nsplit) {
           tc::mbar_wait(&full_bar[stage], phase);
           tc::fence_after_sync();
-          const uint32_t sa = tc::smem_u32(smem + stage * stage_stride);
-          const uint32_t sb = sa + a_bytes;
+          // MN-major descriptors: LBO = distance between channel chunks (tiles), SBO = 8 pixel rows; only the
+          // start-address field changes per MMA (16 pixel rows further), so hi words / LBO are hoisted
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage16;
+          const uint32_t b_lo = a_lo + a_bytes16;
+#pragma unroll
           for (int kk = 0; kk < 8; ++kk) {                              // 8 x 16 pixels
-            // MN-major: LBO = distance between channel chunks (tiles), SBO = 8 pixel rows
-            uint64_t ad = tc::smem_desc(sa + kk * 16 * rowa, a_tile, 8 * rowa, la);
-            uint64_t bd = tc::smem_desc(sb + kk * 16 * rowb, b_tile, 8 * rowb, lb);
-            tc::mma_f16_ss(d_tmem, ad, bd, idesc, first ? 0u : 1u);
-            first = 0;
+            const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + kk * ka16);
+            const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo - a_lbo16 + b_lbo16 + kk * kb16);
+            tc::mma_f16_ss(d_tmem, ad, bd, idesc, (kk != 0) ? 1u : (first ? 0u : 1u));
           }
+          first = 0;
           tc::mma_commit(&empty_bar[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
