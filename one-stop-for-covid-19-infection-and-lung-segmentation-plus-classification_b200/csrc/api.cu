@@ -43,12 +43,30 @@ extern "C" int b2u_set_option(const char* name, int value) {
     g_b2u_tc_halo = value;
     return old;
   }
+  if (strcmp(name, "tc_debug") == 0) {
+    if (value && g_b2u_dbg == nullptr) {
+      if (cudaMalloc(&g_b2u_dbg, 64 * 8 * sizeof(long long)) != cudaSuccess) return -1;
+      cudaMemset(g_b2u_dbg, 0, 64 * 8 * sizeof(long long));
+    } else if (!value && g_b2u_dbg != nullptr) {
+      cudaFree(g_b2u_dbg);
+      g_b2u_dbg = nullptr;
+    }
+    return 0;
+  }
+  if (strcmp(name, "tc_debug_read") == 0) {   // value = host pointer low bits are not passable: see b2u_debug_read
+    return g_b2u_dbg != nullptr;
+  }
   if (strcmp(name, "tensor_path") == 0) {
     int old = b2u_tensor_path_available();
     g_tc_state = value ? (b2u_tc_compiled() ? 1 : 0) : 0;
     return old;
   }
   return -1;
+}
+
+extern "C" int b2u_debug_read(long long* h_out, int count) {
+  if (g_b2u_dbg == nullptr || count > 64 * 8) return -1;
+  return cudaMemcpy(h_out, g_b2u_dbg, count * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ============================================
-    if (lane == 0) {
+    {   // whole warp in uniform control flow, one elected lane issues (tc_common.cuh)
       const uint32_t idesc = tc::idesc_f16(kTileM, JT, 0, 0);
       const uint64_t layout = KS == 64 ? tc::SWZ_128B : (KS == 32 ? tc::SWZ_64B : tc::SWZ_32B);
       const uint32_t sbo = 8 * KS * 2;                     // 8 rows of KS halves
@@ -178,12 +178,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
           for (int kk = 0; kk < KS / 16; ++kk) {
             const uint64_t ad = ((uint64_t)ab_hi << 32) | (uint64_t)(a_lo + 2 * kk);
             const uint64_t bd = ((uint64_t)ab_hi << 32) | (uint64_t)(b_lo + 2 * kk);
-            tc::mma_f16_ss(d_tmem, ad, bd, idesc, (k | kk) != 0);
+            tc::mma_f16_ss_elect(d_tmem, ad, bd, idesc, (k | kk) != 0);
           }
-          tc::mma_commit(&empty_bar[stage]);
+          tc::mma_commit_elect(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tc::mma_commit(&tfull_bar[acc]);
+        tc::mma_commit_elect(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -220,10 +220,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 b4 = bp[q];
-            v[4 * q + 0] = apply_act(v[4 * q + 0] + b4.x, prm.act);
-            v[4 * q + 1] = apply_act(v[4 * q + 1] + b4.y, prm.act);
-            v[4 * q + 2] = apply_act(v[4 * q + 2] + b4.z, prm.act);
-            v[4 * q + 3] = apply_act(v[4 * q + 3] + b4.w, prm.act);
+            v[4 * q + 0] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+          }
+          if (prm.act == B2U_ACT_RELU) {          // activation switch outside the element loop (branch-free chains)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (prm.act == B2U_ACT_ELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
           }
           __half* dst;
           if (prm.mode == 1) {

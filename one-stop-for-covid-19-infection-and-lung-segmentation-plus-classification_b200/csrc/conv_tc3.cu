@@ -42,6 +42,7 @@ struct C3Params {
   const __half* mask; int ldmask; int mask_act;
   int accumulate;
   double* stats;
+  long long* dbg;         // optional timeline buffer (CTA 0): [iter][8] clock64 stamps
 };
 
 struct C3Maps {
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
         const int th = (int)(r % (unsigned)tiles_h), n = (int)(r / (unsigned)tiles_h);
         for (int ks = 0; ks < kslabs; ++ks) {
           tc::mbar_wait(&a_empty[sa], pa ^ 1);
+          if (prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64) prm.dbg[(tile / gridDim.x) * 8 + 0] = clock64();
           uint8_t* dst = a_ring + (size_t)sa * a_stage;
           tc::mbar_expect_tx(&a_full[sa], a_tx);
           if (prm.amode == 3) {
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
           } else {
             tc::tma_load_4d(dst, &maps.a, &a_full[sa], ks * KS, tw * kTW - 1, th * kTH - 1, n);
           }
+          if (prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64) prm.dbg[(tile / gridDim.x) * 8 + 1] = clock64();
           if (++sa == SA) { sa = 0; pa ^= 1; }
           if (!prm.bres) {
             for (int t = 0; t < 9; ++t) {
@@ -159,7 +162,8 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
     // One thread issues every tcgen05.mma of the CTA.  It is a single dependent instruction stream, so the
     // descriptors are NOT rebuilt per MMA: the high words are constants, the low words (start address >> 4)
     // advance by precomputed offsets, and the 9-tap x K-step nest is fully unrolled (issue_slab<KSTEPS>).
-    if (lane == 0) {
+    // The whole warp runs this loop in uniform control flow; one elected lane issues (see tc_common.cuh).
+    {
       const uint32_t idesc = tc::idesc_f16(128, JT, 0, 0);
       const uint64_t layout = KS == 64 ? tc::SWZ_128B : (KS == 32 ? tc::SWZ_64B : tc::SWZ_32B);
       const uint32_t a_rows = prm.amode == 3 ? 8 : 10;            // halo row pitch in pixels
@@ -196,10 +200,10 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
           for (int kk = 0; kk < KSTEPS; ++kk) {
             const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(at + 2 * kk);
             const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2 * kk);
-            tc::mma_f16_ss(d_tmem, ad, bd, idesc, (t | kk) != 0 ? 1u : (ks != 0 ? 1u : 0u));
+            tc::mma_f16_ss_elect(d_tmem, ad, bd, idesc, (t | kk) != 0 ? 1u : (ks != 0 ? 1u : 0u));
           }
           if (!prm.bres) {
-            tc::mma_commit(&b_empty[sb]);
+            tc::mma_commit_elect(&b_empty[sb]);
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
         }
@@ -207,18 +211,22 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
       for (unsigned tile = blockIdx.x; tile < (unsigned)ntiles; tile += gridDim.x) {
         tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc::fence_after_sync();
+        const bool dbg_on = prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64;
+        if (dbg_on && lane == 0) prm.dbg[(tile / gridDim.x) * 8 + 2] = clock64();
         const uint32_t d_tmem = tmem_base + acc * JT;
         for (int ks = 0; ks < kslabs; ++ks) {
           tc::mbar_wait(&a_full[sa], pa);
           tc::fence_after_sync();
+          if (dbg_on && ks == 0 && lane == 0) prm.dbg[(tile / gridDim.x) * 8 + 3] = clock64();
           const uint32_t a_lo = a_ring_lo + (uint32_t)sa * a_stage16;
           if (KS == 64) issue_slab(std::integral_constant<int, 4>{}, d_tmem, a_lo, ks);
           else if (KS == 32) issue_slab(std::integral_constant<int, 2>{}, d_tmem, a_lo, ks);
           else issue_slab(std::integral_constant<int, 1>{}, d_tmem, a_lo, ks);
-          tc::mma_commit(&a_empty[sa]);
+          tc::mma_commit_elect(&a_empty[sa]);
           if (++sa == SA) { sa = 0; pa ^= 1; }
         }
-        tc::mma_commit(&tfull[acc]);
+        tc::mma_commit_elect(&tfull[acc]);
+        if (dbg_on && lane == 0) prm.dbg[(tile / gridDim.x) * 8 + 4] = clock64();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -255,6 +263,8 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
       const __half* mrow = prm.mask != nullptr ? prm.mask + pix * prm.ldmask + jt * JT : nullptr;
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::fence_after_sync();
+      const bool dbg_e = prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64 && threadIdx.x == 64;
+      if (dbg_e) prm.dbg[(tile / gridDim.x) * 8 + 5] = clock64();
       if (has_cols) {
 #pragma unroll 2
         for (int cc = 0; cc < ccols; cc += 16) {
@@ -265,10 +275,15 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 b4 = bp[q];
-            v[4 * q + 0] = act_fwd(v[4 * q + 0] + b4.x, prm.act);
-            v[4 * q + 1] = act_fwd(v[4 * q + 1] + b4.y, prm.act);
-            v[4 * q + 2] = act_fwd(v[4 * q + 2] + b4.z, prm.act);
-            v[4 * q + 3] = act_fwd(v[4 * q + 3] + b4.w, prm.act);
+            v[4 * q + 0] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+          }
+          // activation switch hoisted out of the element loop: the 16 element chains stay branch-free
+          if (prm.act == B2U_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (prm.act == B2U_ACT_ELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
           }
           if (valid) {
             if (mrow != nullptr) {
@@ -317,6 +332,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
           }
         }
       }
+      if (dbg_e) prm.dbg[(tile / gridDim.x) * 8 + 6] = clock64();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty[acc]);
@@ -388,6 +404,7 @@ CUtensorMapSwizzle swz3(int ks) {
 
 }  // namespace
 
+long long* g_b2u_dbg = nullptr;   // device timeline buffer (b2u_set_option("tc_debug", 1))
 int g_b2u_tc_halo = 1;       // 0: per-tap loads (conv_tc.cu), 1: halo box, 2: halo box + base_offset, 3: three boxes
 
 int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
@@ -404,6 +421,7 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   p.bo_mode = 0;      // descriptor base offsets are wrong for address-anchored swizzles (probed on B200): unused
   p.y = (__half*)y; p.ldy = ldy; p.bias = bias; p.act = act;
   p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate; p.stats = stats;
+  p.dbg = g_b2u_dbg;
   const uint32_t rowb = p.KS * 2;
   const uint32_t rows = p.amode == 3 ? 18 * 8 : 18 * 10;
   p.a_sub = (rows * rowb + 1023) & ~1023u;

@@ -34,9 +34,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// The spin loop lives INSIDE the asm block: a C++ `while (!try_wait)` makes the loop branch depend on a
+// per-thread predicate, after which the compiler treats every loop-carried value of the caller as
+// potentially divergent (descriptor words then take an ELECT / R2UR round trip per tcgen05.mma).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n}"
+      ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
 }
 
 // ---- TMA -----------------------------------------------------------------------------------
@@ -93,6 +103,25 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-uniform variants: every lane of the (converged) warp executes the call with the same operands and
+// one elected lane issues the instruction.  This keeps the surrounding loop in uniform control flow, so the
+// compiler feeds the descriptors from uniform registers directly instead of wrapping every UTCHMMA in a
+// lane-election loop (which costs ~15 dependent instructions per MMA in a `if (lane == 0)` region).
+__device__ __forceinline__ void mma_f16_ss_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p, q;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}"
+      ::"r"(smem_u32(bar))
       : "memory");
 }
 // arrives on the mbarrier once all previously issued MMAs of this thread have completed

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) tc_wgrad_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ============================================
-    if (lane == 0) {
+    {   // whole warp in uniform control flow, one elected lane issues (tc_common.cuh)
       const uint32_t idesc = tc::idesc_f16(128, JT, 1, 1);              // both operands MN-major
       const uint64_t la = KSA == 64 ? tc::SWZ_128B : (KSA == 32 ? tc::SWZ_64B : tc::SWZ_32B);
       const uint64_t lb = KSB == 64 ? tc::SWZ_128B : (KSB == 32 ? tc::SWZ_64B : tc::SWZ_32B);
@@ -141,13 +141,13 @@ __global__ void __launch_bounds__(kThreadsW, 1) tc_wgrad_kernel(const __grid_con
           for (int kk = 0; kk < 8; ++kk) {                              // 8 x 16 pixels
             const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + kk * ka16);
             const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo - a_lbo16 + b_lbo16 + kk * kb16);
-            tc::mma_f16_ss(d_tmem, ad, bd, idesc, (kk != 0) ? 1u : (first ? 0u : 1u));
+            tc::mma_f16_ss_elect(d_tmem, ad, bd, idesc, (kk != 0) ? 1u : (first ? 0u : 1u));
           }
           first = 0;
-          tc::mma_commit(&empty_bar[stage]);
+          tc::mma_commit_elect(&empty_bar[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        tc::mma_commit(&tfull_bar[acc]);
+        tc::mma_commit_elect(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

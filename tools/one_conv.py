@@ -20,3 +20,17 @@ for _ in range(4):
                                   None, n, h, w, ws.data_ptr(), ws.numel(), None))
 torch.cuda.synchronize()
 print("done")
+if len(sys.argv) > 7 and sys.argv[7] == "timeline":
+    import numpy as np
+    lib.b2u_set_option(b"tc_debug", 1)
+    LIB.check(lib.b2u_conv3x3_fwd(1, x.data_ptr(), cin, cin, wt.data_ptr(), b.data_ptr(), 1, y.data_ptr(), cout, cout,
+                                  None, n, h, w, ws.data_ptr(), ws.numel(), None))
+    torch.cuda.synchronize()
+    buf = (C.c_longlong * 512)()
+    lib.b2u_debug_read.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+    assert lib.b2u_debug_read(buf, 512) == 0
+    a = np.array(buf[:], dtype=np.int64).reshape(64, 8)
+    t0 = a[0, 0]
+    print("iter: prod_wait prod_issued | mma_tempty mma_afull mma_commit | epi_tfull epi_done   (cycles from start)")
+    for k in range(24):
+        print(k, [int(v - t0) if v else None for v in a[k, :7]])
