@@ -43,6 +43,11 @@ extern "C" int b2u_set_option(const char* name, int value) {
     g_b2u_tc_halo = value;
     return old;
   }
+  if (strcmp(name, "wgrad_halo") == 0) {
+    int old = g_b2u_wgrad_halo;
+    g_b2u_wgrad_halo = value;
+    return old;
+  }
   if (strcmp(name, "tc_debug") == 0) {
     if (value && g_b2u_dbg == nullptr) {
       if (cudaMalloc(&g_b2u_dbg, 64 * 8 * sizeof(long long)) != cudaSuccess) return -1;

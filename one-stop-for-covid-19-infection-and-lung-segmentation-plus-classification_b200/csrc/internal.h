@@ -23,6 +23,7 @@ int b2u_tc_wgrad_ok(int cin, int cout, int ldx, int lddy);
 int b2u_tc_convt_ok(int cin, int cout, int ld_small, int ld_big);
 int b2u_tc_convt_wgrad_ok(int cin, int cout, int ldx, int lddy);
 extern int g_b2u_tc_halo;
+extern int g_b2u_wgrad_halo;
 extern long long* g_b2u_dbg;
 int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                         int ldy, int J, double* stats, const void* mask, int ldmask, int mask_act, int accumulate,

@@ -184,6 +184,163 @@ __global__ void __launch_bounds__(kThreadsW, 1) tc_wgrad_kernel(const __grid_con
   if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// =====================================================================================================
+// HALO variant for thin, full-resolution layers (Cin = 16 / 32 / 64): the layers whose weight gradient is
+// bound by shared-memory fill bandwidth when every tap re-loads its own shifted x tile.
+//
+// Per 16 x 8 pixel block the CTA loads ONE (18 x 10) halo patch of x and ONE dy tile.  The GEMM K axis is
+// the pixel axis (MN-major operands), a K step of 16 pixels = two 8-pixel tile rows = two 8-row groups
+// SBO = 10 halo rows apart.  The 128 accumulator rows are `128 / Cin` chunks LBO = ONE pixel row apart,
+// i.e. chunk c is the same patch shifted by c pixels: one tcgen05.mma computes the taps (dh, dw = c) for
+// c = 0.. at once (chunks beyond dw = 2 are don't-care rows).  Accumulators: one per (dh, chunk group).
+// =====================================================================================================
+struct WhParams {
+  int N, H, W, cin, cout, JT, KSB;
+  int nacc_per_dh;             // 1 (Cin <= 32: dw 0..2 in one MMA) or 2 (Cin = 64: [dw0,dw1] and [dw2,-])
+  int nsplit, stages;
+  float* dw;
+};
+struct WhMaps { CUtensorMap a, b; };
+
+__global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __grid_constant__ WhMaps maps,
+                                                                      const __grid_constant__ WhParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int cin = prm.cin, JT = prm.JT, KSB = prm.KSB, stages = prm.stages;
+  const uint32_t rowa = cin * 2, rowb = KSB * 2;
+  const uint32_t a_bytes = 180u * rowa, a_stride = (a_bytes + 1023) & ~1023u;
+  const int nb = JT / KSB;
+  const uint32_t b_tile = 128u * rowb, b_bytes = b_tile * nb;
+  const uint32_t stage_stride = a_stride + b_bytes;
+  uint8_t* tail = smem + stages * stage_stride;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tfull_bar = empty_bar + 8;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_w = (prm.W + 7) / 8, tiles_h = (prm.H + 15) / 16;
+  const int nblocks = prm.N * tiles_h * tiles_w;
+  const int nj = prm.cout / JT;
+  const int ntasks = prm.nsplit * nj;
+  const int nacc = 3 * prm.nacc_per_dh;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(nacc * JT)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(tfull_bar, 1);
+    tc::mbar_init(tempty_bar, 4);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const int jt = task % nj, sp = task / nj;
+        for (int blk = sp; blk < nblocks; blk += prm.nsplit) {
+          const int tw = blk % tiles_w, th = (blk / tiles_w) % tiles_h, n = blk / (tiles_w * tiles_h);
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_stride;
+          tc::mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+          tc::tma_load_4d(sa, &maps.a, &full_bar[stage], 0, tw * 8 - 1, th * 16 - 1, n);
+          for (int s = 0; s < nb; ++s)
+            tc::tma_load_4d(sa + a_stride + s * b_tile, &maps.b, &full_bar[stage], jt * JT + s * KSB, tw * 8, th * 16, n);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    {   // whole warp, uniform control flow; one elected lane issues
+      const uint32_t idesc = tc::idesc_f16(128, JT, 1, 1);
+      const uint64_t la = cin == 64 ? tc::SWZ_128B : (cin == 32 ? tc::SWZ_64B : tc::SWZ_32B);
+      const uint64_t lb = KSB == 64 ? tc::SWZ_128B : (KSB == 32 ? tc::SWZ_64B : tc::SWZ_32B);
+      // A: chunks one pixel row apart (LBO = rowa), 8-row K groups 10 halo rows apart (SBO = 10 * rowa)
+      const uint32_t a_hi = (uint32_t)(tc::smem_desc(0, rowa, 10 * rowa, la) >> 32);
+      const uint32_t b_hi = (uint32_t)(tc::smem_desc(0, b_tile, 8 * rowb, lb) >> 32);
+      const uint32_t a_lbo = ((rowa >> 4) & 0x3FFF) << 16, b_lbo = ((b_tile >> 4) & 0x3FFF) << 16;
+      const uint32_t smem_lo = (tc::smem_u32(smem) & 0x3FFFF) >> 4;
+      const uint32_t stage16 = stage_stride >> 4, a_stride16 = a_stride >> 4;
+      const uint32_t rowa16 = rowa >> 4, kb16 = (16 * rowb) >> 4;
+      int stage = 0;
+      uint32_t phase = 0, tphase = 0;
+      for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const int sp = task / nj;
+        tc::mbar_wait(tempty_bar, tphase ^ 1);
+        tc::fence_after_sync();
+        uint32_t first = 1;
+        for (int blk = sp; blk < nblocks; blk += prm.nsplit) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::fence_after_sync();
+          const uint32_t a0 = smem_lo + (uint32_t)stage * stage16;
+          const uint32_t b0 = (a0 + a_stride16) | b_lbo;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b0 + kk * kb16);
+#pragma unroll
+            for (int dh = 0; dh < 3; ++dh) {
+              // halo row of the first pixel of this K step for tap row dh: (2*kk + dh) * 10
+              const uint32_t ar = (a0 + (uint32_t)((2 * kk + dh) * 10) * rowa16) | a_lbo;
+              const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)ar;
+              tc::mma_f16_ss_elect(tmem_base + (dh * prm.nacc_per_dh) * JT, ad, bd, idesc, (kk != 0) ? 1u : (first ? 0u : 1u));
+              if (prm.nacc_per_dh == 2) {
+                const uint64_t ad2 = ((uint64_t)a_hi << 32) | (uint64_t)(ar + 2 * rowa16);
+                tc::mma_f16_ss_elect(tmem_base + (dh * 2 + 1) * JT, ad2, bd, idesc, (kk != 0) ? 1u : (first ? 0u : 1u));
+              }
+            }
+          }
+          first = 0;
+          tc::mma_commit_elect(&empty_bar[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        tc::mma_commit_elect(tfull_bar);
+        tphase ^= 1;
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const int chunk = row / cin, ci = row % cin;              // chunk = dw offset inside an accumulator
+    uint32_t tphase = 0;
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+      const int jt = task % nj;
+      tc::mbar_wait(tfull_bar, tphase);
+      tc::fence_after_sync();
+      for (int a = 0; a < nacc; ++a) {
+        const int dh = a / prm.nacc_per_dh;
+        const int dwp = chunk + (prm.nacc_per_dh == 2 ? 2 * (a % 2) : 0);
+        const bool live = dwp < 3;
+        float* out = prm.dw + ((long long)((dh * 3 + (live ? dwp : 0)) * cin + ci)) * prm.cout + jt * JT;
+        for (int c0 = 0; c0 < JT; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + a * JT + c0, v);
+          if (live) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(out + c0 + i, v[i]);
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tempty_bar);
+      tphase ^= 1;
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -273,11 +430,77 @@ int b2u_tc_convt_wgrad_ok(int cin, int cout, int ldx, int lddy) {
 }
 
 // dw[t][ci][co] += sum_p x[p + off_t][ci] * dy[p][co];  db[co] += sum_p dy[p][co]
+int g_b2u_wgrad_halo = 1;
+bool g_attr_h = false;
+
+static int wgrad_halo(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, int n, int h, int wd,
+                      void* stream) {
+  WhParams p{};
+  p.N = n; p.H = h; p.W = wd; p.cin = cin; p.cout = cout; p.dw = dw;
+  p.nacc_per_dh = cin == 64 ? 2 : 1;
+  const int nacc = 3 * p.nacc_per_dh;
+  int jt = cout <= 128 ? cout : 128;
+  while (nacc * jt > 512 || cout % jt) jt -= 16;
+  B2U_REQUIRE(jt >= 16, "tc_wgrad_halo: no N tile for cout=%d", cout);
+  p.JT = jt;
+  p.KSB = ks_for(jt);
+  const size_t a_stride = ((size_t)180 * cin * 2 + 1023) & ~(size_t)1023, b_bytes = (size_t)jt * 256;
+  const size_t tailb = 256;
+  // two CTAs per SM (two MMA issuers) when both fit TMEM (512 columns per SM) -- else one CTA with a deep ring
+  int cols = 32;
+  while (cols < nacc * jt) cols <<= 1;
+  const int per_sm = cols <= 256 ? 2 : 1;
+  const size_t cap = per_sm == 2 ? 108 * 1024 : 216 * 1024;
+  int st = (int)((cap - 1024 - tailb) / (a_stride + b_bytes));
+  if (st > 8) st = 8;
+  B2U_REQUIRE(st >= 2, "tc_wgrad_halo: tiles do not fit (cin=%d cout=%d)", cin, cout);
+  p.stages = st;
+  const size_t smem = 1024 + (size_t)st * (a_stride + b_bytes) + tailb;
+  const int nblocks = n * b2u_cdiv(h, 16) * b2u_cdiv(wd, 8);
+  const int nj = cout / jt;
+  int ns = (per_sm * B2U_NUM_SMS + nj - 1) / nj;
+  if (ns > nblocks) ns = nblocks;
+  if (ns < 1) ns = 1;
+  p.nsplit = ns;
+  WhMaps maps;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)wd * ldx * 2, (cuuint64_t)h * wd * ldx * 2};
+    cuuint32_t box[4] = {(cuuint32_t)cin, 10, 18, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUtensorMapSwizzle sw = cin == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cin == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = g_enc(&maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b2u_set_error("tc_wgrad_halo: x tensor map failed (%d)", (int)r); return B2U_ERR_CUDA; }
+    cuuint64_t bd[4] = {(cuuint64_t)cout, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t bs[3] = {(cuuint64_t)lddy * 2, (cuuint64_t)wd * lddy * 2, (cuuint64_t)h * wd * lddy * 2};
+    cuuint32_t bb[4] = {(cuuint32_t)p.KSB, 8, 16, 1};
+    CUtensorMapSwizzle swb = p.KSB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.KSB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    r = g_enc(&maps.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(dy), bd, bs, bb, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swb, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b2u_set_error("tc_wgrad_halo: dy tensor map failed (%d)", (int)r); return B2U_ERR_CUDA; }
+  }
+  if (!g_attr_h) {
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    g_attr_h = true;
+  }
+  const int ntasks = ns * nj;
+  const int grid = ntasks < per_sm * B2U_NUM_SMS ? ntasks : per_sm * B2U_NUM_SMS;
+  B2U_LAUNCH(tc_wgrad_halo_kernel, grid, kThreadsW, smem, stream, maps, p);
+  return B2U_OK;
+}
+
 int b2u_tc_conv3x3_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* db,
                          int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
   (void)ws; (void)ws_bytes;
   int rc = get_enc();
   if (rc != B2U_OK) return rc;
+  if (g_b2u_wgrad_halo && (cin == 16 || cin == 32 || cin == 64) && cout % 16 == 0) {
+    rc = wgrad_halo(x, ldx, cin, dy, lddy, cout, dw, n, h, wd, stream);
+    if (rc != B2U_OK) return rc;
+    if (db != nullptr) return b2u_channel_sum_f16(dy, lddy, cout, (long long)n * h * wd, db, stream);
+    return B2U_OK;
+  }
   WgParams p{};
   p.N = n; p.H = h; p.W = wd;
   p.KSA = cin >= 128 ? 64 : ks_for(cin);
