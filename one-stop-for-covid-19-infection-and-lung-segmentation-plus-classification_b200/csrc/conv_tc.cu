@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
   float* s_stats = s_bias + prm.J;                         // [2*J]
   (void)stage_bytes;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (role dispatch)
+  const int lane = threadIdx.x & 31;
   const int tiles_w = (prm.W + kTileW - 1) / kTileW, tiles_h = (prm.H + kTileH - 1) / kTileH;
   const int nj = prm.J / JT;
   const unsigned ntiles = (unsigned)(prm.N * tiles_h * tiles_w * nj);   // host guarantees < 2^31

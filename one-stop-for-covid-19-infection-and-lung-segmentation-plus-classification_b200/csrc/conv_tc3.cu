@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 15) & ~(uintptr_t)15);
   float* s_stats = s_bias + prm.J;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (role dispatch)
+  const int lane = threadIdx.x & 31;
   const int tiles_w = (prm.W + kTW - 1) / kTW, tiles_h = (prm.H + kTH - 1) / kTH;
   const int nj = prm.J / JT;
   const int ntiles = prm.N * tiles_h * tiles_w * nj;          // host guarantees < 2^31

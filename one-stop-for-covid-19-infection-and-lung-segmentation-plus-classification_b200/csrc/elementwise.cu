@@ -60,7 +60,29 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const T* __restrict
 #pragma unroll
       for (int i = 0; i < 8; ++i) { mu[i] = mean[g * 8 + i]; is[i] = invstd[g * 8 + i]; }
     }
-    for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
+    // 4 pixels per trip: 4 (stats) or 8 (backward) independent 16-byte loads in flight per thread
+    const long long stride = (long long)gridDim.x * lanes;
+    long long p = (long long)blockIdx.x * lanes + lane;
+    for (; p + 3 * stride < npix; p += 4 * stride) {
+      float v[4][8], xv[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8<T>(a + (p + u * stride) * lda + g * 8, v[u]);
+      if (kBwd) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8<T>(x + (p + u * stride) * ldx + g * 8, xv[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (kBwd) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s1[i] += v[u][i]; s2[i] += v[u][i] * ((xv[u][i] - mu[i]) * is[i]); }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s1[i] += v[u][i]; s2[i] += v[u][i] * v[u][i]; }
+        }
+      }
+    }
+    for (; p < npix; p += stride) {
       float v[8];
       load8<T>(a + p * lda + g * 8, v);
       if (kBwd) {
@@ -647,7 +669,7 @@ extern "C" int b2u_bn_stats(int dt, const void* x, int ldx, int c, long long npi
   REQ_VEC8(c);
   B2U_REQUIRE(c <= 2048 && ldx % 8 == 0 && aligned16(x), "bn_stats: c<=2048, ld%%8==0, 16B-aligned base required");
   int lanes = kThreads / (c / 8);
-  int grid = stream_grid(npix, lanes, 4);
+  int grid = stream_grid((npix + 3) / 4, lanes, 8);
   size_t smem = 2 * (size_t)c * sizeof(double);
   DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, false>), grid, kThreads, smem, stream, (const T*)x, ldx,
                             (const T*)nullptr, 0, c, npix, (const float*)nullptr, (const float*)nullptr, sums));
@@ -680,7 +702,7 @@ extern "C" int b2u_bn_bwd_reduce(int dt, const void* dy, int lddy, const void* x
   REQ_VEC8(c);
   B2U_REQUIRE(c <= 2048 && ldx % 8 == 0 && lddy % 8 == 0 && aligned16(x) && aligned16(dy), "bn_bwd_reduce: alignment");
   int lanes = kThreads / (c / 8);
-  int grid = stream_grid(npix, lanes, 4);
+  int grid = stream_grid((npix + 3) / 4, lanes, 8);
   size_t smem = 2 * (size_t)c * sizeof(double);
   DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, true>), grid, kThreads, smem, stream, (const T*)dy, lddy,
                             (const T*)x, ldx, c, npix, save_mean, save_invstd, sums));

@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) tc_wgrad_kernel(const __grid_con
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (role dispatch)
+  const int lane = threadIdx.x & 31;
   const int tiles_w = (prm.W + kTileW - 1) / kTileW, tiles_h = (prm.H + kTileH - 1) / kTileH;
   const int nblocks = prm.N * tiles_h * tiles_w;             // K blocks of 128 pixels
   const int nj = prm.J / JT;
@@ -219,7 +220,8 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
   uint64_t* tempty_bar = tfull_bar + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (role dispatch)
+  const int lane = threadIdx.x & 31;
   const int tiles_w = (prm.W + 7) / 8, tiles_h = (prm.H + 15) / 16;
   const int nblocks = prm.N * tiles_h * tiles_w;
   const int nj = prm.cout / JT;

@@ -172,7 +172,7 @@ def test_graph_replay_matches_eager_training(precision):
         outs.append((np.array(losses), eng.get_weights()))
         eng.close()
     # atomics make the reduction order run-dependent: compare with a tolerance, not bit-for-bit
-    assert np.allclose(outs[0][0], outs[1][0], rtol=2e-3 if precision == "float16" else 1e-4)
+    assert np.allclose(outs[0][0], outs[1][0], rtol=1e-2 if precision == "float16" else 1e-4)
     for k in outs[0][1]:
         # Adam turns noise-level gradients (atomics -> run-dependent rounding) into +-lr sized updates
         assert np.abs(outs[0][1][k] - outs[1][1][k]).max() < 2 * 3 * 5e-4 + 1e-6, k
