@@ -30,6 +30,16 @@ UNIT = "slices/s"
 SIZE, BATCH = 512, 8
 # algorithmic train FLOP per 512x512 slice = 2*(3*sum(MAC) - MAC_firstconv), conv/convT only
 TRAIN_FLOP_PER_SLICE = 288652001280
+GRAPH = "unet"
+# other BASELINE.json configs (parity-test cases, selectable for side measurements; the driver's line is unet512)
+WORKLOADS = {
+    "unet512": dict(graph="unet", size=512, batch=8, flop=288652001280, metric=METRIC,
+                    name="Task-1 U-Net 512x512x1 train step, batch 8 per GPU (BASELINE configs[1])"),
+    "unet256": dict(graph="unet", size=256, batch=32, flop=72163000320, metric="CT-slices/sec U-Net 256x256 train step",
+                    name="Task-3 lung U-Net 256x256x1 train step, batch 32 per GPU (BASELINE configs[2])"),
+    "unetpp512": dict(graph="unetpp", size=512, batch=4, flop=418306326528, metric="CT-slices/sec U-Net++ 512x512 train step",
+                      name="Task-1 U-Net++ 512x512x1 train step, batch 4 per GPU (BASELINE configs[3])"),
+}
 
 
 def load_peaks():
@@ -88,13 +98,13 @@ def cpu_port_rate(steps, warmup, budget_s, batch):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     x, t = S.make_slices(batch, SIZE, seed=1234)
-    params, _ = K.init_params("unet", (SIZE, SIZE, 1), seed=42)
+    params, _ = K.init_params(GRAPH, (SIZE, SIZE, 1), seed=42)
     opt = K.Adam(lr=5e-4)
     times = []
     t_begin = time.perf_counter()
     for s in range(warmup + steps):
         t0 = time.perf_counter()
-        K.train_step("unet", params, opt, x, t, dtype=torch.float32, dropout=dict(seed=7, step=s))
+        K.train_step(GRAPH, params, opt, x, t, dtype=torch.float32, dropout=dict(seed=7, step=s))
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
@@ -172,7 +182,7 @@ def run_engine(args):
         comm = E.Comm(rank, world)
     peaks = load_peaks()
     precision = args.precision
-    model = M.Model(graph=G.unet(SIZE, 1), precision=precision, comm=comm, use_graph=not args.no_graph, seed=42)
+    model = M.Model(graph=G.GRAPHS[GRAPH](SIZE, 1), precision=precision, comm=comm, use_graph=not args.no_graph, seed=42)
     model.compile(optimizer=M.Adam(lr=0.0005), loss=LS.bce_dice_loss, metrics=[LS.dice_coeff])
     eng = model.engine
     # device-resident synthetic dataset: 4 batches per rank, per-rank seed
@@ -301,7 +311,7 @@ def run_engine(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16" if precision == "float16" else "f32", "data": "synthetic",
-            "config": {"workload": "Task-1 U-Net 512x512x1 train step, batch %d per GPU (BASELINE configs[1])" % BATCH,
+            "config": {"workload": WORKLOADS[args.workload]["name"],
                        "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                        "precision": "fp16 storage / fp32 accumulate (tcgen05), fp32 params+Adam" if precision == "float16" else "fp32",
                        "l2": "per-step working set (activations + gradients, several GB) exceeds the 126 MB L2",
@@ -331,8 +341,12 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--per-op", action="store_true", help="add per-op device times to op_breakdown_ms")
+    ap.add_argument("--workload", default="unet512", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global METRIC, SIZE, BATCH, TRAIN_FLOP_PER_SLICE, GRAPH
+    wl = WORKLOADS[args.workload]
+    METRIC, SIZE, BATCH, TRAIN_FLOP_PER_SLICE, GRAPH = wl["metric"], wl["size"], wl["batch"], wl["flop"], wl["graph"]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -201,12 +201,15 @@ __global__ void __launch_bounds__(256) conv3x3_c1_wgrad_kernel(const T* __restri
                                                                const T* __restrict__ dy, int lddy,
                                                                float* __restrict__ dw, float* __restrict__ db, int N,
                                                                int H, int W) {
-  // thread = (pixel lane, 8-channel group); registers: 9 taps x 8 channels + 8 bias sums
+  // block = 8 x 32 pixel tiles (grid-stride); thread = (pixel lane, 8-channel group); the x halo of the tile is
+  // staged in shared memory, dy streams straight from HBM in 16-byte pieces; 9 taps x 8 channels (+ bias) of the
+  // gradient accumulate in registers over all tiles of the block and are reduced once at the end.
   constexpr int CG = COUT / 8;
   constexpr int LANES = 256 / CG;
+  constexpr int TH1 = 8, TW1 = 32;
+  __shared__ float xs[TH1 + 2][TW1 + 2 + 1];
   __shared__ float sacc[10 * COUT];
   for (int i = threadIdx.x; i < 10 * COUT; i += 256) sacc[i] = 0.f;
-  __syncthreads();
   const int g = threadIdx.x % CG, lane = threadIdx.x / CG;
   float acc[9][8], accb[8];
 #pragma unroll
@@ -215,28 +218,37 @@ __global__ void __launch_bounds__(256) conv3x3_c1_wgrad_kernel(const T* __restri
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[t][k] = 0.f;
   }
-  const long long npix = (long long)N * H * W;
-  for (long long p = (long long)blockIdx.x * LANES + lane; p < npix; p += (long long)gridDim.x * LANES) {
-    const int wwp = (int)(p % W);
-    const long long tq = p / W;
-    const int hh = (int)(tq % H);
-    float d[8];
-    load8<T>(dy + p * lddy + g * 8, d);
+  const int tiles_w = (W + TW1 - 1) / TW1, tiles_h = (H + TH1 - 1) / TH1;
+  const int ntiles = N * tiles_h * tiles_w;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int h0 = th * TH1, w0 = tw * TW1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (TH1 + 2) * (TW1 + 2); i += 256) {
+      const int rr = i / (TW1 + 2), cc = i % (TW1 + 2), hh = h0 + rr - 1, wwp = w0 + cc - 1;
+      float v = 0.f;
+      if (hh >= 0 && hh < H && wwp >= 0 && wwp < W) v = ldf<T>(x + (((long long)n * H + hh) * W + wwp) * ldx);
+      xs[rr][cc] = v;
+    }
+    __syncthreads();
+    for (int pp = lane; pp < TH1 * TW1; pp += LANES) {
+      const int r = pp / TW1, c = pp % TW1;
+      if (h0 + r >= H || w0 + c >= W) continue;
+      float d[8];
+      load8<T>(dy + (((long long)n * H + h0 + r) * W + w0 + c) * lddy + g * 8, d);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) accb[k] += d[k];
+      for (int k = 0; k < 8; ++k) accb[k] += d[k];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int dh = t / 3 - 1, dwp = t % 3 - 1;
-      float xv = 0.f;
-      if (hh + dh >= 0 && hh + dh < H && wwp + dwp >= 0 && wwp + dwp < W)
-        xv = ldf<T>(x + (p + (long long)dh * W + dwp) * ldx);
+      for (int t = 0; t < 9; ++t) {
+        const float xv = xs[r + t / 3][c + t % 3];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(xv, d[k], acc[t][k]);
+        for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(xv, d[k], acc[t][k]);
+      }
     }
   }
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    // lanes of a warp that share g: reduce across the warp first (stride CG lanes share a group)
     float vb = accb[k];
     for (int o = 16; o >= CG; o >>= 1) vb += __shfl_xor_sync(0xffffffffu, vb, o);
     if ((threadIdx.x & 31) < CG) atomicAdd(&sacc[9 * COUT + g * 8 + k], vb);
@@ -545,10 +557,8 @@ int b2u_direct_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const void
                              float* db, int n, int h, int wd, void* stream) {
   B2U_REQUIRE(n > 0 && h > 0 && wd > 0 && cin > 0 && cout > 0, "conv3x3_wgrad: empty shape");
   if (cin == 1 && lddy % 8 == 0 && (cout == 32 || cout == 16)) {
-    long long npix = (long long)n * h * wd;
-    int lanes = 256 / (cout / 8);
-    long long gl = (npix + lanes - 1) / lanes;
-    int grid1 = (int)(gl < 4 * B2U_NUM_SMS ? gl : 4 * B2U_NUM_SMS);
+    long long gl = (long long)n * b2u_cdiv(h, 8) * b2u_cdiv(wd, 32);
+    int grid1 = (int)(gl < 6 * B2U_NUM_SMS ? gl : 6 * B2U_NUM_SMS);
     if (cout == 32) { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_wgrad_kernel<T, 32>), grid1, 256, 0, stream, (const T*)x, ldx, (const T*)dy, lddy, dw, db, n, h, wd)); }
     else { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_wgrad_kernel<T, 16>), grid1, 256, 0, stream, (const T*)x, ldx, (const T*)dy, lddy, dw, db, n, h, wd)); }
     return B2U_OK;

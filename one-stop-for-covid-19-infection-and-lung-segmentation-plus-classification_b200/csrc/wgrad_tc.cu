@@ -169,8 +169,10 @@ __global__ void __launch_bounds__(kThreadsW, 1) tc_wgrad_kernel(const __grid_con
         float v[16];
         tc::tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * JT + c0, v);
         if (live) {
+// 16-byte vector reductions (red.global.add.v4.f32): 4 L2 atomic operations instead of 16
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(out + c0 + i, v[i]);
+          for (int i = 0; i < 16; i += 4)
+            atomicAdd(reinterpret_cast<float4*>(out + c0 + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
         }
       }
       tc::fence_before_sync();
@@ -325,8 +327,10 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
           float v[16];
           tc::tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + a * JT + c0, v);
           if (live) {
+// 16-byte vector reductions (red.global.add.v4.f32): 4 L2 atomic operations instead of 16
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(out + c0 + i, v[i]);
+            for (int i = 0; i < 16; i += 4)
+              atomicAdd(reinterpret_cast<float4*>(out + c0 + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
           }
         }
       }
@@ -415,13 +419,12 @@ int b2u_channel_sum_f16(const void* dy, int lddy, int c, long long npix, float* 
 
 int b2u_tc_wgrad_ok(int cin, int cout, int ldx, int lddy) {
   if (ks_for(cin) == 0 || ks_for(cout) == 0 || ldx % 8 || lddy % 8 || cout % 16) return 0;
+  // row groups pack (tap, channel-slab) chunks of KSA channels, 128 rows per group; any Cin that is a multiple of
+  // its slab width works (96 -> 3 slabs of 32, 192 -> 3 slabs of 64: U-Net++ concat widths)
   const int ksa = cin >= 128 ? 64 : ks_for(cin);
-  if (cin >= 128 && cin % 128) return 0;
-  if (cin < 128 && 128 % cin) return 0;
-  const int taps_per_group = cin >= 128 ? 1 : 128 / cin;
-  const int groups = cin >= 128 ? 9 * (cin / 128) : (9 + taps_per_group - 1) / taps_per_group;
-  (void)ksa;
-  return groups <= kMaxGroups;
+  if (cin % ksa) return 0;
+  const int chunks = 9 * (cin / ksa), per_group = 128 / ksa;
+  return (chunks + per_group - 1) / per_group <= kMaxGroups;
 }
 int b2u_tc_convt_wgrad_ok(int cin, int cout, int ldx, int lddy) {
   if (ks_for(cin) == 0 || ks_for(cout) == 0 || ldx % 8 || lddy % 8 || cin % 16) return 0;

@@ -119,6 +119,11 @@ class Engine:
         self.set_weights(init_weights(graph, seed))
         if self.comm is not None:
             self.broadcast_weights()
+            # NCCL connects its transports lazily at the first collective; that must not happen inside a CUDA
+            # graph capture, so run one eager all-reduce of the real gradient buffer (zeros) now
+            _lib.check(self.lib.b2u_allreduce(self.comm.handle, C.c_void_p(self.grads.data_ptr()), npar, 0,
+                                              C.c_void_p(self.stream.cuda_stream)), "allreduce warm-up")
+            self.stream.synchronize()
 
     # ---------------------------------------------------------------------------------------
     # step state

@@ -110,3 +110,15 @@ def test_tc_convt_wgrad(n, h, w, cin, cout):
     db = img.farr(img.gr, cout, scale=0.01)
     ops = [P.Op(P.OP_CONVT_WGRAD, dt, [x.ref, dy.ref, dw, db], [x.ld, cin, dy.ld, cout, n, h, w])]
     compare(ops, img, dt, tol=3e-3)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 32, 32, 96, 32), (1, 16, 24, 192, 64), (2, 16, 16, 128, 32)])
+def test_tc_wgrad_unetpp_concat_widths(n, h, w, cin, cout):
+    """U-Net++ level-1/2 'a' convs see 96- and 192-channel concat inputs (UPP:905, 919)"""
+    img = Img(33)
+    x = img.view(n, h, w, cin, dt, fill="uniform")
+    dy = img.view(n, h, w, cout, dt, scale=0.5)
+    dw = img.farr(img.gr, 9 * cin * cout, scale=0.01)
+    db = img.farr(img.gr, cout, scale=0.01)
+    ops = [P.Op(P.OP_CONV3X3_WGRAD, dt, [x.ref, dy.ref, dw, db], [x.ld, cin, dy.ld, cout, n, h, w])]
+    compare(ops, img, dt, tol=3e-3)
