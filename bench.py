@@ -327,8 +327,13 @@ def run_engine(args):
         }
         print(json.dumps(line))
     if world > 1:
-        comm.close()
-        torch.distributed.destroy_process_group()
+        # leave together and without running NCCL / process-group destructors (a rank that tears its communicator
+        # down while a peer is still inside one would hang the launcher until its timeout)
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -60,19 +60,21 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const T* __restrict
 #pragma unroll
       for (int i = 0; i < 8; ++i) { mu[i] = mean[g * 8 + i]; is[i] = invstd[g * 8 + i]; }
     }
-    // 4 pixels per trip: 4 (stats) or 8 (backward) independent 16-byte loads in flight per thread
-    const long long stride = (long long)gridDim.x * lanes;
-    long long p = (long long)blockIdx.x * lanes + lane;
-    for (; p + 3 * stride < npix; p += 4 * stride) {
-      float v[4][8], xv[4][8];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) load8<T>(a + (p + u * stride) * lda + g * 8, v[u]);
+    // two pixel groups per trip, both inside one contiguous span of the block (coalesced, 2-4 loads in flight)
+    const long long stride = (long long)gridDim.x * lanes * 2;
+    for (long long p = (long long)blockIdx.x * lanes * 2 + lane; p < npix; p += stride) {
+      const long long p2 = p + lanes;                       // the block covers 2*lanes contiguous pixels per trip
+      const bool two = p2 < npix;
+      float v[2][8], xv[2][8];
+      load8<T>(a + p * lda + g * 8, v[0]);
+      if (two) load8<T>(a + p2 * lda + g * 8, v[1]);
       if (kBwd) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) load8<T>(x + (p + u * stride) * ldx + g * 8, xv[u]);
+        load8<T>(x + p * ldx + g * 8, xv[0]);
+        if (two) load8<T>(x + p2 * ldx + g * 8, xv[1]);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
         if (kBwd) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) { s1[i] += v[u][i]; s2[i] += v[u][i] * ((xv[u][i] - mu[i]) * is[i]); }
@@ -80,19 +82,6 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const T* __restrict
 #pragma unroll
           for (int i = 0; i < 8; ++i) { s1[i] += v[u][i]; s2[i] += v[u][i] * v[u][i]; }
         }
-      }
-    }
-    for (; p < npix; p += stride) {
-      float v[8];
-      load8<T>(a + p * lda + g * 8, v);
-      if (kBwd) {
-        float xv[8];
-        load8<T>(x + p * ldx + g * 8, xv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { s1[i] += v[i]; s2[i] += v[i] * ((xv[i] - mu[i]) * is[i]); }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { s1[i] += v[i]; s2[i] += v[i] * v[i]; }
       }
     }
 #pragma unroll
@@ -669,7 +658,7 @@ extern "C" int b2u_bn_stats(int dt, const void* x, int ldx, int c, long long npi
   REQ_VEC8(c);
   B2U_REQUIRE(c <= 2048 && ldx % 8 == 0 && aligned16(x), "bn_stats: c<=2048, ld%%8==0, 16B-aligned base required");
   int lanes = kThreads / (c / 8);
-  int grid = stream_grid((npix + 3) / 4, lanes, 8);
+  int grid = stream_grid((npix + 1) / 2, lanes, 8);
   size_t smem = 2 * (size_t)c * sizeof(double);
   DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, false>), grid, kThreads, smem, stream, (const T*)x, ldx,
                             (const T*)nullptr, 0, c, npix, (const float*)nullptr, (const float*)nullptr, sums));
@@ -702,7 +691,7 @@ extern "C" int b2u_bn_bwd_reduce(int dt, const void* dy, int lddy, const void* x
   REQ_VEC8(c);
   B2U_REQUIRE(c <= 2048 && ldx % 8 == 0 && lddy % 8 == 0 && aligned16(x) && aligned16(dy), "bn_bwd_reduce: alignment");
   int lanes = kThreads / (c / 8);
-  int grid = stream_grid((npix + 3) / 4, lanes, 8);
+  int grid = stream_grid((npix + 1) / 2, lanes, 8);
   size_t smem = 2 * (size_t)c * sizeof(double);
   DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, true>), grid, kThreads, smem, stream, (const T*)dy, lddy,
                             (const T*)x, ldx, c, npix, save_mean, save_invstd, sums));
