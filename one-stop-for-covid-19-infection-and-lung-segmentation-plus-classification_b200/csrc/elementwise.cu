@@ -46,8 +46,10 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const T* __restrict
                                                              const float* __restrict__ invstd,
                                                              double* __restrict__ sums) {
   // kBwd == false: a = x (stats of a).  kBwd == true: a = dy, x = bn input; sums of dy and dy*xhat.
-  extern __shared__ double sacc[];   // [2*C]
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.0;
+  // block-level partial sums in fp32 (native shared-memory atomics; fp64 shared atomics are CAS loops and
+  // cost more than the streaming loop), one fp64 global atomic per channel per block
+  extern __shared__ float sacc[];   // [2*C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
   const int cg = C >> 3;
   const int lanes = kThreads / cg;              // pixel lanes per block
@@ -86,12 +88,12 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const T* __restrict
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sacc[g * 8 + i], (double)s1[i]);
-      atomicAdd(&sacc[C + g * 8 + i], (double)s2[i]);
+      atomicAdd(&sacc[g * 8 + i], s1[i]);
+      atomicAdd(&sacc[C + g * 8 + i], s2[i]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], sacc[i]);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)sacc[i]);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long count,
@@ -658,8 +660,8 @@ extern "C" int b2u_bn_stats(int dt, const void* x, int ldx, int c, long long npi
   REQ_VEC8(c);
   B2U_REQUIRE(c <= 2048 && ldx % 8 == 0 && aligned16(x), "bn_stats: c<=2048, ld%%8==0, 16B-aligned base required");
   int lanes = kThreads / (c / 8);
-  int grid = stream_grid((npix + 1) / 2, lanes, 8);
-  size_t smem = 2 * (size_t)c * sizeof(double);
+  int grid = stream_grid((npix + 1) / 2, lanes, 4);
+  size_t smem = 2 * (size_t)c * sizeof(float);
   DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, false>), grid, kThreads, smem, stream, (const T*)x, ldx,
                             (const T*)nullptr, 0, c, npix, (const float*)nullptr, (const float*)nullptr, sums));
   return B2U_OK;
@@ -691,8 +693,8 @@ extern "C" int b2u_bn_bwd_reduce(int dt, const void* dy, int lddy, const void* x
   REQ_VEC8(c);
   B2U_REQUIRE(c <= 2048 && ldx % 8 == 0 && lddy % 8 == 0 && aligned16(x) && aligned16(dy), "bn_bwd_reduce: alignment");
   int lanes = kThreads / (c / 8);
-  int grid = stream_grid((npix + 1) / 2, lanes, 8);
-  size_t smem = 2 * (size_t)c * sizeof(double);
+  int grid = stream_grid((npix + 1) / 2, lanes, 4);
+  size_t smem = 2 * (size_t)c * sizeof(float);
   DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, true>), grid, kThreads, smem, stream, (const T*)dy, lddy,
                             (const T*)x, ldx, c, npix, save_mean, save_invstd, sums));
   return B2U_OK;

@@ -42,24 +42,34 @@ p = {k: v.copy() for k, v in params0.items()}
 opt = K.Adam(lr=5e-4)
 step = 0
 for ep in range(epochs):
+    ep_stats = []
     for lo in range(0, len(xtr), batch):
-        K.train_step("unet", p, opt, xtr[lo:lo + batch], ttr[lo:lo + batch], dtype=torch.float32, dropout=dict(seed=7, step=step))
+        l_, d_ = K.train_step("unet", p, opt, xtr[lo:lo + batch], ttr[lo:lo + batch], dtype=torch.float32, dropout=dict(seed=7, step=step))
+        ep_stats.append((l_, d_, len(xtr[lo:lo + batch])))
         step += 1
+w_ = np.array([a[2] for a in ep_stats], float)
+o_train_loss = float((np.array([a[0] for a in ep_stats]) * w_).sum() / w_.sum())
+o_train_dice = float((np.array([a[1] for a in ep_stats]) * w_).sum() / w_.sum())
 pv, _ = K.forward("unet", p, xva, training=False, dtype=torch.float32)
 res["oracle_cpu_fp32"] = dict(val_dice=float(K.dice_coeff(torch.from_numpy(tva).double(), torch.from_numpy(pv).double())),
-                              best_thr_dice=float(best_dice(tva, pv)), seconds=time.time() - t0)
-for prec in ("float32", "float16"):
+                              best_thr_dice=float(best_dice(tva, pv)), train_loss=o_train_loss, train_dice=o_train_dice,
+                              seconds=time.time() - t0)
+arms = [("float32", 7), ("float16", 7)] + [("float16", int(sd)) for sd in os.environ.get("EXTRA_SEEDS", "").split(",") if sd] \
+    + [("float32", int(sd)) for sd in os.environ.get("EXTRA_SEEDS", "").split(",") if sd]
+for prec, dseed in arms:
     t0 = time.time()
-    m = M.Model(graph=G.unet(size, 1), precision=prec, dropout_seed=7)
+    m = M.Model(graph=G.unet(size, 1), precision=prec, dropout_seed=dseed)
     m.set_weights_dict(params0)
     m.compile(optimizer=M.Adam(lr=0.0005), loss=LS.bce_dice_loss, metrics=[LS.dice_coeff])
     h = m.fit(xtr, ttr, batch_size=batch, epochs=epochs, validation_data=(xva, tva), shuffle=False, verbose=0)
     pr = m.predict(xva, batch_size=batch)
-    res["engine_" + prec] = dict(val_dice=float(h.history["val_dice_coeff"][-1]), best_thr_dice=float(best_dice(tva, pr)),
-                                 train_loss=float(h.history["loss"][-1]), seconds=time.time() - t0)
+    res["engine_" + prec + ("" if dseed == 7 else "_dropseed%d" % dseed)] = dict(val_dice=float(h.history["val_dice_coeff"][-1]), best_thr_dice=float(best_dice(tva, pr)),
+                                 train_loss=float(h.history["loss"][-1]), train_dice=float(h.history["dice_coeff"][-1]),
+                                 seconds=time.time() - t0)
 o = res["oracle_cpu_fp32"]
-for prec in ("float32", "float16"):
-    e = res["engine_" + prec]
+for key in [k for k in res if k.startswith("engine_")]:
+    e = res[key]
     e["delta_val_dice_pt"] = 100 * (e["val_dice"] - o["val_dice"])
     e["delta_best_dice_pt"] = 100 * (e["best_thr_dice"] - o["best_thr_dice"])
+    e["delta_train_dice_pt"] = 100 * (e["train_dice"] - o["train_dice"])
 print(json.dumps(res))
