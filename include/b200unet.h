@@ -81,8 +81,11 @@ int b2u_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, i
 
 /* ---- Conv2DTranspose 2x2 stride 2 (T1H:886, 893, 900, 907; UPP:890 ...) --------------------- */
 /* y[n,2i+a,2j+b,co] = sum_ci x[n,i,j,ci] * w[a,b,co,ci] + bias[co]; (h,wd) are INPUT dims */
+/* stats != NULL: also accumulate per-channel sum / sum-of-squares of y for a following BatchNormalization
+ * (stats[c] += sum, stats[stats_sq_off + c] += sum of squares; the BN may span a wider concat buffer) */
 int b2u_convt2x2_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias,
-                     void* y, int ldy, int cout, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+                     void* y, int ldy, int cout, double* stats, int stats_sq_off, int n, int h, int wd,
+                     void* ws, size_t ws_bytes, void* stream);
 int b2u_convt2x2_dgrad(int dt, const void* dy, int lddy, int cout, const float* w,
                        void* dx, int lddx, int cin, const void* mask, int ldmask, int mask_act,
                        int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
@@ -96,8 +99,10 @@ int b2u_bn_stats(int dt, const void* x, int ldx, int c, long long npix, double* 
 int b2u_bn_finalize(const double* sums, long long count, const float* gamma, const float* beta,
                     float* moving_mean, float* moving_var, float momentum, float eps, int training,
                     float* scale, float* shift, float* save_mean, float* save_invstd, int c, void* stream);
+/* out_stats != NULL: also accumulate sum / sum-of-squares of the values written to y (the statistics a
+ * BatchNormalization over a concat buffer that contains y needs): out_stats[c], out_stats[out_sq_off + c] */
 int b2u_bn_apply(int dt, const void* x, int ldx, void* y, int ldy, int c, long long npix,
-                 const float* scale, const float* shift, void* stream);
+                 const float* scale, const float* shift, double* out_stats, int out_sq_off, void* stream);
 /* sums[0:c] += sum(dy), sums[c:2c] += sum(dy * xhat) */
 int b2u_bn_bwd_reduce(int dt, const void* dy, int lddy, const void* x, int ldx, int c, long long npix,
                       const float* save_mean, const float* save_invstd, double* sums, void* stream);
@@ -115,7 +120,11 @@ int b2u_maxpool_fwd(int dt, const void* x, int ldx, void* y, int ldy, int c, int
 /* dx[first arg-max of each window] (+)= dy*keep/(1-p), other window elements (+)= 0 */
 int b2u_maxpool_bwd(int dt, const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int c,
                     int n, int h, int wd, float p_drop, int op_id, const b2u_step_state* d_state,
-                    int accumulate, void* stream);
+                    int accumulate, double* bn_sums, const float* bn_gamma, const float* bn_beta, void* stream);
+/* bn_sums != NULL: x is the output of a training-mode BatchNormalization (x = gamma*xhat + beta) and this call
+ * completes its gradient; the kernel then also accumulates that BN's backward statistics from the values it
+ * already holds -- bn_sums[0:c] += sum(dx), bn_sums[c:2c] += sum(dx * xhat), xhat = (x - beta)/gamma -- which
+ * replaces a separate b2u_bn_bwd_reduce pass over dx and the BN input. */
 /* ---- Dropout(p) (UPP:864, 879; T2:777) -------------------------------------------------------- */
 int b2u_dropout_fwd(int dt, const void* x, int ldx, void* y, int ldy, int c, long long npix, float p,
                     int op_id, const b2u_step_state* d_state, void* stream);

@@ -76,7 +76,7 @@ def lib():
     l.b2u_conv3x3_fwd.argtypes = [i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, vp, i32, i32, i32, vp, sz, vp]
     l.b2u_conv3x3_dgrad.argtypes = [i32, vp, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]
     l.b2u_conv3x3_wgrad.argtypes = [i32, vp, i32, i32, vp, i32, i32, vp, vp, i32, i32, i32, vp, sz, vp]
-    l.b2u_convt2x2_fwd.argtypes = [i32, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
+    l.b2u_convt2x2_fwd.argtypes = [i32, vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, vp, sz, vp]
     l.b2u_convt2x2_dgrad.argtypes = [i32, vp, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]
     l.b2u_convt2x2_wgrad.argtypes = [i32, vp, i32, i32, vp, i32, i32, vp, vp, i32, i32, i32, vp, sz, vp]
     l.b2u_adam.argtypes = [vp, vp, vp, vp, i64, vp, vp]

@@ -105,10 +105,13 @@ extern "C" int b2u_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const 
 }
 
 extern "C" int b2u_convt2x2_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, void* y,
-                                int ldy, int cout, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+                                int ldy, int cout, double* stats, int stats_sq_off, int n, int h, int wd, void* ws,
+                                size_t ws_bytes, void* stream) {
   if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_convt_ok(cin, cout, ldx, ldy))
-    return b2u_tc_convt_fwd(x, ldx, cin, w, bias, y, ldy, cout, n, h, wd, ws, ws_bytes, stream);
-  return b2u_direct_convt_fwd(dt, x, ldx, cin, w, bias, y, ldy, cout, n, h, wd, stream);
+    return b2u_tc_convt_fwd(x, ldx, cin, w, bias, y, ldy, cout, stats, stats_sq_off, n, h, wd, ws, ws_bytes, stream);
+  int rc = b2u_direct_convt_fwd(dt, x, ldx, cin, w, bias, y, ldy, cout, n, h, wd, stream);
+  if (rc != B2U_OK || stats == nullptr) return rc;
+  return b2u_bn_stats_off(dt, y, ldy, cout, 4LL * n * h * wd, stats, stats_sq_off, stream);   // exact path: extra pass
 }
 
 extern "C" int b2u_convt2x2_dgrad(int dt, const void* dy, int lddy, int cout, const float* w, void* dx, int lddx,
@@ -149,8 +152,8 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
       return b2u_conv3x3_wgrad(dt, p[0], I(0), I(1), p[1], I(2), I(3), (float*)p[2], (float*)p[3], I(4), I(5), I(6), ws,
                                wsb, s);
     case B2U_OP_CONVT_FWD:
-      return b2u_convt2x2_fwd(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], p[3], I(2), I(3), I(4), I(5),
-                              I(6), ws, wsb, s);
+      return b2u_convt2x2_fwd(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], p[3], I(2), I(3),
+                              (double*)p[4], I(7), I(4), I(5), I(6), ws, wsb, s);
     case B2U_OP_CONVT_DGRAD:
       return b2u_convt2x2_dgrad(dt, p[0], I(0), I(1), (const float*)p[1], p[2], I(2), I(3), p[3], I(4), I(5), I(6), I(7),
                                 I(8), I(9), ws, wsb, s);
@@ -164,7 +167,8 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
                              (float*)p[4], f[0], f[1], I(1), (float*)p[5], (float*)p[6], (float*)p[7], (float*)p[8], I(2),
                              s);
     case B2U_OP_BN_APPLY:
-      return b2u_bn_apply(dt, p[0], I(0), p[1], I(1), I(2), i[3], (const float*)p[2], (const float*)p[3], s);
+      return b2u_bn_apply(dt, p[0], I(0), p[1], I(1), I(2), i[3], (const float*)p[2], (const float*)p[3], (double*)p[4],
+                          I(4), s);
     case B2U_OP_BN_BWD_REDUCE:
       return b2u_bn_bwd_reduce(dt, p[0], I(0), p[1], I(1), I(2), i[3], (const float*)p[2], (const float*)p[3],
                                (double*)p[4], s);
@@ -177,7 +181,7 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
                              (const b2u_step_state*)p[2], s);
     case B2U_OP_MAXPOOL_BWD:
       return b2u_maxpool_bwd(dt, p[0], I(0), p[1], I(1), p[2], I(2), I(3), I(4), I(5), I(6), f[0], I(7),
-                             (const b2u_step_state*)p[3], I(8), s);
+                             (const b2u_step_state*)p[3], I(8), (double*)p[4], (const float*)p[5], (const float*)p[6], s);
     case B2U_OP_DROPOUT_FWD:
       return b2u_dropout_fwd(dt, p[0], I(0), p[1], I(1), I(2), i[3], f[0], I(4), (const b2u_step_state*)p[2], s);
     case B2U_OP_DROPOUT_BWD:

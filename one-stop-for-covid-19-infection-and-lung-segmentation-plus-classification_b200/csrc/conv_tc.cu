@@ -49,7 +49,8 @@ struct TcParams {
   int act;
   const __half* mask; int ldmask; int mask_act;
   int accumulate;
-  double* stats;          // [2*J] or null
+  double* stats;          // sums at stats[c], squares at stats[stats_sq_off + c]; null: none
+  int stats_sq_off;
 };
 
 struct TcMaps {
@@ -267,8 +268,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
             float s1 = transpose_reduce16(q, lane);
             float s2 = transpose_reduce16(sq, lane);
             if (lane < 16) {
-              atomicAdd(&s_stats[j0 + lane], s1);
-              atomicAdd(&s_stats[prm.J + j0 + lane], s2);
+              const int sc = prm.mode == 1 ? (j0 % prm.cout) : j0;       // scatter mode: column -> output channel
+              atomicAdd(&s_stats[sc + lane], s1);
+              atomicAdd(&s_stats[prm.J + sc + lane], s2);
             }
           }
         }
@@ -284,9 +286,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
   __syncthreads();
   tc::fence_after_sync();
   if (prm.stats != nullptr) {
-    for (int i = threadIdx.x; i < 2 * prm.J; i += kThreadsTc) {
-      float s = s_stats[i];
-      if (s != 0.f) atomicAdd(&prm.stats[i], (double)s);
+    const int nstat = prm.mode == 1 ? prm.cout : prm.J;
+    for (int i = threadIdx.x; i < nstat; i += kThreadsTc) {
+      atomicAdd(&prm.stats[i], (double)s_stats[i]);
+      atomicAdd(&prm.stats[prm.stats_sq_off + i], (double)s_stats[prm.J + i]);
     }
   }
   if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
@@ -441,6 +444,7 @@ int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, con
   for (int t = 0; t < 9; ++t) { p.tap_dh[t] = t / 3 - 1; p.tap_dw[t] = t % 3 - 1; p.tap_map[t] = 0; }
   p.mode = 0; p.cout = J; p.y = (__half*)y; p.ldy = ldy; p.bias = bias; p.act = act;
   p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate; p.stats = stats;
+  p.stats_sq_off = J;
   rc = pack(w, ws, ws_bytes, dgrad ? 1 : 0, 9, J, K, stream);
   if (rc != B2U_OK) return rc;
   TcMaps maps;
@@ -453,7 +457,7 @@ int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, con
 }
 
 int b2u_tc_convt_fwd(const void* x, int ldx, int cin, const float* w, const float* bias, void* y, int ldy, int cout,
-                     int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+                     double* stats, int stats_sq_off, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
   int rc = get_encode();
   if (rc != B2U_OK) return rc;
   TcParams p{};
@@ -461,6 +465,7 @@ int b2u_tc_convt_fwd(const void* x, int ldx, int cin, const float* w, const floa
   if (p.JT > cout && p.JT % cout != 0) p.JT = cout;       // a 16-column chunk must not straddle two (a,b) groups
   p.ntaps = 1; p.tap_dh[0] = 0; p.tap_dw[0] = 0; p.tap_map[0] = 0;
   p.mode = 1; p.cout = cout; p.y = (__half*)y; p.ldy = ldy; p.bias = bias; p.act = B2U_ACT_NONE;
+  p.stats = stats; p.stats_sq_off = stats_sq_off;
   rc = pack(w, ws, ws_bytes, 2, 1, 4 * cout, cin, stream);
   if (rc != B2U_OK) return rc;
   TcMaps maps;

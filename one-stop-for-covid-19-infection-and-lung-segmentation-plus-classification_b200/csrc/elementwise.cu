@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const T* __restrict
                                                              const T* __restrict__ x, int ldx, int C,
                                                              long long npix, const float* __restrict__ mean,
                                                              const float* __restrict__ invstd,
-                                                             double* __restrict__ sums) {
+                                                             double* __restrict__ sums, int sq_off) {
   // kBwd == false: a = x (stats of a).  kBwd == true: a = dy, x = bn input; sums of dy and dy*xhat.
   // block-level partial sums in fp32 (native shared-memory atomics; fp64 shared atomics are CAS loops and
   // cost more than the streaming loop), one fp64 global atomic per channel per block
@@ -93,7 +93,10 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const T* __restrict
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)sacc[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&sums[i], (double)sacc[i]);
+    atomicAdd(&sums[sq_off + i], (double)sacc[C + i]);
+  }
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long count,
@@ -132,7 +135,16 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y,
                                                             int ldy, int C, long long npix,
                                                             const float* __restrict__ scale,
-                                                            const float* __restrict__ shift) {
+                                                            const float* __restrict__ shift,
+                                                            double* __restrict__ out_stats, int out_sq_off) {
+  extern __shared__ float sst[];          // [2*C] block partials of the optional output statistics
+  float o1[8], o2[8];
+  if (out_stats != nullptr) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sst[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { o1[k] = 0.f; o2[k] = 0.f; }
+    __syncthreads();
+  }
   float sc[8], sh[8];
   {
     const int g0 = (threadIdx.x % (C >> 3)) * 8;
@@ -145,6 +157,24 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
     store8<T>(y + p * ldy + g * 8, v);
+    if (out_stats != nullptr) {
+      float r[8];
+      load8<T>(y + p * ldy + g * 8, r);      // statistics of the value as stored (fp16 rounding included)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { o1[k] += r[k]; o2[k] = fmaf(r[k], r[k], o2[k]); }
+    }
+  }
+  if (out_stats != nullptr) {
+    const int g0 = (threadIdx.x % (C >> 3)) * 8;
+    if (threadIdx.x / (C >> 3) < kThreads / (C >> 3)) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { atomicAdd(&sst[g0 + k], o1[k]); atomicAdd(&sst[C + g0 + k], o2[k]); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      atomicAdd(&out_stats[i], (double)sst[i]);
+      atomicAdd(&out_stats[out_sq_off + i], (double)sst[C + i]);
+    }
   }
 }
 
@@ -244,7 +274,24 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const T* __restri
                                                                T* __restrict__ dx, int lddx, int C, int N, int H,
                                                                int W, float p_drop, int op_id,
                                                                const b2u_step_state* __restrict__ st,
-                                                               int accumulate) {
+                                                               int accumulate, double* __restrict__ bn_sums,
+                                                               const float* __restrict__ bn_gamma,
+                                                               const float* __restrict__ bn_beta) {
+  extern __shared__ float sbn[];          // [2*C] block partials of the fused BN-backward statistics
+  float rg[8], bt[8], t1[8], t2[8];
+  if (bn_sums != nullptr) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sbn[i] = 0.f;
+    const int g0 = (threadIdx.x % (C >> 3)) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float gm = bn_gamma[g0 + k];
+      rg[k] = fabsf(gm) > 1e-12f ? 1.f / gm : 0.f;
+      bt[k] = bn_beta[g0 + k];
+      t1[k] = 0.f;
+      t2[k] = 0.f;
+    }
+    __syncthreads();
+  }
   const int Ho = H >> 1, Wo = W >> 1;
   const long long nopix = (long long)N * Ho * Wo;            // < 2^31 for any tensor that fits in HBM here
   PIXEL_LANE_LOOP(C, nopix) {
@@ -299,6 +346,26 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const T* __restri
     store8<T>(ob_ + lddx, ob);
     store8<T>(ob_ + (long long)W * lddx, oc);
     store8<T>(ob_ + (long long)W * lddx + lddx, od);
+    if (bn_sums != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        t1[k] += (oa[k] + ob[k]) + (oc[k] + od[k]);
+        t2[k] += oa[k] * ((a[k] - bt[k]) * rg[k]) + ob[k] * ((b[k] - bt[k]) * rg[k]) +
+                 oc[k] * ((c[k] - bt[k]) * rg[k]) + od[k] * ((d[k] - bt[k]) * rg[k]);
+      }
+    }
+  }
+  if (bn_sums != nullptr) {
+    const int g0 = (threadIdx.x % (C >> 3)) * 8;
+    if (threadIdx.x / (C >> 3) < kThreads / (C >> 3)) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        atomicAdd(&sbn[g0 + k], t1[k]);
+        atomicAdd(&sbn[C + g0 + k], t2[k]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&bn_sums[i], (double)sbn[i]);
   }
 }
 
@@ -663,7 +730,19 @@ extern "C" int b2u_bn_stats(int dt, const void* x, int ldx, int c, long long npi
   int grid = stream_grid((npix + 1) / 2, lanes, 4);
   size_t smem = 2 * (size_t)c * sizeof(float);
   DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, false>), grid, kThreads, smem, stream, (const T*)x, ldx,
-                            (const T*)nullptr, 0, c, npix, (const float*)nullptr, (const float*)nullptr, sums));
+                            (const T*)nullptr, 0, c, npix, (const float*)nullptr, (const float*)nullptr, sums, c));
+  return B2U_OK;
+}
+
+// statistics of a tensor into a (possibly wider) BN sums buffer: sums[i], sums[sq_off + i]
+int b2u_bn_stats_off(int dt, const void* x, int ldx, int c, long long npix, double* sums, int sq_off, void* stream) {
+  REQ_VEC8(c);
+  B2U_REQUIRE(c <= 2048 && ldx % 8 == 0 && aligned16(x), "bn_stats: c<=2048, ld%%8==0, 16B-aligned base required");
+  int lanes = kThreads / (c / 8);
+  int grid = stream_grid((npix + 1) / 2, lanes, 4);
+  size_t smem = 2 * (size_t)c * sizeof(float);
+  DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, false>), grid, kThreads, smem, stream, (const T*)x, ldx,
+                            (const T*)nullptr, 0, c, npix, (const float*)nullptr, (const float*)nullptr, sums, sq_off));
   return B2U_OK;
 }
 
@@ -678,13 +757,15 @@ extern "C" int b2u_bn_finalize(const double* sums, long long count, const float*
 }
 
 extern "C" int b2u_bn_apply(int dt, const void* x, int ldx, void* y, int ldy, int c, long long npix,
-                            const float* scale, const float* shift, void* stream) {
+                            const float* scale, const float* shift, double* out_stats, int out_sq_off,
+                            void* stream) {
   REQ_VEC8(c);
   B2U_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "bn_apply: alignment");
   B2U_REQUIRE(c <= 2048, "bn_apply: c <= 2048");
-  int grid = lane_grid(npix, c);
-  DISPATCH_T(dt, B2U_LAUNCH(bn_apply_kernel<T>, grid, kThreads, 0, stream, (const T*)x, ldx, (T*)y, ldy, c, npix,
-                            scale, shift));
+  int grid = lane_grid(npix, c, out_stats != nullptr ? 4 : 8);
+  size_t smem = out_stats != nullptr ? 2 * (size_t)c * sizeof(float) : 0;
+  DISPATCH_T(dt, B2U_LAUNCH(bn_apply_kernel<T>, grid, kThreads, smem, stream, (const T*)x, ldx, (T*)y, ldy, c, npix,
+                            scale, shift, out_stats, out_sq_off));
   return B2U_OK;
 }
 
@@ -696,7 +777,7 @@ extern "C" int b2u_bn_bwd_reduce(int dt, const void* dy, int lddy, const void* x
   int grid = stream_grid((npix + 1) / 2, lanes, 4);
   size_t smem = 2 * (size_t)c * sizeof(float);
   DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, true>), grid, kThreads, smem, stream, (const T*)dy, lddy,
-                            (const T*)x, ldx, c, npix, save_mean, save_invstd, sums));
+                            (const T*)x, ldx, c, npix, save_mean, save_invstd, sums, c));
   return B2U_OK;
 }
 
@@ -730,14 +811,18 @@ extern "C" int b2u_maxpool_fwd(int dt, const void* x, int ldx, void* y, int ldy,
 
 extern "C" int b2u_maxpool_bwd(int dt, const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int c,
                                int n, int h, int wd, float p_drop, int op_id, const b2u_step_state* d_state,
-                               int accumulate, void* stream) {
+                               int accumulate, double* bn_sums, const float* bn_gamma, const float* bn_beta,
+                               void* stream) {
   REQ_VEC8(c);
   B2U_REQUIRE(h % 2 == 0 && wd % 2 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0, "maxpool_bwd: shape");
   B2U_REQUIRE(p_drop == 0.f || d_state != nullptr, "maxpool_bwd: dropout needs a step state");
   B2U_REQUIRE(c <= 2048 && (long long)n * h * wd < (1LL << 31), "maxpool_bwd: tensor too large");
   int grid = lane_grid((long long)n * (h / 2) * (wd / 2), c);
-  DISPATCH_T(dt, B2U_LAUNCH(maxpool_bwd_kernel<T>, grid, kThreads, 0, stream, (const T*)x, ldx, (const T*)dy, lddy,
-                            (T*)dx, lddx, c, n, h, wd, p_drop, op_id, d_state, accumulate));
+  B2U_REQUIRE(bn_sums == nullptr || (bn_gamma != nullptr && bn_beta != nullptr), "maxpool_bwd: fused BN statistics need gamma/beta");
+  if (bn_sums != nullptr && grid > 4 * B2U_NUM_SMS) grid = 4 * B2U_NUM_SMS;     // fewer block epilogues
+  size_t smem = bn_sums != nullptr ? 2 * (size_t)c * sizeof(float) : 0;
+  DISPATCH_T(dt, B2U_LAUNCH(maxpool_bwd_kernel<T>, grid, kThreads, smem, stream, (const T*)x, ldx, (const T*)dy, lddy,
+                            (T*)dx, lddx, c, n, h, wd, p_drop, op_id, d_state, accumulate, bn_sums, bn_gamma, bn_beta));
   return B2U_OK;
 }
 

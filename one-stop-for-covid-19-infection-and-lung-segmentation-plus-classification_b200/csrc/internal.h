@@ -34,7 +34,8 @@ int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, con
 int b2u_tc_conv3x3_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* db,
                          int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
 int b2u_tc_convt_fwd(const void* x, int ldx, int cin, const float* w, const float* bias, void* y, int ldy, int cout,
-                     int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+                     double* stats, int stats_sq_off, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+int b2u_bn_stats_off(int dt, const void* x, int ldx, int c, long long npix, double* sums, int sq_off, void* stream);
 int b2u_tc_convt_dgrad(const void* dy, int lddy, int cout, const float* w, void* dx, int lddx, int cin,
                        const void* mask, int ldmask, int mask_act, int accumulate, int n, int h, int wd, void* ws,
                        size_t ws_bytes, void* stream);

@@ -127,11 +127,13 @@ class Plan:
     """Op lists + arena sizes for one (graph, batch size, storage type, mode) combination."""
 
     def __init__(self, graph, n, dt=F32, training=True, dropout=True, loss="bce_dice", world=1,
-                 sync_stats=False, layout=None, rank=0):
+                 sync_stats=False, layout=None, rank=0, fuse_bn_bwd=True, fuse_bn_stats=True):
         self.graph, self.n, self.dt, self.training = graph, int(n), dt, training
         self.dropout = dropout and training
         self.loss, self.world, self.sync_stats = loss, int(world), bool(sync_stats) and world > 1
         self.rank = int(rank)
+        self.fuse_bn_bwd = bool(fuse_bn_bwd)
+        self.fuse_bn_stats = bool(fuse_bn_stats)
         self.layout = layout or ParamLayout(graph)
         self.act, self.f32, self.zero = Arena("act"), Arena("f32"), Arena("zero")
         self.fwd, self.bwd, self.opt = [], [], []
@@ -220,6 +222,7 @@ class Plan:
                 drop_index[id(l)] = k
                 k += 1
         self.n_dropout_ops = k
+        prod_op = {}             # id(tensor) -> forward Op that can emit BN statistics of what it writes
         fused_drop = set()       # dropout layers folded into the preceding max-pool
         bn_aux = {}              # id(bn layer) -> dict of small buffers
         written = set()          # id(tensor) whose gradient view has been written (backward)
@@ -255,8 +258,9 @@ class Plan:
             elif l.kind == "conv2d_transpose":
                 place(t, dt)
                 yv = self.views[id(t)]
-                self.fwd.append(Op(OP_CONVT_FWD, dt, [xv.ref, self._w(l, "kernel"), self._w(l, "bias"), yv.ref],
-                                   [xv.ld, xv.c, yv.ld, yv.c, n, xv.h, xv.w], tag=l.name))
+                self.fwd.append(Op(OP_CONVT_FWD, dt, [xv.ref, self._w(l, "kernel"), self._w(l, "bias"), yv.ref, None],
+                                   [xv.ld, xv.c, yv.ld, yv.c, n, xv.h, xv.w, 0], tag=l.name))
+                prod_op[id(t)] = self.fwd[-1]
             elif l.kind == "batch_normalization":
                 place(t, xv.dt)
                 yv = self.views[id(t)]
@@ -268,7 +272,21 @@ class Plan:
                 if self.training:
                     if "sums" not in aux:
                         aux["sums"] = self.zero.alloc(2 * c * 8)
-                        self.fwd.append(Op(OP_BN_STATS, xv.dt, [xv.ref, aux["sums"]], [xv.ld, c, count], tag=l.name))
+                        src = x.producer
+                        fusable = (self.fuse_bn_stats and src.kind == "concatenate" and
+                                   all(home[id(ti)][0] is src and id(ti) in prod_op and prod_op[id(ti)].p[4] is None
+                                       for ti in src.inputs))
+                        if fusable:
+                            # BN over a concat buffer: every producer (transposed conv epilogue, encoder BN apply)
+                            # accumulates the statistics of the channel slice it writes -- no pass over the buffer
+                            off = 0
+                            for ti in src.inputs:
+                                po = prod_op[id(ti)]
+                                po.p[4] = aux["sums"] + off * 8
+                                po.i[7 if po.kind == OP_CONVT_FWD else 4] = c
+                                off += ti.channels
+                        else:
+                            self.fwd.append(Op(OP_BN_STATS, xv.dt, [xv.ref, aux["sums"]], [xv.ld, c, count], tag=l.name))
                     if self.sync_stats:
                         self.fwd.append(Op(OP_ALLREDUCE_F64, 0, [aux["sums"]], [2 * c], tag=l.name))
                         count *= self.world
@@ -277,8 +295,10 @@ class Plan:
                                    [aux.get("sums"), self._w(l, "gamma"), self._w(l, "beta"), self._w(l, "moving_mean"),
                                     self._w(l, "moving_variance"), aux["scale"], aux["shift"], aux["mean"], aux["invstd"]],
                                    [count, 1 if self.training else 0, c], [l.momentum, l.epsilon], tag=l.name))
-                self.fwd.append(Op(OP_BN_APPLY, xv.dt, [xv.ref, yv.ref, aux["scale"], aux["shift"]],
-                                   [xv.ld, yv.ld, c, self._npix(xv)], tag=l.name))
+                self.fwd.append(Op(OP_BN_APPLY, xv.dt, [xv.ref, yv.ref, aux["scale"], aux["shift"], None],
+                                   [xv.ld, yv.ld, c, self._npix(xv), 0], tag=l.name))
+                if self.training:
+                    prod_op[id(t)] = self.fwd[-1]
             elif l.kind == "max_pooling2d":
                 place(t, xv.dt)
                 yv = self.views[id(t)]
@@ -410,15 +430,18 @@ class Plan:
             elif l.kind == "batch_normalization":
                 aux = bn_aux[id(l)]
                 c = xv.c
-                bsums = self.zero.alloc(2 * c * 8)
                 if id(x) in written:
                     raise NotImplementedError("BN backward accumulate")
                 gx = self.gviews[id(x)]
                 mv, ma = self._mask_for(x)
-                self.bwd.append(Op(OP_BN_BWD_REDUCE, xv.dt, [gy.ref, xv.ref, aux["mean"], aux["invstd"], bsums],
-                                   [gy.ld, xv.ld, c, self._npix(xv)], tag=l.name))
-                if self.sync_stats:
-                    self.bwd.append(Op(OP_ALLREDUCE_F64, 0, [bsums], [2 * c], tag=l.name))
+                if "bwd_sums" in aux:                       # produced by the max-pool backward that completed gy
+                    bsums = aux["bwd_sums"]
+                else:
+                    bsums = self.zero.alloc(2 * c * 8)
+                    self.bwd.append(Op(OP_BN_BWD_REDUCE, xv.dt, [gy.ref, xv.ref, aux["mean"], aux["invstd"], bsums],
+                                       [gy.ld, xv.ld, c, self._npix(xv)], tag=l.name))
+                    if self.sync_stats:
+                        self.bwd.append(Op(OP_ALLREDUCE_F64, 0, [bsums], [2 * c], tag=l.name))
                 # npix is the LOCAL pixel count; the divisor (count) is the global one under sync_stats,
                 # where the all-reduced sums must enter dgamma/dbeta on one rank only (grads are summed)
                 own = (not self.sync_stats) or self.rank == 0
@@ -434,9 +457,21 @@ class Plan:
                 p_drop, op_id = l._pool_drop
                 if self._act_of(x) is not None:
                     raise NotImplementedError("max-pool directly after an activated conv")
-                self.bwd.append(Op(OP_MAXPOOL_BWD, xv.dt, [xv.ref, gy.ref, gx.ref, self.step_ref if p_drop > 0 else None],
+                # when this pool is the LAST contribution to the gradient of a BatchNorm output, the kernel also
+                # produces that BN's backward statistics (sum dx, sum dx*xhat with xhat = (x - beta)/gamma) from the
+                # values it already holds: no separate BN_BWD_REDUCE pass over dx and the BN input
+                fuse = None
+                bn = x.producer
+                if bn.kind == "batch_normalization" and all(cn._seq >= l._seq for cn in x.consumers) and self.fuse_bn_bwd:
+                    fuse = self.zero.alloc(2 * xv.c * 8)
+                    bn_aux[id(bn)]["bwd_sums"] = fuse
+                self.bwd.append(Op(OP_MAXPOOL_BWD, xv.dt,
+                                   [xv.ref, gy.ref, gx.ref, self.step_ref if p_drop > 0 else None, fuse,
+                                    self._w(bn, "gamma") if fuse else None, self._w(bn, "beta") if fuse else None],
                                    [xv.ld, gy.ld, gx.ld, xv.c, n, xv.h, xv.w, op_id, 1 if id(x) in written else 0],
                                    [p_drop], tag=l.name))
+                if fuse is not None and self.sync_stats:
+                    self.bwd.append(Op(OP_ALLREDUCE_F64, 0, [fuse], [2 * xv.c], tag=l.name))
                 written.add(id(x))
             elif l.kind == "dropout":
                 if self.views[id(t)] is xv:                     # identity alias

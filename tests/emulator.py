@@ -126,6 +126,12 @@ class Emulator:
                                torch.from_numpy(b.copy()), stride=2).permute(0, 2, 3, 1).numpy()
         yv = self.view(o.p[3], ldy, cout, n * 4 * h * w, o.dt)
         yv[:] = y.reshape(-1, cout).astype(yv.dtype)
+        if len(o.p) > 4 and o.p[4] is not None:          # statistics for a following BN over the concat buffer
+            sq = o.i[7]
+            s = self.f64(o.p[4], sq + cout)
+            ys = yv.astype(np.float64)
+            s[:cout] += ys.sum(0)
+            s[sq:sq + cout] += (ys * ys).sum(0)
 
     def op_convt_dgrad(self, o):
         lddy, cout, lddx, cin, ldm, mact, acc, n, h, w = o.i[:10]
@@ -184,6 +190,12 @@ class Emulator:
         x = self.view(o.p[0], ldx, c, npix, o.dt).astype(np.float32)
         y = self.view(o.p[1], ldy, c, npix, o.dt)
         y[:] = (x * self.f32(o.p[2], c) + self.f32(o.p[3], c)).astype(y.dtype)
+        if len(o.p) > 4 and o.p[4] is not None:
+            sq = o.i[4]
+            s = self.f64(o.p[4], sq + c)
+            ys = y.astype(np.float64)
+            s[:c] += ys.sum(0)
+            s[sq:sq + c] += (ys * ys).sum(0)
 
     def op_bn_bwd_reduce(self, o):
         lddy, ldx, c, npix = o.i[:4]
@@ -241,6 +253,14 @@ class Emulator:
         if acc:
             g = g + dv.astype(np.float32)
         dv[:] = g.astype(dv.dtype)
+        if len(o.p) > 4 and o.p[4] is not None:          # fused BN-backward statistics (x = gamma*xhat + beta)
+            gm, bt = self.f32(o.p[5], c), self.f32(o.p[6], c)
+            xs = self.view(o.p[0], ldx, c, n * h * w, o.dt).astype(np.float32)
+            rg = np.where(np.abs(gm) > 1e-12, 1.0 / np.where(gm == 0, 1, gm), 0.0).astype(np.float32)
+            xh = (xs - bt) * rg
+            s = self.f64(o.p[4], 2 * c)
+            s[:c] += g.astype(np.float64).sum(0)
+            s[c:] += (g * xh).astype(np.float64).sum(0)
 
     def op_dropout_fwd(self, o):
         ldx, ldy, c, npix, op_id = o.i[:5]

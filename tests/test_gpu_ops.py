@@ -129,7 +129,7 @@ def test_convt2x2(dt, n, h, w, cin, cout):
     b = img.farr(img.par, cout, scale=0.1)
     dw = img.farr(img.gr, 4 * cout * cin, fill="zero")
     db = img.farr(img.gr, cout, fill="zero")
-    ops = [P.Op(P.OP_CONVT_FWD, dt, [x.ref, wt, b, y.ref], [x.ld, cin, y.ld, cout, n, h, w]),
+    ops = [P.Op(P.OP_CONVT_FWD, dt, [x.ref, wt, b, y.ref, None], [x.ld, cin, y.ld, cout, n, h, w, 0]),
            P.Op(P.OP_CONVT_DGRAD, dt, [dy.ref, wt, dx.ref, x.ref], [dy.ld, cout, dx.ld, cin, x.ld, 1, 1, n, h, w]),
            P.Op(P.OP_CONVT_WGRAD, dt, [x.ref, dy.ref, dw, db], [x.ld, cin, dy.ld, cout, n, h, w])]
     compare(ops, img, dt, tol=4e-3 if dt == P.F16 else 5e-5)
@@ -153,7 +153,7 @@ def test_batchnorm_all_passes(dt, c, npix_shape):
     for training in (1, 0):
         ops = [P.Op(P.OP_BN_STATS, dt, [x.ref, s1], [x.ld, c, npix]),
                P.Op(P.OP_BN_FINALIZE, 0, [s1, gamma, beta, mm, mv, scale, shift, mean, inv], [npix, training, c], [0.99, 1e-3]),
-               P.Op(P.OP_BN_APPLY, dt, [x.ref, y.ref, scale, shift], [x.ld, y.ld, c, npix])]
+               P.Op(P.OP_BN_APPLY, dt, [x.ref, y.ref, scale, shift, None], [x.ld, y.ld, c, npix, 0])]
         if training:
             ops += [P.Op(P.OP_BN_BWD_REDUCE, dt, [dy.ref, x.ref, mean, inv, s2], [dy.ld, x.ld, c, npix]),
                     P.Op(P.OP_BN_BWD_APPLY, dt, [dy.ref, x.ref, dx.ref, gamma, mean, inv, s2, dg, dbt, x.ref],
@@ -321,3 +321,20 @@ def test_graph_capture_equals_eager():
            P.Op(P.OP_CONV3X3_FWD, dt, [x.ref, wt, b, y.ref, None], [x.ld, cin, 1, y.ld, cout, n, h, w])]
     img.zero.alloc(8)
     compare(ops, img, dt, graph=True)
+
+
+@pytest.mark.parametrize("dt", [P.F32, P.F16])
+@pytest.mark.parametrize("acc", [0, 1])
+def test_maxpool_bwd_with_fused_bn_backward_statistics(dt, acc):
+    """max-pool backward that completes a BatchNorm output's gradient also emits sum(dx), sum(dx*xhat)"""
+    n, h, w, c = 2, 16, 24, 64
+    img = Img(12)
+    x = img.view(n, h, w, c, dt, ld=2 * c, c0=c)
+    dy = img.view(n, h // 2, w // 2, c, dt)
+    dx = img.view(n, h, w, c, dt, ld=2 * c, c0=c, scale=0.1)
+    gamma, beta = img.farr(img.par, c, fill="pos"), img.farr(img.par, c, scale=0.2)
+    sums = img.zero.alloc(2 * c * 8)
+    step = P.Ref("step", 0)
+    ops = [P.Op(P.OP_MAXPOOL_BWD, dt, [x.ref, dy.ref, dx.ref, step, sums, gamma, beta],
+                [x.ld, dy.ld, dx.ld, c, n, h, w, 1, acc], [0.25])]
+    compare(ops, img, dt, state=dict(seed=5, step=3), tol=3e-3 if dt == P.F16 else 3e-5)

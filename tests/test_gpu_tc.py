@@ -64,7 +64,7 @@ def test_tc_convt(n, h, w, cin, cout):
     wt = img.farr(img.par, 4 * cout * cin, scale=(1.0 / cin) ** 0.5)
     b = img.farr(img.par, cout, scale=0.1)
     for acc in (0, 1):
-        ops = [P.Op(P.OP_CONVT_FWD, dt, [x.ref, wt, b, y.ref], [x.ld, cin, y.ld, cout, n, h, w]),
+        ops = [P.Op(P.OP_CONVT_FWD, dt, [x.ref, wt, b, y.ref, None], [x.ld, cin, y.ld, cout, n, h, w, 0]),
                P.Op(P.OP_CONVT_DGRAD, dt, [dy.ref, wt, dx.ref, x.ref], [dy.ld, cout, dx.ld, cin, x.ld, 1, acc, n, h, w])]
         compare(ops, img, dt, tol=4e-3)
 

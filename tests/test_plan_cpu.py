@@ -73,7 +73,8 @@ def test_unet_concat_is_zero_copy_and_fused():
     kinds = [o.kind for o in plan.train_ops()]
     assert P.OP_COPY_SLICE not in kinds                  # skips + upsampled halves are written in place
     assert P.OP_DROPOUT_FWD not in kinds                 # dropout folded into the max-pool pass
-    assert kinds.count(P.OP_BN_STATS) == 4               # only the 4 concat BNs need a separate statistics pass
+    assert kinds.count(P.OP_BN_STATS) == 0               # concat BN statistics come from the producers' epilogues
+    assert kinds.count(P.OP_BN_BWD_REDUCE) == 4          # encoder BN backward statistics ride on the max-pool backward
     assert kinds.count(P.OP_CONV3X3_FWD) == 18 and kinds.count(P.OP_CONVT_FWD) == 4
 
 
