@@ -155,59 +155,96 @@ __global__ void __launch_bounds__(256) conv3x3_direct_kernel(
 // K = 9: no tensor-core shape, pure HBM streaming (writes COUT x what it reads).  One thread per pixel,
 // 64-byte (fp16) contiguous stores; the backward accumulates the 9 x COUT weight gradient in registers.
 // ==========================================================================================
-template <typename T, int COUT>
-__global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const T* __restrict__ x, int ldx,
-                                                             const float* __restrict__ w,
-                                                             const float* __restrict__ bias, int act,
-                                                             T* __restrict__ y, int ldy, int N, int H, int W) {
-  __shared__ float xs[18][18 + 1];
-  __shared__ float ws[9][COUT];
-  __shared__ float bs[COUT];
-  const int tiles_w = (W + 15) / 16;
-  const int h0 = (blockIdx.x / tiles_w) * 16, w0 = (blockIdx.x % tiles_w) * 16, n = blockIdx.y;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 18 * 18; i += 256) {
-    int rr = i / 18, cc = i % 18, hh = h0 + rr - 1, wwp = w0 + cc - 1;
+// Thread = (pixel lane, 8-channel group): the 9 x 8 weights of the group live in registers, a warp's 16-byte
+// stores cover 8 pixels x COUT channels = one contiguous 512-byte (COUT = 32) span, and the x halo of the NEXT
+// tile is fetched into registers while the current one is computed (persistent blocks, 2 per SM).
+constexpr int C1_TH = 8, C1_TW = 32;                        // pixel tile of the Cin == 1 kernels
+constexpr int C1_HALO = (C1_TH + 2) * (C1_TW + 2);          // 612 halo elements
+constexpr int C1_XR = (C1_HALO + 255) / 256;                // halo elements per thread
+
+template <typename T>
+__device__ __forceinline__ void c1_load_halo(const T* __restrict__ x, int ldx, int H, int W, int tile, int tiles_w,
+                                             int tiles_h, float xr[C1_XR]) {
+  const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+  const int h0 = th * C1_TH - 1, w0 = tw * C1_TW - 1;
+#pragma unroll
+  for (int k = 0; k < C1_XR; ++k) {
+    const int i = threadIdx.x + k * 256;
+    const int rr = i / (C1_TW + 2), cc = i % (C1_TW + 2), hh = h0 + rr, wwp = w0 + cc;
     float v = 0.f;
-    if (hh >= 0 && hh < H && wwp >= 0 && wwp < W) v = ldf<T>(x + (((long long)n * H + hh) * W + wwp) * ldx);
-    xs[rr][cc] = v;
-  }
-  for (int i = tid; i < 9 * COUT; i += 256) ws[i / COUT][i % COUT] = w[i];
-  for (int i = tid; i < COUT; i += 256) bs[i] = bias ? bias[i] : 0.f;
-  __syncthreads();
-  const int r = tid / 16, c = tid % 16;
-  const int hh = h0 + r, wwp = w0 + c;
-  if (hh >= H || wwp >= W) return;
-  float xv[9];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) xv[t] = xs[r + t / 3][c + t % 3];
-  T* dst = y + (((long long)n * H + hh) * W + wwp) * ldy;
-#pragma unroll
-  for (int g = 0; g < COUT / 8; ++g) {
-    float o[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float a = bs[g * 8 + k];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) a = fmaf(xv[t], ws[t][g * 8 + k], a);
-      o[k] = act_fwd(a, act);
-    }
-    store8<T>(dst + g * 8, o);
+    if (i < C1_HALO && hh >= 0 && hh < H && wwp >= 0 && wwp < W) v = ldf<T>(x + (((long long)n * H + hh) * W + wwp) * ldx);
+    xr[k] = v;
   }
 }
 
 template <typename T, int COUT>
-__global__ void __launch_bounds__(256) conv3x3_c1_wgrad_kernel(const T* __restrict__ x, int ldx,
-                                                               const T* __restrict__ dy, int lddy,
-                                                               float* __restrict__ dw, float* __restrict__ db, int N,
-                                                               int H, int W) {
-  // block = 8 x 32 pixel tiles (grid-stride); thread = (pixel lane, 8-channel group); the x halo of the tile is
-  // staged in shared memory, dy streams straight from HBM in 16-byte pieces; 9 taps x 8 channels (+ bias) of the
-  // gradient accumulate in registers over all tiles of the block and are reduced once at the end.
+__global__ void __launch_bounds__(256, 2) conv3x3_c1_fwd_kernel(const T* __restrict__ x, int ldx,
+                                                                const float* __restrict__ w,
+                                                                const float* __restrict__ bias, int act,
+                                                                T* __restrict__ y, int ldy, int N, int H, int W) {
+  constexpr int CG = COUT / 8, LANES = 256 / CG;
+  __shared__ float xs[C1_HALO + 2];
+  const int g = threadIdx.x % CG, lane = threadIdx.x / CG;
+  float wr[9][8], br[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    br[k] = bias ? bias[g * 8 + k] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[t][k] = w[t * COUT + g * 8 + k];
+  }
+  const int tiles_w = (W + C1_TW - 1) / C1_TW, tiles_h = (H + C1_TH - 1) / C1_TH;
+  const int ntiles = N * tiles_h * tiles_w;
+  float xr[C1_XR];
+  if ((int)blockIdx.x < ntiles) c1_load_halo<T>(x, ldx, H, W, blockIdx.x, tiles_w, tiles_h, xr);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int h0 = th * C1_TH, w0 = tw * C1_TW;
+    __syncthreads();                                         // the previous tile's readers are done
+#pragma unroll
+    for (int k = 0; k < C1_XR; ++k)
+      if (threadIdx.x + k * 256 < C1_HALO) xs[threadIdx.x + k * 256] = xr[k];
+    __syncthreads();
+    if (tile + (int)gridDim.x < ntiles) c1_load_halo<T>(x, ldx, H, W, tile + gridDim.x, tiles_w, tiles_h, xr);
+#pragma unroll 2
+    for (int pp = lane; pp < C1_TH * C1_TW; pp += LANES) {
+      const int r = pp / C1_TW, c = pp % C1_TW;
+      if (h0 + r >= H || w0 + c >= W) continue;
+      float xv[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) xv[t] = xs[(r + t / 3) * (C1_TW + 2) + c + t % 3];
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float a = br[k];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) a = fmaf(xv[t], wr[t][k], a);
+        o[k] = a;
+      }
+      if (act == B2U_ACT_RELU) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
+      } else if (act != B2U_ACT_NONE) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = act_fwd(o[k], act);
+      }
+      store8<T>(y + (((long long)n * H + h0 + r) * W + w0 + c) * ldy + g * 8, o);
+    }
+  }
+}
+
+template <typename T, int COUT>
+__global__ void __launch_bounds__(256, 2) conv3x3_c1_wgrad_kernel(const T* __restrict__ x, int ldx,
+                                                                  const T* __restrict__ dy, int lddy,
+                                                                  float* __restrict__ dw, float* __restrict__ db, int N,
+                                                                  int H, int W) {
+  // block = 8 x 32 pixel tiles (grid-stride); thread = (pixel lane, 8-channel group).  The loads of the NEXT tile
+  // (the thread's share of the x halo, its pixels' 16-byte dy pieces) are issued before the current tile is
+  // reduced, so a block keeps ~17 KB in flight all the time; 9 taps x 8 channels (+ bias) of the gradient
+  // accumulate in registers over all tiles of the block and are reduced once at the end.
   constexpr int CG = COUT / 8;
   constexpr int LANES = 256 / CG;
-  constexpr int TH1 = 8, TW1 = 32;
-  __shared__ float xs[TH1 + 2][TW1 + 2 + 1];
+  constexpr int PPT = C1_TH * C1_TW / LANES;                 // pixels per thread and tile (4 at COUT = 32)
+  __shared__ float xs[C1_HALO + 2];
   __shared__ float sacc[10 * COUT];
   for (int i = threadIdx.x; i < 10 * COUT; i += 256) sacc[i] = 0.f;
   const int g = threadIdx.x % CG, lane = threadIdx.x / CG;
@@ -218,29 +255,57 @@ __global__ void __launch_bounds__(256) conv3x3_c1_wgrad_kernel(const T* __restri
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[t][k] = 0.f;
   }
-  const int tiles_w = (W + TW1 - 1) / TW1, tiles_h = (H + TH1 - 1) / TH1;
+  const int tiles_w = (W + C1_TW - 1) / C1_TW, tiles_h = (H + C1_TH - 1) / C1_TH;
   const int ntiles = N * tiles_h * tiles_w;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  float xr[C1_XR];
+  constexpr int RW = sizeof(T) == 2 ? 1 : 2;                 // 16-byte words per 8 channels
+  uint4 dn[PPT][RW];                                         // next tile's dy (prefetched, still packed)
+  auto load_dy = [&](int tile) {
     const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
-    const int h0 = th * TH1, w0 = tw * TW1;
-    __syncthreads();
-    for (int i = threadIdx.x; i < (TH1 + 2) * (TW1 + 2); i += 256) {
-      const int rr = i / (TW1 + 2), cc = i % (TW1 + 2), hh = h0 + rr - 1, wwp = w0 + cc - 1;
-      float v = 0.f;
-      if (hh >= 0 && hh < H && wwp >= 0 && wwp < W) v = ldf<T>(x + (((long long)n * H + hh) * W + wwp) * ldx);
-      xs[rr][cc] = v;
+    const int h0 = th * C1_TH, w0 = tw * C1_TW;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      const int pp = lane + q * LANES;
+      const int r = pp / C1_TW, c = pp % C1_TW;
+#pragma unroll
+      for (int i = 0; i < RW; ++i) dn[q][i] = make_uint4(0u, 0u, 0u, 0u);
+      if (h0 + r < H && w0 + c < W) {
+        const uint4* src = reinterpret_cast<const uint4*>(dy + (((long long)n * H + h0 + r) * W + w0 + c) * lddy + g * 8);
+#pragma unroll
+        for (int i = 0; i < RW; ++i) dn[q][i] = src[i];
+      }
     }
+  };
+  if ((int)blockIdx.x < ntiles) {
+    c1_load_halo<T>(x, ldx, H, W, blockIdx.x, tiles_w, tiles_h, xr);
+    load_dy(blockIdx.x);
+  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();                                         // the previous tile's readers are done
+#pragma unroll
+    for (int k = 0; k < C1_XR; ++k)
+      if (threadIdx.x + k * 256 < C1_HALO) xs[threadIdx.x + k * 256] = xr[k];
+    uint4 dc[PPT][RW];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q)
+#pragma unroll
+      for (int i = 0; i < RW; ++i) dc[q][i] = dn[q][i];
     __syncthreads();
-    for (int pp = lane; pp < TH1 * TW1; pp += LANES) {
-      const int r = pp / TW1, c = pp % TW1;
-      if (h0 + r >= H || w0 + c >= W) continue;
+    if (tile + (int)gridDim.x < ntiles) {                    // next tile's loads fly while this one is reduced
+      c1_load_halo<T>(x, ldx, H, W, tile + gridDim.x, tiles_w, tiles_h, xr);
+      load_dy(tile + gridDim.x);
+    }
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      const int pp = lane + q * LANES;
+      const int r = pp / C1_TW, c = pp % C1_TW;
       float d[8];
-      load8<T>(dy + (((long long)n * H + h0 + r) * W + w0 + c) * lddy + g * 8, d);
+      load8<T>(reinterpret_cast<const T*>(&dc[q][0]), d);    // unpack from registers
 #pragma unroll
       for (int k = 0; k < 8; ++k) accb[k] += d[k];
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const float xv = xs[r + t / 3][c + t % 3];
+        const float xv = xs[(r + t / 3) * (C1_TW + 2) + c + t % 3];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(xv, d[k], acc[t][k]);
       }
@@ -536,7 +601,8 @@ int b2u_direct_conv3x3(int dt, const void* x, int ldx, int K, const float* w, in
   B2U_REQUIRE((K % 8 != 0) || (ldx % 8 == 0), "conv3x3: ldx must be a multiple of 8 when Cin %% 8 == 0");
   int tiles = b2u_cdiv(h, TH) * b2u_cdiv(wd, TW);
   if (K == 1 && !dgrad && stats == nullptr && mask == nullptr && !accumulate && ldy % 8 == 0 && (J == 32 || J == 16)) {
-    dim3 grid1(tiles, n);
+    long long gl1 = (long long)n * b2u_cdiv(h, C1_TH) * b2u_cdiv(wd, C1_TW);
+    int grid1 = (int)(gl1 < 2 * B2U_NUM_SMS ? gl1 : 2 * B2U_NUM_SMS);
     if (J == 32) { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_fwd_kernel<T, 32>), grid1, 256, 0, stream, (const T*)x, ldx, w, bias, act, (T*)y, ldy, n, h, wd)); }
     else { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_fwd_kernel<T, 16>), grid1, 256, 0, stream, (const T*)x, ldx, w, bias, act, (T*)y, ldy, n, h, wd)); }
     return B2U_OK;
@@ -557,8 +623,8 @@ int b2u_direct_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const void
                              float* db, int n, int h, int wd, void* stream) {
   B2U_REQUIRE(n > 0 && h > 0 && wd > 0 && cin > 0 && cout > 0, "conv3x3_wgrad: empty shape");
   if (cin == 1 && lddy % 8 == 0 && (cout == 32 || cout == 16)) {
-    long long gl = (long long)n * b2u_cdiv(h, 8) * b2u_cdiv(wd, 32);
-    int grid1 = (int)(gl < 6 * B2U_NUM_SMS ? gl : 6 * B2U_NUM_SMS);
+    long long gl = (long long)n * b2u_cdiv(h, C1_TH) * b2u_cdiv(wd, C1_TW);
+    int grid1 = (int)(gl < 2 * B2U_NUM_SMS ? gl : 2 * B2U_NUM_SMS);
     if (cout == 32) { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_wgrad_kernel<T, 32>), grid1, 256, 0, stream, (const T*)x, ldx, (const T*)dy, lddy, dw, db, n, h, wd)); }
     else { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_wgrad_kernel<T, 16>), grid1, 256, 0, stream, (const T*)x, ldx, (const T*)dy, lddy, dw, db, n, h, wd)); }
     return B2U_OK;

@@ -31,7 +31,8 @@ namespace {
 
 constexpr int kMaxStages = 12;
 constexpr int kTileH = 8, kTileW = 16, kTileM = 128;       // 8 x 16 output pixels per tile
-constexpr int kEpiWarpsTc = 8;                             // two per TMEM lane group (column halves)
+constexpr int kEpiWarpsTc = 16;                            // four per TMEM lane group (column quarters): the epilogue
+                                                           // is instruction-latency bound, more warps hide it
 constexpr int kThreadsTc = 64 + 32 * kEpiWarpsTc;
 constexpr int kMaxTaps = 9;
 
@@ -78,6 +79,10 @@ __device__ __forceinline__ float transpose_reduce16(float v[16], int lane) {
   return v[0];      // lane (l & 15) owns column (l & 15); both half-warps hold the same totals
 }
 
+// kRegStats: BatchNorm statistics accumulate in registers over ALL tiles of the persistent CTA (a thread owns
+// <= 32 fixed columns; requires gridDim.x % (J / JT) == 0 so that the CTA always sees the same N tile) and are
+// reduced across lanes once at the end, instead of two 31-shuffle transposes per 16 columns per tile.
+template <bool kRegStats>
 __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_constant__ TcMaps maps,
                                                                  const __grid_constant__ TcParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -191,13 +196,17 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
     }
   } else {
     // ===================================== epilogue ==============================================
-    // 8 warps: TMEM lane group = warp & 3, column half = (warp - 2) >> 2
+    // 16 warps: TMEM lane group = warp & 3, column part = (warp - 2) >> 2 of `nparts` equal parts of the N tile
     const int lg = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;
     const int row = lg * 32 + lane;                        // tile row = pixel (row / 16, row % 16)
-    const int ccols = JT / 2 >= 16 ? JT / 2 : JT;
-    const int cbeg = JT / 2 >= 16 ? half * ccols : 0;
-    const bool has_cols = JT / 2 >= 16 || half == 0;
+    const int nparts = JT % 64 == 0 ? 4 : (JT % 32 == 0 ? 2 : 1);
+    const int ccols = JT / nparts;
+    const int cbeg = part * ccols;
+    const bool has_cols = part < nparts;
+    float rs1[kRegStats ? 32 : 1], rs2[kRegStats ? 32 : 1];
+#pragma unroll
+    for (int i = 0; i < (kRegStats ? 32 : 1); ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -213,6 +222,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::fence_after_sync();
       if (has_cols) {
+#pragma unroll 2
         for (int cc = 0; cc < ccols; cc += 16) {
           const int c0 = cbeg + cc;
           float v[16];
@@ -261,7 +271,17 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
             store8<__half>(dst, v);
             store8<__half>(dst + 8, v + 8);
           }
-          if (prm.stats != nullptr) {
+          if (kRegStats) {
+            if (valid) {
+              if (cc == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { rs1[i] += v[i]; rs2[i] = fmaf(v[i], v[i], rs2[i]); }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { rs1[(kRegStats ? 16 : 0) + i] += v[i]; rs2[(kRegStats ? 16 : 0) + i] = fmaf(v[i], v[i], rs2[(kRegStats ? 16 : 0) + i]); }
+              }
+            }
+          } else if (prm.stats != nullptr) {
             float q[16], sq[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) { q[i] = valid ? v[i] : 0.f; sq[i] = q[i] * q[i]; }
@@ -279,6 +299,26 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (kRegStats && has_cols && blockIdx.x < ntiles) {
+      // the CTA's N tile is fixed (gridDim.x % nj == 0): registers hold columns [cbeg, cbeg + ccols) of it
+      const int jt = (int)(blockIdx.x % (unsigned)nj);
+      for (int cc = 0; cc < ccols; cc += 16) {
+        float q[16], sq[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          q[i] = cc == 0 ? rs1[i] : rs1[(kRegStats ? 16 : 0) + i];
+          sq[i] = cc == 0 ? rs2[i] : rs2[(kRegStats ? 16 : 0) + i];
+        }
+        float s1 = transpose_reduce16(q, lane);
+        float s2 = transpose_reduce16(sq, lane);
+        if (lane < 16) {
+          const int j0 = jt * JT + cbeg + cc;
+          const int sc = prm.mode == 1 ? (j0 % prm.cout) : j0;
+          atomicAdd(&s_stats[sc + lane], s1);
+          atomicAdd(&s_stats[prm.J + sc + lane], s2);
+        }
+      }
     }
   }
 
@@ -402,13 +442,23 @@ int launch_tc(const TcMaps& maps, TcParams& prm, void* stream) {
   size_t smem = smem_bytes_for(prm.KS, prm.JT, prm.J, prm.stages);
   B2U_REQUIRE(smem <= 227 * 1024, "tc_conv: shared memory %zu exceeds 227 KB", smem);
   if (!g_attr_set) {
-    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr_set = true;
   }
-  long long tiles = (long long)prm.N * b2u_cdiv(prm.H, kTileH) * b2u_cdiv(prm.W, kTileW) * (prm.J / prm.JT);
+  const int nj = prm.J / prm.JT;
+  long long tiles = (long long)prm.N * b2u_cdiv(prm.H, kTileH) * b2u_cdiv(prm.W, kTileW) * nj;
   B2U_REQUIRE(tiles < (1LL << 31), "tc_conv: too many tiles");
   int grid = (int)(tiles < B2U_NUM_SMS ? tiles : B2U_NUM_SMS);
-  B2U_LAUNCH(tc_conv_kernel, grid, kThreadsTc, smem, stream, maps, prm);
+  // register statistics need a fixed N tile per CTA (grid a multiple of nj) and <= 32 columns per epilogue thread
+  const int nparts = prm.JT % 64 == 0 ? 4 : (prm.JT % 32 == 0 ? 2 : 1);
+  bool reg_stats = prm.stats != nullptr && prm.JT / nparts <= 32 && nj <= B2U_NUM_SMS;
+  if (reg_stats) {
+    const int g2 = grid / nj * nj;
+    if (g2 >= 1) grid = g2; else reg_stats = false;
+  }
+  if (reg_stats) { B2U_LAUNCH(tc_conv_kernel<true>, grid, kThreadsTc, smem, stream, maps, prm); }
+  else { B2U_LAUNCH(tc_conv_kernel<false>, grid, kThreadsTc, smem, stream, maps, prm); }
   return B2U_OK;
 }
 
@@ -462,6 +512,7 @@ int b2u_tc_convt_fwd(const void* x, int ldx, int cin, const float* w, const floa
   if (rc != B2U_OK) return rc;
   TcParams p{};
   p.N = n; p.H = h; p.W = wd; p.K = cin; p.J = 4 * cout; p.KS = pick_ks(cin); p.JT = pick_jt(4 * cout);
+  if (stats != nullptr && p.J % 128 == 0) p.JT = 128;     // <= 32 columns per epilogue thread: statistics stay in registers
   if (p.JT > cout && p.JT % cout != 0) p.JT = cout;       // a 16-column chunk must not straddle two (a,b) groups
   p.ntaps = 1; p.tap_dh[0] = 0; p.tap_dw[0] = 0; p.tap_map[0] = 0;
   p.mode = 1; p.cout = cout; p.y = (__half*)y; p.ldy = ldy; p.bias = bias; p.act = B2U_ACT_NONE;

@@ -40,7 +40,7 @@ __host__ int stream_grid(long long work_items, int per_block = kThreads, int wav
 // BatchNorm statistics: sums[c] += sum x, sums[C + c] += sum x^2   (double accumulators)
 // ------------------------------------------------------------------------------------------
 template <typename T, bool kBwd>
-__global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const T* __restrict__ a, int lda,
+__global__ void __launch_bounds__(kThreads, 4) bn_reduce_kernel(const T* __restrict__ a, int lda,
                                                              const T* __restrict__ x, int ldx, int C,
                                                              long long npix, const float* __restrict__ mean,
                                                              const float* __restrict__ invstd,
@@ -55,13 +55,12 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const T* __restrict
   const int lanes = kThreads / cg;              // pixel lanes per block
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
   if (lane < lanes) {
-    float s1[8], s2[8], mu[8], is[8];
+    // kBwd accumulates sum dy*x and applies  sum dy*xhat = invstd * (sum dy*x - mean * sum dy)  once per thread
+    // (a thread's partial sums are short, so the subtraction loses nothing): no per-channel constants live in
+    // the loop, which keeps the kernel at 4 blocks per SM
+    float s1[8], s2[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; mu[i] = 0.f; is[i] = 1.f; }
-    if (kBwd) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { mu[i] = mean[g * 8 + i]; is[i] = invstd[g * 8 + i]; }
-    }
+    for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
     // two pixel groups per trip, both inside one contiguous span of the block (coalesced, 2-4 loads in flight)
     const long long stride = (long long)gridDim.x * lanes * 2;
     for (long long p = (long long)blockIdx.x * lanes * 2 + lane; p < npix; p += stride) {
@@ -79,12 +78,16 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const T* __restrict
         if (u == 1 && !two) break;
         if (kBwd) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { s1[i] += v[u][i]; s2[i] += v[u][i] * ((xv[u][i] - mu[i]) * is[i]); }
+          for (int i = 0; i < 8; ++i) { s1[i] += v[u][i]; s2[i] = fmaf(v[u][i], xv[u][i], s2[i]); }
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) { s1[i] += v[u][i]; s2[i] += v[u][i] * v[u][i]; }
         }
       }
+    }
+    if (kBwd) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s2[i] = invstd[g * 8 + i] * (s2[i] - mean[g * 8 + i] * s1[i]);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -268,28 +271,48 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const T* __restri
   }
 }
 
+// Register budget matters here: the four window values stay PACKED (as loaded) and are unpacked one window
+// position at a time, so three 256-thread blocks fit an SM (the all-unpacked version needed 158 registers:
+// one block per SM, 12 % occupancy, a third of the HBM rate).
+template <typename T> struct Pack8;
+template <> struct Pack8<__half> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __half* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float v[8]) const {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+};
+template <> struct Pack8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void get(float v[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
 template <typename T>
-__global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const T* __restrict__ x, int ldx,
-                                                               const T* __restrict__ dy, int lddy,
-                                                               T* __restrict__ dx, int lddx, int C, int N, int H,
-                                                               int W, float p_drop, int op_id,
-                                                               const b2u_step_state* __restrict__ st,
-                                                               int accumulate, double* __restrict__ bn_sums,
-                                                               const float* __restrict__ bn_gamma,
-                                                               const float* __restrict__ bn_beta) {
+__global__ void __launch_bounds__(kThreads, 2) maxpool_bwd_kernel(const T* __restrict__ x, int ldx,
+                                                                  const T* __restrict__ dy, int lddy,
+                                                                  T* __restrict__ dx, int lddx, int C, int N, int H,
+                                                                  int W, float p_drop, int op_id,
+                                                                  const b2u_step_state* __restrict__ st,
+                                                                  int accumulate, double* __restrict__ bn_sums,
+                                                                  const float* __restrict__ bn_gamma,
+                                                                  const float* __restrict__ bn_beta) {
   extern __shared__ float sbn[];          // [2*C] block partials of the fused BN-backward statistics
-  float rg[8], bt[8], t1[8], t2[8];
+  float t1[8], t2[8], bt[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { t1[k] = 0.f; t2[k] = 0.f; bt[k] = 0.f; }
   if (bn_sums != nullptr) {
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sbn[i] = 0.f;
     const int g0 = (threadIdx.x % (C >> 3)) * 8;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float gm = bn_gamma[g0 + k];
-      rg[k] = fabsf(gm) > 1e-12f ? 1.f / gm : 0.f;
-      bt[k] = bn_beta[g0 + k];
-      t1[k] = 0.f;
-      t2[k] = 0.f;
-    }
+    for (int k = 0; k < 8; ++k) bt[k] = bn_beta[g0 + k];
     __syncthreads();
   }
   const int Ho = H >> 1, Wo = W >> 1;
@@ -301,67 +324,76 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const T* __restri
     const unsigned t = opu / (unsigned)Wo;
     const int ho = (int)(t % (unsigned)Ho);
     const int n = (int)(t / (unsigned)Ho);
-    long long ip = ((long long)n * H + 2 * ho) * W + 2 * wo;
+    const long long ip = ((long long)n * H + 2 * ho) * W + 2 * wo;
     const T* base = x + ip * ldx + g * 8;
-    float a[8], b[8], c[8], d[8], gy[8];
-    load8<T>(base, a);
-    load8<T>(base + ldx, b);
-    load8<T>(base + (long long)W * ldx, c);
-    load8<T>(base + (long long)W * ldx + ldx, d);
-    load8<T>(dy + op * lddy + g * 8, gy);
+    T* ob_ = dx + ip * lddx + g * 8;
+    // all loads of the window first (packed), then the arithmetic
+    Pack8<T> xw[4], ew[4], gp;
+    xw[0].load(base);
+    xw[1].load(base + ldx);
+    xw[2].load(base + (long long)W * ldx);
+    xw[3].load(base + (long long)W * ldx + ldx);
+    gp.load(dy + op * lddy + g * 8);
+    if (accumulate) {
+      ew[0].load(ob_);
+      ew[1].load(ob_ + lddx);
+      ew[2].load(ob_ + (long long)W * lddx);
+      ew[3].load(ob_ + (long long)W * lddx + lddx);
+    }
+    float gy[8];
+    gp.get(gy);
     if (p_drop > 0.f) {
       float f[8];
       keep_factors(p_drop, (uint64_t)op * C + g * 8, st, op_id, f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) gy[k] *= f[k];
     }
-    float oa[8], ob[8], oc[8], od[8];
+    // first maximum in window order (0,0),(0,1),(1,0),(1,1) takes the gradient (TF/torch tie rule)
+    int sel[8];
+    {
+      float a[8], b[8], m[8];
+      xw[0].get(a);
+      xw[1].get(b);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      // first maximum in window order (0,0),(0,1),(1,0),(1,1) takes the gradient (TF/torch tie rule)
-      float m = fmaxf(fmaxf(a[k], b[k]), fmaxf(c[k], d[k]));
-      int sel = (a[k] == m) ? 0 : (b[k] == m) ? 1 : (c[k] == m) ? 2 : 3;
-      oa[k] = sel == 0 ? gy[k] : 0.f;
-      ob[k] = sel == 1 ? gy[k] : 0.f;
-      oc[k] = sel == 2 ? gy[k] : 0.f;
-      od[k] = sel == 3 ? gy[k] : 0.f;
-    }
-    T* ob_ = dx + ip * lddx + g * 8;
-    if (accumulate) {
-      float e[8];
-      load8<T>(ob_, e);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) oa[k] += e[k];
-      load8<T>(ob_ + lddx, e);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) ob[k] += e[k];
-      load8<T>(ob_ + (long long)W * lddx, e);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) oc[k] += e[k];
-      load8<T>(ob_ + (long long)W * lddx + lddx, e);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) od[k] += e[k];
-    }
-    store8<T>(ob_, oa);
-    store8<T>(ob_ + lddx, ob);
-    store8<T>(ob_ + (long long)W * lddx, oc);
-    store8<T>(ob_ + (long long)W * lddx + lddx, od);
-    if (bn_sums != nullptr) {
+      for (int k = 0; k < 8; ++k) { sel[k] = b[k] > a[k] ? 1 : 0; m[k] = fmaxf(a[k], b[k]); }
+      xw[2].get(a);
+      xw[3].get(b);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        t1[k] += (oa[k] + ob[k]) + (oc[k] + od[k]);
-        t2[k] += oa[k] * ((a[k] - bt[k]) * rg[k]) + ob[k] * ((b[k] - bt[k]) * rg[k]) +
-                 oc[k] * ((c[k] - bt[k]) * rg[k]) + od[k] * ((d[k] - bt[k]) * rg[k]);
+        if (a[k] > m[k]) { sel[k] = 2; m[k] = a[k]; }
+        if (b[k] > m[k]) { sel[k] = 3; }
+      }
+    }
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = sel[k] == pos ? gy[k] : 0.f;
+      if (accumulate) {
+        float e[8];
+        ew[pos].get(e);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += e[k];
+      }
+      store8<T>(ob_ + (pos >> 1) * (long long)W * lddx + (pos & 1) * lddx, o);
+      if (bn_sums != nullptr) {
+        float xv[8];
+        xw[pos].get(xv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { t1[k] += o[k]; t2[k] = fmaf(o[k], xv[k] - bt[k], t2[k]); }
       }
     }
   }
   if (bn_sums != nullptr) {
+    // sum dx * xhat with xhat = (x - beta) / gamma: the division by gamma is applied once per thread
     const int g0 = (threadIdx.x % (C >> 3)) * 8;
     if (threadIdx.x / (C >> 3) < kThreads / (C >> 3)) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
+        const float gm = bn_gamma[g0 + k];
+        const float rg = fabsf(gm) > 1e-12f ? 1.f / gm : 0.f;
         atomicAdd(&sbn[g0 + k], t1[k]);
-        atomicAdd(&sbn[C + g0 + k], t2[k]);
+        atomicAdd(&sbn[C + g0 + k], t2[k] * rg);
       }
     }
     __syncthreads();

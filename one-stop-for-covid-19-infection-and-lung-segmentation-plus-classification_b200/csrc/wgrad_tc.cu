@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) tc_wgrad_kernel(const __grid_con
 // =====================================================================================================
 struct WhParams {
   int N, H, W, cin, cout, JT, KSB;
-  int nacc_per_dh;             // 1 (Cin <= 32: dw 0..2 in one MMA) or 2 (Cin = 64: [dw0,dw1] and [dw2,-])
+  int cs, nslab;               // channel slab of x handled by one task (16 / 32 / 64), cin / cs slabs
+  int nacc_per_dh;             // 1 (slab <= 32: dw 0..2 in one MMA) or 2 (slab = 64: [dw0,dw1] and [dw2,-])
   int nsplit, stages;
   float* dw;
 };
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
                                                                       const __grid_constant__ WhParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int cin = prm.cin, JT = prm.JT, KSB = prm.KSB, stages = prm.stages;
+  const int cin = prm.cs, JT = prm.JT, KSB = prm.KSB, stages = prm.stages;   // `cin` = slab width from here on
   const uint32_t rowa = cin * 2, rowb = KSB * 2;
   const uint32_t a_bytes = 180u * rowa, a_stride = (a_bytes + 1023) & ~1023u;
   const int nb = JT / KSB;
@@ -227,7 +228,8 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
   const int tiles_w = (prm.W + 7) / 8, tiles_h = (prm.H + 15) / 16;
   const int nblocks = prm.N * tiles_h * tiles_w;
   const int nj = prm.cout / JT;
-  const int ntasks = prm.nsplit * nj;
+  const int njs = nj * prm.nslab;                             // task = (split, slab, jt), jt fastest
+  const int ntasks = prm.nsplit * njs;
   const int nacc = 3 * prm.nacc_per_dh;
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(nacc * JT)) tmem_cols <<= 1;
@@ -249,13 +251,13 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
       int stage = 0;
       uint32_t phase = 0;
       for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
-        const int jt = task % nj, sp = task / nj;
+        const int jt = task % nj, slab = (task / nj) % prm.nslab, sp = task / njs;
         for (int blk = sp; blk < nblocks; blk += prm.nsplit) {
           const int tw = blk % tiles_w, th = (blk / tiles_w) % tiles_h, n = blk / (tiles_w * tiles_h);
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_stride;
           tc::mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-          tc::tma_load_4d(sa, &maps.a, &full_bar[stage], 0, tw * 8 - 1, th * 16 - 1, n);
+          tc::tma_load_4d(sa, &maps.a, &full_bar[stage], slab * cin, tw * 8 - 1, th * 16 - 1, n);
           for (int s = 0; s < nb; ++s)
             tc::tma_load_4d(sa + a_stride + s * b_tile, &maps.b, &full_bar[stage], jt * JT + s * KSB, tw * 8, th * 16, n);
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
       for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
-        const int sp = task / nj;
+        const int sp = task / njs;
         tc::mbar_wait(tempty_bar, tphase ^ 1);
         tc::fence_after_sync();
         uint32_t first = 1;
@@ -315,14 +317,14 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
     const int chunk = row / cin, ci = row % cin;              // chunk = dw offset inside an accumulator
     uint32_t tphase = 0;
     for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
-      const int jt = task % nj;
+      const int jt = task % nj, slab = (task / nj) % prm.nslab;
       tc::mbar_wait(tfull_bar, tphase);
       tc::fence_after_sync();
       for (int a = 0; a < nacc; ++a) {
         const int dh = a / prm.nacc_per_dh;
         const int dwp = chunk + (prm.nacc_per_dh == 2 ? 2 * (a % 2) : 0);
         const bool live = dwp < 3;
-        float* out = prm.dw + ((long long)((dh * 3 + (live ? dwp : 0)) * cin + ci)) * prm.cout + jt * JT;
+        float* out = prm.dw + ((long long)((dh * 3 + (live ? dwp : 0)) * prm.cin + slab * cin + ci)) * prm.cout + jt * JT;
         for (int c0 = 0; c0 < JT; c0 += 16) {
           float v[16];
           tc::tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + a * JT + c0, v);
@@ -435,21 +437,41 @@ int b2u_tc_convt_wgrad_ok(int cin, int cout, int ldx, int lddy) {
 }
 
 // dw[t][ci][co] += sum_p x[p + off_t][ci] * dy[p][co];  db[co] += sum_p dy[p][co]
-int g_b2u_wgrad_halo = 1;
+int g_b2u_wgrad_halo = 2;   // 0: per-tap tiles only, 1: halo for Cin <= 64, 2: + 32-channel slabs for wide layers, 3: 64-channel slabs
 bool g_attr_h = false;
 
-static int wgrad_halo(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, int n, int h, int wd,
-                      void* stream) {
+// Split-K factor: tasks = ns * base are dealt round-robin to `ctas` persistent CTAs, so the last round is
+// only full when ns * base is close to a multiple of ctas; each task should still own >= ~6 pixel blocks so
+// that its pipeline fill and its accumulator flush (fp32 atomics) stay amortised.
+static int pick_nsplit(int base, int ctas, int nblocks) {
+  int best = 1;
+  double best_score = -1.0;
+  for (int ns = 1; ns <= nblocks && ns <= 64; ++ns) {
+    const long long tasks = (long long)ns * base;
+    const long long rounds = (tasks + ctas - 1) / ctas;
+    const double eff = (double)tasks / (double)(rounds * ctas);
+    const int blocks_per_task = nblocks / ns;
+    if (ns > 1 && blocks_per_task < 6) break;
+    // per-task fixed cost ~ 2 pixel blocks (fill + flush)
+    const double score = eff * (double)blocks_per_task / (double)(blocks_per_task + 2);
+    if (score > best_score + 1e-9) { best_score = score; best = ns; }
+  }
+  return best;
+}
+
+static int wgrad_halo(const void* x, int ldx, int cin, int cs, const void* dy, int lddy, int cout, float* dw, int n, int h,
+                      int wd, void* stream) {
   WhParams p{};
   p.N = n; p.H = h; p.W = wd; p.cin = cin; p.cout = cout; p.dw = dw;
-  p.nacc_per_dh = cin == 64 ? 2 : 1;
+  p.cs = cs; p.nslab = cin / cs;
+  p.nacc_per_dh = cs == 64 ? 2 : 1;
   const int nacc = 3 * p.nacc_per_dh;
   int jt = cout <= 128 ? cout : 128;
   while (nacc * jt > 512 || cout % jt) jt -= 16;
   B2U_REQUIRE(jt >= 16, "tc_wgrad_halo: no N tile for cout=%d", cout);
   p.JT = jt;
   p.KSB = ks_for(jt);
-  const size_t a_stride = ((size_t)180 * cin * 2 + 1023) & ~(size_t)1023, b_bytes = (size_t)jt * 256;
+  const size_t a_stride = ((size_t)180 * cs * 2 + 1023) & ~(size_t)1023, b_bytes = (size_t)jt * 256;
   const size_t tailb = 256;
   // two CTAs per SM (two MMA issuers) when both fit TMEM (512 columns per SM) -- else one CTA with a deep ring
   int cols = 32;
@@ -463,17 +485,23 @@ static int wgrad_halo(const void* x, int ldx, int cin, const void* dy, int lddy,
   const size_t smem = 1024 + (size_t)st * (a_stride + b_bytes) + tailb;
   const int nblocks = n * b2u_cdiv(h, 16) * b2u_cdiv(wd, 8);
   const int nj = cout / jt;
-  int ns = (per_sm * B2U_NUM_SMS + nj - 1) / nj;
-  if (ns > nblocks) ns = nblocks;
-  if (ns < 1) ns = 1;
+  const int base = nj * p.nslab;
+  int ns;
+  if (p.nslab == 1) {
+    ns = (per_sm * B2U_NUM_SMS + nj - 1) / nj;
+    if (ns > nblocks) ns = nblocks;
+    if (ns < 1) ns = 1;
+  } else {
+    ns = pick_nsplit(base, per_sm * B2U_NUM_SMS, nblocks);
+  }
   p.nsplit = ns;
   WhMaps maps;
   {
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)wd * ldx * 2, (cuuint64_t)h * wd * ldx * 2};
-    cuuint32_t box[4] = {(cuuint32_t)cin, 10, 18, 1};
+    cuuint32_t box[4] = {(cuuint32_t)cs, 10, 18, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUtensorMapSwizzle sw = cin == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cin == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUtensorMapSwizzle sw = cs == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cs == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult r = g_enc(&maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b2u_set_error("tc_wgrad_halo: x tensor map failed (%d)", (int)r); return B2U_ERR_CUDA; }
@@ -489,7 +517,7 @@ static int wgrad_halo(const void* x, int ldx, int cin, const void* dy, int lddy,
     B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr_h = true;
   }
-  const int ntasks = ns * nj;
+  const int ntasks = ns * base;
   const int grid = ntasks < per_sm * B2U_NUM_SMS ? ntasks : per_sm * B2U_NUM_SMS;
   B2U_LAUNCH(tc_wgrad_halo_kernel, grid, kThreadsW, smem, stream, maps, p);
   return B2U_OK;
@@ -500,8 +528,14 @@ int b2u_tc_conv3x3_wgrad(const void* x, int ldx, int cin, const void* dy, int ld
   (void)ws; (void)ws_bytes;
   int rc = get_enc();
   if (rc != B2U_OK) return rc;
-  if (g_b2u_wgrad_halo && (cin == 16 || cin == 32 || cin == 64) && cout % 16 == 0) {
-    rc = wgrad_halo(x, ldx, cin, dy, lddy, cout, dw, n, h, wd, stream);
+  // halo variant: thin layers take the whole Cin as one slab; wide layers (wgrad_halo >= 2) are cut into 32-channel
+  // slabs (64-channel with wgrad_halo == 3), one slab per task -- 4x less L2 -> shared-memory traffic than the
+  // per-tap tiles below, which is what bounds them (42 B/clk/SM of L2 bandwidth against 128 B/clk of operands)
+  int cs = 0;
+  if (g_b2u_wgrad_halo && (cin == 16 || cin == 32 || cin == 64)) cs = (g_b2u_wgrad_halo == 4 && cin == 64) ? 32 : cin;
+  else if (g_b2u_wgrad_halo >= 2 && cin > 64 && cin % 32 == 0) cs = (g_b2u_wgrad_halo == 3 && cin % 64 == 0) ? 64 : 32;
+  if (cs != 0 && cout % 16 == 0) {
+    rc = wgrad_halo(x, ldx, cin, cs, dy, lddy, cout, dw, n, h, wd, stream);
     if (rc != B2U_OK) return rc;
     if (db != nullptr) return b2u_channel_sum_f16(dy, lddy, cout, (long long)n * h * wd, db, stream);
     return B2U_OK;
