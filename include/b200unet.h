@@ -195,7 +195,11 @@ enum {
   B2U_OP_GATHER_BATCH
 };
 /* one record; the meaning of p[]/i[]/f[] per kind is the argument order of the function above
- * (pointers in order into p[], ints/long longs into i[], floats into f[]). */
+ * (pointers in order into p[], ints/long longs into i[], floats into f[]).
+ * Op lists only -- one optional trailing pointer `colsum` (fp32 [C], may be NULL) on the ops that write the final
+ * gradient of a conv output: CONV3X3_DGRAD p[4], CONVT_DGRAD p[4], BN_BWD_APPLY p[10], HEAD_BWD p[9].  The kernel adds
+ * the per-channel sums of the dx values it writes, which is that conv's bias gradient (Keras: the `bias` slot of
+ * Conv2D, T1H:859); the matching *_WGRAD op is then given db = NULL and skips its own pass over the gradient. */
 typedef struct b2u_op {
   int32_t kind;
   int32_t dt;

@@ -82,19 +82,31 @@ extern "C" int b2u_conv3x3_fwd(int dt, const void* x, int ldx, int cin, const fl
                                size_t ws_bytes, void* stream) {
   if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy))
     return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats,
-                                                                  nullptr, 0, 0, 0, n, h, wd, ws, ws_bytes, stream);
+                                                                  nullptr, nullptr, 0, 0, 0, n, h, wd, ws, ws_bytes,
+                                                                  stream);
   return b2u_direct_conv3x3(dt, x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, 0, 0, 0, n, h, wd, stream);
+}
+
+// data gradient + optional `colsum` (op lists only): colsum[c] += sum over pixels of the dx values written, i.e. the
+// bias gradient of the layer that produced the tensor dx belongs to
+static int conv3x3_dgrad_cs(int dt, const void* dy, int lddy, int cout, const float* w, void* dx, int lddx, int cin,
+                            const void* mask, int ldmask, int mask_act, int accumulate, float* colsum, int n, int h,
+                            int wd, void* ws, size_t ws_bytes, void* stream) {
+  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cout, cin, lddy, lddx))
+    return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx,
+                                                                  cin, nullptr, colsum, mask, ldmask, mask_act,
+                                                                  accumulate, n, h, wd, ws, ws_bytes, stream);
+  int rc = b2u_direct_conv3x3(dt, dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, mask, ldmask,
+                              mask_act, accumulate, n, h, wd, stream);
+  if (rc != B2U_OK || colsum == nullptr) return rc;
+  return b2u_channel_sum(dt, dx, lddx, cin, (long long)n * h * wd, colsum, stream);       // exact path: extra pass
 }
 
 extern "C" int b2u_conv3x3_dgrad(int dt, const void* dy, int lddy, int cout, const float* w, void* dx, int lddx,
                                  int cin, const void* mask, int ldmask, int mask_act, int accumulate, int n, int h,
                                  int wd, void* ws, size_t ws_bytes, void* stream) {
-  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cout, cin, lddy, lddx))
-    return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx,
-                                                                  cin, nullptr, mask, ldmask, mask_act, accumulate, n, h,
-                                                                  wd, ws, ws_bytes, stream);
-  return b2u_direct_conv3x3(dt, dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, mask, ldmask,
-                            mask_act, accumulate, n, h, wd, stream);
+  return conv3x3_dgrad_cs(dt, dy, lddy, cout, w, dx, lddx, cin, mask, ldmask, mask_act, accumulate, nullptr, n, h, wd,
+                          ws, ws_bytes, stream);
 }
 
 extern "C" int b2u_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, int lddy, int cout,
@@ -114,14 +126,23 @@ extern "C" int b2u_convt2x2_fwd(int dt, const void* x, int ldx, int cin, const f
   return b2u_bn_stats_off(dt, y, ldy, cout, 4LL * n * h * wd, stats, stats_sq_off, stream);   // exact path: extra pass
 }
 
+static int convt2x2_dgrad_cs(int dt, const void* dy, int lddy, int cout, const float* w, void* dx, int lddx, int cin,
+                             const void* mask, int ldmask, int mask_act, int accumulate, float* colsum, int n, int h,
+                             int wd, void* ws, size_t ws_bytes, void* stream) {
+  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_convt_ok(cin, cout, lddx, lddy))
+    return b2u_tc_convt_dgrad(dy, lddy, cout, w, dx, lddx, cin, mask, ldmask, mask_act, accumulate, colsum, n, h, wd,
+                              ws, ws_bytes, stream);
+  int rc = b2u_direct_convt_dgrad(dt, dy, lddy, cout, w, dx, lddx, cin, mask, ldmask, mask_act, accumulate, n, h, wd,
+                                  stream);
+  if (rc != B2U_OK || colsum == nullptr) return rc;
+  return b2u_channel_sum(dt, dx, lddx, cin, (long long)n * h * wd, colsum, stream);       // exact path: extra pass
+}
+
 extern "C" int b2u_convt2x2_dgrad(int dt, const void* dy, int lddy, int cout, const float* w, void* dx, int lddx,
                                   int cin, const void* mask, int ldmask, int mask_act, int accumulate, int n, int h,
                                   int wd, void* ws, size_t ws_bytes, void* stream) {
-  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_convt_ok(cin, cout, lddx, lddy))
-    return b2u_tc_convt_dgrad(dy, lddy, cout, w, dx, lddx, cin, mask, ldmask, mask_act, accumulate, n, h, wd, ws,
-                              ws_bytes, stream);
-  return b2u_direct_convt_dgrad(dt, dy, lddy, cout, w, dx, lddx, cin, mask, ldmask, mask_act, accumulate, n, h, wd,
-                                stream);
+  return convt2x2_dgrad_cs(dt, dy, lddy, cout, w, dx, lddx, cin, mask, ldmask, mask_act, accumulate, nullptr, n, h, wd,
+                           ws, ws_bytes, stream);
 }
 
 extern "C" int b2u_convt2x2_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, int lddy, int cout,
@@ -145,18 +166,18 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
     case B2U_OP_CONV3X3_FWD:
       return b2u_conv3x3_fwd(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], I(2), p[3], I(3), I(4),
                              (double*)p[4], I(5), I(6), I(7), ws, wsb, s);
-    case B2U_OP_CONV3X3_DGRAD:
-      return b2u_conv3x3_dgrad(dt, p[0], I(0), I(1), (const float*)p[1], p[2], I(2), I(3), p[3], I(4), I(5), I(6), I(7),
-                               I(8), I(9), ws, wsb, s);
+    case B2U_OP_CONV3X3_DGRAD:       // p[4] (optional): colsum
+      return conv3x3_dgrad_cs(dt, p[0], I(0), I(1), (const float*)p[1], p[2], I(2), I(3), p[3], I(4), I(5), I(6),
+                              (float*)p[4], I(7), I(8), I(9), ws, wsb, s);
     case B2U_OP_CONV3X3_WGRAD:
       return b2u_conv3x3_wgrad(dt, p[0], I(0), I(1), p[1], I(2), I(3), (float*)p[2], (float*)p[3], I(4), I(5), I(6), ws,
                                wsb, s);
     case B2U_OP_CONVT_FWD:
       return b2u_convt2x2_fwd(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], p[3], I(2), I(3),
                               (double*)p[4], I(7), I(4), I(5), I(6), ws, wsb, s);
-    case B2U_OP_CONVT_DGRAD:
-      return b2u_convt2x2_dgrad(dt, p[0], I(0), I(1), (const float*)p[1], p[2], I(2), I(3), p[3], I(4), I(5), I(6), I(7),
-                                I(8), I(9), ws, wsb, s);
+    case B2U_OP_CONVT_DGRAD:         // p[4] (optional): colsum
+      return convt2x2_dgrad_cs(dt, p[0], I(0), I(1), (const float*)p[1], p[2], I(2), I(3), p[3], I(4), I(5), I(6),
+                               (float*)p[4], I(7), I(8), I(9), ws, wsb, s);
     case B2U_OP_CONVT_WGRAD:
       return b2u_convt2x2_wgrad(dt, p[0], I(0), I(1), p[1], I(2), I(3), (float*)p[2], (float*)p[3], I(4), I(5), I(6), ws,
                                 wsb, s);
@@ -172,10 +193,10 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
     case B2U_OP_BN_BWD_REDUCE:
       return b2u_bn_bwd_reduce(dt, p[0], I(0), p[1], I(1), I(2), i[3], (const float*)p[2], (const float*)p[3],
                                (double*)p[4], s);
-    case B2U_OP_BN_BWD_APPLY:
-      return b2u_bn_bwd_apply(dt, p[0], I(0), p[1], I(1), p[2], I(2), I(3), i[4], i[7], (const float*)p[3],
-                              (const float*)p[4], (const float*)p[5], (const double*)p[6], (float*)p[7], (float*)p[8],
-                              p[9], I(5), I(6), s);
+    case B2U_OP_BN_BWD_APPLY:        // p[10] (optional): colsum
+      return b2u_bn_bwd_apply_cs(dt, p[0], I(0), p[1], I(1), p[2], I(2), I(3), i[4], i[7], (const float*)p[3],
+                                 (const float*)p[4], (const float*)p[5], (const double*)p[6], (float*)p[7],
+                                 (float*)p[8], p[9], I(5), I(6), (float*)p[10], s);
     case B2U_OP_MAXPOOL_FWD:
       return b2u_maxpool_fwd(dt, p[0], I(0), p[1], I(1), I(2), I(3), I(4), I(5), f[0], I(6),
                              (const b2u_step_state*)p[2], s);
@@ -195,10 +216,10 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
       return b2u_bce_dice_sums((const float*)p[0], (const float*)p[1], i[0], (double*)p[2], s);
     case B2U_OP_BCE_DICE_FINALIZE:
       return b2u_bce_dice_finalize((const double*)p[0], i[0], (float*)p[1], s);
-    case B2U_OP_HEAD_BWD:
-      return b2u_head_bwd(dt, (const float*)p[0], (const float*)p[1], (const double*)p[2], i[0],
-                          (const b2u_step_state*)p[3], p[4], I(1), I(2), (const float*)p[5], p[6], I(3), I(4),
-                          (float*)p[7], (float*)p[8], i[5], s);
+    case B2U_OP_HEAD_BWD:            // p[9] (optional): colsum
+      return b2u_head_bwd_cs(dt, (const float*)p[0], (const float*)p[1], (const double*)p[2], i[0],
+                             (const b2u_step_state*)p[3], p[4], I(1), I(2), (const float*)p[5], p[6], I(3), I(4),
+                             (float*)p[7], (float*)p[8], i[5], (float*)p[9], s);
     case B2U_OP_DENSE_FWD:
       return b2u_dense_fwd(dt, p[0], I(0), (const float*)p[1], (const float*)p[2], I(1), p[3], I(2), I(3), s);
     case B2U_OP_DENSE_BWD:

@@ -641,6 +641,16 @@ int b2u_direct_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const void
 }
 
 // db[c] += sum over pixels of dy[.][c]  (bias gradient beside the tcgen05 weight-gradient kernel)
+// db[c] += sum over pixels of dy[p][c] for either storage type (fallback for producers that cannot emit the sums)
+int b2u_channel_sum(int dt, const void* dy, int lddy, int c, long long npix, float* db, void* stream) {
+  B2U_REQUIRE(c % 8 == 0 && lddy % 8 == 0 && c <= 2048, "channel_sum: c%%8==0 required");
+  int lanes = 256 / (c / 8);
+  long long g = (npix + lanes - 1) / lanes;
+  if (g > 4LL * B2U_NUM_SMS) g = 4LL * B2U_NUM_SMS;
+  DISPATCH_T(dt, B2U_LAUNCH(channel_sum_kernel<T>, (int)g, 256, c * sizeof(float), stream, (const T*)dy, lddy, c, npix, db));
+  return B2U_OK;
+}
+
 int b2u_channel_sum_f16(const void* dy, int lddy, int c, long long npix, float* db, void* stream) {
   B2U_REQUIRE(c % 8 == 0 && lddy % 8 == 0 && c <= 2048, "channel_sum: c%%8==0 required");
   int lanes = 256 / (c / 8);

@@ -52,6 +52,8 @@ struct TcParams {
   int accumulate;
   double* stats;          // sums at stats[c], squares at stats[stats_sq_off + c]; null: none
   int stats_sq_off;
+  float* colsum;          // per-column sums of the stored values (fp32 atomics): the bias gradient of the layer whose
+                          // output gradient this kernel writes; null: none
 };
 
 struct TcMaps {
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
             store8<__half>(dst, v);
             store8<__half>(dst + 8, v + 8);
           }
-          if (kRegStats) {
+          if (kRegStats) {                       // (launched only when statistics or column sums are wanted)
             if (valid) {
               if (cc == 0) {
 #pragma unroll
@@ -281,17 +283,20 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
                 for (int i = 0; i < 16; ++i) { rs1[(kRegStats ? 16 : 0) + i] += v[i]; rs2[(kRegStats ? 16 : 0) + i] = fmaf(v[i], v[i], rs2[(kRegStats ? 16 : 0) + i]); }
               }
             }
-          } else if (prm.stats != nullptr) {
-            float q[16], sq[16];
+          } else if (prm.stats != nullptr || prm.colsum != nullptr) {
+            const int sc = prm.mode == 1 ? (j0 % prm.cout) : j0;         // scatter mode: column -> output channel
+            float q[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { q[i] = valid ? v[i] : 0.f; sq[i] = q[i] * q[i]; }
-            float s1 = transpose_reduce16(q, lane);
-            float s2 = transpose_reduce16(sq, lane);
-            if (lane < 16) {
-              const int sc = prm.mode == 1 ? (j0 % prm.cout) : j0;       // scatter mode: column -> output channel
-              atomicAdd(&s_stats[sc + lane], s1);
-              atomicAdd(&s_stats[prm.J + sc + lane], s2);
+            for (int i = 0; i < 16; ++i) q[i] = valid ? v[i] : 0.f;
+            if (prm.stats != nullptr) {
+              float sq[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sq[i] = q[i] * q[i];
+              float s2 = transpose_reduce16(sq, lane);
+              if (lane < 16) atomicAdd(&s_stats[prm.J + sc + lane], s2);
             }
+            float s1 = transpose_reduce16(q, lane);
+            if (lane < 16) atomicAdd(&s_stats[sc + lane], s1);
           }
         }
       }
@@ -330,6 +335,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
     for (int i = threadIdx.x; i < nstat; i += kThreadsTc) {
       atomicAdd(&prm.stats[i], (double)s_stats[i]);
       atomicAdd(&prm.stats[prm.stats_sq_off + i], (double)s_stats[prm.J + i]);
+    }
+  }
+  if (prm.colsum != nullptr) {
+    const int nstat = prm.mode == 1 ? prm.cout : prm.J;
+    for (int i = threadIdx.x; i < nstat; i += kThreadsTc) {
+      const float sv = s_stats[i];
+      if (sv != 0.f) atomicAdd(&prm.colsum[i], sv);
     }
   }
   if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
@@ -452,7 +464,7 @@ int launch_tc(const TcMaps& maps, TcParams& prm, void* stream) {
   int grid = (int)(tiles < B2U_NUM_SMS ? tiles : B2U_NUM_SMS);
   // register statistics need a fixed N tile per CTA (grid a multiple of nj) and <= 32 columns per epilogue thread
   const int nparts = prm.JT % 64 == 0 ? 4 : (prm.JT % 32 == 0 ? 2 : 1);
-  bool reg_stats = prm.stats != nullptr && prm.JT / nparts <= 32 && nj <= B2U_NUM_SMS;
+  bool reg_stats = (prm.stats != nullptr || prm.colsum != nullptr) && prm.JT / nparts <= 32 && nj <= B2U_NUM_SMS;
   if (reg_stats) {
     const int g2 = grid / nj * nj;
     if (g2 >= 1) grid = g2; else reg_stats = false;
@@ -485,8 +497,8 @@ int b2u_tc_convt_ok(int cin, int cout, int ld_small, int ld_big) {
 }
 
 int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
-                   int ldy, int J, double* stats, const void* mask, int ldmask, int mask_act, int accumulate, int n,
-                   int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+                   int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
+                   int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
   int rc = get_encode();
   if (rc != B2U_OK) return rc;
   TcParams p{};
@@ -494,7 +506,8 @@ int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, con
   for (int t = 0; t < 9; ++t) { p.tap_dh[t] = t / 3 - 1; p.tap_dw[t] = t % 3 - 1; p.tap_map[t] = 0; }
   p.mode = 0; p.cout = J; p.y = (__half*)y; p.ldy = ldy; p.bias = bias; p.act = act;
   p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate; p.stats = stats;
-  p.stats_sq_off = J;
+  p.stats_sq_off = J; p.colsum = colsum;
+  if (colsum != nullptr && J % 128 == 0 && p.JT > 128) p.JT = 128;
   rc = pack(w, ws, ws_bytes, dgrad ? 1 : 0, 9, J, K, stream);
   if (rc != B2U_OK) return rc;
   TcMaps maps;
@@ -529,8 +542,8 @@ int b2u_tc_convt_fwd(const void* x, int ldx, int cin, const float* w, const floa
 }
 
 int b2u_tc_convt_dgrad(const void* dy, int lddy, int cout, const float* w, void* dx, int lddx, int cin,
-                       const void* mask, int ldmask, int mask_act, int accumulate, int n, int h, int wd, void* ws,
-                       size_t ws_bytes, void* stream) {
+                       const void* mask, int ldmask, int mask_act, int accumulate, float* colsum, int n, int h, int wd,
+                       void* ws, size_t ws_bytes, void* stream) {
   int rc = get_encode();
   if (rc != B2U_OK) return rc;
   TcParams p{};
@@ -538,6 +551,8 @@ int b2u_tc_convt_dgrad(const void* dy, int lddy, int cout, const float* w, void*
   for (int t = 0; t < 4; ++t) { p.tap_dh[t] = 0; p.tap_dw[t] = 0; p.tap_map[t] = t; }
   p.mode = 0; p.cout = cin; p.y = (__half*)dx; p.ldy = lddx; p.bias = nullptr; p.act = B2U_ACT_NONE;
   p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate;
+  p.colsum = colsum;
+  if (colsum != nullptr && cin % 128 == 0 && p.JT > 128) p.JT = 128;   // <= 32 columns per epilogue thread
   rc = pack(w, ws, ws_bytes, 3, 4, cin, cout, stream);
   if (rc != B2U_OK) return rc;
   TcMaps maps;

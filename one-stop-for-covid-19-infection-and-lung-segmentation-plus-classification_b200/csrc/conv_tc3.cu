@@ -41,7 +41,9 @@ struct C3Params {
   const float* bias; int act;
   const __half* mask; int ldmask; int mask_act;
   int accumulate;
-  double* stats;
+  double* stats;          // BatchNorm statistics of the stored values: sums at [c], squares at [J + c]
+  float* colsum;          // per-channel sums of the stored values, added with fp32 atomics (bias gradient of the
+                          // layer whose output gradient this kernel writes)
   long long* dbg;         // optional timeline buffer (CTA 0): [iter][8] clock64 stamps
 };
 
@@ -245,7 +247,8 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
     const int ccols = split ? JT / 2 : JT;                        // columns owned by this warp within a tile
     const int cbeg = split ? half * ccols : 0;
     const bool has_cols = split || half == 0;
-    const bool reg_stats = prm.stats != nullptr && ccols <= 32 && nj == 1;
+    const bool want_sums = prm.stats != nullptr || prm.colsum != nullptr;
+    const bool reg_stats = want_sums && ccols <= 32 && nj == 1;
     float rs1[32], rs2[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
             store8<__half>(yrow + c0, v);
             store8<__half>(yrow + c0 + 8, v + 8);
           }
-          if (prm.stats != nullptr) {
+          if (want_sums) {
             if (reg_stats) {
               if (valid) {
                 if (cc == 0) {
@@ -320,15 +323,18 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
                 }
               }
             } else {
-              float q[16], sq[16];
+              float q[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) { q[i] = valid ? v[i] : 0.f; sq[i] = q[i] * q[i]; }
-              float s1 = transpose_reduce16_(q, lane);
-              float s2 = transpose_reduce16_(sq, lane);
-              if (lane < 16) {
-                atomicAdd(&s_stats[jt * JT + c0 + lane], s1);
-                atomicAdd(&s_stats[prm.J + jt * JT + c0 + lane], s2);
+              for (int i = 0; i < 16; ++i) q[i] = valid ? v[i] : 0.f;
+              if (prm.stats != nullptr) {
+                float sq[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sq[i] = q[i] * q[i];
+                float s2 = transpose_reduce16_(sq, lane);
+                if (lane < 16) atomicAdd(&s_stats[prm.J + jt * JT + c0 + lane], s2);
               }
+              float s1 = transpose_reduce16_(q, lane);
+              if (lane < 16) atomicAdd(&s_stats[jt * JT + c0 + lane], s1);
             }
           }
         }
@@ -362,6 +368,12 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
     for (int i = threadIdx.x; i < 2 * prm.J; i += blockDim.x) {
       float s = s_stats[i];
       if (s != 0.f) atomicAdd(&prm.stats[i], (double)s);
+    }
+  }
+  if (prm.colsum != nullptr) {
+    for (int i = threadIdx.x; i < prm.J; i += blockDim.x) {
+      float s = s_stats[i];
+      if (s != 0.f) atomicAdd(&prm.colsum[i], s);
     }
   }
   if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
@@ -409,8 +421,8 @@ long long* g_b2u_dbg = nullptr;   // device timeline buffer (b2u_set_option("tc_
 int g_b2u_tc_halo = 1;       // 0: per-tap loads (conv_tc.cu), 1: halo box, 2: halo box + base_offset, 3: three boxes
 
 int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
-                        int ldy, int J, double* stats, const void* mask, int ldmask, int mask_act, int accumulate,
-                        int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+                        int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
+                        int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
   int rc = get_enc3();
   if (rc != B2U_OK) return rc;
   C3Params p{};
@@ -422,6 +434,7 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   p.bo_mode = 0;      // descriptor base offsets are wrong for address-anchored swizzles (probed on B200): unused
   p.y = (__half*)y; p.ldy = ldy; p.bias = bias; p.act = act;
   p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate; p.stats = stats;
+  p.colsum = colsum;
   p.dbg = g_b2u_dbg;
   const uint32_t rowb = p.KS * 2;
   const uint32_t rows = p.amode == 3 ? 18 * 8 : 18 * 10;

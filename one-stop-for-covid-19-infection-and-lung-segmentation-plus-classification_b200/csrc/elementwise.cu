@@ -2,6 +2,7 @@
 // dropout, concat slice copies, the 1x1+sigmoid head with the BCE+Dice loss, Adam, batch gather.
 // All are coalesced 8-channel-vector streaming kernels with grids sized in multiples of the SM count.
 #include "common.cuh"
+#include "internal.h"
 #include "launch.cuh"
 
 namespace {
@@ -181,12 +182,21 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
   }
 }
 
-template <typename T>
+template <typename T, bool kColsum>
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
     const T* __restrict__ dy, int lddy, const T* __restrict__ x, int ldx, T* __restrict__ dx, int lddx, int C,
     long long npix, long long count, const float* __restrict__ gamma, const float* __restrict__ mean,
     const float* __restrict__ invstd, const double* __restrict__ sums, float* __restrict__ dgamma,
-    float* __restrict__ dbeta, const T* __restrict__ mask, int ldmask, int mask_act) {
+    float* __restrict__ dbeta, const T* __restrict__ mask, int ldmask, int mask_act, float* __restrict__ colsum) {
+  // colsum (optional): per-channel sums of the dx values written = bias gradient of the conv that feeds this BN
+  extern __shared__ float scs[];          // [C] block partials of colsum
+  float cs[kColsum ? 8 : 1];
+#pragma unroll
+  for (int k = 0; k < (kColsum ? 8 : 1); ++k) cs[k] = 0.f;
+  if (kColsum) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) scs[i] = 0.f;
+    __syncthreads();
+  }
   const float inv_n = 1.f / (float)count;
   if (blockIdx.x == 0 && dgamma != nullptr) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -223,6 +233,19 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
       for (int k = 0; k < 8; ++k) o[k] *= act_bwd_from_y(mv[k], mask_act);
     }
     store8<T>(dx + p * lddx + g * 8, o);
+    if (kColsum) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[kColsum ? k : 0] += o[k];
+    }
+  }
+  if (kColsum) {
+    const int g0 = (threadIdx.x % (C >> 3)) * 8;
+    if (threadIdx.x / (C >> 3) < kThreads / (C >> 3)) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&scs[g0 + k], cs[kColsum ? k : 0]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&colsum[i], scs[i]);
   }
 }
 
@@ -500,55 +523,81 @@ __global__ void bce_dice_finalize_kernel(const double* __restrict__ sums, long l
   out[1] = (float)dice;
 }
 
-template <typename T, int CIN>
+// Thread = (pixel lane, 8-channel group): 16-byte coalesced loads / stores, the per-pixel loss derivative is
+// recomputed by the C/8 threads of a pixel (prob / target are broadcast loads).  Besides dW (sum dl * x) and db it
+// can emit `colsum` = per-channel sums of the dx values written (the bias gradient of the conv feeding the head).
+template <typename T>
 __global__ void __launch_bounds__(kThreads) head_bwd_kernel(
     const float* __restrict__ prob, const float* __restrict__ tgt, const double* __restrict__ sums,
     long long count, const b2u_step_state* __restrict__ st, const T* __restrict__ x, int ldx,
     const float* __restrict__ w, T* __restrict__ dx, int lddx, int x_act, float* __restrict__ dw,
-    float* __restrict__ db, long long npix) {
-  __shared__ float sacc[CIN + 1];
-  for (int i = threadIdx.x; i < CIN + 1; i += blockDim.x) sacc[i] = 0.f;
+    float* __restrict__ db, long long npix, int C, float* __restrict__ colsum) {
+  extern __shared__ float sacc[];          // [2*C + 1]: dW partials, colsum partials, db partial
+  for (int i = threadIdx.x; i < 2 * C + 1; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
-  float wr[CIN], acc[CIN];
+  float wr[8], acc[8], cs[8];
+  {
+    const int g0 = (threadIdx.x % (C >> 3)) * 8;
 #pragma unroll
-  for (int k = 0; k < CIN; ++k) { wr[k] = __ldg(w + k); acc[k] = 0.f; }
+    for (int k = 0; k < 8; ++k) { wr[k] = __ldg(w + g0 + k); acc[k] = 0.f; cs[k] = 0.f; }
+  }
   float accb = 0.f;
   const double I = sums[0], S = sums[1] + sums[2];
   const float inv_s1 = (float)(1.0 / (S + 1.0));
   const float two_i1 = (float)(2.0 * I + 1.0);
   const float scale = st->loss_scale;
   const float half_inv_n = 0.5f / (float)count;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
-       p += (long long)gridDim.x * blockDim.x) {
-    float pr = prob[p], t = tgt[p];
-    float g = 0.f;
-    if (pr >= 1e-7f && pr <= 1.f - 1e-7f) g = half_inv_n * (-t / pr + (1.f - t) / (1.f - pr));
-    // d(1-dice)/dp = -(2 t (S+1) - (2I+1)) / (S+1)^2
-    g -= 0.5f * (2.f * t - two_i1 * inv_s1) * inv_s1;
-    float dl = g * pr * (1.f - pr) * scale;
-    accb += dl;
+  // two pixels per trip (both inside the block's contiguous span): all loads are issued before the arithmetic
+  const int cg = C >> 3;
+  const int lanes = kThreads / cg;
+  const int g = threadIdx.x % cg, lane_ = threadIdx.x / cg;
+  if (lane_ < lanes) {
+    for (long long p0 = (long long)blockIdx.x * lanes * 2 + lane_; p0 < npix; p0 += (long long)gridDim.x * lanes * 2) {
+      const long long p1 = p0 + lanes;
+      const bool two = p1 < npix;
+      float v[2][8], pr[2], tt[2];
+      pr[0] = prob[p0]; tt[0] = tgt[p0];
+      load8<T>(x + p0 * ldx + g * 8, v[0]);
+      pr[1] = two ? prob[p1] : 0.5f; tt[1] = two ? tgt[p1] : 0.f;
+      if (two) load8<T>(x + p1 * ldx + g * 8, v[1]);
 #pragma unroll
-    for (int gq = 0; gq < CIN / 8; ++gq) {
-      float v[8], o[8];
-      load8<T>(x + p * ldx + gq * 8, v);
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+        const float prv = pr[u], t = tt[u];
+        float gq = 0.f;
+        if (prv >= 1e-7f && prv <= 1.f - 1e-7f) gq = half_inv_n * (-t / prv + (1.f - t) / (1.f - prv));
+        // d(1-dice)/dp = -(2 t (S+1) - (2I+1)) / (S+1)^2
+        gq -= 0.5f * (2.f * t - two_i1 * inv_s1) * inv_s1;
+        const float dl = gq * prv * (1.f - prv) * scale;
+        if (g == 0) accb += dl;
+        float o[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        acc[gq * 8 + k] = fmaf(dl, v[k], acc[gq * 8 + k]);
-        o[k] = dl * wr[gq * 8 + k] * act_bwd_from_y(v[k], x_act);
+        for (int k = 0; k < 8; ++k) {
+          acc[k] = fmaf(dl, v[u][k], acc[k]);
+          o[k] = dl * wr[k] * act_bwd_from_y(v[u][k], x_act);
+          cs[k] += o[k];
+        }
+        store8<T>(dx + (u ? p1 : p0) * lddx + g * 8, o);
       }
-      store8<T>(dx + p * lddx + gq * 8, o);
     }
   }
+  {
+    const int g0 = (threadIdx.x % (C >> 3)) * 8;
+    if (threadIdx.x / (C >> 3) < kThreads / (C >> 3)) {
 #pragma unroll
-  for (int k = 0; k < CIN; ++k) {
-    float s = warp_sum(acc[k]);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[k], s);
+      for (int k = 0; k < 8; ++k) {
+        atomicAdd(&sacc[g0 + k], acc[k]);
+        atomicAdd(&sacc[C + g0 + k], cs[k]);
+      }
+      if (g0 == 0) atomicAdd(&sacc[2 * C], accb);
+    }
   }
-  float sb = warp_sum(accb);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[CIN], sb);
   __syncthreads();
-  for (int i = threadIdx.x; i < CIN; i += blockDim.x) atomicAdd(&dw[i], sacc[i]);
-  if (threadIdx.x == 0) atomicAdd(db, sacc[CIN]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&dw[i], sacc[i]);
+    if (colsum != nullptr) atomicAdd(&colsum[i], sacc[C + i]);
+  }
+  if (threadIdx.x == 0) atomicAdd(db, sacc[2 * C]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -817,14 +866,28 @@ extern "C" int b2u_bn_bwd_apply(int dt, const void* dy, int lddy, const void* x,
                                 long long npix, long long count, const float* gamma, const float* save_mean,
                                 const float* save_invstd, const double* sums, float* dgamma, float* dbeta,
                                 const void* mask, int ldmask, int mask_act, void* stream) {
+  return b2u_bn_bwd_apply_cs(dt, dy, lddy, x, ldx, dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums, dgamma,
+                             dbeta, mask, ldmask, mask_act, nullptr, stream);
+}
+
+int b2u_bn_bwd_apply_cs(int dt, const void* dy, int lddy, const void* x, int ldx, void* dx, int lddx, int c,
+                        long long npix, long long count, const float* gamma, const float* save_mean,
+                        const float* save_invstd, const double* sums, float* dgamma, float* dbeta, const void* mask,
+                        int ldmask, int mask_act, float* colsum, void* stream) {
   REQ_VEC8(c);
   B2U_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && (mask == nullptr || ldmask % 8 == 0),
               "bn_bwd_apply: alignment");
   B2U_REQUIRE(c <= 2048, "bn_bwd_apply: c <= 2048");
   int grid = lane_grid(npix, c);
-  DISPATCH_T(dt, B2U_LAUNCH(bn_bwd_apply_kernel<T>, grid, kThreads, 0, stream, (const T*)dy, lddy, (const T*)x, ldx,
-                            (T*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums, dgamma, dbeta,
-                            (const T*)mask, ldmask, mask_act));
+  if (colsum != nullptr) {
+    DISPATCH_T(dt, B2U_LAUNCH((bn_bwd_apply_kernel<T, true>), grid, kThreads, c * sizeof(float), stream, (const T*)dy,
+                              lddy, (const T*)x, ldx, (T*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums,
+                              dgamma, dbeta, (const T*)mask, ldmask, mask_act, colsum));
+  } else {
+    DISPATCH_T(dt, B2U_LAUNCH((bn_bwd_apply_kernel<T, false>), grid, kThreads, 0, stream, (const T*)dy,
+                              lddy, (const T*)x, ldx, (T*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums,
+                              dgamma, dbeta, (const T*)mask, ldmask, mask_act, colsum));
+  }
   return B2U_OK;
 }
 
@@ -918,12 +981,18 @@ extern "C" int b2u_bce_dice_finalize(const double* sums, long long count, float*
 extern "C" int b2u_head_bwd(int dt, const float* prob, const float* target, const double* sums, long long count,
                             const b2u_step_state* d_state, const void* x, int ldx, int cin, const float* w,
                             void* dx, int lddx, int x_act, float* dw, float* db, long long npix, void* stream) {
-  B2U_REQUIRE(cin == 32 || cin == 16 || cin == 64, "head_bwd: cin must be 16, 32 or 64 (got %d)", cin);
+  return b2u_head_bwd_cs(dt, prob, target, sums, count, d_state, x, ldx, cin, w, dx, lddx, x_act, dw, db, npix, nullptr,
+                         stream);
+}
+
+int b2u_head_bwd_cs(int dt, const float* prob, const float* target, const double* sums, long long count,
+                    const b2u_step_state* d_state, const void* x, int ldx, int cin, const float* w, void* dx, int lddx,
+                    int x_act, float* dw, float* db, long long npix, float* colsum, void* stream) {
+  B2U_REQUIRE(cin % 8 == 0 && cin >= 8 && cin <= 256, "head_bwd: cin must be a multiple of 8 in [8, 256] (got %d)", cin);
   B2U_REQUIRE(ldx % 8 == 0 && lddx % 8 == 0 && d_state != nullptr, "head_bwd: args");
-  int grid = stream_grid(npix, kThreads, 4);
-#define HEAD_BWD(CI) DISPATCH_T(dt, B2U_LAUNCH((head_bwd_kernel<T, CI>), grid, kThreads, 0, stream, prob, target, sums, count, d_state, (const T*)x, ldx, w, (T*)dx, lddx, x_act, dw, db, npix))
-  if (cin == 32) { HEAD_BWD(32); } else if (cin == 16) { HEAD_BWD(16); } else { HEAD_BWD(64); }
-#undef HEAD_BWD
+  int grid = lane_grid((npix + 1) / 2, cin);
+  DISPATCH_T(dt, B2U_LAUNCH(head_bwd_kernel<T>, grid, kThreads, (2 * cin + 1) * sizeof(float), stream, prob, target,
+                            sums, count, d_state, (const T*)x, ldx, w, (T*)dx, lddx, x_act, dw, db, npix, cin, colsum));
   return B2U_OK;
 }
 

@@ -127,13 +127,15 @@ class Plan:
     """Op lists + arena sizes for one (graph, batch size, storage type, mode) combination."""
 
     def __init__(self, graph, n, dt=F32, training=True, dropout=True, loss="bce_dice", world=1,
-                 sync_stats=False, layout=None, rank=0, fuse_bn_bwd=True, fuse_bn_stats=True):
+                 sync_stats=False, layout=None, rank=0, fuse_bn_bwd=True, fuse_bn_stats=True, fuse_bias_grad=True):
         self.graph, self.n, self.dt, self.training = graph, int(n), dt, training
         self.dropout = dropout and training
         self.loss, self.world, self.sync_stats = loss, int(world), bool(sync_stats) and world > 1
         self.rank = int(rank)
         self.fuse_bn_bwd = bool(fuse_bn_bwd)
         self.fuse_bn_stats = bool(fuse_bn_stats)
+        self.fuse_bias_grad = bool(fuse_bias_grad)
+        self._bias_done = set()          # id(conv layer) whose bias gradient is produced by another backward op
         self.layout = layout or ParamLayout(graph)
         self.act, self.f32, self.zero = Arena("act"), Arena("f32"), Arena("zero")
         self.fwd, self.bwd, self.opt = [], [], []
@@ -178,6 +180,21 @@ class Plan:
         if len(t.consumers) != 1:
             raise NotImplementedError("activated tensor %r with %d consumers" % (t, len(t.consumers)))
         return self.views[id(t)], ACT[a]
+
+    def _bias_sink(self, t):
+        """The op that writes the FINAL gradient of tensor t (activation derivative applied, single writer) can also
+        emit its per-channel sums: that is the bias gradient of the conv that produced t, so the weight-gradient op
+        need not read the whole gradient again.  Returns the Ref of that bias gradient (and remembers the layer),
+        or None when t is not such a tensor."""
+        if not self.fuse_bias_grad:
+            return None
+        while t.producer.kind == "dropout" and self.views[id(t)] is self.views[id(t.producer.inputs[0])]:
+            t = t.producer.inputs[0]
+        l = t.producer
+        if l.kind != "conv2d" or tuple(l.kernel_size) != (3, 3) or len(t.consumers) != 1 or t.channels % 8:
+            return None
+        self._bias_done.add(id(l))
+        return self._w(l, "bias", "grads")
 
     # ---------------------------------------------------------------------------------------
     # lowering
@@ -394,7 +411,8 @@ class Plan:
                 gx = self.gviews[id(x)]
                 mv, ma = self._mask_for(x)
                 self.bwd.append(Op(OP_HEAD_BWD, dt, [self.prob, self.target, self.loss_sums, self.step_ref, xv.ref,
-                                                     self._w(l, "kernel"), gx.ref, grads(l, "kernel"), grads(l, "bias")],
+                                                     self._w(l, "kernel"), gx.ref, grads(l, "kernel"), grads(l, "bias"),
+                                                     self._bias_sink(x) if mv is not None else None],
                                    [self.loss_count, xv.ld, xv.c, gx.ld, ma, self._npix(xv)], tag=l.name))
                 written.add(id(x))
                 continue
@@ -409,22 +427,33 @@ class Plan:
                 raise RuntimeError("no gradient reached %s" % l.name)
             gy = self.gviews[id(t)]
             if l.kind == "conv2d":
-                self.bwd.append(Op(OP_CONV3X3_WGRAD, dt, [xv.ref, gy.ref, grads(l, "kernel"), grads(l, "bias")],
+                self.bwd.append(Op(OP_CONV3X3_WGRAD, dt, [xv.ref, gy.ref, grads(l, "kernel"),
+                                                          None if id(l) in self._bias_done else grads(l, "bias")],
                                    [xv.ld, xv.c, gy.ld, gy.c, n, xv.h, xv.w], tag=l.name))
                 if not x_is_input:
                     gx = self.gviews[id(x)]
                     mv, ma = self._mask_for(x)
-                    self.bwd.append(Op(OP_CONV3X3_DGRAD, dt, [gy.ref, self._w(l, "kernel"), gx.ref, mv.ref if mv else None],
-                                       [gy.ld, gy.c, gx.ld, gx.c, mv.ld if mv else 0, ma, 1 if id(x) in written else 0,
+                    acc = 1 if id(x) in written else 0
+                    sink = self._bias_sink(x) if (mv is not None and not acc) else None
+                    self.bwd.append(Op(OP_CONV3X3_DGRAD, dt, [gy.ref, self._w(l, "kernel"), gx.ref, mv.ref if mv else None, sink],
+                                       [gy.ld, gy.c, gx.ld, gx.c, mv.ld if mv else 0, ma, acc,
                                         n, xv.h, xv.w], tag=l.name))
                     written.add(id(x))
             elif l.kind == "conv2d_transpose":
-                self.bwd.append(Op(OP_CONVT_WGRAD, dt, [xv.ref, gy.ref, grads(l, "kernel"), grads(l, "bias")],
+                # a transposed conv whose output only feeds (through a concatenate) a training-mode BatchNorm has an
+                # analytically zero bias gradient: the BN backward output sums to zero over every channel
+                zero_db = (self.fuse_bias_grad and len(t.consumers) == 1 and t.consumers[0].kind == "concatenate" and
+                           len(t.consumers[0].output.consumers) == 1 and
+                           t.consumers[0].output.consumers[0].kind == "batch_normalization")
+                self.bwd.append(Op(OP_CONVT_WGRAD, dt, [xv.ref, gy.ref, grads(l, "kernel"),
+                                                        None if zero_db else grads(l, "bias")],
                                    [xv.ld, xv.c, gy.ld, gy.c, n, xv.h, xv.w], tag=l.name))
                 gx = self.gviews[id(x)]
                 mv, ma = self._mask_for(x)
-                self.bwd.append(Op(OP_CONVT_DGRAD, dt, [gy.ref, self._w(l, "kernel"), gx.ref, mv.ref if mv else None],
-                                   [gy.ld, gy.c, gx.ld, gx.c, mv.ld if mv else 0, ma, 1 if id(x) in written else 0,
+                acc = 1 if id(x) in written else 0
+                sink = self._bias_sink(x) if (mv is not None and not acc) else None
+                self.bwd.append(Op(OP_CONVT_DGRAD, dt, [gy.ref, self._w(l, "kernel"), gx.ref, mv.ref if mv else None, sink],
+                                   [gy.ld, gy.c, gx.ld, gx.c, mv.ld if mv else 0, ma, acc,
                                     n, xv.h, xv.w], tag=l.name))
                 written.add(id(x))
             elif l.kind == "batch_normalization":
@@ -448,7 +477,7 @@ class Plan:
                 self.bwd.append(Op(OP_BN_BWD_APPLY, xv.dt,
                                    [gy.ref, xv.ref, gx.ref, self._w(l, "gamma"), aux["mean"], aux["invstd"], bsums,
                                     grads(l, "gamma") if own else None, grads(l, "beta") if own else None,
-                                    mv.ref if mv else None],
+                                    mv.ref if mv else None, self._bias_sink(x) if mv is not None else None],
                                    [gy.ld, xv.ld, gx.ld, c, self._npix(xv), mv.ld if mv else 0, ma, aux["count"]],
                                    tag=l.name))
                 written.add(id(x))

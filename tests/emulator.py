@@ -105,6 +105,12 @@ class Emulator:
         if acc:
             dx = dx + dv.astype(np.float32)
         dv[:] = dx.astype(dv.dtype)
+        self._colsum(o, 4, dv, cin)
+
+    def _colsum(self, o, k, dv, c):
+        """optional trailing pointer p[k]: per-channel sums of the values just written (a bias gradient)"""
+        if len(o.p) > k and o.p[k] is not None:
+            self.f32(o.p[k], c)[:] += dv.astype(np.float32).sum(0)
 
     def op_conv3x3_wgrad(self, o):
         ldx, cin, lddy, cout, n, h, w = o.i[:7]
@@ -115,7 +121,8 @@ class Emulator:
         y = F.conv2d(xt, wz, padding=1)
         (gw,) = torch.autograd.grad(y, wz, torch.from_numpy(dy).permute(0, 3, 1, 2))
         self.f32(o.p[2], 9 * cin * cout)[:] += gw.permute(2, 3, 1, 0).reshape(-1).numpy()
-        self.f32(o.p[3], cout)[:] += dy.reshape(-1, cout).sum(0)
+        if o.p[3] is not None:
+            self.f32(o.p[3], cout)[:] += dy.reshape(-1, cout).sum(0)
 
     def op_convt_fwd(self, o):
         ldx, cin, ldy, cout, n, h, w = o.i[:7]
@@ -145,6 +152,7 @@ class Emulator:
         if acc:
             dx = dx + dv.astype(np.float32)
         dv[:] = dx.astype(dv.dtype)
+        self._colsum(o, 4, dv, cin)
 
     def op_convt_wgrad(self, o):
         ldx, cin, lddy, cout, n, h, w = o.i[:7]
@@ -154,7 +162,8 @@ class Emulator:
         d5 = dy.reshape(n, h, 2, w, 2, cout)
         gw = np.einsum("nijc,niajbo->aboc", x, d5)
         self.f32(o.p[2], 4 * cout * cin)[:] += gw.reshape(-1)
-        self.f32(o.p[3], cout)[:] += dy.reshape(-1, cout).sum(0)
+        if o.p[3] is not None:
+            self.f32(o.p[3], cout)[:] += dy.reshape(-1, cout).sum(0)
 
     def op_bn_stats(self, o):
         ldx, c, npix = o.i[:3]
@@ -218,6 +227,7 @@ class Emulator:
             dx = dx * self._dact(self.view(o.p[9], ldm, c, npix, o.dt), mact)
         dv = self.view(o.p[2], lddx, c, npix, o.dt)
         dv[:] = dx.astype(dv.dtype)
+        self._colsum(o, 10, dv, c)
         if o.p[7] is not None:
             self.f32(o.p[7], c)[:] += s[c:].astype(np.float32)
             self.f32(o.p[8], c)[:] += s[:c].astype(np.float32)
@@ -329,6 +339,7 @@ class Emulator:
         dx = dl[:, None] * w[None, :] * self._dact(x, xact)
         dv = self.view(o.p[6], lddx, cin, npix, o.dt)
         dv[:] = dx.astype(dv.dtype)
+        self._colsum(o, 9, dv, cin)
         self.f32(o.p[7], cin)[:] += (dl[:, None] * x).sum(0)
         self.f32(o.p[8], 1)[:] += dl.sum()
 

@@ -122,3 +122,72 @@ def test_tc_wgrad_unetpp_concat_widths(n, h, w, cin, cout):
     db = img.farr(img.gr, cout, scale=0.01)
     ops = [P.Op(P.OP_CONV3X3_WGRAD, dt, [x.ref, dy.ref, dw, db], [x.ld, cin, dy.ld, cout, n, h, w])]
     compare(ops, img, dt, tol=3e-3)
+
+
+# ---- producer-side bias gradients: `colsum` outputs (trailing optional pointers of the backward ops) -----------
+COLSUM_CONV = [  # n, h, w, cin (columns written), cout (reduction)
+    (2, 32, 32, 32, 32), (1, 32, 40, 64, 32), (1, 16, 16, 64, 64), (2, 24, 40, 128, 128), (1, 16, 16, 256, 512),
+    (1, 14, 14, 512, 256), (1, 56, 56, 16, 16),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", COLSUM_CONV)
+def test_tc_conv3x3_dgrad_colsum(n, h, w, cin, cout):
+    img = Img(41)
+    dy = img.view(n, h, w, cout, dt, ld=cout + 8, scale=0.5)
+    dx = img.view(n, h, w, cin, dt, ld=2 * cin, c0=cin, fill=None)
+    mask = img.view(n, h, w, cin, dt)
+    wt = img.farr(img.par, 9 * cin * cout, scale=(2.0 / (9 * cin)) ** 0.5)
+    db = img.farr(img.gr, cin, scale=0.01)
+    ops = [P.Op(P.OP_CONV3X3_DGRAD, dt, [dy.ref, wt, dx.ref, mask.ref, db],
+                [dy.ld, cout, dx.ld, cin, mask.ld, 1, 0, n, h, w])]
+    compare(ops, img, dt, tol=4e-3)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 8, 8, 64, 32), (1, 32, 32, 128, 64), (2, 16, 16, 256, 128), (1, 8, 8, 512, 256),
+                                            (1, 10, 6, 32, 16)])
+def test_tc_convt_dgrad_colsum(n, h, w, cin, cout):
+    img = Img(42)
+    x = img.view(n, h, w, cin, dt, fill="normal")
+    dy = img.view(n, 2 * h, 2 * w, cout, dt, ld=2 * cout, c0=cout, scale=0.5)
+    dx = img.view(n, h, w, cin, dt, fill=None)
+    wt = img.farr(img.par, 4 * cout * cin, scale=(1.0 / cin) ** 0.5)
+    db = img.farr(img.gr, cin, scale=0.01)
+    ops = [P.Op(P.OP_CONVT_DGRAD, dt, [dy.ref, wt, dx.ref, x.ref, db], [dy.ld, cout, dx.ld, cin, x.ld, 1, 0, n, h, w])]
+    compare(ops, img, dt, tol=4e-3)
+
+
+@pytest.mark.parametrize("c,npix", [(32, 5000), (64, 1111), (256, 300)])
+def test_bn_bwd_apply_colsum(c, npix):
+    img = Img(43)
+    dy = img.view(1, 1, npix, c, dt, scale=0.5)
+    x = img.view(1, 1, npix, c, dt, ld=2 * c, c0=c)
+    dx = img.view(1, 1, npix, c, dt, fill=None)
+    mask = img.view(1, 1, npix, c, dt)
+    gamma = img.farr(img.par, c, fill="pos")
+    mean = img.farr(img.f32, c, scale=0.1)
+    inv = img.farr(img.f32, c, fill="pos")
+    sums = img.farr(img.zero, 2 * c, scale=3.0, dtype=np.float64)
+    dgamma, dbeta, db = img.farr(img.gr, c, fill=None), img.farr(img.gr, c, fill=None), img.farr(img.gr, c, scale=0.01)
+    ops = [P.Op(P.OP_BN_BWD_APPLY, dt, [dy.ref, x.ref, dx.ref, gamma, mean, inv, sums, dgamma, dbeta, mask.ref, db],
+                [dy.ld, x.ld, dx.ld, c, npix, mask.ld, 1, npix])]
+    compare(ops, img, dt, tol=4e-3)
+
+
+@pytest.mark.parametrize("c,npix", [(32, 4096), (16, 999), (64, 2500)])
+def test_head_bwd_colsum(c, npix):
+    img = Img(44)
+    x = img.view(1, 1, npix, c, dt, fill="uniform")
+    dx = img.view(1, 1, npix, c, dt, ld=c + 8, fill=None)
+    wt, b = img.farr(img.par, c, scale=0.5), img.farr(img.par, 1, scale=0.1)
+    prob = img.f32.alloc(npix * 4)
+    tgt = img.farr(img.f32, npix, fill="uniform")
+    out = img.f32.alloc(16)
+    sums = img.zero.alloc(32)
+    dw, db1, db = img.farr(img.gr, c, fill="zero"), img.farr(img.gr, 4, fill="zero"), img.farr(img.gr, c, scale=0.01)
+    step = P.Ref("step", 0)
+    ops = [P.Op(P.OP_HEAD_FWD, dt, [x.ref, wt, b, prob], [x.ld, c, npix]),
+           P.Op(P.OP_BCE_DICE_SUMS, 0, [prob, tgt, sums], [npix]),
+           P.Op(P.OP_BCE_DICE_FINALIZE, 0, [sums, out], [npix]),
+           P.Op(P.OP_HEAD_BWD, dt, [prob, tgt, sums, step, x.ref, wt, dx.ref, dw, db1, db], [npix, x.ld, c, dx.ld, 1, npix])]
+    compare(ops, img, dt, state=dict(loss_scale=256.0), tol=4e-3)
