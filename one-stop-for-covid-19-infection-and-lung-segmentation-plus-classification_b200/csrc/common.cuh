@@ -58,6 +58,16 @@ template <> __device__ __forceinline__ void load8<__half>(const __half* p, float
 #pragma unroll
   for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
+// 8 packed halves held in a register quad -> fp32
+__device__ __forceinline__ void unpack8h(const uint4& u, float v[8]) {
+  const __half2 h0 = *reinterpret_cast<const __half2*>(&u.x), h1 = *reinterpret_cast<const __half2*>(&u.y);
+  const __half2 h2 = *reinterpret_cast<const __half2*>(&u.z), h3 = *reinterpret_cast<const __half2*>(&u.w);
+  float2 f;
+  f = __half22float2(h0); v[0] = f.x; v[1] = f.y;
+  f = __half22float2(h1); v[2] = f.x; v[3] = f.y;
+  f = __half22float2(h2); v[4] = f.x; v[5] = f.y;
+  f = __half22float2(h3); v[6] = f.x; v[7] = f.y;
+}
 template <typename T> __device__ __forceinline__ void store8(T* p, const float v[8]);
 template <> __device__ __forceinline__ void store8<float>(float* p, const float v[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -88,6 +98,30 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Block-level per-channel partial sums of the streaming kernels.  Thread t owns the 8-channel group g = t % cg
+// (cg = C / 8) and adds v[0..7] to sdst[g*8 .. g*8+7] in shared memory.  fp32 shared-memory atomicAdd compiles to a
+// compare-and-swap retry loop on sm_100 (ATOMS.CAST.SPIN), so first fold the lanes of a warp that own the same group
+// with shuffles (cg a power of two <= 16: lanes l and l ^ o share g for o >= cg) and issue one atomic per group and
+// warp.  Must be called by all 32 lanes of the warp when cg is a power of two <= 16.
+__device__ __forceinline__ void group_add8(float* sdst, const float v[8], int cg, int g) {
+  if (cg <= 16 && (cg & (cg - 1)) == 0) {
+    float r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = v[k];
+    for (int o = 16; o >= cg; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
+    }
+    if ((int)(threadIdx.x & 31) < cg) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&sdst[g * 8 + k], r[k]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&sdst[g * 8 + k], v[k]);
+  }
+}
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -567,18 +567,19 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ 
   const int cg = C >> 3;
   const int lanes = 256 / cg;
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
-  if (lane < lanes) {
+  {
     float s[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = 0.f;
-    for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
-      float v[8];
-      load8<T>(dy + p * lddy + g * 8, v);
+    if (lane < lanes) {
+      for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
+        float v[8];
+        load8<T>(dy + p * lddy + g * 8, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s[i] += v[i];
+        for (int i = 0; i < 8; ++i) s[i] += v[i];
+      }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&sacc[g * 8 + i], s[i]);
+    if (lane < lanes || (cg & (cg - 1)) == 0) group_add8(sacc, s, cg, g);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&db[i], sacc[i]);

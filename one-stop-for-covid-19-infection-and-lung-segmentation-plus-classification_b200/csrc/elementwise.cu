@@ -55,13 +55,14 @@ __global__ void __launch_bounds__(kThreads, 4) bn_reduce_kernel(const T* __restr
   const int cg = C >> 3;
   const int lanes = kThreads / cg;              // pixel lanes per block
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
-  if (lane < lanes) {
+  {
     // kBwd accumulates sum dy*x and applies  sum dy*xhat = invstd * (sum dy*x - mean * sum dy)  once per thread
     // (a thread's partial sums are short, so the subtraction loses nothing): no per-channel constants live in
     // the loop, which keeps the kernel at 4 blocks per SM
     float s1[8], s2[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+    if (lane < lanes) {
     // two pixel groups per trip, both inside one contiguous span of the block (coalesced, 2-4 loads in flight)
     const long long stride = (long long)gridDim.x * lanes * 2;
     for (long long p = (long long)blockIdx.x * lanes * 2 + lane; p < npix; p += stride) {
@@ -90,10 +91,10 @@ __global__ void __launch_bounds__(kThreads, 4) bn_reduce_kernel(const T* __restr
 #pragma unroll
       for (int i = 0; i < 8; ++i) s2[i] = invstd[g * 8 + i] * (s2[i] - mean[g * 8 + i] * s1[i]);
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sacc[g * 8 + i], s1[i]);
-      atomicAdd(&sacc[C + g * 8 + i], s2[i]);
+    }
+    if (lane < lanes || (cg & (cg - 1)) == 0) {      // (all threads are pixel lanes when cg is a power of two)
+      group_add8(sacc, s1, cg, g);
+      group_add8(sacc + C, s2, cg, g);
     }
   }
   __syncthreads();
@@ -169,10 +170,9 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
     }
   }
   if (out_stats != nullptr) {
-    const int g0 = (threadIdx.x % (C >> 3)) * 8;
     if (threadIdx.x / (C >> 3) < kThreads / (C >> 3)) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { atomicAdd(&sst[g0 + k], o1[k]); atomicAdd(&sst[C + g0 + k], o2[k]); }
+      group_add8(sst, o1, C >> 3, threadIdx.x % (C >> 3));
+      group_add8(sst + C, o2, C >> 3, threadIdx.x % (C >> 3));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -239,10 +239,11 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
     }
   }
   if (kColsum) {
-    const int g0 = (threadIdx.x % (C >> 3)) * 8;
     if (threadIdx.x / (C >> 3) < kThreads / (C >> 3)) {
+      float c8[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) atomicAdd(&scs[g0 + k], cs[kColsum ? k : 0]);
+      for (int k = 0; k < 8; ++k) c8[k] = cs[kColsum ? k : 0];
+      group_add8(scs, c8, C >> 3, threadIdx.x % (C >> 3));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&colsum[i], scs[i]);
@@ -414,10 +415,10 @@ __global__ void __launch_bounds__(kThreads, 2) maxpool_bwd_kernel(const T* __res
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float gm = bn_gamma[g0 + k];
-        const float rg = fabsf(gm) > 1e-12f ? 1.f / gm : 0.f;
-        atomicAdd(&sbn[g0 + k], t1[k]);
-        atomicAdd(&sbn[C + g0 + k], t2[k] * rg);
+        t2[k] *= fabsf(gm) > 1e-12f ? 1.f / gm : 0.f;
       }
+      group_add8(sbn, t1, C >> 3, threadIdx.x % (C >> 3));
+      group_add8(sbn + C, t2, C >> 3, threadIdx.x % (C >> 3));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&bn_sums[i], (double)sbn[i]);
@@ -582,15 +583,13 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(
     }
   }
   {
-    const int g0 = (threadIdx.x % (C >> 3)) * 8;
     if (threadIdx.x / (C >> 3) < kThreads / (C >> 3)) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        atomicAdd(&sacc[g0 + k], acc[k]);
-        atomicAdd(&sacc[C + g0 + k], cs[k]);
-      }
-      if (g0 == 0) atomicAdd(&sacc[2 * C], accb);
+      group_add8(sacc, acc, C >> 3, threadIdx.x % (C >> 3));
+      group_add8(sacc + C, cs, C >> 3, threadIdx.x % (C >> 3));
     }
+    // db: only the g == 0 thread of a pixel accumulated it (others hold 0): plain warp sum
+    const float sb = warp_sum(accb);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[2 * C], sb);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) {

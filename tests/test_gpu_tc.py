@@ -69,6 +69,28 @@ def test_tc_convt(n, h, w, cin, cout):
         compare(ops, img, dt, tol=4e-3)
 
 
+def test_tc_streamed_weights_two_subtiles_many_tiles():
+    """wide layer with streamed weights: 32 x 8 CTA tiles (two sub-tiles per weight tile), more tiles than SMs, both
+    accumulator stages, forward with BN statistics and data gradient with mask + column sums"""
+    n, h, w, cin, cout = 4, 128, 128, 128, 128
+    img = Img(25)
+    x = img.view(n, h, w, cin, dt, fill="uniform")
+    y = img.view(n, h, w, cout, dt, ld=2 * cout, c0=cout, fill=None)
+    wt = img.farr(img.par, 9 * cin * cout, scale=(2.0 / (9 * cin)) ** 0.5)
+    b = img.farr(img.par, cout, scale=0.1)
+    stats = img.zero.alloc(2 * cout * 8)
+    ops = [P.Op(P.OP_CONV3X3_FWD, dt, [x.ref, wt, b, y.ref, stats], [x.ld, cin, 1, y.ld, cout, n, h, w])]
+    compare(ops, img, dt, tol=3e-3)
+    img = Img(26)
+    dy = img.view(n, h, w, cout, dt, scale=0.5)
+    dx = img.view(n, h, w, cin, dt, fill=None)
+    mask = img.view(n, h, w, cin, dt)
+    wt = img.farr(img.par, 9 * cin * cout, scale=(2.0 / (9 * cin)) ** 0.5)
+    db = img.farr(img.gr, cin, scale=0.01)
+    ops = [P.Op(P.OP_CONV3X3_DGRAD, dt, [dy.ref, wt, dx.ref, mask.ref, db], [dy.ld, cout, dx.ld, cin, mask.ld, 1, 0, n, h, w])]
+    compare(ops, img, dt, tol=4e-3)
+
+
 def test_tc_large_layer_many_tiles():
     """more tiles than SMs: exercises the persistent loop, the smem ring wrap-around and both TMEM stages"""
     n, h, w, cin, cout = 2, 128, 128, 32, 32
