@@ -183,6 +183,18 @@ int b2u_clahe_u8(const uint8_t* in, uint8_t* out, int n, int h, int wd, float cl
 int b2u_crop_resize(const uint8_t* in, int n, int h, int wd, const int* boxes, int half_w, int out_h,
                     int final_dim, uint8_t* mid_u8, float* out, void* stream);
 
+/* ---- fp16 operand copies of all conv / transposed-conv kernels of a model in ONE launch ---------- */
+/* The tcgen05 kernels read weights as fp16 [tap][out][in] tiles.  `d_table` holds n_entries (<= 128) records of 8
+ * int64: {src element offset in params, dst element offset in wpack, first work tile, mode, taps, J, K, 0}; a work
+ * tile is a 32 x 32 piece of one tap matrix, an entry has taps * ceil(J/32) * ceil(K/32) of them and `total` is their
+ * sum over all entries;
+ * mode 0: conv fwd  Wp[t][co][ci] = w[t][ci][co]        1: conv dgrad  Wp[t][ci][co] = w[8-t][ci][co]
+ *      2: convT fwd Wp[q][ci]     = w[q][ci]             3: convT dgrad Wp[ab][ci][co] = w[ab][co][ci]
+ * (Keras layouts, T1H:859 / T1H:886).  Op lists pass the packed tile address as the optional trailing pointer p[5] of
+ * CONV3X3_FWD / CONV3X3_DGRAD / CONVT_FWD / CONVT_DGRAD; without it every conv call packs its own weights first. */
+int b2u_pack_weights(const long long* d_table, int n_entries, const float* params, void* wpack, long long total,
+                     void* stream);
+
 /* ---- plan executor: a whole forward / train step as one array of op records ------------------- */
 enum {
   B2U_OP_CONV3X3_FWD = 1, B2U_OP_CONV3X3_DGRAD, B2U_OP_CONV3X3_WGRAD,
@@ -192,7 +204,7 @@ enum {
   B2U_OP_HEAD_FWD, B2U_OP_BCE_DICE_SUMS, B2U_OP_BCE_DICE_FINALIZE, B2U_OP_HEAD_BWD,
   B2U_OP_DENSE_FWD, B2U_OP_DENSE_BWD, B2U_OP_BCE_FWD, B2U_OP_BCE_SIGMOID_BWD,
   B2U_OP_ADAM, B2U_OP_MEMSET, B2U_OP_ALLREDUCE_F32, B2U_OP_ALLREDUCE_F64, B2U_OP_STATE_ADVANCE,
-  B2U_OP_GATHER_BATCH
+  B2U_OP_GATHER_BATCH, B2U_OP_PACK_WEIGHTS
 };
 /* one record; the meaning of p[]/i[]/f[] per kind is the argument order of the function above
  * (pointers in order into p[], ints/long longs into i[], floats into f[]).

@@ -39,7 +39,7 @@ SYMBOLS = [
     "b2u_dense_fwd", "b2u_dense_bwd", "b2u_bce_fwd", "b2u_bce_sigmoid_bwd", "b2u_adam", "b2u_gather_batch",
     "b2u_threshold_counts", "b2u_clahe_u8", "b2u_crop_resize", "b2u_run_ops", "b2u_run_ops_timed", "b2u_graph_create",
     "b2u_graph_launch", "b2u_graph_destroy", "b2u_launch_count", "b2u_comm_unique_id", "b2u_comm_create",
-    "b2u_comm_destroy", "b2u_allreduce",
+    "b2u_comm_destroy", "b2u_allreduce", "b2u_pack_weights",
 ]
 
 
@@ -80,6 +80,7 @@ def lib():
     l.b2u_convt2x2_dgrad.argtypes = [i32, vp, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]
     l.b2u_convt2x2_wgrad.argtypes = [i32, vp, i32, i32, vp, i32, i32, vp, vp, i32, i32, i32, vp, sz, vp]
     l.b2u_adam.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    l.b2u_pack_weights.argtypes = [vp, i32, vp, vp, i64, vp]
     l.b2u_state_advance.argtypes = [vp, vp]
     _lib = l
     return l

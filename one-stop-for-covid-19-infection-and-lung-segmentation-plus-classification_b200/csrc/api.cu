@@ -77,25 +77,31 @@ extern "C" int b2u_debug_read(long long* h_out, int count) {
 // ------------------------------------------------------------------------------------------
 // conv dispatch
 // ------------------------------------------------------------------------------------------
+static int conv3x3_fwd_wp(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, int act, void* y,
+                          int ldy, int cout, double* stats, int n, int h, int wd, void* ws, size_t ws_bytes,
+                          const void* wp, void* stream) {
+  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy))
+    return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats,
+                                                                  nullptr, nullptr, 0, 0, 0, n, h, wd, ws, ws_bytes, wp,
+                                                                  stream);
+  return b2u_direct_conv3x3(dt, x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, 0, 0, 0, n, h, wd, stream);
+}
+
 extern "C" int b2u_conv3x3_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, int act,
                                void* y, int ldy, int cout, double* stats, int n, int h, int wd, void* ws,
                                size_t ws_bytes, void* stream) {
-  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy))
-    return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats,
-                                                                  nullptr, nullptr, 0, 0, 0, n, h, wd, ws, ws_bytes,
-                                                                  stream);
-  return b2u_direct_conv3x3(dt, x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, 0, 0, 0, n, h, wd, stream);
+  return conv3x3_fwd_wp(dt, x, ldx, cin, w, bias, act, y, ldy, cout, stats, n, h, wd, ws, ws_bytes, nullptr, stream);
 }
 
 // data gradient + optional `colsum` (op lists only): colsum[c] += sum over pixels of the dx values written, i.e. the
 // bias gradient of the layer that produced the tensor dx belongs to
 static int conv3x3_dgrad_cs(int dt, const void* dy, int lddy, int cout, const float* w, void* dx, int lddx, int cin,
                             const void* mask, int ldmask, int mask_act, int accumulate, float* colsum, int n, int h,
-                            int wd, void* ws, size_t ws_bytes, void* stream) {
+                            int wd, void* ws, size_t ws_bytes, const void* wp, void* stream) {
   if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cout, cin, lddy, lddx))
     return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx,
                                                                   cin, nullptr, colsum, mask, ldmask, mask_act,
-                                                                  accumulate, n, h, wd, ws, ws_bytes, stream);
+                                                                  accumulate, n, h, wd, ws, ws_bytes, wp, stream);
   int rc = b2u_direct_conv3x3(dt, dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, mask, ldmask,
                               mask_act, accumulate, n, h, wd, stream);
   if (rc != B2U_OK || colsum == nullptr) return rc;
@@ -106,7 +112,7 @@ extern "C" int b2u_conv3x3_dgrad(int dt, const void* dy, int lddy, int cout, con
                                  int cin, const void* mask, int ldmask, int mask_act, int accumulate, int n, int h,
                                  int wd, void* ws, size_t ws_bytes, void* stream) {
   return conv3x3_dgrad_cs(dt, dy, lddy, cout, w, dx, lddx, cin, mask, ldmask, mask_act, accumulate, nullptr, n, h, wd,
-                          ws, ws_bytes, stream);
+                          ws, ws_bytes, nullptr, stream);
 }
 
 extern "C" int b2u_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, int lddy, int cout,
@@ -116,11 +122,22 @@ extern "C" int b2u_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const 
   return b2u_direct_conv3x3_wgrad(dt, x, ldx, cin, dy, lddy, cout, dw, db, n, h, wd, stream);
 }
 
+static int convt2x2_fwd_wp(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, void* y, int ldy,
+                           int cout, double* stats, int stats_sq_off, int n, int h, int wd, void* ws, size_t ws_bytes,
+                           const void* wp, void* stream);
+
 extern "C" int b2u_convt2x2_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, void* y,
                                 int ldy, int cout, double* stats, int stats_sq_off, int n, int h, int wd, void* ws,
                                 size_t ws_bytes, void* stream) {
+  return convt2x2_fwd_wp(dt, x, ldx, cin, w, bias, y, ldy, cout, stats, stats_sq_off, n, h, wd, ws, ws_bytes, nullptr,
+                         stream);
+}
+
+static int convt2x2_fwd_wp(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, void* y, int ldy,
+                           int cout, double* stats, int stats_sq_off, int n, int h, int wd, void* ws, size_t ws_bytes,
+                           const void* wp, void* stream) {
   if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_convt_ok(cin, cout, ldx, ldy))
-    return b2u_tc_convt_fwd(x, ldx, cin, w, bias, y, ldy, cout, stats, stats_sq_off, n, h, wd, ws, ws_bytes, stream);
+    return b2u_tc_convt_fwd(x, ldx, cin, w, bias, y, ldy, cout, stats, stats_sq_off, n, h, wd, ws, ws_bytes, wp, stream);
   int rc = b2u_direct_convt_fwd(dt, x, ldx, cin, w, bias, y, ldy, cout, n, h, wd, stream);
   if (rc != B2U_OK || stats == nullptr) return rc;
   return b2u_bn_stats_off(dt, y, ldy, cout, 4LL * n * h * wd, stats, stats_sq_off, stream);   // exact path: extra pass
@@ -128,10 +145,10 @@ extern "C" int b2u_convt2x2_fwd(int dt, const void* x, int ldx, int cin, const f
 
 static int convt2x2_dgrad_cs(int dt, const void* dy, int lddy, int cout, const float* w, void* dx, int lddx, int cin,
                              const void* mask, int ldmask, int mask_act, int accumulate, float* colsum, int n, int h,
-                             int wd, void* ws, size_t ws_bytes, void* stream) {
+                             int wd, void* ws, size_t ws_bytes, const void* wp, void* stream) {
   if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_convt_ok(cin, cout, lddx, lddy))
     return b2u_tc_convt_dgrad(dy, lddy, cout, w, dx, lddx, cin, mask, ldmask, mask_act, accumulate, colsum, n, h, wd,
-                              ws, ws_bytes, stream);
+                              ws, ws_bytes, wp, stream);
   int rc = b2u_direct_convt_dgrad(dt, dy, lddy, cout, w, dx, lddx, cin, mask, ldmask, mask_act, accumulate, n, h, wd,
                                   stream);
   if (rc != B2U_OK || colsum == nullptr) return rc;
@@ -142,7 +159,7 @@ extern "C" int b2u_convt2x2_dgrad(int dt, const void* dy, int lddy, int cout, co
                                   int cin, const void* mask, int ldmask, int mask_act, int accumulate, int n, int h,
                                   int wd, void* ws, size_t ws_bytes, void* stream) {
   return convt2x2_dgrad_cs(dt, dy, lddy, cout, w, dx, lddx, cin, mask, ldmask, mask_act, accumulate, nullptr, n, h, wd,
-                           ws, ws_bytes, stream);
+                           ws, ws_bytes, nullptr, stream);
 }
 
 extern "C" int b2u_convt2x2_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, int lddy, int cout,
@@ -163,21 +180,21 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
   const int dt = o.dt;
 #define I(k) ((int)i[k])
   switch (o.kind) {
-    case B2U_OP_CONV3X3_FWD:
-      return b2u_conv3x3_fwd(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], I(2), p[3], I(3), I(4),
-                             (double*)p[4], I(5), I(6), I(7), ws, wsb, s);
+    case B2U_OP_CONV3X3_FWD:         // p[5] (optional): packed weights
+      return conv3x3_fwd_wp(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], I(2), p[3], I(3), I(4),
+                            (double*)p[4], I(5), I(6), I(7), ws, wsb, p[5], s);
     case B2U_OP_CONV3X3_DGRAD:       // p[4] (optional): colsum
       return conv3x3_dgrad_cs(dt, p[0], I(0), I(1), (const float*)p[1], p[2], I(2), I(3), p[3], I(4), I(5), I(6),
-                              (float*)p[4], I(7), I(8), I(9), ws, wsb, s);
+                              (float*)p[4], I(7), I(8), I(9), ws, wsb, p[5], s);
     case B2U_OP_CONV3X3_WGRAD:
       return b2u_conv3x3_wgrad(dt, p[0], I(0), I(1), p[1], I(2), I(3), (float*)p[2], (float*)p[3], I(4), I(5), I(6), ws,
                                wsb, s);
-    case B2U_OP_CONVT_FWD:
-      return b2u_convt2x2_fwd(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], p[3], I(2), I(3),
-                              (double*)p[4], I(7), I(4), I(5), I(6), ws, wsb, s);
+    case B2U_OP_CONVT_FWD:           // p[5] (optional): packed weights
+      return convt2x2_fwd_wp(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], p[3], I(2), I(3),
+                             (double*)p[4], I(7), I(4), I(5), I(6), ws, wsb, p[5], s);
     case B2U_OP_CONVT_DGRAD:         // p[4] (optional): colsum
       return convt2x2_dgrad_cs(dt, p[0], I(0), I(1), (const float*)p[1], p[2], I(2), I(3), p[3], I(4), I(5), I(6),
-                               (float*)p[4], I(7), I(8), I(9), ws, wsb, s);
+                               (float*)p[4], I(7), I(8), I(9), ws, wsb, p[5], s);
     case B2U_OP_CONVT_WGRAD:
       return b2u_convt2x2_wgrad(dt, p[0], I(0), I(1), p[1], I(2), I(3), (float*)p[2], (float*)p[3], I(4), I(5), I(6), ws,
                                 wsb, s);
@@ -243,6 +260,8 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
       return b2u_state_advance((b2u_step_state*)p[0], s);
     case B2U_OP_GATHER_BATCH:
       return b2u_gather_batch(dt, (const float*)p[0], (const int*)p[1], p[2], i[0], I(1), s);
+    case B2U_OP_PACK_WEIGHTS:
+      return b2u_pack_weights((const long long*)p[0], I(0), (const float*)p[1], p[2], i[1], s);
     default:
       b2u_set_error("run_ops: unknown op kind %d", o.kind);
       return B2U_ERR_ARG;

@@ -370,6 +370,56 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restr
   }
 }
 
+// all layers of a model in one launch (b2u_pack_weights): table of 8 x int64 records, see include/b200unet.h.
+// Work unit = one 32 x 32 tile of one tap matrix, staged through shared memory so that both the fp32 reads and the
+// fp16 writes are coalesced whether the mode transposes (0, 3) or copies (1, 2).
+__global__ void __launch_bounds__(256) pack_all_kernel(const long long* __restrict__ tab, int n_entries,
+                                                       const float* __restrict__ params, __half* __restrict__ wpack,
+                                                       long long total_tiles) {
+  __shared__ long long st[128 * 8];
+  __shared__ float tile[32][33];
+  for (int i = threadIdx.x; i < n_entries * 8; i += blockDim.x) st[i] = tab[i];
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+  for (long long u = blockIdx.x; u < total_tiles; u += gridDim.x) {
+    int lo = 0, hi = n_entries - 1;                                 // last entry whose first tile is <= u
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (st[mid * 8 + 2] <= u) lo = mid; else hi = mid - 1;
+    }
+    const long long* e = st + lo * 8;
+    const float* w = params + e[0];
+    __half* dst = wpack + e[1];
+    const int mode = (int)e[3], J = (int)e[5], K = (int)e[6];
+    const int tj = (J + 31) >> 5, tk = (K + 31) >> 5;
+    const int lu = (int)(u - e[2]);
+    const int t = lu / (tj * tk), r = lu % (tj * tk);
+    const int j0 = (r / tk) * 32, k0 = (r % tk) * 32;
+    const bool transpose = mode == 0 || mode == 3;                  // source tap matrix is [K][J] (else [J][K])
+    const float* src = w + (long long)(mode == 1 ? 8 - t : t) * J * K;
+    __syncthreads();                                                // previous tile's readers are done
+    if (transpose) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {                                 // rows = k, columns = j (coalesced in j)
+        const int k = k0 + ty + 8 * i, j = j0 + tx;
+        tile[ty + 8 * i][tx] = (k < K && j < J) ? src[(long long)k * J + j] : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {                                 // rows = j, columns = k (coalesced in k)
+        const int j = j0 + ty + 8 * i, k = k0 + tx;
+        tile[tx][ty + 8 * i] = (j < J && k < K) ? src[(long long)j * K + k] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                                   // dst[t][j][k], coalesced in k; tile[k][j]
+      const int j = j0 + ty + 8 * i, k = k0 + tx;
+      if (j < J && k < K) dst[((long long)t * J + j) * K + k] = __float2half_rn(tile[tx][ty + 8 * i]);
+    }
+  }
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -488,6 +538,15 @@ int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int J, i
 
 int b2u_tc_compiled(void) { return 1; }
 
+extern "C" int b2u_pack_weights(const long long* d_table, int n_entries, const float* params, void* wpack,
+                                long long total, void* stream) {
+  B2U_REQUIRE(d_table != nullptr && params != nullptr && wpack != nullptr && n_entries >= 1 && n_entries <= 128 && total > 0,
+              "pack_weights: bad arguments (1..128 table entries)");
+  long long grid = total < 8LL * B2U_NUM_SMS ? total : 8LL * B2U_NUM_SMS;
+  B2U_LAUNCH(pack_all_kernel, (int)grid, 256, 0, stream, d_table, n_entries, params, (__half*)wpack, total);
+  return B2U_OK;
+}
+
 int b2u_tc_conv3x3_ok(int k, int j, int ld_in, int ld_out) {
   return pick_ks(k) != 0 && j % 16 == 0 && pick_jt(j) != 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && j <= 1024;
 }
@@ -498,7 +557,7 @@ int b2u_tc_convt_ok(int cin, int cout, int ld_small, int ld_big) {
 
 int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                    int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
-                   int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+                   int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream) {
   int rc = get_encode();
   if (rc != B2U_OK) return rc;
   TcParams p{};
@@ -508,19 +567,23 @@ int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, con
   p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate; p.stats = stats;
   p.stats_sq_off = J; p.colsum = colsum;
   if (colsum != nullptr && J % 128 == 0 && p.JT > 128) p.JT = 128;
-  rc = pack(w, ws, ws_bytes, dgrad ? 1 : 0, 9, J, K, stream);
-  if (rc != B2U_OK) return rc;
+  if (wp == nullptr) {
+    rc = pack(w, ws, ws_bytes, dgrad ? 1 : 0, 9, J, K, stream);
+    if (rc != B2U_OK) return rc;
+    wp = ws;
+  }
   TcMaps maps;
   rc = make_act_map(&maps.a[0], x, K, wd, h, n, ldx, (long long)wd * ldx, (long long)h * wd * ldx, p.KS);
   if (rc != B2U_OK) return rc;
   for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
-  rc = make_w_map(&maps.b, ws, K, J, 9, p.KS, p.JT);
+  rc = make_w_map(&maps.b, wp, K, J, 9, p.KS, p.JT);
   if (rc != B2U_OK) return rc;
   return launch_tc(maps, p, stream);
 }
 
 int b2u_tc_convt_fwd(const void* x, int ldx, int cin, const float* w, const float* bias, void* y, int ldy, int cout,
-                     double* stats, int stats_sq_off, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+                     double* stats, int stats_sq_off, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp,
+                     void* stream) {
   int rc = get_encode();
   if (rc != B2U_OK) return rc;
   TcParams p{};
@@ -530,20 +593,23 @@ int b2u_tc_convt_fwd(const void* x, int ldx, int cin, const float* w, const floa
   p.ntaps = 1; p.tap_dh[0] = 0; p.tap_dw[0] = 0; p.tap_map[0] = 0;
   p.mode = 1; p.cout = cout; p.y = (__half*)y; p.ldy = ldy; p.bias = bias; p.act = B2U_ACT_NONE;
   p.stats = stats; p.stats_sq_off = stats_sq_off;
-  rc = pack(w, ws, ws_bytes, 2, 1, 4 * cout, cin, stream);
-  if (rc != B2U_OK) return rc;
+  if (wp == nullptr) {
+    rc = pack(w, ws, ws_bytes, 2, 1, 4 * cout, cin, stream);
+    if (rc != B2U_OK) return rc;
+    wp = ws;
+  }
   TcMaps maps;
   rc = make_act_map(&maps.a[0], x, cin, wd, h, n, ldx, (long long)wd * ldx, (long long)h * wd * ldx, p.KS);
   if (rc != B2U_OK) return rc;
   for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
-  rc = make_w_map(&maps.b, ws, cin, 4 * cout, 1, p.KS, p.JT);
+  rc = make_w_map(&maps.b, wp, cin, 4 * cout, 1, p.KS, p.JT);
   if (rc != B2U_OK) return rc;
   return launch_tc(maps, p, stream);
 }
 
 int b2u_tc_convt_dgrad(const void* dy, int lddy, int cout, const float* w, void* dx, int lddx, int cin,
                        const void* mask, int ldmask, int mask_act, int accumulate, float* colsum, int n, int h, int wd,
-                       void* ws, size_t ws_bytes, void* stream) {
+                       void* ws, size_t ws_bytes, const void* wp, void* stream) {
   int rc = get_encode();
   if (rc != B2U_OK) return rc;
   TcParams p{};
@@ -553,8 +619,11 @@ int b2u_tc_convt_dgrad(const void* dy, int lddy, int cout, const float* w, void*
   p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate;
   p.colsum = colsum;
   if (colsum != nullptr && cin % 128 == 0 && p.JT > 128) p.JT = 128;   // <= 32 columns per epilogue thread
-  rc = pack(w, ws, ws_bytes, 3, 4, cin, cout, stream);
-  if (rc != B2U_OK) return rc;
+  if (wp == nullptr) {
+    rc = pack(w, ws, ws_bytes, 3, 4, cin, cout, stream);
+    if (rc != B2U_OK) return rc;
+    wp = ws;
+  }
   TcMaps maps;
   // tap (a,b): the sub-grid dy[n, 2i+a, 2j+b, :] seen as an (N,H,W,C) tensor with doubled pixel strides
   for (int t = 0; t < 4; ++t) {
@@ -562,7 +631,7 @@ int b2u_tc_convt_dgrad(const void* dy, int lddy, int cout, const float* w, void*
     rc = make_act_map(&maps.a[t], base, cout, wd, h, n, 2LL * lddy, 4LL * wd * lddy, 4LL * h * wd * lddy, p.KS);
     if (rc != B2U_OK) return rc;
   }
-  rc = make_w_map(&maps.b, ws, cout, cin, 4, p.KS, p.JT);
+  rc = make_w_map(&maps.b, wp, cout, cin, 4, p.KS, p.JT);
   if (rc != B2U_OK) return rc;
   return launch_tc(maps, p, stream);
 }

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
     const int lg = warp & 3;
     const int half = ew >> 2;
     const int row = lg * 32 + lane;
-    const bool split = prm.epi_warps == 8 && JT / 2 >= 16;          // two warps share a lane group's columns
+    const bool split = prm.epi_warps == 8 && JT % 32 == 0;          // two warps share a lane group's columns (halves of whole 16-column chunks)
     const int ccols = split ? JT / 2 : JT;                        // columns owned by this warp within a tile
     const int cbeg = split ? half * ccols : 0;
     const bool has_cols = split || half == 0;
@@ -422,7 +422,7 @@ int g_b2u_tc_halo = 1;       // 0: per-tap loads (conv_tc.cu), 1: halo box, 2: h
 
 int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                         int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
-                        int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+                        int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream) {
   int rc = get_enc3();
   if (rc != B2U_OK) return rc;
   C3Params p{};
@@ -475,14 +475,15 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   const size_t smem = 1024 + (size_t)p.SA * a_stage + (p.bres ? wres : (size_t)p.SB * b_tile) + tail;
   B2U_REQUIRE(smem <= 227 * 1024, "tc_conv3: shared memory %zu exceeds 227 KB", smem);
 
-  // packed fp16 weights in the workspace
-  const size_t need = 9 * (size_t)J * K * 2;
-  B2U_REQUIRE(ws != nullptr && need <= ws_bytes, "tc_conv3: workspace too small");
-  {
+  // packed fp16 weights: the caller's (b2u_pack_weights, once per step for the whole model) or packed here
+  if (wp == nullptr) {
+    const size_t need = 9 * (size_t)J * K * 2;
+    B2U_REQUIRE(ws != nullptr && need <= ws_bytes, "tc_conv3: workspace too small");
     long long total = 9LL * J * K;
     int grid = (int)((total + 255) / 256);
     if (grid > 8 * B2U_NUM_SMS) grid = 8 * B2U_NUM_SMS;
     B2U_LAUNCH(pack3_kernel, grid, 256, 0, stream, w, (__half*)ws, dgrad, J, K);
+    wp = ws;
   }
   C3Maps maps;
   {
@@ -498,7 +499,7 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
     cuuint64_t bs[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * J * 2};
     cuuint32_t bb[3] = {(cuuint32_t)p.KS, (cuuint32_t)p.JT, 1};
     cuuint32_t be[3] = {1, 1, 1};
-    r = g_enc3(&maps.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ws, bd, bs, bb, be, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    r = g_enc3(&maps.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(wp), bd, bs, bb, be, CU_TENSOR_MAP_INTERLEAVE_NONE,
                swz3(p.KS), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b2u_set_error("tc_conv3: weight tensor map failed (%d)", (int)r); return B2U_ERR_CUDA; }
   }

@@ -605,23 +605,52 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(
 __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, long long n,
                                                         b2u_step_state* __restrict__ st) {
+  // 16-byte accesses (the flat buffers are 16-byte aligned and every tensor is padded to 4 elements), two
+  // quads per trip so that eight independent loads are in flight per thread
   const float b1 = st->beta1, b2 = st->beta2, eps = st->eps;
   const float lr_t = st->lr * sqrtf(1.f - st->beta2_pow) / (1.f - st->beta1_pow);
   const float gs = 1.f / (st->loss_scale * st->grad_div);
   bool bad = false;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    float gi = g[i] * gs;
-    if (!isfinite(gi)) { bad = true; continue; }
-    float mi = b1 * m[i] + (1.f - b1) * gi;
-    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  const long long nq = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  auto upd = [&](float gi, float& mi, float& vi, float& pi) {
+    gi *= gs;
+    if (!isfinite(gi)) { bad = true; return; }
+    mi = b1 * mi + (1.f - b1) * gi;
+    vi = b2 * vi + (1.f - b2) * gi * gi;
+    pi -= lr_t * mi / (sqrtf(vi) + eps);
+  };
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += 2 * stride) {
+    const long long q2 = q + stride;
+    const bool two = q2 < nq;
+    float4 g4[2], m4[2], v4[2], p4[2];
+    g4[0] = reinterpret_cast<const float4*>(g)[q]; m4[0] = reinterpret_cast<const float4*>(m)[q];
+    v4[0] = reinterpret_cast<const float4*>(v)[q]; p4[0] = reinterpret_cast<const float4*>(p)[q];
+    if (two) {
+      g4[1] = reinterpret_cast<const float4*>(g)[q2]; m4[1] = reinterpret_cast<const float4*>(m)[q2];
+      v4[1] = reinterpret_cast<const float4*>(v)[q2]; p4[1] = reinterpret_cast<const float4*>(p)[q2];
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      upd(g4[u].x, m4[u].x, v4[u].x, p4[u].x);
+      upd(g4[u].y, m4[u].y, v4[u].y, p4[u].y);
+      upd(g4[u].z, m4[u].z, v4[u].z, p4[u].z);
+      upd(g4[u].w, m4[u].w, v4[u].w, p4[u].w);
+      const long long qq = u ? q2 : q;
+      reinterpret_cast<float4*>(m)[qq] = m4[u];
+      reinterpret_cast<float4*>(v)[qq] = v4[u];
+      reinterpret_cast<float4*>(p)[qq] = p4[u];
+    }
+  }
+  // tail (n is a multiple of 4 for the engine's buffers; kept for direct callers)
+  for (long long i = (nq << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float mi = m[i], vi = v[i], pi = p[i];
+    upd(g[i], mi, vi, pi);
+    m[i] = mi; v[i] = vi; p[i] = pi;
   }
   if (bad) atomicOr(&st->overflow, 1u);
 }
-
 __global__ void state_advance_kernel(b2u_step_state* st) {
   st->step += 1;
   st->beta1_pow *= st->beta1;
@@ -999,7 +1028,8 @@ extern "C" int b2u_adam(float* params, const float* grads, float* m, float* v, l
                         void* stream) {
   B2U_REQUIRE(n >= 0 && d_state != nullptr, "adam: args");
   if (n == 0) return B2U_OK;
-  B2U_LAUNCH(adam_kernel, stream_grid(n), kThreads, 0, stream, params, grads, m, v, n, d_state);
+  B2U_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam: buffers must be 16-byte aligned");
+  B2U_LAUNCH(adam_kernel, stream_grid((n + 7) / 8), kThreads, 0, stream, params, grads, m, v, n, d_state);
   return B2U_OK;
 }
 

@@ -25,14 +25,15 @@ int b2u_tc_convt_wgrad_ok(int cin, int cout, int ldx, int lddy);
 extern int g_b2u_tc_halo;
 extern int g_b2u_wgrad_halo;
 extern long long* g_b2u_dbg;
+// `wp` (optional): fp16 weights already packed by b2u_pack_weights (else packed into `ws` by the call)
 // `colsum` (optional): per-channel sums of the values written, added with fp32 atomics -- the bias gradient of the
 // layer whose output gradient the call produces (saves a separate pass over that gradient)
 int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                         int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
-                        int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+                        int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream);
 int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                    int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
-                   int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+                   int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream);
 int b2u_channel_sum(int dt, const void* dy, int lddy, int c, long long npix, float* db, void* stream);
 int b2u_bn_bwd_apply_cs(int dt, const void* dy, int lddy, const void* x, int ldx, void* dx, int lddx, int c,
                         long long npix, long long count, const float* gamma, const float* save_mean,
@@ -41,11 +42,12 @@ int b2u_bn_bwd_apply_cs(int dt, const void* dy, int lddy, const void* x, int ldx
 int b2u_tc_conv3x3_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* db,
                          int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
 int b2u_tc_convt_fwd(const void* x, int ldx, int cin, const float* w, const float* bias, void* y, int ldy, int cout,
-                     double* stats, int stats_sq_off, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+                     double* stats, int stats_sq_off, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp,
+                     void* stream);
 int b2u_bn_stats_off(int dt, const void* x, int ldx, int c, long long npix, double* sums, int sq_off, void* stream);
 int b2u_tc_convt_dgrad(const void* dy, int lddy, int cout, const float* w, void* dx, int lddx, int cin,
                        const void* mask, int ldmask, int mask_act, int accumulate, float* colsum, int n, int h, int wd,
-                       void* ws, size_t ws_bytes, void* stream);
+                       void* ws, size_t ws_bytes, const void* wp, void* stream);
 int b2u_tc_convt_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* db,
                        int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
 int b2u_head_bwd_cs(int dt, const float* prob, const float* target, const double* sums, long long count,

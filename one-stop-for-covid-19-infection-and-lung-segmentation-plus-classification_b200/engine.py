@@ -77,6 +77,7 @@ class _Bound:
         self.plan = plan
         self.ops = {}          # name -> (ctypes array, n)
         self.graphs = {}       # name -> graph handle
+        self.wtab = None       # device copy of plan.pack_table()
 
 
 class Engine:
@@ -231,8 +232,12 @@ class Engine:
             b = _Bound(pl)
             self._bound[key] = b
         sizes = b.plan.arena_sizes()
-        for name in ("act", "f32", "zero"):
+        for name in ("act", "f32", "zero", "wpack"):
             self._arena(name, sizes[name])
+        if b.wtab is None:              # the plan's weight-packing table (OP_PACK_WEIGHTS), uploaded once
+            with torch.cuda.stream(self.stream):
+                b.wtab = torch.from_numpy(b.plan.pack_table().reshape(-1).copy()).to(self.device)
+            self.stream.synchronize()
         return b
 
     def _resolve(self, ref):
@@ -260,7 +265,8 @@ class Engine:
             pl = b.plan
             lst = {"train": pl.train_ops, "forward": pl.forward_ops,
                    "forward_loss": lambda: pl.forward_ops(with_loss=True)}[name]()
-            b.ops[name] = (_lib.make_ops(lst, self._resolve), len(lst))
+            resolve = lambda ref: (b.wtab.data_ptr() + ref.off) if ref.arena == "wtab" else self._resolve(ref)
+            b.ops[name] = (_lib.make_ops(lst, resolve), len(lst))
         return b.ops[name]
 
     def _run(self, b, name):

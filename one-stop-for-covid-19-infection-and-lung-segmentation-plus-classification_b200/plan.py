@@ -22,7 +22,7 @@ ACT = {None: 0, "linear": 0, "relu": 1, "elu": 2, "sigmoid": 3}
  OP_BN_STATS, OP_BN_FINALIZE, OP_BN_APPLY, OP_BN_BWD_REDUCE, OP_BN_BWD_APPLY, OP_MAXPOOL_FWD, OP_MAXPOOL_BWD,
  OP_DROPOUT_FWD, OP_DROPOUT_BWD, OP_COPY_SLICE, OP_HEAD_FWD, OP_BCE_DICE_SUMS, OP_BCE_DICE_FINALIZE, OP_HEAD_BWD,
  OP_DENSE_FWD, OP_DENSE_BWD, OP_BCE_FWD, OP_BCE_SIGMOID_BWD, OP_ADAM, OP_MEMSET, OP_ALLREDUCE_F32,
- OP_ALLREDUCE_F64, OP_STATE_ADVANCE, OP_GATHER_BATCH) = range(1, 31)
+ OP_ALLREDUCE_F64, OP_STATE_ADVANCE, OP_GATHER_BATCH, OP_PACK_WEIGHTS) = range(1, 32)
 OP_NAMES = {v: k for k, v in list(globals().items()) if k.startswith("OP_")}
 
 ELEM = {F32: 4, F16: 2}
@@ -127,7 +127,8 @@ class Plan:
     """Op lists + arena sizes for one (graph, batch size, storage type, mode) combination."""
 
     def __init__(self, graph, n, dt=F32, training=True, dropout=True, loss="bce_dice", world=1,
-                 sync_stats=False, layout=None, rank=0, fuse_bn_bwd=True, fuse_bn_stats=True, fuse_bias_grad=True):
+                 sync_stats=False, layout=None, rank=0, fuse_bn_bwd=True, fuse_bn_stats=True, fuse_bias_grad=True,
+                 prepack=True):
         self.graph, self.n, self.dt, self.training = graph, int(n), dt, training
         self.dropout = dropout and training
         self.loss, self.world, self.sync_stats = loss, int(world), bool(sync_stats) and world > 1
@@ -136,6 +137,11 @@ class Plan:
         self.fuse_bn_stats = bool(fuse_bn_stats)
         self.fuse_bias_grad = bool(fuse_bias_grad)
         self._bias_done = set()          # id(conv layer) whose bias gradient is produced by another backward op
+        # fp16 operand copies of the conv kernels: ONE pack launch per step for the whole model (OP_PACK_WEIGHTS)
+        # instead of one small launch in front of every conv call
+        self.prepack = bool(prepack) and dt == F16
+        self.wpack = Arena("wpack")
+        self.pack_entries = []           # [src element offset, dst element offset, mode, taps, J, K]
         self.layout = layout or ParamLayout(graph)
         self.act, self.f32, self.zero = Arena("act"), Arena("f32"), Arena("zero")
         self.fwd, self.bwd, self.opt = [], [], []
@@ -149,6 +155,30 @@ class Plan:
     # ---------------------------------------------------------------------------------------
     def _npix(self, v):
         return self.n * v.h * v.w
+
+    def _packed(self, layer, mode, taps, j, k):
+        """Ref of the packed fp16 copy of `layer`'s kernel for `mode` (include/b200unet.h b2u_pack_weights), or None
+        when the tensor-core kernels cannot take the shape anyway."""
+        if not self.prepack or j % 16 or k % 16:
+            return None
+        ref = self.wpack.alloc(taps * j * k * 2)
+        arena, off, _ = self.layout.offsets["%s/kernel" % layer.name]
+        self.pack_entries.append([off, ref.off // 2, mode, taps, j, k])
+        return ref
+
+    def pack_table(self):
+        """int64 (n, 8) table for OP_PACK_WEIGHTS: src, dst, first 32x32 work tile, mode, taps, J, K, 0"""
+        import numpy as np
+        tab = np.zeros((max(len(self.pack_entries), 1), 8), np.int64)
+        start = 0
+        for r, (src, dst, mode, taps, j, k) in enumerate(self.pack_entries):
+            tab[r] = (src, dst, start, mode, taps, j, k, 0)
+            start += self._pack_tiles(taps, j, k)
+        return tab
+
+    @staticmethod
+    def _pack_tiles(taps, j, k):
+        return taps * ((j + 31) // 32) * ((k + 31) // 32)
 
     def _alloc_view(self, shape, dt, arena=None):
         if len(shape) == 3:
@@ -262,7 +292,8 @@ class Plan:
                 if self.training and len(cons) == 1 and cons[0].kind == "batch_normalization":
                     stats = self.zero.alloc(2 * t.channels * 8)
                     bn_aux[id(cons[0])] = {"sums": stats, "fused": True}
-                self.fwd.append(Op(OP_CONV3X3_FWD, dt, [xv.ref, self._w(l, "kernel"), self._w(l, "bias"), yv.ref, stats],
+                self.fwd.append(Op(OP_CONV3X3_FWD, dt, [xv.ref, self._w(l, "kernel"), self._w(l, "bias"), yv.ref, stats,
+                                                        self._packed(l, 0, 9, yv.c, xv.c)],
                                    [xv.ld, xv.c, ACT[l.activation], yv.ld, yv.c, n, xv.h, xv.w], tag=l.name))
             elif l.kind == "conv2d":      # 1x1 output head
                 if l.activation != "sigmoid" or l.filters != 1 or t is not g.output:
@@ -275,7 +306,8 @@ class Plan:
             elif l.kind == "conv2d_transpose":
                 place(t, dt)
                 yv = self.views[id(t)]
-                self.fwd.append(Op(OP_CONVT_FWD, dt, [xv.ref, self._w(l, "kernel"), self._w(l, "bias"), yv.ref, None],
+                self.fwd.append(Op(OP_CONVT_FWD, dt, [xv.ref, self._w(l, "kernel"), self._w(l, "bias"), yv.ref, None,
+                                                      self._packed(l, 2, 1, 4 * yv.c, xv.c)],
                                    [xv.ld, xv.c, yv.ld, yv.c, n, xv.h, xv.w, 0], tag=l.name))
                 prod_op[id(t)] = self.fwd[-1]
             elif l.kind == "batch_normalization":
@@ -435,7 +467,8 @@ class Plan:
                     mv, ma = self._mask_for(x)
                     acc = 1 if id(x) in written else 0
                     sink = self._bias_sink(x) if (mv is not None and not acc) else None
-                    self.bwd.append(Op(OP_CONV3X3_DGRAD, dt, [gy.ref, self._w(l, "kernel"), gx.ref, mv.ref if mv else None, sink],
+                    self.bwd.append(Op(OP_CONV3X3_DGRAD, dt, [gy.ref, self._w(l, "kernel"), gx.ref, mv.ref if mv else None, sink,
+                                                              self._packed(l, 1, 9, gx.c, gy.c)],
                                        [gy.ld, gy.c, gx.ld, gx.c, mv.ld if mv else 0, ma, acc,
                                         n, xv.h, xv.w], tag=l.name))
                     written.add(id(x))
@@ -452,7 +485,8 @@ class Plan:
                 mv, ma = self._mask_for(x)
                 acc = 1 if id(x) in written else 0
                 sink = self._bias_sink(x) if (mv is not None and not acc) else None
-                self.bwd.append(Op(OP_CONVT_DGRAD, dt, [gy.ref, self._w(l, "kernel"), gx.ref, mv.ref if mv else None, sink],
+                self.bwd.append(Op(OP_CONVT_DGRAD, dt, [gy.ref, self._w(l, "kernel"), gx.ref, mv.ref if mv else None, sink,
+                                                        self._packed(l, 3, 4, gx.c, gy.c)],
                                    [gy.ld, gy.c, gx.ld, gx.c, mv.ld if mv else 0, ma, acc,
                                     n, xv.h, xv.w], tag=l.name))
                 written.add(id(x))
@@ -559,6 +593,10 @@ class Plan:
     def prologue(self):
         """ops that must run before every step: clear the statistics arena (and gradients)."""
         ops = []
+        if self.pack_entries:
+            total = sum(self._pack_tiles(t, j, k) for _, _, _, t, j, k in self.pack_entries)
+            ops.append(Op(OP_PACK_WEIGHTS, 0, [Ref("wtab", 0), Ref("params", 0), Ref("wpack", 0)],
+                          [len(self.pack_entries), total], tag="pack-weights"))
         if self.zero.size:
             ops.append(Op(OP_MEMSET, 0, [Ref("zero", 0)], [self.zero.size], tag="zero-sums"))
         if self.training:
@@ -573,5 +611,6 @@ class Plan:
 
     def arena_sizes(self):
         return {"act": self.act.size, "f32": self.f32.size, "zero": max(self.zero.size, 8),
+                "wpack": max(self.wpack.size, 8),
                 "params": self.layout.n_params * 4, "state": max(self.layout.n_state * 4, 4),
                 "step": STEP_STATE_BYTES}

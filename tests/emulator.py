@@ -73,6 +73,9 @@ class Emulator:
         for o in ops:
             getattr(self, "op_" + P.OP_NAMES[o.kind][3:].lower())(o)
 
+    def op_pack_weights(self, o):
+        pass        # fp16 operand copies are an implementation detail of the tensor-core kernels
+
     def op_memset(self, o):
         self.arr(o.p[0], o.i[0], np.uint8)[:] = 0
 

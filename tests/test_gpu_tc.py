@@ -24,6 +24,7 @@ def test_tensor_path_is_live():
 TC_CONV = [  # n, h, w, cin, cout
     (1, 16, 16, 64, 64), (2, 32, 32, 32, 32), (1, 32, 32, 256, 512), (1, 16, 16, 512, 256), (2, 24, 40, 128, 128),
     (1, 14, 14, 256, 512), (1, 28, 28, 96, 32), (1, 56, 56, 16, 16), (3, 8, 8, 192, 64), (1, 64, 64, 64, 32),
+    (1, 16, 16, 32, 80), (1, 16, 16, 32, 48), (1, 16, 16, 48, 32), (1, 16, 16, 80, 32),      # 16-channel K slabs, odd N tiles
 ]
 
 
@@ -213,3 +214,56 @@ def test_head_bwd_colsum(c, npix):
            P.Op(P.OP_BCE_DICE_FINALIZE, 0, [sums, out], [npix]),
            P.Op(P.OP_HEAD_BWD, dt, [prob, tgt, sums, step, x.ref, wt, dx.ref, dw, db1, db], [npix, x.ld, c, dx.ld, 1, npix])]
     compare(ops, img, dt, state=dict(loss_scale=256.0), tol=4e-3)
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 32), (80, 48)])
+def test_pack_weights_table_matches_per_call_packing(cin, cout):
+    """OP_PACK_WEIGHTS (one launch for all layers) + packed-weight pointers give bit-identical results to the
+    per-call packing for every mode: conv fwd / dgrad, transposed-conv fwd / dgrad"""
+    from gpu_harness import run_ops_gpu
+    n, h, w = 1, 16, 16                       # (80, 48): not multiples of 32 -> ragged pack tiles
+    img = Img(51)
+    x = img.view(n, h, w, cin, dt, fill="uniform")
+    y = img.view(n, h, w, cout, dt, fill=None)
+    dy = img.view(n, h, w, cout, dt, scale=0.5)
+    dx = img.view(n, h, w, cin, dt, fill=None)
+    up = img.view(n, 2 * h, 2 * w, cout, dt, fill=None)
+    dup = img.view(n, 2 * h, 2 * w, cout, dt, scale=0.5)
+    dxt = img.view(n, h, w, cin, dt, fill=None)
+    wt = img.farr(img.par, 9 * cin * cout, scale=0.05)
+    b = img.farr(img.par, cout, scale=0.1)
+    wtt = img.farr(img.par, 4 * cout * cin, scale=0.1)
+    entries = [(wt.off // 4, 0, 9, cout, cin), (wt.off // 4, 1, 9, cin, cout), (wtt.off // 4, 2, 1, 4 * cout, cin),
+               (wtt.off // 4, 3, 4, cin, cout)]
+    tab = np.zeros((len(entries), 8), np.int64)
+    refs, start, dst = [], 0, 0
+    for r, (src, mode, taps, j, k) in enumerate(entries):
+        tab[r] = (src, dst, start, mode, taps, j, k, 0)
+        refs.append(P.Ref("wpack", dst * 2))
+        start += taps * ((j + 31) // 32) * ((k + 31) // 32)
+        dst += (taps * j * k + 127) // 128 * 128
+    def ops(packed):
+        pk = refs if packed else [None] * 4
+        lst = [P.Op(P.OP_CONV3X3_FWD, dt, [x.ref, wt, b, y.ref, None, pk[0]], [x.ld, cin, 1, y.ld, cout, n, h, w]),
+               P.Op(P.OP_CONV3X3_DGRAD, dt, [dy.ref, wt, dx.ref, None, None, pk[1]], [dy.ld, cout, dx.ld, cin, 0, 0, 0, n, h, w]),
+               P.Op(P.OP_CONVT_FWD, dt, [x.ref, wtt, b, up.ref, None, pk[2]], [x.ld, cin, up.ld, cout, n, h, w, 0]),
+               P.Op(P.OP_CONVT_DGRAD, dt, [dup.ref, wtt, dxt.ref, None, None, pk[3]], [dup.ld, cout, dxt.ld, cin, 0, 0, 0, n, h, w])]
+        if packed:
+            lst.insert(0, P.Op(P.OP_PACK_WEIGHTS, 0, [P.Ref("wtab", 0), P.Ref("params", 0), P.Ref("wpack", 0)], [len(entries), start]))
+        return lst
+    mem = img.mem()
+    mem["wtab"] = tab.reshape(-1).view(np.uint8).copy()
+    mem["wpack"] = np.zeros(dst * 2 + 256, np.uint8)
+    st = E.Emulator({"act": 0, "f32": 0, "zero": 0, "params": 0, "state": 0, "step": 0}).state
+    compare(ops(False), img, dt, tol=4e-3)          # per-call packing against the emulator first
+    out0, _ = run_ops_gpu(ops(False), mem, st)
+    out1, _ = run_ops_gpu(ops(True), mem, st)
+    a0 = np.frombuffer(out0["act"], np.float16, (len(out0["act"]) - 256) // 2).astype(np.float32)
+    a1 = np.frombuffer(out1["act"], np.float16, (len(out1["act"]) - 256) // 2).astype(np.float32)
+    for name, v, npx in (("conv fwd", y, n * h * w), ("conv dgrad", dx, n * h * w), ("convT fwd", up, 4 * n * h * w),
+                         ("convT dgrad", dxt, n * h * w)):
+        lo, cnt = v.ref.off // 2, npx * v.ld
+        d = np.abs(a0[lo:lo + cnt] - a1[lo:lo + cnt])
+        assert d.max() == 0, "%s: packed-weight path differs, max |d| %.3e at %d (of %d), values %.4f vs %.4f" % (
+            name, d.max(), int(d.argmax()), cnt, a0[lo + d.argmax()], a1[lo + d.argmax()])
+        assert np.abs(a1[lo:lo + cnt]).max() > 0

@@ -12,3 +12,5 @@ timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo
 tail -15 $OUT/pytest_gpu.log
 timeout 300 python tools/ab_ops.py ${2:+--opt $2} > $OUT/ab_ops.txt 2>&1; echo "ab rc=$?" | tee -a $OUT/rc.txt
 tail -24 $OUT/ab_ops.txt
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu > $OUT/bench_nocpu.json 2>$OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/rc.txt
+head -c 400 $OUT/bench_nocpu.json; echo
