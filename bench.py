@@ -181,6 +181,9 @@ def run_engine(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         comm = E.Comm(rank, world)
     peaks = load_peaks()
+    for kv in args.opt:                       # library options for A/B runs, e.g. --opt pdl=0
+        k, v = kv.split("=")
+        importlib.import_module(PKG + "._lib").lib().b2u_set_option(k.encode(), int(v))
     precision = args.precision
     model = M.Model(graph=G.GRAPHS[GRAPH](SIZE, 1), precision=precision, comm=comm, use_graph=not args.no_graph, seed=42)
     model.compile(optimizer=M.Adam(lr=0.0005), loss=LS.bce_dice_loss, metrics=[LS.dice_coeff])
@@ -347,6 +350,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--per-op", action="store_true", help="add per-op device times to op_breakdown_ms")
     ap.add_argument("--workload", default="unet512", choices=sorted(WORKLOADS))
+    ap.add_argument("--opt", action="append", default=[], help="library option name=int (b2u_set_option), repeatable")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     global METRIC, SIZE, BATCH, TRAIN_FLOP_PER_SLICE, GRAPH

@@ -8,6 +8,7 @@
 #include "internal.h"
 
 unsigned long long g_b2u_launches = 0;
+int g_b2u_pdl = 0;          // programmatic dependent launch (launch.cuh); measured 4 % slower on the U-Net step: off
 
 static thread_local char g_err[1024] = "";
 
@@ -41,6 +42,11 @@ extern "C" int b2u_set_option(const char* name, int value) {
   if (strcmp(name, "tc_halo") == 0) {
     int old = g_b2u_tc_halo;
     g_b2u_tc_halo = value;
+    return old;
+  }
+  if (strcmp(name, "pdl") == 0) {
+    int old = g_b2u_pdl;
+    g_b2u_pdl = value ? 1 : 0;
     return old;
   }
   if (strcmp(name, "wgrad_halo") == 0) {

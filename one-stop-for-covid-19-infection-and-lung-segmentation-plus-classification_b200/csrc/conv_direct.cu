@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256) conv3x3_direct_kernel(
     const T* __restrict__ x, int ldx, int K, const float* __restrict__ w, int dgrad,
     const float* __restrict__ bias, int act, T* __restrict__ y, int ldy, int J, double* __restrict__ stats,
     const T* __restrict__ mask, int ldmask, int mask_act, int accumulate, int N, int H, int W) {
+  B2U_PDL_PROLOGUE();
   constexpr int NCG = TCO / 4;             // channel groups of 4
   constexpr int NPG = 256 / NCG;           // pixel groups
   constexpr int PX = (TH * TW) / NPG;      // pixels per thread: 8 (TCO=32) or 16 (TCO=64)
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(256, 2) conv3x3_c1_fwd_kernel(const T* __restr
                                                                 const float* __restrict__ w,
                                                                 const float* __restrict__ bias, int act,
                                                                 T* __restrict__ y, int ldy, int N, int H, int W) {
+  B2U_PDL_PROLOGUE();
   constexpr int CG = COUT / 8, LANES = 256 / CG;
   __shared__ float xs[C1_HALO + 2];
   const int g = threadIdx.x % CG, lane = threadIdx.x / CG;
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(256, 2) conv3x3_c1_wgrad_kernel(const T* __res
                                                                   const T* __restrict__ dy, int lddy,
                                                                   float* __restrict__ dw, float* __restrict__ db, int N,
                                                                   int H, int W) {
+  B2U_PDL_PROLOGUE();
   // block = 8 x 32 pixel tiles (grid-stride); thread = (pixel lane, 8-channel group).  The loads of the NEXT tile
   // (the thread's share of the x halo, its pixels' 16-byte dy pieces) are issued before the current tile is
   // reduced, so a block keeps ~17 KB in flight all the time; 9 taps x 8 channels (+ bias) of the gradient
@@ -342,6 +345,7 @@ __global__ void __launch_bounds__(128) conv3x3_wgrad_direct_kernel(const T* __re
                                                                    const T* __restrict__ dy, int lddy, int Cout,
                                                                    float* __restrict__ dw, float* __restrict__ db,
                                                                    int N, int H, int W, int nsplit) {
+  B2U_PDL_PROLOGUE();
   __shared__ __align__(16) float xs[WG_TH + 2][WG_TW + 2][WG_CI];
   __shared__ __align__(16) float ds[WG_TH][WG_TW][WG_CO];
   const int ci0 = blockIdx.y * WG_CI, co0 = blockIdx.z * WG_CO;
@@ -434,6 +438,7 @@ __global__ void __launch_bounds__(128) conv3x3_wgrad_direct_kernel(const T* __re
 template <typename LA, typename LB, typename EP>
 __global__ void __launch_bounds__(256) gemm64_kernel(LA la, LB lb, EP ep, long long M, int Nn, long long Kk,
                                                      int ksplit) {
+  B2U_PDL_PROLOGUE();
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const long long m0 = (long long)blockIdx.x * 64;
@@ -561,6 +566,7 @@ struct CtWgradEp {
 template <typename T>
 __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ dy, int lddy, int C, long long npix,
                                                           float* __restrict__ db) {
+  B2U_PDL_PROLOGUE();
   extern __shared__ float sacc[];
   for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();

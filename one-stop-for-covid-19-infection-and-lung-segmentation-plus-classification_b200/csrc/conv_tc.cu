@@ -87,6 +87,7 @@ __device__ __forceinline__ float transpose_reduce16(float v[16], int lane) {
 template <bool kRegStats>
 __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_constant__ TcMaps maps,
                                                                  const __grid_constant__ TcParams prm) {
+  B2U_PDL_LAUNCH_DEPENDENTS();      // B2U_PDL_WAIT() follows the CTA-local setup (barriers, TMEM)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A tile 128 x KS halves][B tile JT x KS halves] | barriers | tmem ptr | bias | stats
   const int KS = prm.KS, JT = prm.JT;
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
+  B2U_PDL_WAIT();                    // everything below may read what the preceding kernel wrote
   for (int i = threadIdx.x; i < prm.J; i += kThreadsTc) {
     float b = 0.f;
     if (prm.bias != nullptr) b = prm.bias[prm.mode == 1 ? (i % prm.cout) : i];
@@ -354,6 +356,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
 // mode 3 (convT dgrad): Wp[ab][ci][co] = w[ab][co][ci]
 __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ wp, int mode, int taps, int J,
                                     int K) {
+  B2U_PDL_PROLOGUE();
   long long total = (long long)taps * J * K;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -376,6 +379,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restr
 __global__ void __launch_bounds__(256) pack_all_kernel(const long long* __restrict__ tab, int n_entries,
                                                        const float* __restrict__ params, __half* __restrict__ wpack,
                                                        long long total_tiles) {
+  B2U_PDL_PROLOGUE();
   __shared__ long long st[128 * 8];
   __shared__ float tile[32][33];
   for (int i = threadIdx.x; i < n_entries * 8; i += blockDim.x) st[i] = tab[i];

@@ -70,6 +70,7 @@ __device__ __forceinline__ float transpose_reduce16_(float v[16], int lane) {
 
 __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_constant__ C3Maps maps,
                                                                  const __grid_constant__ C3Params prm) {
+  B2U_PDL_LAUNCH_DEPENDENTS();      // B2U_PDL_WAIT() follows the CTA-local setup (barriers, TMEM)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int KS = prm.KS, JT = prm.JT, SA = prm.SA, SB = prm.SB;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
+  B2U_PDL_WAIT();                    // everything below may read what the preceding kernel wrote
   for (int i = threadIdx.x; i < prm.J; i += blockDim.x) s_bias[i] = prm.bias ? prm.bias[i] : 0.f;
   for (int i = threadIdx.x; i < 2 * prm.J; i += blockDim.x) s_stats[i] = 0.f;
   tc::fence_before_sync();
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
 }
 
 __global__ void pack3_kernel(const float* __restrict__ w, __half* __restrict__ wp, int dgrad, int J, int K) {
+  B2U_PDL_PROLOGUE();
   // fwd: Wp[t][co][ci] = w[t][ci][co];  dgrad: Wp[t][ci][co] = w[8-t][ci][co]
   long long total = 9LL * J * K;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;

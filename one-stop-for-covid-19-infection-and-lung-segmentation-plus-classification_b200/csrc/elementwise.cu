@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kThreads, 4) bn_reduce_kernel(const T* __restr
                                                              long long npix, const float* __restrict__ mean,
                                                              const float* __restrict__ invstd,
                                                              double* __restrict__ sums, int sq_off) {
+  B2U_PDL_PROLOGUE();
   // kBwd == false: a = x (stats of a).  kBwd == true: a = dy, x = bn input; sums of dy and dy*xhat.
   // block-level partial sums in fp32 (native shared-memory atomics; fp64 shared atomics are CAS loops and
   // cost more than the streaming loop), one fp64 global atomic per channel per block
@@ -110,6 +111,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long co
                                    float eps, int training, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ save_mean,
                                    float* __restrict__ save_invstd, int C) {
+  B2U_PDL_PROLOGUE();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mean, var;
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift,
                                                             double* __restrict__ out_stats, int out_sq_off) {
+  B2U_PDL_PROLOGUE();
   extern __shared__ float sst[];          // [2*C] block partials of the optional output statistics
   float o1[8], o2[8];
   if (out_stats != nullptr) {
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
     long long npix, long long count, const float* __restrict__ gamma, const float* __restrict__ mean,
     const float* __restrict__ invstd, const double* __restrict__ sums, float* __restrict__ dgamma,
     float* __restrict__ dbeta, const T* __restrict__ mask, int ldmask, int mask_act, float* __restrict__ colsum) {
+  B2U_PDL_PROLOGUE();
   // colsum (optional): per-channel sums of the dx values written = bias gradient of the conv that feeds this BN
   extern __shared__ float scs[];          // [C] block partials of colsum
   float cs[kColsum ? 8 : 1];
@@ -268,6 +272,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y,
                                                                int ldy, int C, int N, int H, int W, float p_drop,
                                                                int op_id, const b2u_step_state* __restrict__ st) {
+  B2U_PDL_PROLOGUE();
   const int Ho = H >> 1, Wo = W >> 1;
   const long long nopix = (long long)N * Ho * Wo;            // < 2^31 for any tensor that fits in HBM here
   PIXEL_LANE_LOOP(C, nopix) {
@@ -328,6 +333,7 @@ __global__ void __launch_bounds__(kThreads, 2) maxpool_bwd_kernel(const T* __res
                                                                   int accumulate, double* __restrict__ bn_sums,
                                                                   const float* __restrict__ bn_gamma,
                                                                   const float* __restrict__ bn_beta) {
+  B2U_PDL_PROLOGUE();
   extern __shared__ float sbn[];          // [2*C] block partials of the fused BN-backward statistics
   float t1[8], t2[8], bt[8];
 #pragma unroll
@@ -430,6 +436,7 @@ __global__ void __launch_bounds__(kThreads) dropout_kernel(const T* __restrict__
                                                            int ldy, int C, long long npix, float prob, int op_id,
                                                            const b2u_step_state* __restrict__ st,
                                                            const T* __restrict__ mask, int ldmask, int mask_act) {
+  B2U_PDL_PROLOGUE();
   PIXEL_LANE_LOOP(C, npix) {
     const long long px = p;
     float v[8], f[8];
@@ -450,6 +457,7 @@ __global__ void __launch_bounds__(kThreads) dropout_kernel(const T* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(kThreads) copy_slice_kernel(const T* __restrict__ s, int lds, T* __restrict__ d,
                                                               int ldd, int C, long long npix, int accumulate) {
+  B2U_PDL_PROLOGUE();
   PIXEL_LANE_LOOP(C, npix) {
     const long long px = p;
     float v[8];
@@ -472,6 +480,7 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(const T* __restrict_
                                                             const float* __restrict__ w,
                                                             const float* __restrict__ bias,
                                                             float* __restrict__ prob, long long npix) {
+  B2U_PDL_PROLOGUE();
   float wr[CIN];
 #pragma unroll
   for (int k = 0; k < CIN; ++k) wr[k] = __ldg(w + k);
@@ -499,6 +508,7 @@ __device__ __forceinline__ float bce_term(float t, float p) {
 __global__ void __launch_bounds__(kThreads) bce_dice_sums_kernel(const float* __restrict__ prob,
                                                                  const float* __restrict__ tgt, long long count,
                                                                  double* __restrict__ sums) {
+  B2U_PDL_PROLOGUE();
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
        i += (long long)gridDim.x * blockDim.x) {
@@ -518,6 +528,7 @@ __global__ void __launch_bounds__(kThreads) bce_dice_sums_kernel(const float* __
 }
 
 __global__ void bce_dice_finalize_kernel(const double* __restrict__ sums, long long count, float* __restrict__ out) {
+  B2U_PDL_PROLOGUE();
   double I = sums[0], S = sums[1] + sums[2];
   double dice = (2.0 * I + 1.0) / (S + 1.0);
   out[0] = (float)(0.5 * sums[3] / (double)count + 0.5 * (1.0 - dice));
@@ -533,6 +544,7 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(
     long long count, const b2u_step_state* __restrict__ st, const T* __restrict__ x, int ldx,
     const float* __restrict__ w, T* __restrict__ dx, int lddx, int x_act, float* __restrict__ dw,
     float* __restrict__ db, long long npix, int C, float* __restrict__ colsum) {
+  B2U_PDL_PROLOGUE();
   extern __shared__ float sacc[];          // [2*C + 1]: dW partials, colsum partials, db partial
   for (int i = threadIdx.x; i < 2 * C + 1; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
@@ -605,6 +617,7 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(
 __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, long long n,
                                                         b2u_step_state* __restrict__ st) {
+  B2U_PDL_PROLOGUE();
   // 16-byte accesses (the flat buffers are 16-byte aligned and every tensor is padded to 4 elements), two
   // quads per trip so that eight independent loads are in flight per thread
   const float b1 = st->beta1, b2 = st->beta2, eps = st->eps;
@@ -652,6 +665,7 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, c
   if (bad) atomicOr(&st->overflow, 1u);
 }
 __global__ void state_advance_kernel(b2u_step_state* st) {
+  B2U_PDL_PROLOGUE();
   st->step += 1;
   st->beta1_pow *= st->beta1;
   st->beta2_pow *= st->beta2;
@@ -661,6 +675,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) gather_batch_kernel(const float* __restrict__ src,
                                                                 const int* __restrict__ idx, T* __restrict__ dst,
                                                                 long long per_sample, int nb) {
+  B2U_PDL_PROLOGUE();
   const long long total = (long long)nb * per_sample;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -679,6 +694,7 @@ __global__ void __launch_bounds__(kThreads) threshold_counts_kernel(const float*
                                                                     const float* __restrict__ thr, int nthr,
                                                                     double* __restrict__ tp, double* __restrict__ spr,
                                                                     double* __restrict__ sgt) {
+  B2U_PDL_PROLOGUE();
   extern __shared__ float sh[];   // [nthr] tp, [nthr] cnt, [1] gt
   for (int i = threadIdx.x; i < 2 * nthr + 1; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
@@ -717,6 +733,7 @@ __global__ void __launch_bounds__(kThreads) dense_fwd_kernel(const T* __restrict
                                                              const float* __restrict__ w,
                                                              const float* __restrict__ bias, int act,
                                                              float* __restrict__ y) {
+  B2U_PDL_PROLOGUE();
   // one block per sample; threads split K; each keeps M partial outputs (y is always fp32)
   __shared__ float sacc[M];
   for (int i = threadIdx.x; i < M; i += blockDim.x) sacc[i] = 0.f;
@@ -751,6 +768,7 @@ __global__ void __launch_bounds__(kThreads) dense_bwd_kernel(const T* __restrict
                                                              int act, const float* __restrict__ dy, T* __restrict__ dx,
                                                              const T* __restrict__ mask, int mask_act,
                                                              float* __restrict__ dw, float* __restrict__ db, int N) {
+  B2U_PDL_PROLOGUE();
   // grid over K chunks: each thread owns one k and loops over samples (N small) -> dw row + dx column
   extern __shared__ float dpre[];   // [N][M]
   for (int i = threadIdx.x; i < N * M; i += blockDim.x) {
@@ -789,6 +807,7 @@ __global__ void __launch_bounds__(kThreads) dense_bwd_kernel(const T* __restrict
 
 __global__ void bce_fwd_kernel(const float* __restrict__ prob, const float* __restrict__ tgt,
                                const float* __restrict__ sw, int n, float* __restrict__ out) {
+  B2U_PDL_PROLOGUE();
   // single block; keras: mean over batch of w_i * bce_i
   __shared__ float sh;
   if (threadIdx.x == 0) sh = 0.f;
@@ -805,6 +824,7 @@ template <typename T>
 __global__ void bce_sigmoid_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ tgt,
                                        const float* __restrict__ sw, int n, const b2u_step_state* __restrict__ st,
                                        T* __restrict__ dlogit) {
+  B2U_PDL_PROLOGUE();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float p = prob[i], t = tgt[i], g = 0.f;

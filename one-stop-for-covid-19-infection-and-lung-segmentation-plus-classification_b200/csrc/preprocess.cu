@@ -14,6 +14,7 @@ namespace {
 
 __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ lut, int H,
                                                         int W, int tiles, int clip_limit, float lut_scale) {
+  B2U_PDL_PROLOGUE();
   // one block per (image, tile_y, tile_x); thread i owns histogram bin i
   __shared__ int hist[256];
   __shared__ int scan[256];
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
 
 __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ lut,
                                                            uint8_t* __restrict__ out, int N, int H, int W, int tiles) {
+  B2U_PDL_PROLOGUE();
   const int th = H / tiles, tw = W / tiles;
   const float inv_tw = __fdiv_rn(1.0f, (float)tw), inv_th = __fdiv_rn(1.0f, (float)th);
   const long long total = (long long)N * H * W;
@@ -112,6 +114,7 @@ __device__ __forceinline__ float area_axis_weight(int s, float lo, float hi) {
 __global__ void __launch_bounds__(256) crop_area_resize_kernel(const uint8_t* __restrict__ in, int H, int W,
                                                                const int* __restrict__ boxes, int half_w, int out_h,
                                                                uint8_t* __restrict__ mid, int N) {
+  B2U_PDL_PROLOGUE();
   const int ow = 2 * half_w;
   const long long total = (long long)N * out_h * ow;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -173,6 +176,7 @@ __global__ void __launch_bounds__(256) crop_area_resize_kernel(const uint8_t* __
 // coefficients, two-pass with the (>>4, >>16, +2 >>2) rounding of its 8-bit VResizeLinear) then /255.
 __global__ void __launch_bounds__(256) linear_resize_scale_kernel(const uint8_t* __restrict__ mid, int mh, int mw, int fd,
                                                                   float* __restrict__ out, int N) {
+  B2U_PDL_PROLOGUE();
   const long long total = (long long)N * fd * fd;
   const float scx = (float)mw / (float)fd, scy = (float)mh / (float)fd;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;

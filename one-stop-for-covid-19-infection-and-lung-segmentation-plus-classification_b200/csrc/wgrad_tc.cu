@@ -47,6 +47,7 @@ struct WgMaps {
 
 __global__ void __launch_bounds__(kThreadsW, 1) tc_wgrad_kernel(const __grid_constant__ WgMaps maps,
                                                                  const __grid_constant__ WgParams prm) {
+  B2U_PDL_LAUNCH_DEPENDENTS();      // B2U_PDL_WAIT() follows the CTA-local setup (barriers, TMEM)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int KSA = prm.KSA, KSB = prm.KSB, JT = prm.JT, nchunks = prm.nchunks, stages = prm.stages;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) tc_wgrad_kernel(const __grid_con
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
+  B2U_PDL_WAIT();                    // everything below may read what the preceding kernel wrote
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -208,6 +210,7 @@ struct WhMaps { CUtensorMap a, b; };
 
 __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __grid_constant__ WhMaps maps,
                                                                       const __grid_constant__ WhParams prm) {
+  B2U_PDL_LAUNCH_DEPENDENTS();      // B2U_PDL_WAIT() follows the CTA-local setup (barriers, TMEM)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int cin = prm.cs, JT = prm.JT, KSB = prm.KSB, stages = prm.stages;   // `cin` = slab width from here on
@@ -241,6 +244,7 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
+  B2U_PDL_WAIT();                    // everything below may read what the preceding kernel wrote
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
