@@ -183,6 +183,16 @@ int b2u_clahe_u8(const uint8_t* in, uint8_t* out, int n, int h, int wd, float cl
 int b2u_crop_resize(const uint8_t* in, int n, int h, int wd, const int* boxes, int half_w, int out_h,
                     int final_dim, uint8_t* mid_u8, float* out, void* stream);
 
+/* ---- BatchNormalization backward statistics without a pass over the activations ------------------ */
+/* For a BN whose output y feeds exactly one Conv2D 3x3 (U-Net decoder: concat -> BN -> conv, T1H:888-889) the two
+ * per-channel sums its backward needs follow from quantities the conv backward already produced:
+ *   sum_p dy[p][c] * y[p][c] = sum_{tap,co} W[tap][c][co] * dW[tap][c][co]      (adjoint identity of the convolution)
+ *   sum_p dy[p][c]           = `colsum` emitted by the conv's data-gradient kernel
+ * so sums[c] = colsum[c] and sums[C + c] = sum dy * xhat = (<W, dW>_c - beta[c] * colsum[c]) / gamma[c].
+ * w, dw: Keras HWIO (taps, C, cout) fp32; dw must hold only this step's gradient of that conv. */
+int b2u_bn_bwd_sums_from_wgrad(const float* w, const float* dw, const float* colsum, const float* gamma,
+                               const float* beta, double* sums, int c, int cout, int taps, void* stream);
+
 /* ---- fp16 operand copies of all conv / transposed-conv kernels of a model in ONE launch ---------- */
 /* The tcgen05 kernels read weights as fp16 [tap][out][in] tiles.  `d_table` holds n_entries (<= 128) records of 8
  * int64: {src element offset in params, dst element offset in wpack, first work tile, mode, taps, J, K, 0}; a work
@@ -204,7 +214,7 @@ enum {
   B2U_OP_HEAD_FWD, B2U_OP_BCE_DICE_SUMS, B2U_OP_BCE_DICE_FINALIZE, B2U_OP_HEAD_BWD,
   B2U_OP_DENSE_FWD, B2U_OP_DENSE_BWD, B2U_OP_BCE_FWD, B2U_OP_BCE_SIGMOID_BWD,
   B2U_OP_ADAM, B2U_OP_MEMSET, B2U_OP_ALLREDUCE_F32, B2U_OP_ALLREDUCE_F64, B2U_OP_STATE_ADVANCE,
-  B2U_OP_GATHER_BATCH, B2U_OP_PACK_WEIGHTS
+  B2U_OP_GATHER_BATCH, B2U_OP_PACK_WEIGHTS, B2U_OP_BN_BWD_SUMS_WGRAD
 };
 /* one record; the meaning of p[]/i[]/f[] per kind is the argument order of the function above
  * (pointers in order into p[], ints/long longs into i[], floats into f[]).

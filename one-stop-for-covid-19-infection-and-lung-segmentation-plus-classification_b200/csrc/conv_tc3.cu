@@ -250,7 +250,10 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
     const int cbeg = split ? half * ccols : 0;
     const bool has_cols = split || half == 0;
     const bool want_sums = prm.stats != nullptr || prm.colsum != nullptr;
-    const bool reg_stats = want_sums && ccols <= 32 && nj == 1;
+    // register accumulators: 32 columns of (sum, sum of squares), or -- column sums only -- 64 columns of sums
+    // (rs2 then holds columns 32..63)
+    const bool wide_sums = prm.stats == nullptr && ccols > 32;
+    const bool reg_stats = want_sums && nj == 1 && (ccols <= 32 || (wide_sums && ccols <= 64));
     float rs1[32], rs2[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
@@ -316,12 +319,26 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
           if (want_sums) {
             if (reg_stats) {
               if (valid) {
-                if (cc == 0) {
+                if (!wide_sums) {
+                  if (cc == 0) {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) { rs1[i] += v[i]; rs2[i] = fmaf(v[i], v[i], rs2[i]); }
+                    for (int i = 0; i < 16; ++i) { rs1[i] += v[i]; rs2[i] = fmaf(v[i], v[i], rs2[i]); }
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { rs1[16 + i] += v[i]; rs2[16 + i] = fmaf(v[i], v[i], rs2[16 + i]); }
+                  }
+                } else if (cc == 0) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) rs1[i] += v[i];
+                } else if (cc == 16) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) rs1[16 + i] += v[i];
+                } else if (cc == 32) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) rs2[i] += v[i];
                 } else {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) { rs1[16 + i] += v[i]; rs2[16 + i] = fmaf(v[i], v[i], rs2[16 + i]); }
+                  for (int i = 0; i < 16; ++i) rs2[16 + i] += v[i];
                 }
               }
             } else {
@@ -352,12 +369,15 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
       for (int cc = 0; cc < ccols; cc += 16) {
         float q[16], sq[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { q[i] = cc == 0 ? rs1[i] : rs1[16 + i]; sq[i] = cc == 0 ? rs2[i] : rs2[16 + i]; }
+        for (int i = 0; i < 16; ++i) {
+          if (!wide_sums) { q[i] = cc == 0 ? rs1[i] : rs1[16 + i]; sq[i] = cc == 0 ? rs2[i] : rs2[16 + i]; }
+          else { q[i] = cc == 0 ? rs1[i] : (cc == 16 ? rs1[16 + i] : (cc == 32 ? rs2[i] : rs2[16 + i])); sq[i] = 0.f; }
+        }
         float s1 = transpose_reduce16_(q, lane);
-        float s2 = transpose_reduce16_(sq, lane);
-        if (lane < 16) {
-          atomicAdd(&s_stats[cbeg + cc + lane], s1);
-          atomicAdd(&s_stats[prm.J + cbeg + cc + lane], s2);
+        if (lane < 16) atomicAdd(&s_stats[cbeg + cc + lane], s1);
+        if (!wide_sums) {
+          float s2 = transpose_reduce16_(sq, lane);
+          if (lane < 16) atomicAdd(&s_stats[prm.J + cbeg + cc + lane], s2);
         }
       }
     }

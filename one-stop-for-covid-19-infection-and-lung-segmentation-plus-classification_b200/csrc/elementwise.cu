@@ -105,6 +105,34 @@ __global__ void __launch_bounds__(kThreads, 4) bn_reduce_kernel(const T* __restr
   }
 }
 
+// sums[c] = colsum[c];  sums[C + c] = (sum_{tap,co} W[tap][c][co] * dW[tap][c][co] - beta[c] * colsum[c]) / gamma[c]
+// one block per input channel c (see include/b200unet.h: the adjoint identity of the convolution)
+__global__ void __launch_bounds__(128) bn_bwd_sums_wgrad_kernel(const float* __restrict__ w, const float* __restrict__ dw,
+                                                                const float* __restrict__ colsum,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, double* __restrict__ sums,
+                                                                int C, int cout, int taps) {
+  B2U_PDL_PROLOGUE();
+  __shared__ double part[4];
+  const int c = blockIdx.x;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < taps * cout; i += blockDim.x) {
+    const int t = i / cout, co = i - t * cout;
+    const long long idx = ((long long)t * C + c) * cout + co;
+    acc += (double)w[idx] * (double)dw[idx];
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double tot = part[0] + part[1] + part[2] + part[3];
+    const double s1 = (double)colsum[c];
+    const double g = (double)gamma[c];
+    sums[c] += s1;
+    sums[C + c] += fabs(g) > 1e-12 ? (tot - (double)beta[c] * s1) / g : 0.0;
+  }
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ mmean, float* __restrict__ mvar, float momentum,
@@ -895,6 +923,13 @@ extern "C" int b2u_bn_apply(int dt, const void* x, int ldx, void* y, int ldy, in
   size_t smem = out_stats != nullptr ? 2 * (size_t)c * sizeof(float) : 0;
   DISPATCH_T(dt, B2U_LAUNCH(bn_apply_kernel<T>, grid, kThreads, smem, stream, (const T*)x, ldx, (T*)y, ldy, c, npix,
                             scale, shift, out_stats, out_sq_off));
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_bwd_sums_from_wgrad(const float* w, const float* dw, const float* colsum, const float* gamma,
+                                          const float* beta, double* sums, int c, int cout, int taps, void* stream) {
+  B2U_REQUIRE(w && dw && colsum && gamma && beta && sums && c > 0 && cout > 0 && taps > 0, "bn_bwd_sums_from_wgrad: args");
+  B2U_LAUNCH(bn_bwd_sums_wgrad_kernel, c, 128, 0, stream, w, dw, colsum, gamma, beta, sums, c, cout, taps);
   return B2U_OK;
 }
 

@@ -22,7 +22,7 @@ ACT = {None: 0, "linear": 0, "relu": 1, "elu": 2, "sigmoid": 3}
  OP_BN_STATS, OP_BN_FINALIZE, OP_BN_APPLY, OP_BN_BWD_REDUCE, OP_BN_BWD_APPLY, OP_MAXPOOL_FWD, OP_MAXPOOL_BWD,
  OP_DROPOUT_FWD, OP_DROPOUT_BWD, OP_COPY_SLICE, OP_HEAD_FWD, OP_BCE_DICE_SUMS, OP_BCE_DICE_FINALIZE, OP_HEAD_BWD,
  OP_DENSE_FWD, OP_DENSE_BWD, OP_BCE_FWD, OP_BCE_SIGMOID_BWD, OP_ADAM, OP_MEMSET, OP_ALLREDUCE_F32,
- OP_ALLREDUCE_F64, OP_STATE_ADVANCE, OP_GATHER_BATCH, OP_PACK_WEIGHTS) = range(1, 32)
+ OP_ALLREDUCE_F64, OP_STATE_ADVANCE, OP_GATHER_BATCH, OP_PACK_WEIGHTS, OP_BN_BWD_SUMS_WGRAD) = range(1, 33)
 OP_NAMES = {v: k for k, v in list(globals().items()) if k.startswith("OP_")}
 
 ELEM = {F32: 4, F16: 2}
@@ -128,7 +128,7 @@ class Plan:
 
     def __init__(self, graph, n, dt=F32, training=True, dropout=True, loss="bce_dice", world=1,
                  sync_stats=False, layout=None, rank=0, fuse_bn_bwd=True, fuse_bn_stats=True, fuse_bias_grad=True,
-                 prepack=True):
+                 prepack=True, fuse_bn_bwd_wgrad=True):
         self.graph, self.n, self.dt, self.training = graph, int(n), dt, training
         self.dropout = dropout and training
         self.loss, self.world, self.sync_stats = loss, int(world), bool(sync_stats) and world > 1
@@ -136,6 +136,7 @@ class Plan:
         self.fuse_bn_bwd = bool(fuse_bn_bwd)
         self.fuse_bn_stats = bool(fuse_bn_stats)
         self.fuse_bias_grad = bool(fuse_bias_grad)
+        self.fuse_bn_bwd_wgrad = bool(fuse_bn_bwd_wgrad)
         self._bias_done = set()          # id(conv layer) whose bias gradient is produced by another backward op
         # fp16 operand copies of the conv kernels: ONE pack launch per step for the whole model (OP_PACK_WEIGHTS)
         # instead of one small launch in front of every conv call
@@ -432,6 +433,7 @@ class Plan:
 
         # ======================================= backward =========================================
         grads = lambda l, s: self._w(l, s, "grads")
+        yv_c = lambda l: self.views[id(l.output)].c
         for l in reversed(layers):
             t = l.output
             if l.kind == "input":
@@ -467,6 +469,14 @@ class Plan:
                     mv, ma = self._mask_for(x)
                     acc = 1 if id(x) in written else 0
                     sink = self._bias_sink(x) if (mv is not None and not acc) else None
+                    bn = x.producer
+                    if (self.fuse_bn_bwd_wgrad and sink is None and not acc and bn.kind == "batch_normalization" and
+                            len(x.consumers) == 1 and "bwd_sums" not in bn_aux[id(bn)] and x.channels % 8 == 0):
+                        # x is a BatchNorm output read by this conv only: the BN backward statistics follow from this
+                        # conv's weight gradient (<W, dW> per input channel) and the column sums of the gradient written
+                        # here -- no pass over dy and the BN input (include/b200unet.h b2u_bn_bwd_sums_from_wgrad)
+                        sink = self.zero.alloc(x.channels * 4)
+                        bn_aux[id(bn)]["wgrad_sums"] = (sink, self._w(l, "kernel"), grads(l, "kernel"), yv_c(l))
                     self.bwd.append(Op(OP_CONV3X3_DGRAD, dt, [gy.ref, self._w(l, "kernel"), gx.ref, mv.ref if mv else None, sink,
                                                               self._packed(l, 1, 9, gx.c, gy.c)],
                                        [gy.ld, gy.c, gx.ld, gx.c, mv.ld if mv else 0, ma, acc,
@@ -499,6 +509,13 @@ class Plan:
                 mv, ma = self._mask_for(x)
                 if "bwd_sums" in aux:                       # produced by the max-pool backward that completed gy
                     bsums = aux["bwd_sums"]
+                elif "wgrad_sums" in aux:                   # from the consumer conv's weight gradient
+                    csum, wref, dwref, cout = aux["wgrad_sums"]
+                    bsums = self.zero.alloc(2 * c * 8)
+                    self.bwd.append(Op(OP_BN_BWD_SUMS_WGRAD, 0, [wref, dwref, csum, self._w(l, "gamma"), self._w(l, "beta"),
+                                                                 bsums], [c, cout, 9], tag=l.name))
+                    if self.sync_stats:
+                        self.bwd.append(Op(OP_ALLREDUCE_F64, 0, [bsums], [2 * c], tag=l.name))
                 else:
                     bsums = self.zero.alloc(2 * c * 8)
                     self.bwd.append(Op(OP_BN_BWD_REDUCE, xv.dt, [gy.ref, xv.ref, aux["mean"], aux["invstd"], bsums],

@@ -209,6 +209,16 @@ class Emulator:
             s[:c] += ys.sum(0)
             s[sq:sq + c] += (ys * ys).sum(0)
 
+    def op_bn_bwd_sums_wgrad(self, o):
+        c, cout, taps = o.i[:3]
+        w = self.f32(o.p[0], taps * c * cout).reshape(taps, c, cout).astype(np.float64)
+        dw = self.f32(o.p[1], taps * c * cout).reshape(taps, c, cout).astype(np.float64)
+        cs = self.f32(o.p[2], c).astype(np.float64)
+        g, b = self.f32(o.p[3], c).astype(np.float64), self.f32(o.p[4], c).astype(np.float64)
+        s = self.f64(o.p[5], 2 * c)
+        s[:c] += cs
+        s[c:] += np.where(np.abs(g) > 1e-12, ((w * dw).sum((0, 2)) - b * cs) / np.where(np.abs(g) > 1e-12, g, 1.0), 0.0)
+
     def op_bn_bwd_reduce(self, o):
         lddy, ldx, c, npix = o.i[:4]
         dy = self.view(o.p[0], lddy, c, npix, o.dt).astype(np.float32)

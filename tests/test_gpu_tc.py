@@ -267,3 +267,15 @@ def test_pack_weights_table_matches_per_call_packing(cin, cout):
         assert d.max() == 0, "%s: packed-weight path differs, max |d| %.3e at %d (of %d), values %.4f vs %.4f" % (
             name, d.max(), int(d.argmax()), cnt, a0[lo + d.argmax()], a1[lo + d.argmax()])
         assert np.abs(a1[lo:lo + cnt]).max() > 0
+
+
+@pytest.mark.parametrize("c,cout", [(64, 32), (512, 256), (96, 32)])
+def test_bn_bwd_sums_from_wgrad(c, cout):
+    img = Img(61)
+    w = img.farr(img.par, 9 * c * cout, scale=0.1)
+    dw = img.farr(img.gr, 9 * c * cout, scale=2.0)
+    cs = img.farr(img.f32, c, scale=5.0)
+    gamma, beta = img.farr(img.par, c, fill="pos"), img.farr(img.par, c, scale=0.3)
+    sums = img.farr(img.zero, 2 * c, scale=1.0, dtype=np.float64)
+    ops = [P.Op(P.OP_BN_BWD_SUMS_WGRAD, 0, [w, dw, cs, gamma, beta, sums], [c, cout, 9])]
+    compare(ops, img, P.F32, tol=1e-5)

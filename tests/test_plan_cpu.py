@@ -74,7 +74,11 @@ def test_unet_concat_is_zero_copy_and_fused():
     assert P.OP_COPY_SLICE not in kinds                  # skips + upsampled halves are written in place
     assert P.OP_DROPOUT_FWD not in kinds                 # dropout folded into the max-pool pass
     assert kinds.count(P.OP_BN_STATS) == 0               # concat BN statistics come from the producers' epilogues
-    assert kinds.count(P.OP_BN_BWD_REDUCE) == 4          # encoder BN backward statistics ride on the max-pool backward
+    # BN backward statistics: encoder ones ride on the max-pool backward, decoder ones follow from the weight
+    # gradient of the conv that reads the BN output (adjoint identity) -- no reduction pass is left
+    assert kinds.count(P.OP_BN_BWD_REDUCE) == 0 and kinds.count(P.OP_BN_BWD_SUMS_WGRAD) == 4
+    legacy = [o.kind for o in P.Plan(G.unet(32, 1), 2, dt=P.F16, training=True, fuse_bn_bwd_wgrad=False).train_ops()]
+    assert legacy.count(P.OP_BN_BWD_REDUCE) == 4
     assert kinds.count(P.OP_CONV3X3_FWD) == 18 and kinds.count(P.OP_CONVT_FWD) == 4
 
 
