@@ -68,8 +68,15 @@ __device__ __forceinline__ float transpose_reduce16_(float v[16], int lane) {
   return v[0];
 }
 
+// kFlags specialises the epilogue at compile time (the kernel sits at the 168-register limit of its launch
+// bounds and its thin-layer speed moves by 20 % with register allocation, so features a launch does not use must not
+// cost it anything): bit 0 = activation-derivative mask and/or accumulate (data gradients), bit 1 = BatchNorm
+// statistics and/or column sums.
+constexpr int kF_MASKACC = 1, kF_SUMS = 2;
+template <int kFlags>
 __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_constant__ C3Maps maps,
                                                                  const __grid_constant__ C3Params prm) {
+  constexpr bool kMaskAcc = (kFlags & kF_MASKACC) != 0, kSums = (kFlags & kF_SUMS) != 0;
   B2U_PDL_LAUNCH_DEPENDENTS();      // B2U_PDL_WAIT() follows the CTA-local setup (barriers, TMEM)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -249,14 +256,16 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
     const int ccols = split ? JT / 2 : JT;                        // columns owned by this warp within a tile
     const int cbeg = split ? half * ccols : 0;
     const bool has_cols = split || half == 0;
-    const bool want_sums = prm.stats != nullptr || prm.colsum != nullptr;
+    const bool want_sums = kSums && (prm.stats != nullptr || prm.colsum != nullptr);
     // register accumulators: 32 columns of (sum, sum of squares), or -- column sums only -- 64 columns of sums
     // (rs2 then holds columns 32..63)
     const bool wide_sums = prm.stats == nullptr && ccols > 32;
     const bool reg_stats = want_sums && nj == 1 && (ccols <= 32 || (wide_sums && ccols <= 64));
-    float rs1[32], rs2[32];
+    constexpr int kRS = kSums ? 32 : 1;                            // register accumulators exist in kSums variants only
+    constexpr int kR16 = kSums ? 16 : 0;
+    float rs1[kRS], rs2[kRS];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
+    for (int i = 0; i < kRS; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (unsigned tile = blockIdx.x; tile < (unsigned)ntiles; tile += gridDim.x) {
@@ -269,7 +278,17 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
       const bool valid = h < prm.H && w < prm.W;
       const long long pix = ((long long)n * prm.H + h) * prm.W + w;
       __half* yrow = prm.y + pix * prm.ldy + jt * JT;
-      const __half* mrow = prm.mask != nullptr ? prm.mask + pix * prm.ldmask + jt * JT : nullptr;
+      const __half* mrow = (kMaskAcc && prm.mask != nullptr) ? prm.mask + pix * prm.ldmask + jt * JT : nullptr;
+      // thin layers: issue the tile's activation-derivative mask loads BEFORE waiting for the accumulator, so that
+      // their DRAM round trip overlaps the wait instead of following it chunk by chunk
+      const bool mask_early = kMaskAcc && mrow != nullptr && ccols <= 32 && has_cols && valid;
+      uint4 mk[4];
+      if (mask_early) {
+        const uint4* mp = reinterpret_cast<const uint4*>(mrow + cbeg);
+        mk[0] = __ldg(mp);
+        mk[1] = __ldg(mp + 1);
+        if (ccols > 16) { mk[2] = __ldg(mp + 2); mk[3] = __ldg(mp + 3); }
+      }
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::fence_after_sync();
       const bool dbg_e = prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64 && threadIdx.x == 64;
@@ -295,7 +314,15 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
             for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
           }
           if (valid) {
-            if (mrow != nullptr) {
+            if (mask_early) {
+              float m[8];
+              unpack8h(cc == 0 ? mk[0] : mk[2], m);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= act_bwd_from_y(m[i], prm.mask_act);
+              unpack8h(cc == 0 ? mk[1] : mk[3], m);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 + i] *= act_bwd_from_y(m[i], prm.mask_act);
+            } else if (mrow != nullptr) {
               float m[8];
               load8<__half>(mrow + c0, m);
 #pragma unroll
@@ -304,7 +331,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[8 + i] *= act_bwd_from_y(m[i], prm.mask_act);
             }
-            if (prm.accumulate) {
+            if (kMaskAcc && prm.accumulate) {
               float e[8];
               load8<__half>(yrow + c0, e);
 #pragma unroll
@@ -322,23 +349,23 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
                 if (!wide_sums) {
                   if (cc == 0) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { rs1[i] += v[i]; rs2[i] = fmaf(v[i], v[i], rs2[i]); }
+                    for (int i = 0; i < kR16; ++i) { rs1[i] += v[i]; rs2[i] = fmaf(v[i], v[i], rs2[i]); }
                   } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { rs1[16 + i] += v[i]; rs2[16 + i] = fmaf(v[i], v[i], rs2[16 + i]); }
+                    for (int i = 0; i < kR16; ++i) { rs1[kR16 + i] += v[i]; rs2[kR16 + i] = fmaf(v[i], v[i], rs2[kR16 + i]); }
                   }
                 } else if (cc == 0) {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) rs1[i] += v[i];
+                  for (int i = 0; i < kR16; ++i) rs1[i] += v[i];
                 } else if (cc == 16) {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) rs1[16 + i] += v[i];
+                  for (int i = 0; i < kR16; ++i) rs1[kR16 + i] += v[i];
                 } else if (cc == 32) {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) rs2[i] += v[i];
+                  for (int i = 0; i < kR16; ++i) rs2[i] += v[i];
                 } else {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) rs2[16 + i] += v[i];
+                  for (int i = 0; i < kR16; ++i) rs2[kR16 + i] += v[i];
                 }
               }
             } else {
@@ -370,8 +397,9 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
         float q[16], sq[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          if (!wide_sums) { q[i] = cc == 0 ? rs1[i] : rs1[16 + i]; sq[i] = cc == 0 ? rs2[i] : rs2[16 + i]; }
-          else { q[i] = cc == 0 ? rs1[i] : (cc == 16 ? rs1[16 + i] : (cc == 32 ? rs2[i] : rs2[16 + i])); sq[i] = 0.f; }
+          const int i0 = kSums ? i : 0, i1 = kSums ? 16 + i : 0;       // (never executed without kSums)
+          if (!wide_sums) { q[i] = cc == 0 ? rs1[i0] : rs1[i1]; sq[i] = cc == 0 ? rs2[i0] : rs2[i1]; }
+          else { q[i] = cc == 0 ? rs1[i0] : (cc == 16 ? rs1[i1] : (cc == 32 ? rs2[i0] : rs2[i1])); sq[i] = 0.f; }
         }
         float s1 = transpose_reduce16_(q, lane);
         if (lane < 16) atomicAdd(&s_stats[cbeg + cc + lane], s1);
@@ -527,7 +555,10 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
     if (r != CUDA_SUCCESS) { b2u_set_error("tc_conv3: weight tensor map failed (%d)", (int)r); return B2U_ERR_CUDA; }
   }
   if (!g_attr3) {
-    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr3 = true;
   }
   long long tiles = (long long)n * b2u_cdiv(h, kTH) * b2u_cdiv(wd, kTW) * (J / p.JT);
@@ -537,6 +568,13 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   int ctas = B2U_NUM_SMS;
   if (two_per_sm && tiles >= 4 * B2U_NUM_SMS) ctas = 2 * B2U_NUM_SMS;
   int grid = (int)(tiles < ctas ? tiles : ctas);
-  B2U_LAUNCH(tc_conv3_kernel, grid, 64 + 32 * p.epi_warps, smem, stream, maps, p);
+  const int flags = ((mask != nullptr || accumulate) ? kF_MASKACC : 0) | ((stats != nullptr || colsum != nullptr) ? kF_SUMS : 0);
+  const int nthr = 64 + 32 * p.epi_warps;
+  switch (flags) {
+    case 0: B2U_LAUNCH(tc_conv3_kernel<0>, grid, nthr, smem, stream, maps, p); break;
+    case 1: B2U_LAUNCH(tc_conv3_kernel<1>, grid, nthr, smem, stream, maps, p); break;
+    case 2: B2U_LAUNCH(tc_conv3_kernel<2>, grid, nthr, smem, stream, maps, p); break;
+    default: B2U_LAUNCH(tc_conv3_kernel<3>, grid, nthr, smem, stream, maps, p); break;
+  }
   return B2U_OK;
 }
