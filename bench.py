@@ -138,6 +138,29 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def conv_bytes(op, P, elem=2):
+    """algorithmic HBM bytes of one 3x3 conv forward / data-gradient op: input read once, output written once,
+    plus the mask read / accumulate read where the op has them (weights excluded: < 2 %)"""
+    i = op.i
+    if op.kind == P.OP_CONV3X3_FWD:
+        ldx, cin, act, ldy, cout, n, h, w = i[:8]
+        return n * h * w * (cin + cout) * elem
+    if op.kind == P.OP_CONV3X3_DGRAD:
+        lddy, cout, lddx, cin, ldm, mact, acc = i[:7]
+        n, h, w = i[7:10]
+        return n * h * w * (cout + cin + (cin if mact else 0) + (cin if acc else 0)) * elem
+    return 0
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full summary (profiles/ncu_traffic.json)"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return d[kernel]["dram_bytes_per_launch"], d[kernel]["source"]
+    except Exception:
+        return None, None
+
+
 def conv_flops(op, P):
     """algorithmic FLOPs of one conv-family op record (2*MAC), 0 for everything else"""
     i = op.i
@@ -203,13 +226,15 @@ def run_engine(args):
         torch.cuda.synchronize()
 
     lib = eng.lib
+    # clocks / throttle reasons are sampled from the warm-up until the end of the end-to-end region (both timed
+    # regions and nothing but training steps in between: a 20-step region alone is shorter than one nvidia-smi call)
+    sampler = ClockSampler(local)
+    sampler.start()
     # ---------------- device-resident timing ----------------
     for s in range(args.warmup):
         eng.train_batch(xd, td, idx[s % 4], BATCH)
     barrier()
     l0 = lib.b2u_launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(eng.stream)
@@ -217,7 +242,6 @@ def run_engine(args):
         b = eng.train_batch(xd, td, idx[s % 4], BATCH)
     ev1.record(eng.stream)
     barrier()
-    clocks = sampler.finish()
     ms_total = ev0.elapsed_time(ev1)
     loss_last = eng.loss_dev(b).cpu().numpy().tolist()
     per_step_launch = None
@@ -251,7 +275,8 @@ def run_engine(args):
         out = model.train_on_batch(xh[s % 4], th[s % 4])
     e1.record(eng.stream)
     barrier()
-    e2e_ms = max(e0.elapsed_time(e1), 1000.0 * (time.perf_counter() - t0) * 0.0)
+    clocks = sampler.finish()
+    e2e_ms = e0.elapsed_time(e1)
     if world > 1:
         tt = torch.tensor([e2e_ms], device="cuda")
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
@@ -279,12 +304,17 @@ def run_engine(args):
         tc_ms = sum(kinds[k][0] for k in tc_names if k in kinds)
         tc_fl = sum(kinds[k][2] for k in tc_names if k in kinds)
         tc_n = sum(kinds[k][1] for k in tc_names if k in kinds)
+        tc_by = sum(conv_bytes(op, P) for op, _ in prof)
         if tc_ms > 0:
             ach = tc_fl / (tc_ms / 1000.0) / 1e12
-            roof = {"bound": "tensor", "kernel": "tc_conv_kernel (3x3 conv fwd + dgrad, tcgen05)", "achieved": ach,
-                    "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sus"], "traffic": None,
+            traffic, tsrc = ncu_traffic("tc_conv3_kernel")
+            roof = {"bound": "tensor", "kernel": "tc_conv3_kernel (3x3 conv forward + data gradient, tcgen05 halo-tile)",
+                    "achieved": ach, "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sus"],
+                    "traffic": traffic, "traffic_source": tsrc,
                     "launches_per_step": tc_n, "avg_launch_ms": tc_ms / max(tc_n, 1), "share_of_step": tc_ms / step_ms,
-                    "flop_per_launch": tc_fl / max(tc_n, 1), "peak_source": peaks["src"] + " (sustained bf16 cuBLAS)"}
+                    "flop_per_launch": tc_fl / max(tc_n, 1), "algorithmic_bytes_per_launch": tc_by / max(tc_n, 1),
+                    "hbm_gbs_algorithmic": tc_by / (tc_ms / 1000.0) / 1e9, "hbm_peak_gbs": peaks["hbm"],
+                    "peak_source": peaks["src"] + " (sustained bf16 cuBLAS)"}
         else:
             fl = sum(v[2] for v in kinds.values())
             ach = fl / (step_ms / 1000.0) / 1e12

@@ -18,11 +18,11 @@ if has bench; then
   timeout 600 python bench.py --steps 20 --warmup 5 --per-op > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/rc.txt
 fi
 if has list; then
-  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 900 -c 260 --csv \
+  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 700 -c 200 --csv \
     --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > $OUT/ncu_launch.log 2>&1; echo "ncu-list rc=$?" | tee -a $OUT/rc.txt
 fi
 if has full; then
-  timeout 600 ncu --set full --clock-control none -k regex:"tc_conv3_kernel|tc_wgrad|tc_conv_kernel" --launch-skip 190 -c 62 \
+  timeout 600 ncu --set full --clock-control none -k regex:"tc_conv3_kernel|tc_wgrad|tc_conv_kernel" --launch-skip 150 -c 44 \
     -f -o $OUT/tc_full python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > $OUT/ncu_full.log 2>&1; echo "ncu-full rc=$?" | tee -a $OUT/rc.txt
   python tools/ncu_summary.py $OUT/tc_full.ncu-rep $OUT/tc_full_summary.csv >> $OUT/ncu_full.log 2>&1
   rm -f $OUT/tc_full.ncu-rep
