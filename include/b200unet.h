@@ -222,6 +222,9 @@ enum {
  * gradient of a conv output: CONV3X3_DGRAD p[4], CONVT_DGRAD p[4], BN_BWD_APPLY p[10], HEAD_BWD p[9].  The kernel adds
  * the per-channel sums of the dx values it writes, which is that conv's bias gradient (Keras: the `bias` slot of
  * Conv2D, T1H:859); the matching *_WGRAD op is then given db = NULL and skips its own pass over the gradient. */
+/* executor flags, OR-ed into b2u_op.dt above the storage type (dt & 0xff): */
+#define B2U_OPF_SIDE 0x100 /* may run on the executor's side stream (forked / joined with events; weight gradients) */
+#define B2U_OPF_JOIN 0x200 /* reads what earlier B2U_OPF_SIDE ops wrote: wait for the side stream first            */
 typedef struct b2u_op {
   int32_t kind;
   int32_t dt;

@@ -37,6 +37,8 @@ extern "C" int b2u_tensor_path_available(void) {
   return g_tc_state;
 }
 
+extern int g_b2u_side_stream;
+static int side_init();
 extern "C" int b2u_set_option(const char* name, int value) {
   if (name == nullptr) return -1;
   if (strcmp(name, "tc_halo") == 0) {
@@ -47,6 +49,12 @@ extern "C" int b2u_set_option(const char* name, int value) {
   if (strcmp(name, "pdl") == 0) {
     int old = g_b2u_pdl;
     g_b2u_pdl = value ? 1 : 0;
+    return old;
+  }
+  if (strcmp(name, "side_stream") == 0) {
+    int old = g_b2u_side_stream;
+    if (value && side_init() != B2U_OK) return -1;        // create the stream / events outside any stream capture
+    g_b2u_side_stream = value ? 1 : 0;
     return old;
   }
   if (strcmp(name, "wgrad_halo") == 0) {
@@ -183,7 +191,7 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
   void* const* p = o.p;
   const int64_t* i = o.i;
   const float* f = o.f;
-  const int dt = o.dt;
+  const int dt = o.dt & 0xff;          // bits 8.. are executor flags (B2U_OPF_*)
 #define I(k) ((int)i[k])
   switch (o.kind) {
     case B2U_OP_CONV3X3_FWD:         // p[5] (optional): packed weights
@@ -278,19 +286,57 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
 #undef I
 }
 
+// Side stream: ops flagged B2U_OPF_SIDE (the planner flags the weight-gradient kernels: nothing but the optimizer
+// and the BN-statistics identity reads what they write) are issued on a second stream forked from the main one by an
+// event, so they overlap the HBM-bound kernels of the main chain; an op flagged B2U_OPF_JOIN, and the end of the
+// list, wait for everything issued there.  Works unchanged under stream capture (the side stream joins the capture
+// through the fork event and is joined back before the list ends).
+int g_b2u_side_stream = 0;             // b2u_set_option("side_stream", 0/1); side_init() runs when it is enabled
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+
+static int side_init() {
+  if (g_side != nullptr) return B2U_OK;
+  B2U_CHECK_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+  B2U_CHECK_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+  B2U_CHECK_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+  return B2U_OK;
+}
+
 extern "C" int b2u_run_ops(const b2u_op* h_ops, int n_ops, void* ws, size_t ws_bytes, void* comm, void* stream) {
   B2U_REQUIRE(h_ops != nullptr || n_ops == 0, "run_ops: null op list");
-  for (int k = 0; k < n_ops; ++k) {
-    int rc = run_one(h_ops[k], ws, ws_bytes, comm, stream);
+  cudaStream_t main_s = (cudaStream_t)stream;
+  bool side_pending = false;
+  int rc = B2U_OK;
+  for (int k = 0; k < n_ops && rc == B2U_OK; ++k) {
+    const int flags = h_ops[k].dt >> 8;
+    if (g_b2u_side_stream && (flags & (B2U_OPF_SIDE >> 8))) {
+      rc = side_init();
+      if (rc != B2U_OK) break;
+      B2U_CHECK_CUDA(cudaEventRecord(g_ev_fork, main_s));
+      B2U_CHECK_CUDA(cudaStreamWaitEvent(g_side, g_ev_fork, 0));
+      rc = run_one(h_ops[k], ws, ws_bytes, comm, (void*)g_side);
+      side_pending = true;
+    } else {
+      if (side_pending && (flags & (B2U_OPF_JOIN >> 8))) {
+        B2U_CHECK_CUDA(cudaEventRecord(g_ev_join, g_side));
+        B2U_CHECK_CUDA(cudaStreamWaitEvent(main_s, g_ev_join, 0));
+        side_pending = false;
+      }
+      rc = run_one(h_ops[k], ws, ws_bytes, comm, stream);
+    }
     if (rc != B2U_OK) {
       char tmp[900];
       strncpy(tmp, g_err, sizeof(tmp) - 1);
       tmp[sizeof(tmp) - 1] = 0;
       b2u_set_error("op %d (kind %d): %s", k, h_ops[k].kind, tmp);
-      return rc;
     }
   }
-  return B2U_OK;
+  if (side_pending) {                                    // always rejoin (also on errors: a capture must be closed)
+    cudaEventRecord(g_ev_join, g_side);
+    cudaStreamWaitEvent(main_s, g_ev_join, 0);
+  }
+  return rc;
 }
 
 // same as b2u_run_ops, with a CUDA event between consecutive ops on the launching stream:

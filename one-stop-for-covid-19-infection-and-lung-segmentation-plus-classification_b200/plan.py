@@ -25,6 +25,7 @@ ACT = {None: 0, "linear": 0, "relu": 1, "elu": 2, "sigmoid": 3}
  OP_ALLREDUCE_F64, OP_STATE_ADVANCE, OP_GATHER_BATCH, OP_PACK_WEIGHTS, OP_BN_BWD_SUMS_WGRAD) = range(1, 33)
 OP_NAMES = {v: k for k, v in list(globals().items()) if k.startswith("OP_")}
 
+OPF_SIDE, OPF_JOIN = 0x100, 0x200       # executor flags OR-ed into Op.dt (include/b200unet.h B2U_OPF_*)
 ELEM = {F32: 4, F16: 2}
 STEP_STATE_BYTES = 64
 
@@ -461,7 +462,7 @@ class Plan:
                 raise RuntimeError("no gradient reached %s" % l.name)
             gy = self.gviews[id(t)]
             if l.kind == "conv2d":
-                self.bwd.append(Op(OP_CONV3X3_WGRAD, dt, [xv.ref, gy.ref, grads(l, "kernel"),
+                self.bwd.append(Op(OP_CONV3X3_WGRAD, dt | OPF_SIDE, [xv.ref, gy.ref, grads(l, "kernel"),
                                                           None if id(l) in self._bias_done else grads(l, "bias")],
                                    [xv.ld, xv.c, gy.ld, gy.c, n, xv.h, xv.w], tag=l.name))
                 if not x_is_input:
@@ -488,7 +489,7 @@ class Plan:
                 zero_db = (self.fuse_bias_grad and len(t.consumers) == 1 and t.consumers[0].kind == "concatenate" and
                            len(t.consumers[0].output.consumers) == 1 and
                            t.consumers[0].output.consumers[0].kind == "batch_normalization")
-                self.bwd.append(Op(OP_CONVT_WGRAD, dt, [xv.ref, gy.ref, grads(l, "kernel"),
+                self.bwd.append(Op(OP_CONVT_WGRAD, dt | OPF_SIDE, [xv.ref, gy.ref, grads(l, "kernel"),
                                                         None if zero_db else grads(l, "bias")],
                                    [xv.ld, xv.c, gy.ld, gy.c, n, xv.h, xv.w], tag=l.name))
                 gx = self.gviews[id(x)]
@@ -512,7 +513,7 @@ class Plan:
                 elif "wgrad_sums" in aux:                   # from the consumer conv's weight gradient
                     csum, wref, dwref, cout = aux["wgrad_sums"]
                     bsums = self.zero.alloc(2 * c * 8)
-                    self.bwd.append(Op(OP_BN_BWD_SUMS_WGRAD, 0, [wref, dwref, csum, self._w(l, "gamma"), self._w(l, "beta"),
+                    self.bwd.append(Op(OP_BN_BWD_SUMS_WGRAD, OPF_JOIN, [wref, dwref, csum, self._w(l, "gamma"), self._w(l, "beta"),
                                                                  bsums], [c, cout, 9], tag=l.name))
                     if self.sync_stats:
                         self.bwd.append(Op(OP_ALLREDUCE_F64, 0, [bsums], [2 * c], tag=l.name))
@@ -601,8 +602,8 @@ class Plan:
         # ======================================= optimizer ========================================
         npar = self.layout.n_params
         if self.world > 1:
-            self.opt.append(Op(OP_ALLREDUCE_F32, 0, [Ref("grads", 0)], [npar], tag="allreduce"))
-        self.opt.append(Op(OP_ADAM, 0, [Ref("params", 0), Ref("grads", 0), Ref("adam_m", 0), Ref("adam_v", 0), self.step_ref],
+            self.opt.append(Op(OP_ALLREDUCE_F32, OPF_JOIN, [Ref("grads", 0)], [npar], tag="allreduce"))
+        self.opt.append(Op(OP_ADAM, OPF_JOIN, [Ref("params", 0), Ref("grads", 0), Ref("adam_m", 0), Ref("adam_v", 0), self.step_ref],
                            [npar], tag="adam"))
         self.opt.append(Op(OP_STATE_ADVANCE, 0, [self.step_ref], tag="advance"))
 

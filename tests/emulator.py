@@ -71,6 +71,8 @@ class Emulator:
     # ---- the interpreter -------------------------------------------------------------------
     def run(self, ops):
         for o in ops:
+            if o.dt > 0xff:                  # executor flags (side stream / join) do not change what an op computes
+                o = P.Op(o.kind, o.dt & 0xff, o.p, o.i, o.f, o.tag)
             getattr(self, "op_" + P.OP_NAMES[o.kind][3:].lower())(o)
 
     def op_pack_weights(self, o):

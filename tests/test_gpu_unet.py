@@ -237,3 +237,38 @@ def test_model_facade_fit_matches_oracle_training():
     for k, th in enumerate([0.3, 0.5, 0.7]):
         want = K.sm_threshold_metrics(tva, pr, th)
         assert sw["f1"][k] == pytest.approx(want["f1"], rel=1e-4) and sw["iou"][k] == pytest.approx(want["iou"], rel=1e-4)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_side_stream_weight_gradients_match_single_stream(use_graph):
+    """executor option side_stream: weight-gradient ops on a forked stream (eager and captured) give the same
+    gradients, loss and updated weights as the single-stream schedule (fp32 atomics: order-of-summation noise only)"""
+    lib = importlib.import_module(PKG + "._lib").lib()
+    gname, hw, n = "unet", 64, 4
+    params = perturbed_params(gname, hw)
+    x, t = synth_batch(n, hw, seg=True)
+    outs = []
+    for side in (0, 1):
+        assert lib.b2u_set_option(b"side_stream", side) >= 0
+        try:
+            # exact (fp32) mode: with fp16 storage the atomic-order noise of the BN statistics flips ReLU / max-pool
+            # decisions, so two runs of the SAME schedule already differ by a few per cent in the early layers
+            eng = engine_for(gname, hw, "float32", params, use_graph=use_graph)
+            # lr = 0: Adam's first steps move every weight by +-lr whatever the gradient's magnitude, so the
+            # summation-order noise of near-zero gradients would otherwise show up in the second step's loss
+            eng._set_fields(step=5, lr=0.0)
+            for _ in range(2):                        # second step replays the captured graph
+                b = eng.train_batch(dev(x).view(n, hw, hw, 1), dev(t), None, n)
+            eng.stream.synchronize()
+            outs.append((eng.loss_dev(b).cpu().numpy().copy(), {k: v.copy() for k, v in eng.get_grads().items()},
+                         eng.get_weights()))
+            eng.close()
+        finally:
+            lib.b2u_set_option(b"side_stream", 0)
+    (l0, g0, w0), (l1, g1, w1) = outs
+    assert np.allclose(l0, l1, rtol=2e-4, atol=1e-5)      # (BN statistics are summed with atomics: order noise)
+    for k in g0:
+        a, b_ = g0[k].astype(np.float64), g1[k].astype(np.float64)
+        assert np.linalg.norm(a - b_) <= 1e-3 * (np.linalg.norm(a) + 1e-12) + 1e-6, k
+    for k in w0:
+        assert np.abs(w0[k] - w1[k]).max() < 1e-5, k
