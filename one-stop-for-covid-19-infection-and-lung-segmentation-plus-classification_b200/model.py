@@ -86,6 +86,20 @@ class CosineAnnealingScheduler(Callback):
             logs['lr'] = self.model.optimizer.lr
 
 
+class PendingBatch:
+    """result of Model.train_on_batch(..., wait=False): `.get()` blocks until that step has finished and returns
+    [loss, metric] from the pinned host buffer the step wrote them to"""
+
+    def __init__(self, event, out):
+        self._event, self._out, self._val = event, out, None
+
+    def get(self):
+        if self._val is None:
+            self._event.synchronize()
+            self._val = [float(self._out[0]), float(self._out[1])]
+        return self._val
+
+
 class ModelCheckpoint(Callback):
     """keras ModelCheckpoint(filepath, monitor, save_best_only, mode) -- T1H:1044-1047 (weights as .npz)."""
 
@@ -389,10 +403,14 @@ class Model:
         v = np.asarray(vals).reshape(len(thresholds), 4)
         return {"threshold": np.asarray(thresholds), "f1": v[:, 0], "iou": v[:, 1], "precision": v[:, 2], "recall": v[:, 3]}
 
-    def train_on_batch(self, x, y, sample_weight=None, dropout=True):
+    def train_on_batch(self, x, y, sample_weight=None, dropout=True, wait=True):
         """keras Model.train_on_batch: one optimisation step on a HOST batch; returns [loss, metric].
         The host->device copy of the batch and the device->host read of the loss are part of the call
-        (this is the end-to-end path bench.py times).  x / y may be numpy arrays or pinned torch tensors."""
+        (this is the end-to-end path bench.py times).  x / y may be numpy arrays or pinned torch tensors.
+
+        The batch is copied on a separate copy stream into one of two staging slots, so with `wait=False` (the call
+        then returns a `PendingBatch` whose `.get()` gives [loss, metric]) the copy of the next batch overlaps the
+        training step of the current one: call, then `.get()` the handle of the PREVIOUS call."""
         eng = self.engine
         n = len(x)
         xt = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
@@ -400,22 +418,36 @@ class Model:
         key = (n, tuple(xt.shape[1:]))
         st = getattr(self, "_stage", None)
         if st is None or st[0] != key:
+            eng.stream.synchronize()
+            slots = []
             with torch.cuda.stream(eng.stream):
-                st = (key, torch.empty(xt.shape, dtype=torch.float32, device=eng.device),
-                      torch.empty((n, int(yt.numel() // n)), dtype=torch.float32, device=eng.device),
-                      torch.ones(n, dtype=torch.float32, device=eng.device),
-                      torch.empty(2, dtype=torch.float32).pin_memory())
-            self._stage = st
-        _, xd, yd, swd, out = st
-        with torch.cuda.stream(eng.stream):
-            xd.copy_(xt, non_blocking=True)
-            yd.copy_(yt.reshape(n, -1), non_blocking=True)
+                for _ in range(2):
+                    slots.append(dict(x=torch.empty(xt.shape, dtype=torch.float32, device=eng.device),
+                                      y=torch.empty((n, int(yt.numel() // n)), dtype=torch.float32, device=eng.device),
+                                      sw=torch.ones(n, dtype=torch.float32, device=eng.device),
+                                      out=torch.empty(2, dtype=torch.float32).pin_memory(),
+                                      copied=torch.cuda.Event(), consumed=None, done=torch.cuda.Event()))
+            eng.stream.synchronize()
+            st = self._stage = (key, slots, [0], torch.cuda.Stream(eng.device))
+        _, slots, turn, copy_stream = st
+        slot = slots[turn[0]]
+        turn[0] ^= 1
+        with torch.cuda.stream(copy_stream):
+            if slot["consumed"] is not None:
+                copy_stream.wait_event(slot["consumed"])        # the step that last used this slot has finished
+            slot["x"].copy_(xt, non_blocking=True)
+            slot["y"].copy_(yt.reshape(n, -1), non_blocking=True)
             if sample_weight is not None:
-                swd.copy_(torch.as_tensor(sample_weight, dtype=torch.float32), non_blocking=True)
-            b = eng.train_batch(xd, yd, None, n, dropout=dropout, sw_src=swd)
-            out.copy_(eng.loss_dev(b), non_blocking=True)
-        eng.stream.synchronize()
-        return [float(out[0]), float(out[1])]
+                slot["sw"].copy_(torch.as_tensor(sample_weight, dtype=torch.float32), non_blocking=True)
+            slot["copied"].record(copy_stream)
+        with torch.cuda.stream(eng.stream):
+            eng.stream.wait_event(slot["copied"])
+            b = eng.train_batch(slot["x"], slot["y"], None, n, dropout=dropout, sw_src=slot["sw"])
+            slot["out"].copy_(eng.loss_dev(b), non_blocking=True)
+            slot["done"].record(eng.stream)
+            slot["consumed"] = slot["done"]
+        pending = PendingBatch(slot["done"], slot["out"])
+        return pending.get() if wait else pending
 
     def fit(self, x, y, batch_size=32, epochs=1, validation_data=None, callbacks=None, class_weight=None,
             shuffle=True, verbose=1, initial_epoch=0, dropout=True, **kw):

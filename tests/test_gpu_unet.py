@@ -272,3 +272,38 @@ def test_side_stream_weight_gradients_match_single_stream(use_graph):
         assert np.linalg.norm(a - b_) <= 1e-3 * (np.linalg.norm(a) + 1e-12) + 1e-6, k
     for k in w0:
         assert np.abs(w0[k] - w1[k]).max() < 1e-5, k
+
+
+def test_train_on_batch_pipelined_matches_blocking():
+    """Model.train_on_batch(wait=False): double-buffered staging on a copy stream; every step must train on ITS batch
+    and return ITS loss (lr = 0 so that the steps are independent and comparable)."""
+    M = importlib.import_module(PKG + ".model")
+    LS = importlib.import_module(PKG + ".losses")
+    hw, n = 32, 2
+    batches = [synth_batch(n, hw, seg=True) for _ in range(3)]
+    batches = [(x + 0.05 * k, t) for k, (x, t) in enumerate(batches)]
+    seqs = []
+    for pipelined in (False, True):
+        m = M.Model(graph=G.unet(hw, 1), precision="float32", seed=42, use_graph=True)
+        m.compile(optimizer=M.Adam(lr=0.0005), loss=LS.bce_dice_loss, metrics=[LS.dice_coeff])
+        m.engine._set_fields(lr=0.0)
+        out, pending = [], None
+        for s in range(7):
+            x, t = batches[s % 3]
+            xt = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).pin_memory()
+            tt = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)).pin_memory()
+            if pipelined:
+                h = m.train_on_batch(xt, tt, wait=False, dropout=False)
+                if pending is not None:
+                    out.append(pending.get())
+                pending = h
+            else:
+                out.append(m.train_on_batch(xt, tt, dropout=False))
+        if pending is not None:
+            out.append(pending.get())
+        seqs.append(np.asarray(out))
+        m.engine.close()
+    assert seqs[0].shape == seqs[1].shape == (7, 2)
+    # BN moving statistics do not enter training-mode losses, so step s only depends on batch s % 3
+    assert np.allclose(seqs[0], seqs[1], rtol=1e-4, atol=1e-6), (seqs[0], seqs[1])
+    assert np.allclose(seqs[0][0], seqs[0][3], rtol=1e-4) and not np.allclose(seqs[0][0], seqs[0][1], rtol=1e-3)
