@@ -123,6 +123,20 @@ def runner_classification(cts=None, y_label=None, new_dim=224, epochs=25, batch_
     return out
 
 
+def load_cases(cases, new_dim=224):
+    """File-driven front end of the runners (the reference reads its 20 Kaggle volumes in a loop, T1H:390-393):
+    `cases` = iterable of (ct_path, lung_mask_path, infection_mask_path or None) NIfTI files -> (cts, lungs-free
+    infections) arrays ready for the runners above, with the reference's empty-mask filter left to the caller."""
+    from . import nifti
+    xs, ys = [], []
+    for ct, lung, inf in cases:
+        x, y, _ = nifti.preprocess_case(ct, lung, inf, new_dim=new_dim)
+        xs.append(x)
+        if y is not None:
+            ys.append(y)
+    return np.concatenate(xs), (np.concatenate(ys) if ys else None)
+
+
 RUNNERS = {
     "one": three_fold_runner_unet_infection_segmentation, "two": four_fold_runner_unet_infection_segmentation,
     "three": holdout_runner_unet_infection_segmentation, "four": holdout_runner_unetplusplus_infection_segmentation,

@@ -61,3 +61,34 @@ def test_crop_resize_vs_cv2():
         assert d.max() <= 1, "250x250 stage differs by %d" % d.max()
         final = np.uint8(cv2.resize(mid[k], dsize=(224, 224), interpolation=cv2.INTER_LINEAR)) / 255.0
         assert np.abs(got[k, :, :, 0] - final).max() <= 1.0 / 255 + 1e-6
+
+
+def test_nifti_case_to_network_input_vs_reference_lines(tmp_path):
+    """file -> (N,224,224,1) through nifti.preprocess_case (reader + host slice pipeline + device CLAHE / crop / resize)
+    against the reference's own sequence of calls restated with cv2 (T1H:310-368, 485-488, 678-686)."""
+    from test_nifti_cpu import reference_read_nii_demo, synthetic_case
+    N = importlib.import_module(PKG + ".nifti")
+    PP = importlib.import_module(PKG + ".preprocess")
+    ct, lung, inf = synthetic_case(s=20, h=160, w=144)
+    N.save_nii(str(tmp_path / "ct.nii.gz"), np.round(ct).astype(np.int16))
+    N.save_nii(str(tmp_path / "lung.nii"), lung.astype(np.uint8))
+    N.save_nii(str(tmp_path / "inf.nii"), inf.astype(np.uint8), byteorder=">")
+    x, y, boxes = N.preprocess_case(str(tmp_path / "ct.nii.gz"), str(tmp_path / "lung.nii"), str(tmp_path / "inf.nii"))
+    lungs = reference_read_nii_demo(lung.astype(np.uint8).astype(np.float64))
+    cts = reference_read_nii_demo(np.round(ct).astype(np.int16).astype(np.float64))
+    infs = reference_read_nii_demo(inf.astype(np.uint8).astype(np.float64))
+    assert x.shape == (len(cts), 224, 224, 1) and y.shape == x.shape and x.dtype == np.float32
+    clahe = cv2.createCLAHE(clipLimit=3.0, tileGridSize=(8, 8))
+    for k in range(len(cts)):
+        m = lungs[k].copy()
+        m[m > 0] = 1
+        want_box = PP.cropper_boxes(np.uint8(m))
+        assert boxes[k].tolist() == want_box
+        a, b, c, d, e, f, g, h = want_box
+        for got, src in ((x, clahe.apply(np.uint8(cts[k] * 255))), (y, np.uint8(np.nan_to_num(infs[k]) * 255))):
+            i1 = cv2.resize(src[b:b + d, a:a + c], dsize=(125, 250), interpolation=cv2.INTER_AREA)
+            i2 = cv2.resize(src[f:f + h, e:e + g], dsize=(125, 250), interpolation=cv2.INTER_AREA)
+            fused = np.concatenate((i1, i2), axis=1)
+            final = np.uint8(cv2.resize(fused, dsize=(224, 224), interpolation=cv2.INTER_LINEAR)) / 255.0
+            # the device area resize is within 1 LSB of cv2 at the 250 x 250 stage (test_crop_resize_vs_cv2): 2 LSB here
+            assert np.abs(got[k, :, :, 0] - final).max() <= 2.0 / 255 + 1e-6
