@@ -183,6 +183,16 @@ int b2u_clahe_u8(const uint8_t* in, uint8_t* out, int n, int h, int wd, float cl
 int b2u_crop_resize(const uint8_t* in, int n, int h, int wd, const int* boxes, int half_w, int out_h,
                     int final_dim, uint8_t* mid_u8, float* out, void* stream);
 
+/* ---- BatchNormalization apply + MaxPooling2D((2,2)) + Dropout in one pass (encoder level, T1H:861-863) ---- */
+/* y = x * scale + shift is written at full resolution (the skip tensor, possibly a concat slice) and its 2x2 max,
+ * taken over the values as stored and passed through the dropout of b2u_maxpool_fwd, at half resolution into yp --
+ * the skip tensor is not read back.  out_stats as in b2u_bn_apply (statistics of y for a BN over the concat buffer).
+ * Op record: p = {x, y, scale, shift, out_stats, yp, d_state}, i = {ldx, ldy, c, n*h*wd, out_sq_off, n, h, wd, ldp,
+ * op_id}, f = {p_drop}. */
+int b2u_bn_apply_pool(int dt, const void* x, int ldx, void* y, int ldy, int c, int n, int h, int wd, const float* scale,
+                      const float* shift, double* out_stats, int out_sq_off, void* yp, int ldp, float p_drop, int op_id,
+                      const b2u_step_state* d_state, void* stream);
+
 /* ---- BatchNormalization backward statistics without a pass over the activations ------------------ */
 /* For a BN whose output y feeds exactly one Conv2D 3x3 (U-Net decoder: concat -> BN -> conv, T1H:888-889) the two
  * per-channel sums its backward needs follow from quantities the conv backward already produced:
@@ -214,7 +224,7 @@ enum {
   B2U_OP_HEAD_FWD, B2U_OP_BCE_DICE_SUMS, B2U_OP_BCE_DICE_FINALIZE, B2U_OP_HEAD_BWD,
   B2U_OP_DENSE_FWD, B2U_OP_DENSE_BWD, B2U_OP_BCE_FWD, B2U_OP_BCE_SIGMOID_BWD,
   B2U_OP_ADAM, B2U_OP_MEMSET, B2U_OP_ALLREDUCE_F32, B2U_OP_ALLREDUCE_F64, B2U_OP_STATE_ADVANCE,
-  B2U_OP_GATHER_BATCH, B2U_OP_PACK_WEIGHTS, B2U_OP_BN_BWD_SUMS_WGRAD
+  B2U_OP_GATHER_BATCH, B2U_OP_PACK_WEIGHTS, B2U_OP_BN_BWD_SUMS_WGRAD, B2U_OP_BN_APPLY_POOL
 };
 /* one record; the meaning of p[]/i[]/f[] per kind is the argument order of the function above
  * (pointers in order into p[], ints/long longs into i[], floats into f[]).

@@ -39,7 +39,7 @@ SYMBOLS = [
     "b2u_dense_fwd", "b2u_dense_bwd", "b2u_bce_fwd", "b2u_bce_sigmoid_bwd", "b2u_adam", "b2u_gather_batch",
     "b2u_threshold_counts", "b2u_clahe_u8", "b2u_crop_resize", "b2u_run_ops", "b2u_run_ops_timed", "b2u_graph_create",
     "b2u_graph_launch", "b2u_graph_destroy", "b2u_launch_count", "b2u_comm_unique_id", "b2u_comm_create",
-    "b2u_comm_destroy", "b2u_allreduce", "b2u_pack_weights", "b2u_bn_bwd_sums_from_wgrad",
+    "b2u_comm_destroy", "b2u_allreduce", "b2u_pack_weights", "b2u_bn_bwd_sums_from_wgrad", "b2u_bn_apply_pool",
 ]
 
 

@@ -274,6 +274,9 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
       return b2u_state_advance((b2u_step_state*)p[0], s);
     case B2U_OP_GATHER_BATCH:
       return b2u_gather_batch(dt, (const float*)p[0], (const int*)p[1], p[2], i[0], I(1), s);
+    case B2U_OP_BN_APPLY_POOL:
+      return b2u_bn_apply_pool(dt, p[0], I(0), p[1], I(1), I(2), I(5), I(6), I(7), (const float*)p[2], (const float*)p[3],
+                               (double*)p[4], I(4), p[5], I(8), f[0], I(9), (const b2u_step_state*)p[6], s);
     case B2U_OP_BN_BWD_SUMS_WGRAD:
       return b2u_bn_bwd_sums_from_wgrad((const float*)p[0], (const float*)p[1], (const float*)p[2], (const float*)p[3],
                                         (const float*)p[4], (double*)p[5], I(0), I(1), I(2), s);

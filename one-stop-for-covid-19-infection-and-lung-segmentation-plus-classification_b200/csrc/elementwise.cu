@@ -296,6 +296,105 @@ __device__ __forceinline__ void keep_factors(float p, uint64_t e0, const b2u_ste
   f[4] = b.x >= thr ? sc : 0.f; f[5] = b.y >= thr ? sc : 0.f; f[6] = b.z >= thr ? sc : 0.f; f[7] = b.w >= thr ? sc : 0.f;
 }
 
+// 8 channels kept PACKED (as loaded) in registers and unpacked on demand
+template <typename T> struct Pack8;
+template <> struct Pack8<__half> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __half* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float v[8]) const {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+};
+template <> struct Pack8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void get(float v[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+template <typename T> __device__ __forceinline__ float round_to(float v);
+template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_to<__half>(float v) { return __half2float(__float2half_rn(v)); }
+
+// BN apply + 2x2 max-pool (+ dropout) in one pass: thread = (output pixel, 8-channel group) owns the 2x2 window
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_apply_pool_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y,
+                                                                 int ldy, int C, int N, int H, int W,
+                                                                 const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift,
+                                                                 double* __restrict__ out_stats, int out_sq_off,
+                                                                 T* __restrict__ yp, int ldp, float p_drop, int op_id,
+                                                                 const b2u_step_state* __restrict__ st) {
+  B2U_PDL_PROLOGUE();
+  extern __shared__ float sst[];          // [2*C] block partials of the optional output statistics
+  float o1[8], o2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { o1[k] = 0.f; o2[k] = 0.f; }
+  if (out_stats != nullptr) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sst[i] = 0.f;
+    __syncthreads();
+  }
+  float sc[8], sh[8];
+  {
+    const int g0 = (threadIdx.x % (C >> 3)) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = scale[g0 + k]; sh[k] = shift[g0 + k]; }
+  }
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long nopix = (long long)N * Ho * Wo;
+  PIXEL_LANE_LOOP(C, nopix) {
+    const unsigned opu = (unsigned)p;
+    const int wo = (int)(opu % (unsigned)Wo);
+    const unsigned t = opu / (unsigned)Wo;
+    const int ho = (int)(t % (unsigned)Ho);
+    const int n = (int)(t / (unsigned)Ho);
+    const long long ip = ((long long)n * H + 2 * ho) * W + 2 * wo;
+    Pack8<T> xw[4];
+    xw[0].load(x + ip * ldx + g * 8);
+    xw[1].load(x + (ip + 1) * ldx + g * 8);
+    xw[2].load(x + (ip + W) * ldx + g * 8);
+    xw[3].load(x + (ip + W + 1) * ldx + g * 8);
+    float m[8];
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) {
+      float v[8];
+      xw[pos].get(v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[k] = round_to<T>(fmaf(v[k], sc[k], sh[k]));              // the value as stored
+        m[k] = pos == 0 ? v[k] : fmaxf(m[k], v[k]);
+        o1[k] += v[k];
+        o2[k] = fmaf(v[k], v[k], o2[k]);
+      }
+      store8<T>(y + (ip + (pos >> 1) * (long long)W + (pos & 1)) * ldy + g * 8, v);
+    }
+    if (p_drop > 0.f) {
+      float f[8];
+      keep_factors(p_drop, (uint64_t)p * C + g * 8, st, op_id, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] *= f[k];
+    }
+    store8<T>(yp + p * ldp + g * 8, m);
+  }
+  if (out_stats != nullptr) {
+    if (threadIdx.x / (C >> 3) < kThreads / (C >> 3)) {
+      group_add8(sst, o1, C >> 3, threadIdx.x % (C >> 3));
+      group_add8(sst + C, o2, C >> 3, threadIdx.x % (C >> 3));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      atomicAdd(&out_stats[i], (double)sst[i]);
+      atomicAdd(&out_stats[out_sq_off + i], (double)sst[C + i]);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y,
                                                                int ldy, int C, int N, int H, int W, float p_drop,
@@ -331,27 +430,6 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const T* __restri
 // Register budget matters here: the four window values stay PACKED (as loaded) and are unpacked one window
 // position at a time, so three 256-thread blocks fit an SM (the all-unpacked version needed 158 registers:
 // one block per SM, 12 % occupancy, a third of the HBM rate).
-template <typename T> struct Pack8;
-template <> struct Pack8<__half> {
-  uint4 u;
-  __device__ __forceinline__ void load(const __half* p) { u = *reinterpret_cast<const uint4*>(p); }
-  __device__ __forceinline__ void get(float v[8]) const {
-    const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-  }
-};
-template <> struct Pack8<float> {
-  float4 a, b;
-  __device__ __forceinline__ void load(const float* p) {
-    a = *reinterpret_cast<const float4*>(p);
-    b = *reinterpret_cast<const float4*>(p + 4);
-  }
-  __device__ __forceinline__ void get(float v[8]) const {
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  }
-};
-
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2) maxpool_bwd_kernel(const T* __restrict__ x, int ldx,
                                                                   const T* __restrict__ dy, int lddy,
@@ -923,6 +1001,22 @@ extern "C" int b2u_bn_apply(int dt, const void* x, int ldx, void* y, int ldy, in
   size_t smem = out_stats != nullptr ? 2 * (size_t)c * sizeof(float) : 0;
   DISPATCH_T(dt, B2U_LAUNCH(bn_apply_kernel<T>, grid, kThreads, smem, stream, (const T*)x, ldx, (T*)y, ldy, c, npix,
                             scale, shift, out_stats, out_sq_off));
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_apply_pool(int dt, const void* x, int ldx, void* y, int ldy, int c, int n, int h, int wd,
+                                 const float* scale, const float* shift, double* out_stats, int out_sq_off, void* yp,
+                                 int ldp, float p_drop, int op_id, const b2u_step_state* d_state, void* stream) {
+  REQ_VEC8(c);
+  B2U_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldp % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(yp),
+              "bn_apply_pool: alignment");
+  B2U_REQUIRE(h % 2 == 0 && wd % 2 == 0 && c <= 2048 && (long long)n * h * wd < (1LL << 31), "bn_apply_pool: shape");
+  B2U_REQUIRE(p_drop == 0.f || d_state != nullptr, "bn_apply_pool: dropout needs a step state");
+  B2U_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "bn_apply_pool: bad dropout rate");
+  int grid = lane_grid((long long)n * (h / 2) * (wd / 2), c, out_stats != nullptr ? 4 : 8);
+  size_t smem = out_stats != nullptr ? 2 * (size_t)c * sizeof(float) : 0;
+  DISPATCH_T(dt, B2U_LAUNCH(bn_apply_pool_kernel<T>, grid, kThreads, smem, stream, (const T*)x, ldx, (T*)y, ldy, c, n, h,
+                            wd, scale, shift, out_stats, out_sq_off, (T*)yp, ldp, p_drop, op_id, d_state));
   return B2U_OK;
 }
 

@@ -22,7 +22,7 @@ ACT = {None: 0, "linear": 0, "relu": 1, "elu": 2, "sigmoid": 3}
  OP_BN_STATS, OP_BN_FINALIZE, OP_BN_APPLY, OP_BN_BWD_REDUCE, OP_BN_BWD_APPLY, OP_MAXPOOL_FWD, OP_MAXPOOL_BWD,
  OP_DROPOUT_FWD, OP_DROPOUT_BWD, OP_COPY_SLICE, OP_HEAD_FWD, OP_BCE_DICE_SUMS, OP_BCE_DICE_FINALIZE, OP_HEAD_BWD,
  OP_DENSE_FWD, OP_DENSE_BWD, OP_BCE_FWD, OP_BCE_SIGMOID_BWD, OP_ADAM, OP_MEMSET, OP_ALLREDUCE_F32,
- OP_ALLREDUCE_F64, OP_STATE_ADVANCE, OP_GATHER_BATCH, OP_PACK_WEIGHTS, OP_BN_BWD_SUMS_WGRAD) = range(1, 33)
+ OP_ALLREDUCE_F64, OP_STATE_ADVANCE, OP_GATHER_BATCH, OP_PACK_WEIGHTS, OP_BN_BWD_SUMS_WGRAD, OP_BN_APPLY_POOL) = range(1, 34)
 OP_NAMES = {v: k for k, v in list(globals().items()) if k.startswith("OP_")}
 
 OPF_SIDE, OPF_JOIN = 0x100, 0x200       # executor flags OR-ed into Op.dt (include/b200unet.h B2U_OPF_*)
@@ -129,7 +129,7 @@ class Plan:
 
     def __init__(self, graph, n, dt=F32, training=True, dropout=True, loss="bce_dice", world=1,
                  sync_stats=False, layout=None, rank=0, fuse_bn_bwd=True, fuse_bn_stats=True, fuse_bias_grad=True,
-                 prepack=True, fuse_bn_bwd_wgrad=True):
+                 prepack=True, fuse_bn_bwd_wgrad=True, fuse_bn_pool=True):
         self.graph, self.n, self.dt, self.training = graph, int(n), dt, training
         self.dropout = dropout and training
         self.loss, self.world, self.sync_stats = loss, int(world), bool(sync_stats) and world > 1
@@ -138,6 +138,7 @@ class Plan:
         self.fuse_bn_stats = bool(fuse_bn_stats)
         self.fuse_bias_grad = bool(fuse_bias_grad)
         self.fuse_bn_bwd_wgrad = bool(fuse_bn_bwd_wgrad)
+        self.fuse_bn_pool = bool(fuse_bn_pool)
         self._bias_done = set()          # id(conv layer) whose bias gradient is produced by another backward op
         # fp16 operand copies of the conv kernels: ONE pack launch per step for the whole model (OP_PACK_WEIGHTS)
         # instead of one small launch in front of every conv call
@@ -360,8 +361,20 @@ class Plan:
                     if self.dropout:
                         p_drop, op_id = cons[0].rate, drop_index[id(cons[0])]
                 l._pool_drop = (p_drop, op_id)
-                self.fwd.append(Op(OP_MAXPOOL_FWD, xv.dt, [xv.ref, yv.ref, self.step_ref if p_drop > 0 else None],
-                                   [xv.ld, yv.ld, xv.c, n, xv.h, xv.w, op_id], [p_drop], tag=l.name))
+                prev = self.fwd[-1] if self.fwd else None
+                if (self.fuse_bn_pool and prev is not None and prev.kind == OP_BN_APPLY and
+                        x.producer.kind == "batch_normalization" and prev.tag == x.producer.name and
+                        xv.h % 2 == 0 and xv.w % 2 == 0):
+                    # the BN apply that has just written x becomes one pass that also writes its 2x2 max (+ dropout):
+                    # x is not read back (same Op object: later concat-BN statistics fusion patches p[4] / i[4])
+                    prev.kind = OP_BN_APPLY_POOL
+                    prev.p = prev.p[:5] + [yv.ref, self.step_ref if p_drop > 0 else None]
+                    prev.i = prev.i[:5] + [n, xv.h, xv.w, yv.ld, op_id]
+                    prev.f = [float(p_drop)]
+                    prev.tag = prev.tag + "+" + l.name
+                else:
+                    self.fwd.append(Op(OP_MAXPOOL_FWD, xv.dt, [xv.ref, yv.ref, self.step_ref if p_drop > 0 else None],
+                                       [xv.ld, yv.ld, xv.c, n, xv.h, xv.w, op_id], [p_drop], tag=l.name))
             elif l.kind == "dropout":
                 if id(l) in fused_drop or not self.dropout:
                     if id(t) in home:

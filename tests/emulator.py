@@ -211,6 +211,11 @@ class Emulator:
             s[:c] += ys.sum(0)
             s[sq:sq + c] += (ys * ys).sum(0)
 
+    def op_bn_apply_pool(self, o):
+        ldx, ldy, c, npix, sq, n, h, w, ldp, op_id = o.i[:10]
+        self.op_bn_apply(P.Op(P.OP_BN_APPLY, o.dt, o.p[:5], [ldx, ldy, c, npix, sq]))
+        self.op_maxpool_fwd(P.Op(P.OP_MAXPOOL_FWD, o.dt, [o.p[1], o.p[5], o.p[6]], [ldy, ldp, c, n, h, w, op_id], [o.f[0]]))
+
     def op_bn_bwd_sums_wgrad(self, o):
         c, cout, taps = o.i[:3]
         w = self.f32(o.p[0], taps * c * cout).reshape(taps, c, cout).astype(np.float64)

@@ -338,3 +338,19 @@ def test_maxpool_bwd_with_fused_bn_backward_statistics(dt, acc):
     ops = [P.Op(P.OP_MAXPOOL_BWD, dt, [x.ref, dy.ref, dx.ref, step, sums, gamma, beta],
                 [x.ld, dy.ld, dx.ld, c, n, h, w, 1, acc], [0.25])]
     compare(ops, img, dt, state=dict(seed=5, step=3), tol=3e-3 if dt == P.F16 else 3e-5)
+
+
+@pytest.mark.parametrize("dt", [P.F32, P.F16])
+@pytest.mark.parametrize("n,h,w,c,p_drop", [(2, 16, 24, 32, 0.25), (1, 10, 6, 64, 0.0), (3, 8, 8, 256, 0.25), (1, 12, 20, 96, 0.2)])
+def test_bn_apply_pool_fused(dt, n, h, w, c, p_drop):
+    """BN apply + 2x2 max-pool (+ dropout) in one pass: skip tensor into a concat slice, pooled tensor, statistics"""
+    img = Img(71)
+    x = img.view(n, h, w, c, dt, scale=2.0)
+    y = img.view(n, h, w, c, dt, ld=2 * c, c0=c, fill=None)
+    yp = img.view(n, h // 2, w // 2, c, dt, ld=c + 8, fill=None)
+    scale, shift = img.farr(img.f32, c, fill="pos"), img.farr(img.f32, c, scale=0.5)
+    stats = img.zero.alloc((2 * c + c) * 8)
+    step = P.Ref("step", 0)
+    ops = [P.Op(P.OP_BN_APPLY_POOL, dt, [x.ref, y.ref, scale, shift, stats, yp.ref, step if p_drop > 0 else None],
+                [x.ld, y.ld, c, n * h * w, 2 * c, n, h, w, yp.ld, 3], [p_drop])]
+    compare(ops, img, dt, state=dict(seed=11, step=4), tol=2e-3 if dt == P.F16 else 2e-5)
