@@ -71,7 +71,7 @@ def _kfold_runner(n_splits, epochs_per_fold, cts=None, infections=None, new_dim=
     if cts is None:
         cts, infections = _default_data("infection", n_synthetic, new_dim, seed)
     cts, infections = np.asarray(cts), np.asarray(infections)
-    thresholds = thresholds if thresholds is not None else [0.1 * k for k in range(1, 11)]                 # CV4:1229
+    thresholds = thresholds if thresholds is not None else list(np.arange(0.30, 0.80, 0.05))               # CV4:1221
     kf = KFold(n_splits=n_splits, shuffle=True, random_state=42)                                           # CV4:1047
     folds = []
     for fold, (tr, te) in enumerate(kf.split(cts)):
@@ -81,8 +81,29 @@ def _kfold_runner(n_splits, epochs_per_fold, cts=None, infections=None, new_dim=
                       validation_data=(cts[te], infections[te]), verbose=verbose)
         sweep = model.threshold_sweep(cts[te], infections[te], thresholds, batch_size=batch_size)
         folds.append(dict(history=h.history, sweep=sweep))
-    mean = {k: float(np.mean([f["sweep"][k] for f in folds])) for k in ("f1", "iou", "precision", "recall")}
-    return dict(folds=folds, mean=mean)                                                                    # CV4:1272-1364
+    return dict(folds=folds, **cv_report([f["sweep"] for f in folds]))                                     # CV4:1272-1364
+
+
+def cv_report(sweeps):
+    """The cross-validation tables of the reference (task1_crossval_4folds_unet.py:1272-1364): per metric a DataFrame
+    with the thresholds as rows and the split numbers 1..k as columns, the best value and best threshold of every
+    split, the maximum over everything and the mean over all thresholds and splits (the README's headline numbers).
+    `sweeps` = one Model.threshold_sweep result per fold (all thresholds from ONE forward pass per fold instead of the
+    reference's recompile + evaluate per threshold and metric)."""
+    import pandas as pd
+    the_range = np.asarray(sweeps[0]["threshold"], dtype=np.float64)
+    cols = list(range(1, len(sweeps) + 1))
+    tables, best, best_threshold, maximum, mean = {}, {}, {}, {}, {}
+    for key, name in (("f1", "dice"), ("iou", "iou"), ("precision", "precision"), ("recall", "recall")):
+        total = np.transpose(np.array([np.asarray(sw[key], dtype=np.float64) for sw in sweeps]))
+        df = pd.DataFrame(data=total, index=the_range, columns=cols)
+        tables[name] = df
+        best[name] = np.array(df.max(axis=0))
+        best_threshold[name] = [float(the_range[int(np.argmax(df[c].to_numpy()))]) for c in cols]
+        maximum[name] = float(np.max(total))
+        mean[name] = float(df.mean().mean())
+    mean.update(f1=mean["dice"])          # (key used by earlier callers)
+    return dict(tables=tables, best_per_split=best, best_threshold_per_split=best_threshold, maximum=maximum, mean=mean)
 
 
 def four_fold_runner_unet_infection_segmentation(cts=None, infections=None, epochs=80, **kw):
