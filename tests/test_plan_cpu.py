@@ -110,3 +110,26 @@ def test_param_layout_roundtrip_and_counts():
 def test_shape_validation():
     with pytest.raises(ValueError):
         G.unet(30, 1)          # 30 is not divisible by 16: the 2nd pool would see an odd size
+
+
+@pytest.mark.parametrize("flags", [dict(fuse_bias_grad=False), dict(fuse_bn_bwd_wgrad=False), dict(fuse_bn_pool=False),
+                                   dict(fuse_bn_bwd=False, fuse_bn_stats=False), dict(prepack=False)])
+def test_every_fusion_can_be_switched_off(flags):
+    """each planner fusion (producer-side bias gradients, BN backward statistics from the weight gradient / the max-pool
+    backward, BN statistics from producer epilogues, BN apply + pool, one-launch weight packing) is optional: the
+    schedule without it computes the same training step"""
+    gname, hw, n = "unet", 32, 2
+    g = G.GRAPHS[gname](hw, 1)
+    params = perturbed_params(gname, hw)
+    x, t = synth_batch(n, hw, seg=True)
+    r = K.loss_and_grads(gname, params, x, t, dtype=torch.float64, dropout=dict(seed=7, step=5), loss="bce_dice")
+    for kw in (flags, {}):
+        plan = P.Plan(g, n, dt=P.F32, training=True, dropout=True, loss="bce_dice", **kw)
+        em = E.Emulator(plan.arena_sizes())
+        em.state.update(seed=7, step=5)
+        fp, fs = _load(em, plan, params, x, t)
+        em.run(plan.train_ops())
+        assert em.f32(plan.loss_out, 2)[0] == pytest.approx(r["loss"], rel=1e-5)
+        grads = plan.layout.unpack(em.f32(P.Ref("grads", 0), fp.size), None)
+        worst, who = grad_errors(grads, r["grads"])
+        assert worst < 1e-3, (kw, who, worst)
