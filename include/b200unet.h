@@ -34,7 +34,10 @@ extern "C" {
 
 enum { B2U_OK = 0, B2U_ERR_ARG = -1, B2U_ERR_CUDA = -2, B2U_ERR_UNSUPPORTED = -3, B2U_ERR_NCCL = -4 };
 enum { B2U_F32 = 0, B2U_F16 = 1 };
-enum { B2U_ACT_NONE = 0, B2U_ACT_RELU = 1, B2U_ACT_ELU = 2, B2U_ACT_SIGMOID = 3 };
+enum { B2U_ACT_NONE = 0, B2U_ACT_RELU = 1, B2U_ACT_ELU = 2, B2U_ACT_SIGMOID = 3,
+       /* mask_act of the backward ops only: `mask` is a packed 1-bit ReLU mask (bit pix*C + c, little-endian bytes) written by
+        * the forward conv (op lists: CONV3X3_FWD p[6]) instead of the fp16 activation tensor itself */
+       B2U_ACT_RELU_BITS = 4 };
 
 /* Device-resident per-step scalars, read by dropout / Adam / loss kernels so that a captured CUDA
  * graph never bakes them in (lr is set per epoch by CosineAnnealingScheduler, T1H:980-982). */

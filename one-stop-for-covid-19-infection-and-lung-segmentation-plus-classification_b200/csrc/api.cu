@@ -91,20 +91,30 @@ extern "C" int b2u_debug_read(long long* h_out, int count) {
 // ------------------------------------------------------------------------------------------
 // conv dispatch
 // ------------------------------------------------------------------------------------------
+// `relu_bits` (optional, op lists only): packed 1-bit mask of y > 0, written by the halo kernel's epilogue or, on the
+// other paths, by one extra pass over y
 static int conv3x3_fwd_wp(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, int act, void* y,
                           int ldy, int cout, double* stats, int n, int h, int wd, void* ws, size_t ws_bytes,
-                          const void* wp, void* stream) {
-  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy))
-    return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats,
-                                                                  nullptr, nullptr, 0, 0, 0, n, h, wd, ws, ws_bytes, wp,
-                                                                  stream);
-  return b2u_direct_conv3x3(dt, x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, 0, 0, 0, n, h, wd, stream);
+                          const void* wp, void* relu_bits, void* stream) {
+  int rc;
+  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy)) {
+    if (g_b2u_tc_halo)
+      return b2u_tc_conv3x3_halo(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, nullptr, 0, 0, 0, n, h, wd,
+                                 ws, ws_bytes, wp, stream, relu_bits);
+    rc = b2u_tc_conv3x3(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, nullptr, 0, 0, 0, n, h, wd, ws,
+                        ws_bytes, wp, stream, nullptr);
+  } else {
+    rc = b2u_direct_conv3x3(dt, x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, 0, 0, 0, n, h, wd, stream);
+  }
+  if (rc != B2U_OK || relu_bits == nullptr) return rc;
+  return b2u_relu_bits(dt, y, ldy, cout, (long long)n * h * wd, relu_bits, stream);
 }
 
 extern "C" int b2u_conv3x3_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, int act,
                                void* y, int ldy, int cout, double* stats, int n, int h, int wd, void* ws,
                                size_t ws_bytes, void* stream) {
-  return conv3x3_fwd_wp(dt, x, ldx, cin, w, bias, act, y, ldy, cout, stats, n, h, wd, ws, ws_bytes, nullptr, stream);
+  return conv3x3_fwd_wp(dt, x, ldx, cin, w, bias, act, y, ldy, cout, stats, n, h, wd, ws, ws_bytes, nullptr, nullptr,
+                        stream);
 }
 
 // data gradient + optional `colsum` (op lists only): colsum[c] += sum over pixels of the dx values written, i.e. the
@@ -112,12 +122,25 @@ extern "C" int b2u_conv3x3_fwd(int dt, const void* x, int ldx, int cin, const fl
 static int conv3x3_dgrad_cs(int dt, const void* dy, int lddy, int cout, const float* w, void* dx, int lddx, int cin,
                             const void* mask, int ldmask, int mask_act, int accumulate, float* colsum, int n, int h,
                             int wd, void* ws, size_t ws_bytes, const void* wp, void* stream) {
-  if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cout, cin, lddy, lddx))
+  const bool tc = dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cout, cin, lddy, lddx);
+  const bool bits = mask != nullptr && mask_act == B2U_ACT_RELU_BITS;
+  if (tc && (!bits || g_b2u_tc_halo))
     return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx,
                                                                   cin, nullptr, colsum, mask, ldmask, mask_act,
-                                                                  accumulate, n, h, wd, ws, ws_bytes, wp, stream);
-  int rc = b2u_direct_conv3x3(dt, dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, mask, ldmask,
-                              mask_act, accumulate, n, h, wd, stream);
+                                                                  accumulate, n, h, wd, ws, ws_bytes, wp, stream, nullptr);
+  int rc;
+  if (bits) {
+    // 1-bit mask on a path whose kernel cannot read it: unmasked data gradient, then one masking pass
+    B2U_REQUIRE(!accumulate, "conv3x3_dgrad: a 1-bit mask cannot be combined with accumulate");
+    rc = tc ? b2u_tc_conv3x3(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, nullptr, nullptr, 0, 0, 0, n,
+                             h, wd, ws, ws_bytes, wp, stream, nullptr)
+            : b2u_direct_conv3x3(dt, dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, nullptr, 0, 0, 0, n,
+                                 h, wd, stream);
+    if (rc == B2U_OK) rc = b2u_apply_relu_bits(dt, dx, lddx, cin, (long long)n * h * wd, mask, stream);
+  } else {
+    rc = b2u_direct_conv3x3(dt, dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, mask, ldmask,
+                            mask_act, accumulate, n, h, wd, stream);
+  }
   if (rc != B2U_OK || colsum == nullptr) return rc;
   return b2u_channel_sum(dt, dx, lddx, cin, (long long)n * h * wd, colsum, stream);       // exact path: extra pass
 }
@@ -196,7 +219,7 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
   switch (o.kind) {
     case B2U_OP_CONV3X3_FWD:         // p[5] (optional): packed weights
       return conv3x3_fwd_wp(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], I(2), p[3], I(3), I(4),
-                            (double*)p[4], I(5), I(6), I(7), ws, wsb, p[5], s);
+                            (double*)p[4], I(5), I(6), I(7), ws, wsb, p[5], p[6], s);     // p[6] (optional): 1-bit ReLU mask out
     case B2U_OP_CONV3X3_DGRAD:       // p[4] (optional): colsum
       return conv3x3_dgrad_cs(dt, p[0], I(0), I(1), (const float*)p[1], p[2], I(2), I(3), p[3], I(4), I(5), I(6),
                               (float*)p[4], I(7), I(8), I(9), ws, wsb, p[5], s);

@@ -561,7 +561,9 @@ int b2u_tc_convt_ok(int cin, int cout, int ld_small, int ld_big) {
 
 int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                    int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
-                   int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream) {
+                   int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream,
+                   void* relu_bits_out) {
+  B2U_REQUIRE(relu_bits_out == nullptr && mask_act != B2U_ACT_RELU_BITS, "tc_conv3x3 (per-tap): 1-bit masks need the halo kernel");
   int rc = get_encode();
   if (rc != B2U_OK) return rc;
   TcParams p{};

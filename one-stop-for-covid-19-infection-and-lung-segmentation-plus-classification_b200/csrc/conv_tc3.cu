@@ -45,6 +45,9 @@ struct C3Params {
   float* colsum;          // per-channel sums of the stored values, added with fp32 atomics (bias gradient of the
                           // layer whose output gradient this kernel writes)
   long long* dbg;         // optional timeline buffer (CTA 0): [iter][8] clock64 stamps
+  // (appended last: existing constant-bank offsets stay as they were)
+  uint8_t* bits_out;      // kF_BITS_OUT: packed 1-bit ReLU mask of the values stored (bit pix*J + column)
+  const uint8_t* bits_in; // kF_BITS_IN : packed 1-bit ReLU mask applied to the values written (data gradient)
 };
 
 struct C3Maps {
@@ -73,6 +76,7 @@ __device__ __forceinline__ float transpose_reduce16_(float v[16], int lane) {
 // cost it anything): bit 0 = activation-derivative mask and/or accumulate (data gradients), bit 1 = BatchNorm
 // statistics and/or column sums.
 constexpr int kF_MASKACC = 1, kF_SUMS = 2;
+constexpr int kF_BITS_OUT = 4, kF_BITS_IN = 8;
 template <int kFlags>
 __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_constant__ C3Maps maps,
                                                                  const __grid_constant__ C3Params prm) {
@@ -289,6 +293,23 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
         mk[1] = __ldg(mp + 1);
         if (ccols > 16) { mk[2] = __ldg(mp + 2); mk[3] = __ldg(mp + 3); }
       }
+      // 1-bit ReLU mask of this thread's columns (<= 128): a few 2-byte loads issued before the accumulator wait
+      // (`if constexpr`, and the bits live in mk[0] -- unused here, the fp16 mask path is off in these variants -- so
+      // that the other variants compile to the code they had before this feature existed)
+      if constexpr ((kFlags & kF_BITS_IN) != 0) {
+        mk[0] = make_uint4(0u, 0u, 0u, 0u);
+        if (has_cols && valid) {
+          const unsigned short* bp16 =
+              reinterpret_cast<const unsigned short*>(prm.bits_in + ((pix * prm.J + jt * JT + cbeg) >> 3));
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (q * 16 < ccols) {
+              const uint32_t hw = (uint32_t)__ldg(bp16 + q) << (16 * (q & 1));
+              if (q < 2) mk[0].x |= hw; else if (q < 4) mk[0].y |= hw; else if (q < 6) mk[0].z |= hw; else mk[0].w |= hw;
+            }
+          }
+        }
+      }
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::fence_after_sync();
       const bool dbg_e = prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64 && threadIdx.x == 64;
@@ -312,6 +333,14 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
           } else if (prm.act == B2U_ACT_ELU) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+          }
+          if constexpr ((kFlags & kF_BITS_IN) != 0) {
+            if (valid) {
+              const uint32_t w32 = cc < 32 ? mk[0].x : (cc < 64 ? mk[0].y : (cc < 96 ? mk[0].z : mk[0].w));
+              const uint32_t b16 = (w32 >> (cc & 16)) & 0xffffu;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = ((b16 >> i) & 1u) ? v[i] : 0.f;
+            }
           }
           if (valid) {
             if (mask_early) {
@@ -342,6 +371,13 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
             }
             store8<__half>(yrow + c0, v);
             store8<__half>(yrow + c0 + 8, v + 8);
+            if constexpr ((kFlags & kF_BITS_OUT) != 0) {
+              // bit = (the fp16 value just stored > 0): round-to-nearest-even sends v <= 2^-25 to zero
+              uint32_t b16 = 0u;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) b16 |= (v[i] > 2.98023223876953125e-08f ? 1u : 0u) << i;
+              *reinterpret_cast<unsigned short*>(prm.bits_out + ((pix * prm.J + jt * JT + c0) >> 3)) = (unsigned short)b16;
+            }
           }
           if (want_sums) {
             if (reg_stats) {
@@ -473,7 +509,8 @@ int g_b2u_tc_halo = 1;       // 0: per-tap loads (conv_tc.cu), 1: halo box, 2: h
 
 int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                         int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
-                        int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream) {
+                        int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream,
+                        void* relu_bits_out) {
   int rc = get_enc3();
   if (rc != B2U_OK) return rc;
   C3Params p{};
@@ -487,6 +524,12 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate; p.stats = stats;
   p.colsum = colsum;
   p.dbg = g_b2u_dbg;
+  p.bits_out = (uint8_t*)relu_bits_out;
+  if (mask != nullptr && mask_act == B2U_ACT_RELU_BITS) {          // packed 1-bit mask instead of the activation tensor
+    p.bits_in = (const uint8_t*)mask;
+    p.mask = nullptr;
+    mask = nullptr;
+  }
   const uint32_t rowb = p.KS * 2;
   const uint32_t rows = p.amode == 3 ? 18 * 8 : 18 * 10;
   p.a_sub = (rows * rowb + 1023) & ~1023u;
@@ -559,6 +602,10 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
     B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr3 = true;
   }
   long long tiles = (long long)n * b2u_cdiv(h, kTH) * b2u_cdiv(wd, kTW) * (J / p.JT);
@@ -568,13 +615,21 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   int ctas = B2U_NUM_SMS;
   if (two_per_sm && tiles >= 4 * B2U_NUM_SMS) ctas = 2 * B2U_NUM_SMS;
   int grid = (int)(tiles < ctas ? tiles : ctas);
-  const int flags = ((mask != nullptr || accumulate) ? kF_MASKACC : 0) | ((stats != nullptr || colsum != nullptr) ? kF_SUMS : 0);
+  const int flags = ((mask != nullptr || accumulate) ? kF_MASKACC : 0) | ((stats != nullptr || colsum != nullptr) ? kF_SUMS : 0) |
+                    (p.bits_out != nullptr ? kF_BITS_OUT : 0) | (p.bits_in != nullptr ? kF_BITS_IN : 0);
   const int nthr = 64 + 32 * p.epi_warps;
   switch (flags) {
     case 0: B2U_LAUNCH(tc_conv3_kernel<0>, grid, nthr, smem, stream, maps, p); break;
     case 1: B2U_LAUNCH(tc_conv3_kernel<1>, grid, nthr, smem, stream, maps, p); break;
     case 2: B2U_LAUNCH(tc_conv3_kernel<2>, grid, nthr, smem, stream, maps, p); break;
-    default: B2U_LAUNCH(tc_conv3_kernel<3>, grid, nthr, smem, stream, maps, p); break;
+    case 3: B2U_LAUNCH(tc_conv3_kernel<3>, grid, nthr, smem, stream, maps, p); break;
+    case 4: B2U_LAUNCH(tc_conv3_kernel<4>, grid, nthr, smem, stream, maps, p); break;      // forward + bit mask
+    case 6: B2U_LAUNCH(tc_conv3_kernel<6>, grid, nthr, smem, stream, maps, p); break;      // ... + statistics
+    case 8: B2U_LAUNCH(tc_conv3_kernel<8>, grid, nthr, smem, stream, maps, p); break;      // data gradient, 1-bit mask
+    case 10: B2U_LAUNCH(tc_conv3_kernel<10>, grid, nthr, smem, stream, maps, p); break;    // ... + column sums
+    default:
+      b2u_set_error("tc_conv3: unsupported feature combination %d (1-bit masks do not combine with accumulate / fp16 masks)", flags);
+      return B2U_ERR_ARG;
   }
   return B2U_OK;
 }

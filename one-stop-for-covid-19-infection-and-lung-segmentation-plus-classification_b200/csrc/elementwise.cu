@@ -560,6 +560,35 @@ __global__ void __launch_bounds__(kThreads) dropout_kernel(const T* __restrict__
   }
 }
 
+// packed 1-bit ReLU masks (bit index pix*C + c, little-endian within bytes): one byte per thread and pixel
+template <typename T>
+__global__ void __launch_bounds__(kThreads) relu_bits_kernel(const T* __restrict__ y, int ldy, int C, long long npix,
+                                                             uint8_t* __restrict__ bits) {
+  B2U_PDL_PROLOGUE();
+  PIXEL_LANE_LOOP(C, npix) {
+    float v[8];
+    load8<T>(y + p * ldy + g * 8, v);
+    unsigned b = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b |= (v[k] > 0.f ? 1u : 0u) << k;
+    bits[((p * C) >> 3) + g] = (uint8_t)b;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) apply_bits_kernel(T* __restrict__ dx, int lddx, int C, long long npix,
+                                                              const uint8_t* __restrict__ bits) {
+  B2U_PDL_PROLOGUE();
+  PIXEL_LANE_LOOP(C, npix) {
+    float v[8];
+    load8<T>(dx + p * lddx + g * 8, v);
+    const unsigned b = bits[((p * C) >> 3) + g];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = ((b >> k) & 1u) ? v[k] : 0.f;
+    store8<T>(dx + p * lddx + g * 8, v);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) copy_slice_kernel(const T* __restrict__ s, int lds, T* __restrict__ d,
                                                               int ldd, int C, long long npix, int accumulate) {
@@ -1001,6 +1030,22 @@ extern "C" int b2u_bn_apply(int dt, const void* x, int ldx, void* y, int ldy, in
   size_t smem = out_stats != nullptr ? 2 * (size_t)c * sizeof(float) : 0;
   DISPATCH_T(dt, B2U_LAUNCH(bn_apply_kernel<T>, grid, kThreads, smem, stream, (const T*)x, ldx, (T*)y, ldy, c, npix,
                             scale, shift, out_stats, out_sq_off));
+  return B2U_OK;
+}
+
+int b2u_relu_bits(int dt, const void* y, int ldy, int c, long long npix, void* bits, void* stream) {
+  REQ_VEC8(c);
+  B2U_REQUIRE(ldy % 8 == 0 && aligned16(y) && c <= 2048 && bits != nullptr, "relu_bits: args");
+  DISPATCH_T(dt, B2U_LAUNCH(relu_bits_kernel<T>, lane_grid(npix, c), kThreads, 0, stream, (const T*)y, ldy, c, npix,
+                            (uint8_t*)bits));
+  return B2U_OK;
+}
+
+int b2u_apply_relu_bits(int dt, void* dx, int lddx, int c, long long npix, const void* bits, void* stream) {
+  REQ_VEC8(c);
+  B2U_REQUIRE(lddx % 8 == 0 && aligned16(dx) && c <= 2048 && bits != nullptr, "apply_relu_bits: args");
+  DISPATCH_T(dt, B2U_LAUNCH(apply_bits_kernel<T>, lane_grid(npix, c), kThreads, 0, stream, (T*)dx, lddx, c, npix,
+                            (const uint8_t*)bits));
   return B2U_OK;
 }
 

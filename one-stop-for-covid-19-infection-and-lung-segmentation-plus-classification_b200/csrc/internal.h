@@ -30,10 +30,15 @@ extern long long* g_b2u_dbg;
 // layer whose output gradient the call produces (saves a separate pass over that gradient)
 int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                         int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
-                        int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream);
+                        int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream,
+                        void* relu_bits_out);
 int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                    int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
-                   int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream);
+                   int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream,
+                   void* relu_bits_out);
+// packed 1-bit ReLU masks (bit pix*C + c): generic producers / consumers beside the tensor-core epilogues
+int b2u_relu_bits(int dt, const void* y, int ldy, int c, long long npix, void* bits, void* stream);
+int b2u_apply_relu_bits(int dt, void* dx, int lddx, int c, long long npix, const void* bits, void* stream);
 int b2u_channel_sum(int dt, const void* dy, int lddy, int c, long long npix, float* db, void* stream);
 int b2u_bn_bwd_apply_cs(int dt, const void* dy, int lddy, const void* x, int ldx, void* dx, int lddx, int c,
                         long long npix, long long count, const float* gamma, const float* save_mean,

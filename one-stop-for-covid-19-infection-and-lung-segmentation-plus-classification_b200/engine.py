@@ -82,7 +82,7 @@ class _Bound:
 
 class Engine:
     def __init__(self, graph, precision="float16", device=None, seed=42, loss="bce_dice", comm=None,
-                 sync_stats=False, use_graph=True, dropout_seed=7, loss_scale=None):
+                 sync_stats=False, use_graph=True, dropout_seed=7, loss_scale=None, plan_options=None):
         if not torch.cuda.is_available():
             raise _lib.B2UError("the b200unet engine needs a CUDA device (no CPU fallback)")
         self.lib = _lib.lib()
@@ -101,6 +101,7 @@ class Engine:
         self.use_graph = use_graph
         self.layout = P.ParamLayout(graph)
         self.user_loss_scale = loss_scale
+        self.plan_options = dict(plan_options or {})       # extra plan.Plan keyword arguments (fusion switches)
         npar = self.layout.n_params
         dev = self.device
         with torch.cuda.stream(self.stream):
@@ -228,7 +229,8 @@ class Engine:
         b = self._bound.get(key)
         if b is None:
             pl = P.Plan(self.graph, n, dt=self.dt, training=training, dropout=dropout, loss=loss or self.loss,
-                        world=self.world, sync_stats=self.sync_stats, layout=self.layout, rank=self.rank)
+                        world=self.world, sync_stats=self.sync_stats, layout=self.layout, rank=self.rank,
+                        **self.plan_options)
             b = _Bound(pl)
             self._bound[key] = b
         sizes = b.plan.arena_sizes()

@@ -18,6 +18,7 @@ from . import layers as L
 # ---- enums mirrored from include/b200unet.h ------------------------------------------------------
 F32, F16 = 0, 1
 ACT = {None: 0, "linear": 0, "relu": 1, "elu": 2, "sigmoid": 3}
+ACT_RELU_BITS = 4       # mask_act of a backward op whose mask is a packed 1-bit ReLU mask (B2U_ACT_RELU_BITS)
 (OP_CONV3X3_FWD, OP_CONV3X3_DGRAD, OP_CONV3X3_WGRAD, OP_CONVT_FWD, OP_CONVT_DGRAD, OP_CONVT_WGRAD,
  OP_BN_STATS, OP_BN_FINALIZE, OP_BN_APPLY, OP_BN_BWD_REDUCE, OP_BN_BWD_APPLY, OP_MAXPOOL_FWD, OP_MAXPOOL_BWD,
  OP_DROPOUT_FWD, OP_DROPOUT_BWD, OP_COPY_SLICE, OP_HEAD_FWD, OP_BCE_DICE_SUMS, OP_BCE_DICE_FINALIZE, OP_HEAD_BWD,
@@ -129,7 +130,7 @@ class Plan:
 
     def __init__(self, graph, n, dt=F32, training=True, dropout=True, loss="bce_dice", world=1,
                  sync_stats=False, layout=None, rank=0, fuse_bn_bwd=True, fuse_bn_stats=True, fuse_bias_grad=True,
-                 prepack=True, fuse_bn_bwd_wgrad=True, fuse_bn_pool=True):
+                 prepack=True, fuse_bn_bwd_wgrad=True, fuse_bn_pool=True, relu_bits=False):
         self.graph, self.n, self.dt, self.training = graph, int(n), dt, training
         self.dropout = dropout and training
         self.loss, self.world, self.sync_stats = loss, int(world), bool(sync_stats) and world > 1
@@ -139,6 +140,11 @@ class Plan:
         self.fuse_bias_grad = bool(fuse_bias_grad)
         self.fuse_bn_bwd_wgrad = bool(fuse_bn_bwd_wgrad)
         self.fuse_bn_pool = bool(fuse_bn_pool)
+        # 1-bit ReLU masks: a ReLU conv whose only consumer is another 3x3 conv also writes (y > 0) as packed bits, and
+        # that consumer's data gradient reads 1 bit instead of 16 per element (and one word per thread and tile, issued
+        # before the accumulator wait).  Built and emulated in round 1, NOT yet validated on the GPU: off by default.
+        self.relu_bits = bool(relu_bits) and self.training
+        self._bits = {}                  # id(tensor) -> Ref of its packed ReLU mask
         self._bias_done = set()          # id(conv layer) whose bias gradient is produced by another backward op
         # fp16 operand copies of the conv kernels: ONE pack launch per step for the whole model (OP_PACK_WEIGHTS)
         # instead of one small launch in front of every conv call
@@ -295,8 +301,12 @@ class Plan:
                 if self.training and len(cons) == 1 and cons[0].kind == "batch_normalization":
                     stats = self.zero.alloc(2 * t.channels * 8)
                     bn_aux[id(cons[0])] = {"sums": stats, "fused": True}
+                bits = None
+                if (self.relu_bits and l.activation == "relu" and len(cons) == 1 and cons[0].kind == "conv2d" and
+                        tuple(cons[0].kernel_size) == (3, 3) and yv.c % 16 == 0):
+                    bits = self._bits[id(t)] = self.act.alloc(self._npix(yv) * yv.c // 8)
                 self.fwd.append(Op(OP_CONV3X3_FWD, dt, [xv.ref, self._w(l, "kernel"), self._w(l, "bias"), yv.ref, stats,
-                                                        self._packed(l, 0, 9, yv.c, xv.c)],
+                                                        self._packed(l, 0, 9, yv.c, xv.c), bits],
                                    [xv.ld, xv.c, ACT[l.activation], yv.ld, yv.c, n, xv.h, xv.w], tag=l.name))
             elif l.kind == "conv2d":      # 1x1 output head
                 if l.activation != "sigmoid" or l.filters != 1 or t is not g.output:
@@ -483,6 +493,12 @@ class Plan:
                     mv, ma = self._mask_for(x)
                     acc = 1 if id(x) in written else 0
                     sink = self._bias_sink(x) if (mv is not None and not acc) else None
+                    mref, mld = (mv.ref, mv.ld) if mv else (None, 0)
+                    xm = x                                    # the activated tensor behind identity dropouts
+                    while xm.producer.kind == "dropout" and self.views[id(xm)] is self.views[id(xm.producer.inputs[0])]:
+                        xm = xm.producer.inputs[0]
+                    if mv is not None and not acc and id(xm) in self._bits:
+                        mref, mld, ma = self._bits[id(xm)], gx.c, ACT_RELU_BITS
                     bn = x.producer
                     if (self.fuse_bn_bwd_wgrad and sink is None and not acc and bn.kind == "batch_normalization" and
                             len(x.consumers) == 1 and "bwd_sums" not in bn_aux[id(bn)] and x.channels % 8 == 0):
@@ -491,9 +507,9 @@ class Plan:
                         # here -- no pass over dy and the BN input (include/b200unet.h b2u_bn_bwd_sums_from_wgrad)
                         sink = self.zero.alloc(x.channels * 4)
                         bn_aux[id(bn)]["wgrad_sums"] = (sink, self._w(l, "kernel"), grads(l, "kernel"), yv_c(l))
-                    self.bwd.append(Op(OP_CONV3X3_DGRAD, dt, [gy.ref, self._w(l, "kernel"), gx.ref, mv.ref if mv else None, sink,
+                    self.bwd.append(Op(OP_CONV3X3_DGRAD, dt, [gy.ref, self._w(l, "kernel"), gx.ref, mref, sink,
                                                               self._packed(l, 1, 9, gx.c, gy.c)],
-                                       [gy.ld, gy.c, gx.ld, gx.c, mv.ld if mv else 0, ma, acc,
+                                       [gy.ld, gy.c, gx.ld, gx.c, mld, ma, acc,
                                         n, xv.h, xv.w], tag=l.name))
                     written.add(id(x))
             elif l.kind == "conv2d_transpose":

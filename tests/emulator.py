@@ -96,6 +96,9 @@ class Emulator:
             ys = yv.astype(np.float64)
             s[:cout] += ys.sum(0)
             s[cout:] += (ys * ys).sum(0)
+        if len(o.p) > 6 and o.p[6] is not None:          # packed 1-bit ReLU mask of the values as stored
+            packed = np.packbits((yv > 0).reshape(-1), bitorder="little")
+            self.arr(o.p[6], packed.size, np.uint8)[:] = packed
 
     def op_conv3x3_dgrad(self, o):
         lddy, cout, lddx, cin, ldm, mact, acc, n, h, w = o.i[:10]
@@ -104,7 +107,11 @@ class Emulator:
         wo = torch.from_numpy(wt.copy()).permute(3, 2, 0, 1)           # (cout, cin, 3, 3)
         dx = F.conv_transpose2d(torch.from_numpy(dy).permute(0, 3, 1, 2), wo, padding=1).permute(0, 2, 3, 1).numpy()
         dx = dx.reshape(-1, cin)
-        if o.p[3] is not None:
+        if o.p[3] is not None and mact == 4:             # B2U_ACT_RELU_BITS: bit pix*cin + c
+            nbits = n * h * w * cin
+            bits = np.unpackbits(self.arr(o.p[3], nbits // 8, np.uint8), bitorder="little")[:nbits]
+            dx = dx * bits.reshape(-1, cin).astype(np.float32)
+        elif o.p[3] is not None:
             dx = dx * self._dact(self.view(o.p[3], ldm, cin, n * h * w, o.dt), mact)
         dv = self.view(o.p[2], lddx, cin, n * h * w, o.dt)
         if acc:

@@ -113,7 +113,7 @@ def test_shape_validation():
 
 
 @pytest.mark.parametrize("flags", [dict(fuse_bias_grad=False), dict(fuse_bn_bwd_wgrad=False), dict(fuse_bn_pool=False),
-                                   dict(fuse_bn_bwd=False, fuse_bn_stats=False), dict(prepack=False)])
+                                   dict(fuse_bn_bwd=False, fuse_bn_stats=False), dict(prepack=False), dict(relu_bits=True)])
 def test_every_fusion_can_be_switched_off(flags):
     """each planner fusion (producer-side bias gradients, BN backward statistics from the weight gradient / the max-pool
     backward, BN statistics from producer epilogues, BN apply + pool, one-launch weight packing) is optional: the
@@ -133,3 +133,15 @@ def test_every_fusion_can_be_switched_off(flags):
         grads = plan.layout.unpack(em.f32(P.Ref("grads", 0), fp.size), None)
         worst, who = grad_errors(grads, r["grads"])
         assert worst < 1e-3, (kw, who, worst)
+
+
+def test_relu_bits_plan_structure():
+    """relu_bits=True (built in round 1, GPU validation pending, off by default): the nine `a` convs of the U-Net write a
+    packed ReLU mask and the data gradients of the nine `b` convs read it; the default plan is unchanged"""
+    on = P.Plan(G.unet(32, 1), 2, dt=P.F16, training=True, relu_bits=True)
+    off = P.Plan(G.unet(32, 1), 2, dt=P.F16, training=True)
+    assert sum(1 for o in on.fwd if o.kind == P.OP_CONV3X3_FWD and len(o.p) > 6 and o.p[6] is not None) == 9
+    assert sum(1 for o in on.bwd if o.kind == P.OP_CONV3X3_DGRAD and o.i[5] == P.ACT_RELU_BITS) == 9
+    assert all(o.p[6] is None for o in off.fwd if o.kind == P.OP_CONV3X3_FWD)
+    assert not any(o.kind == P.OP_CONV3X3_DGRAD and o.i[5] == P.ACT_RELU_BITS for o in off.bwd)
+    assert on.act.size > off.act.size
