@@ -51,6 +51,16 @@ extern "C" int b2u_set_option(const char* name, int value) {
     g_b2u_pdl = value ? 1 : 0;
     return old;
   }
+  if (strcmp(name, "tc_2sm_max_j") == 0) {
+    int old = g_b2u_tc_2sm_max_j;
+    g_b2u_tc_2sm_max_j = value;
+    return old;
+  }
+  if (strcmp(name, "tc_3sm") == 0) {
+    int old = g_b2u_tc_3sm;
+    g_b2u_tc_3sm = value ? 1 : 0;
+    return old;
+  }
   if (strcmp(name, "side_stream") == 0) {
     int old = g_b2u_side_stream;
     if (value && side_init() != B2U_OK) return -1;        // create the stream / events outside any stream capture

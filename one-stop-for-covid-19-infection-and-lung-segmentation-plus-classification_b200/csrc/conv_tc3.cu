@@ -505,6 +505,8 @@ CUtensorMapSwizzle swz3(int ks) {
 }  // namespace
 
 long long* g_b2u_dbg = nullptr;   // device timeline buffer (b2u_set_option("tc_debug", 1))
+int g_b2u_tc_2sm_max_j = 64;  // largest N tile that runs two CTAs per SM
+int g_b2u_tc_3sm = 0;         // 1: three CTAs per SM for the low-register variants of thin layers (untested)
 int g_b2u_tc_halo = 1;       // 0: per-tap loads (conv_tc.cu), 1: halo box, 2: halo box + base_offset, 3: three boxes
 
 int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
@@ -555,14 +557,19 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   }
   if (p.SA > kMaxSA) p.SA = kMaxSA;
   B2U_REQUIRE(p.SA >= 2 && p.SB >= 1 && (p.bres || p.SB >= 2), "tc_conv3: tiles do not fit shared memory (K=%d J=%d)", K, J);
-  // two CTAs per SM for thin resident-weight layers: cap the A ring so that one CTA stays under ~110 KB
+  // two CTAs per SM for thin resident-weight layers: cap the A ring so that one CTA stays under ~110 KB.
+  // Untuned switches for the next round (defaults = the measured configuration): `tc_2sm_max_j` moves the N-tile limit
+  // of the two-CTA mode, `tc_3sm` lets the <= 80-register variants (no statistics, no fp16 mask) run three CTAs per SM.
   bool two_per_sm = false;
-  if (p.bres && p.JT <= 64) {
-    const size_t cap = 110 * 1024;
+  int per_sm = 1;
+  const bool lowreg = mask == nullptr && !accumulate && stats == nullptr && colsum == nullptr;
+  if (p.bres && p.JT <= g_b2u_tc_2sm_max_j) {
+    const bool three = g_b2u_tc_3sm && lowreg && p.JT <= 64;
+    const size_t cap = three ? 72 * 1024 : 110 * 1024;
     if (1024 + wres + tail + 2 * a_stage <= cap) {
       int sa2 = (int)((cap - 1024 - wres - tail) / a_stage);
       if (sa2 > kMaxSA) sa2 = kMaxSA;
-      if (sa2 >= 2) { p.SA = sa2; two_per_sm = true; }
+      if (sa2 >= 2) { p.SA = sa2; two_per_sm = true; per_sm = three ? 3 : 2; }
     }
   }
   p.epi_warps = two_per_sm ? 4 : 8;
@@ -613,7 +620,7 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   // thin layers are bound by the single MMA-issuing thread (~75 issue cycles per tcgen05.mma): run two CTAs
   // per SM (two issuers) when shared memory and TMEM (2*JT columns each) allow it
   int ctas = B2U_NUM_SMS;
-  if (two_per_sm && tiles >= 4 * B2U_NUM_SMS) ctas = 2 * B2U_NUM_SMS;
+  if (two_per_sm && tiles >= 2 * per_sm * B2U_NUM_SMS) ctas = per_sm * B2U_NUM_SMS;
   int grid = (int)(tiles < ctas ? tiles : ctas);
   const int flags = ((mask != nullptr || accumulate) ? kF_MASKACC : 0) | ((stats != nullptr || colsum != nullptr) ? kF_SUMS : 0) |
                     (p.bits_out != nullptr ? kF_BITS_OUT : 0) | (p.bits_in != nullptr ? kF_BITS_IN : 0);
