@@ -155,10 +155,10 @@ class Model:
     """`Model(inputs=[inputs], outputs=[outputs])` (T1H:915) over a layers.Graph."""
 
     def __init__(self, inputs=None, outputs=None, graph=None, precision="float16", seed=42, comm=None,
-                 sync_stats=False, use_graph=True, device=None, dropout_seed=7, loss_scale=None):
+                 sync_stats=False, use_graph=True, device=None, dropout_seed=7, loss_scale=None, plan_options=None):
         self.graph = graph if graph is not None else L.Graph(inputs, outputs)
         self._eng_kw = dict(precision=precision, seed=seed, comm=comm, sync_stats=sync_stats, use_graph=use_graph,
-                            device=device, dropout_seed=dropout_seed, loss_scale=loss_scale)
+                            device=device, dropout_seed=dropout_seed, loss_scale=loss_scale, plan_options=plan_options)
         self._eng = None
         self.loss_kind = "bce_dice" if len(self.graph.output.shape) == 3 else "bce"
         self.metrics = []
