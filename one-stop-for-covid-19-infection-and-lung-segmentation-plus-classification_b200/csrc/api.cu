@@ -51,6 +51,11 @@ extern "C" int b2u_set_option(const char* name, int value) {
     g_b2u_pdl = value ? 1 : 0;
     return old;
   }
+  if (strcmp(name, "tc_dwmerge") == 0) {
+    int old = g_b2u_tc_dwmerge;
+    g_b2u_tc_dwmerge = value ? 1 : 0;
+    return old;
+  }
   if (strcmp(name, "tc_2sm_max_j") == 0) {
     int old = g_b2u_tc_2sm_max_j;
     g_b2u_tc_2sm_max_j = value;
@@ -108,6 +113,9 @@ static int conv3x3_fwd_wp(int dt, const void* x, int ldx, int cin, const float* 
                           const void* wp, void* relu_bits, void* stream) {
   int rc;
   if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy)) {
+    if (g_b2u_tc_dwmerge && relu_bits == nullptr && b2u_tc_conv3x3_dwmerge_ok(cin, cout))      // (experimental, off)
+      return b2u_tc_conv3x3_dwmerge(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, nullptr, 0, 0, 0, n, h, wd,
+                                    ws, ws_bytes, stream);
     if (g_b2u_tc_halo)
       return b2u_tc_conv3x3_halo(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, nullptr, 0, 0, 0, n, h, wd,
                                  ws, ws_bytes, wp, stream, relu_bits);
@@ -134,6 +142,9 @@ static int conv3x3_dgrad_cs(int dt, const void* dy, int lddy, int cout, const fl
                             int wd, void* ws, size_t ws_bytes, const void* wp, void* stream) {
   const bool tc = dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cout, cin, lddy, lddx);
   const bool bits = mask != nullptr && mask_act == B2U_ACT_RELU_BITS;
+  if (tc && !bits && g_b2u_tc_dwmerge && b2u_tc_conv3x3_dwmerge_ok(cout, cin))                   // (experimental, off)
+    return b2u_tc_conv3x3_dwmerge(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, colsum, mask, ldmask,
+                                  mask_act, accumulate, n, h, wd, ws, ws_bytes, stream);
   if (tc && (!bits || g_b2u_tc_halo))
     return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx,
                                                                   cin, nullptr, colsum, mask, ldmask, mask_act,
