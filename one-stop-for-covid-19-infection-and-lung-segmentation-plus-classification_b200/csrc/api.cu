@@ -53,7 +53,7 @@ extern "C" int b2u_set_option(const char* name, int value) {
   }
   if (strcmp(name, "tc_dwmerge") == 0) {
     int old = g_b2u_tc_dwmerge;
-    g_b2u_tc_dwmerge = value ? 1 : 0;
+    g_b2u_tc_dwmerge = value;
     return old;
   }
   if (strcmp(name, "tc_2sm_max_j") == 0) {
@@ -106,6 +106,15 @@ extern "C" int b2u_debug_read(long long* h_out, int count) {
 // ------------------------------------------------------------------------------------------
 // conv dispatch
 // ------------------------------------------------------------------------------------------
+// Thin layers (N = Cout <= 64): the dw-merged kernel (conv_tc3w.cu) reads the A operand a third as often as the halo
+// kernel.  tc_dwmerge = 1 takes every shape the kernel supports (A/B runs, tests), 2 only the shapes where it measured
+// faster on B200 (tools/ab_ops.py --opt tc_dwmerge=0,1; profiles/).
+static bool use_dwmerge(int K, int J, int h, int wd) {
+  if (g_b2u_tc_dwmerge == 0 || !b2u_tc_conv3x3_dwmerge_ok(K, J)) return false;
+  if (g_b2u_tc_dwmerge == 1) return true;
+  return K >= 128 && J == 64 && (long long)h * wd >= 128 * 128;
+}
+
 // `relu_bits` (optional, op lists only): packed 1-bit mask of y > 0, written by the halo kernel's epilogue or, on the
 // other paths, by one extra pass over y
 static int conv3x3_fwd_wp(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, int act, void* y,
@@ -113,16 +122,19 @@ static int conv3x3_fwd_wp(int dt, const void* x, int ldx, int cin, const float* 
                           const void* wp, void* relu_bits, void* stream) {
   int rc;
   if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy)) {
-    if (g_b2u_tc_dwmerge && relu_bits == nullptr && b2u_tc_conv3x3_dwmerge_ok(cin, cout))      // (experimental, off)
+    if (use_dwmerge(cin, cout, h, wd))
       return b2u_tc_conv3x3_dwmerge(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, nullptr, 0, 0, 0, n, h, wd,
-                                    ws, ws_bytes, stream);
+                                    ws, ws_bytes, wp, stream, relu_bits);
     if (g_b2u_tc_halo)
       return b2u_tc_conv3x3_halo(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, nullptr, 0, 0, 0, n, h, wd,
                                  ws, ws_bytes, wp, stream, relu_bits);
     rc = b2u_tc_conv3x3(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, nullptr, 0, 0, 0, n, h, wd, ws,
                         ws_bytes, wp, stream, nullptr);
   } else {
-    rc = b2u_direct_conv3x3(dt, x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, 0, 0, 0, n, h, wd, stream);
+    int bits_done = 0;
+    rc = b2u_direct_conv3x3(dt, x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, 0, 0, 0, n, h, wd, stream,
+                            relu_bits, &bits_done);
+    if (bits_done) return rc;
   }
   if (rc != B2U_OK || relu_bits == nullptr) return rc;
   return b2u_relu_bits(dt, y, ldy, cout, (long long)n * h * wd, relu_bits, stream);
@@ -142,9 +154,9 @@ static int conv3x3_dgrad_cs(int dt, const void* dy, int lddy, int cout, const fl
                             int wd, void* ws, size_t ws_bytes, const void* wp, void* stream) {
   const bool tc = dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cout, cin, lddy, lddx);
   const bool bits = mask != nullptr && mask_act == B2U_ACT_RELU_BITS;
-  if (tc && !bits && g_b2u_tc_dwmerge && b2u_tc_conv3x3_dwmerge_ok(cout, cin))                   // (experimental, off)
+  if (tc && !(bits && accumulate) && use_dwmerge(cout, cin, h, wd))
     return b2u_tc_conv3x3_dwmerge(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, colsum, mask, ldmask,
-                                  mask_act, accumulate, n, h, wd, ws, ws_bytes, stream);
+                                  mask_act, accumulate, n, h, wd, ws, ws_bytes, wp, stream, nullptr);
   if (tc && (!bits || g_b2u_tc_halo))
     return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx,
                                                                   cin, nullptr, colsum, mask, ldmask, mask_act,

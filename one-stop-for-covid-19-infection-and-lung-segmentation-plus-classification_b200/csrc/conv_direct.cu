@@ -182,9 +182,12 @@ template <typename T, int COUT>
 __global__ void __launch_bounds__(256, 2) conv3x3_c1_fwd_kernel(const T* __restrict__ x, int ldx,
                                                                 const float* __restrict__ w,
                                                                 const float* __restrict__ bias, int act,
-                                                                T* __restrict__ y, int ldy, int N, int H, int W) {
+                                                                T* __restrict__ y, int ldy, int N, int H, int W,
+                                                                uint8_t* __restrict__ bits) {
   B2U_PDL_PROLOGUE();
   constexpr int CG = COUT / 8, LANES = 256 / CG;
+  // a stored value is > 0 iff the fp32 value survives the rounding to the storage type
+  const float pos = sizeof(T) == 2 ? 2.98023223876953125e-08f : 0.f;
   __shared__ float xs[C1_HALO + 2];
   const int g = threadIdx.x % CG, lane = threadIdx.x / CG;
   float wr[9][8], br[8];
@@ -229,7 +232,14 @@ __global__ void __launch_bounds__(256, 2) conv3x3_c1_fwd_kernel(const T* __restr
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = act_fwd(o[k], act);
       }
-      store8<T>(y + (((long long)n * H + h0 + r) * W + w0 + c) * ldy + g * 8, o);
+      const long long pix = ((long long)n * H + h0 + r) * W + w0 + c;
+      store8<T>(y + pix * ldy + g * 8, o);
+      if (bits != nullptr) {               // packed 1-bit ReLU mask (bit pix*COUT + channel): one byte per thread
+        unsigned b = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b |= (o[k] > pos ? 1u : 0u) << k;
+        bits[pix * CG + g] = (uint8_t)b;
+      }
     }
   }
 }
@@ -603,15 +613,17 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ 
 
 int b2u_direct_conv3x3(int dt, const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act,
                        void* y, int ldy, int J, double* stats, const void* mask, int ldmask, int mask_act,
-                       int accumulate, int n, int h, int wd, void* stream) {
+                       int accumulate, int n, int h, int wd, void* stream, void* relu_bits, int* bits_done) {
+  if (bits_done != nullptr) *bits_done = 0;
   B2U_REQUIRE(n > 0 && h > 0 && wd > 0 && K > 0 && J > 0, "conv3x3: empty shape");
   B2U_REQUIRE((K % 8 != 0) || (ldx % 8 == 0), "conv3x3: ldx must be a multiple of 8 when Cin %% 8 == 0");
   int tiles = b2u_cdiv(h, TH) * b2u_cdiv(wd, TW);
   if (K == 1 && !dgrad && stats == nullptr && mask == nullptr && !accumulate && ldy % 8 == 0 && (J == 32 || J == 16)) {
     long long gl1 = (long long)n * b2u_cdiv(h, C1_TH) * b2u_cdiv(wd, C1_TW);
     int grid1 = (int)(gl1 < 2 * B2U_NUM_SMS ? gl1 : 2 * B2U_NUM_SMS);
-    if (J == 32) { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_fwd_kernel<T, 32>), grid1, 256, 0, stream, (const T*)x, ldx, w, bias, act, (T*)y, ldy, n, h, wd)); }
-    else { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_fwd_kernel<T, 16>), grid1, 256, 0, stream, (const T*)x, ldx, w, bias, act, (T*)y, ldy, n, h, wd)); }
+    if (J == 32) { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_fwd_kernel<T, 32>), grid1, 256, 0, stream, (const T*)x, ldx, w, bias, act, (T*)y, ldy, n, h, wd, (uint8_t*)relu_bits)); }
+    else { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_fwd_kernel<T, 16>), grid1, 256, 0, stream, (const T*)x, ldx, w, bias, act, (T*)y, ldy, n, h, wd, (uint8_t*)relu_bits)); }
+    if (bits_done != nullptr && relu_bits != nullptr) *bits_done = 1;
     return B2U_OK;
   }
   if (J > 32) {

@@ -1,9 +1,5 @@
 // tcgen05 3x3 convolution for THIN layers (Cout <= 64) with the three dw taps side by side in N.
 //
-// STATUS: written at the end of round 1 after the GPU budget was spent -- it compiles for sm_100a but has NOT run on a
-// GPU yet.  It is reached only with b2u_set_option("tc_dwmerge", 1) (default 0); enable the parity tests for it
-// (tests/test_gpu_tc.py, marked DWMERGE_PENDING) before switching the default.  profiles/NOTES_r1.md has the analysis.
-//
 // Why: an SS-mode tcgen05.mma reads 128 x 16 fp16 of A (4 KB) per instruction whatever N is; at N = Cout = 32 the
 // halo-tile kernel (conv_tc3.cu) is bound by that shared-memory traffic (measured 40-60 cycles per MMA against 16 math
 // cycles).  Here a CTA tile is an (8 rows x 16 columns) block of INPUT-aligned pixels: 14 output columns plus one halo
@@ -16,6 +12,14 @@
 // accumulator (tap row dh = the ordinary K-major descriptor started 16*dh pixel rows further down the contiguous
 // (10 x 16)-pixel patch: no halo-pitch trick, every start is swizzle-atom aligned), and the dw shift is two
 // __shfl_down_sync per output value in the epilogue (a warp holds two block rows, the neighbours are lanes +1 / +2).
+// The packed weights are the halo kernel's [9][J][K] bank read through a (K, 3J, 3) tensor map: [t = dh*3 + dw][j][k]
+// IS [dh][dw*J + j][k].
+//
+// Round-2 GPU history: the first version (validated against the emulator on B200) was epilogue-bound -- three
+// tcgen05.ld + wait round trips per 16-column chunk and a shuffle-transpose + shared-memory atomics per chunk for the
+// statistics made it 2x slower than the halo kernel on the K = 32 layers.  This version issues the three loads of a chunk
+// back to back with ONE wait, keeps BatchNorm statistics / column sums in registers across all tiles of the persistent
+// CTA, reads / writes 1-bit ReLU masks, and specialises the epilogue at compile time like conv_tc3.cu.
 //
 // Warp roles as in conv_tc3.cu: TMA producer, one MMA-issuing warp (elected lane), 4 or 8 epilogue warps, two TMEM
 // accumulator stages, weights resident in shared memory for the whole persistent CTA.
@@ -44,6 +48,8 @@ struct W3Params {
   int accumulate;
   double* stats;          // BatchNorm statistics of the stored values: sums at [c], squares at [J + c]
   float* colsum;          // per-channel sums of the stored values (fp32 atomics)
+  uint8_t* bits_out;      // kW_BITS_OUT: packed 1-bit ReLU mask of the values stored (bit pix*J + column)
+  const uint8_t* bits_in; // kW_BITS_IN : packed 1-bit ReLU mask applied to the values written (data gradient)
 };
 
 struct W3Maps {
@@ -68,8 +74,14 @@ __device__ __forceinline__ float transpose_reduce16w(float v[16], int lane) {
   return v[0];
 }
 
+// epilogue features as compile-time variants (see conv_tc3.cu): bit 0 = fp16 activation mask and/or accumulate,
+// bit 1 = BatchNorm statistics and/or column sums, bit 2 = write a 1-bit ReLU mask, bit 3 = read one
+constexpr int kW_MASKACC = 1, kW_SUMS = 2, kW_BITS_OUT = 4, kW_BITS_IN = 8;
+
+template <int kFlags>
 __global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_constant__ W3Maps maps,
                                                                    const __grid_constant__ W3Params prm) {
+  constexpr bool kMaskAcc = (kFlags & kW_MASKACC) != 0, kSums = (kFlags & kW_SUMS) != 0;
   B2U_PDL_LAUNCH_DEPENDENTS();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -189,7 +201,13 @@ __global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_c
     const int ccols = split ? J / 2 : J;                          // output channels owned by this warp
     const int cbeg = split ? half * ccols : 0;
     const bool has_cols = split || half == 0;
-    const bool want_sums = prm.stats != nullptr || prm.colsum != nullptr;
+    const bool want_sums = kSums && (prm.stats != nullptr || prm.colsum != nullptr);
+    // statistics of <= 32 owned columns live in registers across all tiles of the persistent CTA
+    const bool reg_stats = want_sums && ccols <= 32;
+    constexpr int kRS = kSums ? 32 : 1, kR16 = kSums ? 16 : 0;
+    float rs1[kRS], rs2[kRS];
+#pragma unroll
+    for (int i = 0; i < kRS; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (unsigned tile = blockIdx.x; tile < (unsigned)ntiles; tile += gridDim.x) {
@@ -200,21 +218,41 @@ __global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_c
       const bool valid = cp < kOW && h < prm.H && w < prm.W;
       const long long pix = ((long long)n * prm.H + (h < prm.H ? h : 0)) * prm.W + (w < prm.W ? w : 0);
       __half* yrow = prm.y + pix * prm.ldy;
-      const __half* mrow = prm.mask != nullptr ? prm.mask + pix * prm.ldmask : nullptr;
+      const __half* mrow = (kMaskAcc && prm.mask != nullptr) ? prm.mask + pix * prm.ldmask : nullptr;
+      // 1-bit ReLU mask of this thread's columns (<= 64): 2-byte loads issued before the accumulator wait
+      uint32_t mb0 = 0u, mb1 = 0u;
+      if constexpr ((kFlags & kW_BITS_IN) != 0) {
+        if (has_cols && valid) {
+          const unsigned short* bp16 = reinterpret_cast<const unsigned short*>(prm.bits_in + ((pix * J + cbeg) >> 3));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q * 16 < ccols) {
+              const uint32_t hw = (uint32_t)__ldg(bp16 + q) << (16 * (q & 1));
+              if (q < 2) mb0 |= hw; else mb1 |= hw;
+            }
+          }
+        }
+      }
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::fence_after_sync();
       if (has_cols) {
+#pragma unroll 1
         for (int cc = 0; cc < ccols; cc += 16) {
           const int c0 = cbeg + cc;
           const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * NT + c0;
-          float v[16], t[16];
-          tc::tmem_ld16(trow, v);                                  // dw = 0: own pixel
-          tc::tmem_ld16(trow + J, t);                              // dw = 1: the pixel one column to the right
+          uint32_t a0[16], a1[16], a2[16];
+          tc::tmem_ld16_nowait(trow, a0);                          // dw = 0: own pixel
+          tc::tmem_ld16_nowait(trow + J, a1);                      // dw = 1: the pixel one column to the right
+          tc::tmem_ld16_nowait(trow + 2 * J, a2);                  // dw = 2: two columns to the right
+          tc::tmem_wait_ld();
+          tc::reg_fence16(a0);
+          tc::reg_fence16(a1);
+          tc::reg_fence16(a2);
+          float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __shfl_down_sync(0xffffffffu, t[i], 1);
-          tc::tmem_ld16(trow + 2 * J, t);                          // dw = 2: two columns to the right
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __shfl_down_sync(0xffffffffu, t[i], 2);
+          for (int i = 0; i < 16; ++i)
+            v[i] = (__uint_as_float(a0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(a1[i]), 1)) +
+                   __shfl_down_sync(0xffffffffu, __uint_as_float(a2[i]), 2);
           const float4* bp = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -228,43 +266,68 @@ __global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_c
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
           }
+          if constexpr ((kFlags & kW_BITS_IN) != 0) {
+            const uint32_t w32 = cc < 32 ? mb0 : mb1;
+            const uint32_t b16 = (w32 >> (cc & 16)) & 0xffffu;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = ((b16 >> i) & 1u) ? v[i] : 0.f;
+          }
           if (valid) {
-            if (mrow != nullptr) {
-              float m[8];
-              load8<__half>(mrow + c0, m);
+            if constexpr (kMaskAcc) {
+              if (mrow != nullptr) {
+                float m[8];
+                load8<__half>(mrow + c0, m);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] *= act_bwd_from_y(m[i], prm.mask_act);
-              load8<__half>(mrow + c0 + 8, m);
+                for (int i = 0; i < 8; ++i) v[i] *= act_bwd_from_y(m[i], prm.mask_act);
+                load8<__half>(mrow + c0 + 8, m);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[8 + i] *= act_bwd_from_y(m[i], prm.mask_act);
-            }
-            if (prm.accumulate) {
-              float e[8];
-              load8<__half>(yrow + c0, e);
+                for (int i = 0; i < 8; ++i) v[8 + i] *= act_bwd_from_y(m[i], prm.mask_act);
+              }
+              if (prm.accumulate) {
+                float e[8];
+                load8<__half>(yrow + c0, e);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += e[i];
-              load8<__half>(yrow + c0 + 8, e);
+                for (int i = 0; i < 8; ++i) v[i] += e[i];
+                load8<__half>(yrow + c0 + 8, e);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[8 + i] += e[i];
+                for (int i = 0; i < 8; ++i) v[8 + i] += e[i];
+              }
             }
             store8<__half>(yrow + c0, v);
             store8<__half>(yrow + c0 + 8, v + 8);
+            if constexpr ((kFlags & kW_BITS_OUT) != 0) {
+              // bit = (the fp16 value just stored > 0): round-to-nearest-even sends v <= 2^-25 to zero
+              uint32_t b16 = 0u;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) b16 |= (v[i] > 2.98023223876953125e-08f ? 1u : 0u) << i;
+              *reinterpret_cast<unsigned short*>(prm.bits_out + ((pix * J + c0) >> 3)) = (unsigned short)b16;
+            }
           }
           if (want_sums) {
-            // first version: the shuffle-transpose reduction per chunk (register accumulation across tiles as in
-            // conv_tc3.cu is the obvious next step once the kernel is validated)
-            float q[16];
+            if (reg_stats) {
+              if (valid) {
+                if (cc == 0) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) q[i] = valid ? v[i] : 0.f;
-            if (prm.stats != nullptr) {
-              float sq[16];
+                  for (int i = 0; i < kR16; ++i) { rs1[i] += v[i]; rs2[i] = fmaf(v[i], v[i], rs2[i]); }
+                } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) sq[i] = q[i] * q[i];
-              const float s2 = transpose_reduce16w(sq, lane);
-              if (lane < 16) atomicAdd(&s_stats[J + c0 + lane], s2);
+                  for (int i = 0; i < kR16; ++i) { rs1[kR16 + i] += v[i]; rs2[kR16 + i] = fmaf(v[i], v[i], rs2[kR16 + i]); }
+                }
+              }
+            } else {
+              float q[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) q[i] = valid ? v[i] : 0.f;
+              if (prm.stats != nullptr) {
+                float sq[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sq[i] = q[i] * q[i];
+                const float s2 = transpose_reduce16w(sq, lane);
+                if (lane < 16) atomicAdd(&s_stats[J + c0 + lane], s2);
+              }
+              const float s1 = transpose_reduce16w(q, lane);
+              if (lane < 16) atomicAdd(&s_stats[c0 + lane], s1);
             }
-            const float s1 = transpose_reduce16w(q, lane);
-            if (lane < 16) atomicAdd(&s_stats[c0 + lane], s1);
           }
         }
       }
@@ -272,6 +335,23 @@ __global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (reg_stats && has_cols) {
+      for (int cc = 0; cc < ccols; cc += 16) {
+        float q[16], sq[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int i0 = kSums ? i : 0, i1 = kSums ? 16 + i : 0;       // (never executed without kSums)
+          q[i] = cc == 0 ? rs1[i0] : rs1[i1];
+          sq[i] = cc == 0 ? rs2[i0] : rs2[i1];
+        }
+        const float s1 = transpose_reduce16w(q, lane);
+        if (lane < 16) atomicAdd(&s_stats[cbeg + cc + lane], s1);
+        if (prm.stats != nullptr) {
+          const float s2 = transpose_reduce16w(sq, lane);
+          if (lane < 16) atomicAdd(&s_stats[J + cbeg + cc + lane], s2);
+        }
+      }
     }
   }
 
@@ -295,6 +375,7 @@ __global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_c
 
 // fwd: Wp[dh][dw*J + co][ci] = w[dh*3 + dw][ci][co]     (w: Keras HWIO, K = Cin, J = Cout)
 // dgrad: Wp[dh][dw*J + j][k] = w[8 - (dh*3 + dw)][j][k]  (j = Cin of the forward = columns written, k = its Cout)
+// (the same bytes as conv_tc3.cu's [9][J][K] bank: used only when the caller has no prepacked copy)
 __global__ void pack3w_kernel(const float* __restrict__ w, __half* __restrict__ wp, int dgrad, int J, int K) {
   B2U_PDL_PROLOGUE();
   const long long total = 9LL * J * K;
@@ -331,7 +412,8 @@ int get_encw() {
 
 }  // namespace
 
-int g_b2u_tc_dwmerge = 0;      // 1: thin layers (Cout <= 64) use tc_conv3w_kernel (NOT yet validated on a GPU)
+// 0: never, 1: every layer the kernel takes (A/B runs), 2: the layers where it measured faster than the halo kernel
+int g_b2u_tc_dwmerge = 0;
 
 // shapes this kernel takes: resident weights and the A ring must fit shared memory
 int b2u_tc_conv3x3_dwmerge_ok(int K, int J) {
@@ -347,17 +429,23 @@ int b2u_tc_conv3x3_dwmerge_ok(int K, int J) {
 
 int b2u_tc_conv3x3_dwmerge(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                            int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
-                           int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream) {
+                           int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream,
+                           void* relu_bits_out) {
   int rc = get_encw();
   if (rc != B2U_OK) return rc;
   B2U_REQUIRE(b2u_tc_conv3x3_dwmerge_ok(K, J), "tc_conv3w: unsupported channel counts K=%d J=%d", K, J);
-  B2U_REQUIRE(mask == nullptr || mask_act != B2U_ACT_RELU_BITS, "tc_conv3w: 1-bit masks are not supported yet");
   W3Params p{};
   p.N = n; p.H = h; p.W = wd; p.K = K; p.J = J;
   p.KS = K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : 16);
   p.y = (__half*)y; p.ldy = ldy; p.bias = bias; p.act = act;
   p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate;
   p.stats = stats; p.colsum = colsum;
+  p.bits_out = (uint8_t*)relu_bits_out;
+  if (mask != nullptr && mask_act == B2U_ACT_RELU_BITS) {          // packed 1-bit mask instead of the activation tensor
+    p.bits_in = (const uint8_t*)mask;
+    p.mask = nullptr;
+    mask = nullptr;
+  }
   const uint32_t rowb = p.KS * 2;
   const int kslabs = K / p.KS, NT = 3 * J;
   p.a_stage = (uint32_t)(((size_t)(kBH + 2) * kBW * rowb + 1023) & ~(size_t)1023);
@@ -375,13 +463,14 @@ int b2u_tc_conv3x3_dwmerge(const void* x, int ldx, int K, const float* w, int dg
   p.epi_warps = two ? 4 : 8;
   const size_t smem = 1024 + (size_t)p.SA * p.a_stage + wres + tail;
 
-  const size_t need = 9 * (size_t)J * K * 2;
-  B2U_REQUIRE(ws != nullptr && need <= ws_bytes, "tc_conv3w: workspace too small");
-  {
+  if (wp == nullptr) {                     // no prepacked bank from the caller: pack into the workspace
+    const size_t need = 9 * (size_t)J * K * 2;
+    B2U_REQUIRE(ws != nullptr && need <= ws_bytes, "tc_conv3w: workspace too small");
     const long long total = 9LL * J * K;
     int grid = (int)((total + 255) / 256);
     if (grid > 8 * B2U_NUM_SMS) grid = 8 * B2U_NUM_SMS;
     B2U_LAUNCH(pack3w_kernel, grid, 256, 0, stream, w, (__half*)ws, dgrad, J, K);
+    wp = ws;
   }
   W3Maps maps;
   {
@@ -399,12 +488,14 @@ int b2u_tc_conv3x3_dwmerge(const void* x, int ldx, int K, const float* w, int dg
     cuuint64_t bs[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * NT * 2};
     cuuint32_t bb[3] = {(cuuint32_t)p.KS, (cuuint32_t)NT, 1};
     cuuint32_t be[3] = {1, 1, 1};
-    r = g_encw(&maps.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ws, bd, bs, bb, be, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    r = g_encw(&maps.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(wp), bd, bs, bb, be,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b2u_set_error("tc_conv3w: weight tensor map failed (%d)", (int)r); return B2U_ERR_CUDA; }
   }
   if (!g_attrw) {
-    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define B2U_W3_ATTR(F) B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3w_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+    B2U_W3_ATTR(0); B2U_W3_ATTR(1); B2U_W3_ATTR(2); B2U_W3_ATTR(3); B2U_W3_ATTR(4); B2U_W3_ATTR(6); B2U_W3_ATTR(8); B2U_W3_ATTR(10);
+#undef B2U_W3_ATTR
     g_attrw = true;
   }
   const long long tiles = (long long)n * b2u_cdiv(h, kBH) * b2u_cdiv(wd, kOW);
@@ -412,6 +503,21 @@ int b2u_tc_conv3x3_dwmerge(const void* x, int ldx, int K, const float* w, int dg
   int ctas = B2U_NUM_SMS;
   if (two && tiles >= 4 * B2U_NUM_SMS) ctas = 2 * B2U_NUM_SMS;
   const int grid = (int)(tiles < ctas ? tiles : ctas);
-  B2U_LAUNCH(tc_conv3w_kernel, grid, 64 + 32 * p.epi_warps, smem, stream, maps, p);
+  const int flags = ((mask != nullptr || accumulate) ? kW_MASKACC : 0) | ((stats != nullptr || colsum != nullptr) ? kW_SUMS : 0) |
+                    (p.bits_out != nullptr ? kW_BITS_OUT : 0) | (p.bits_in != nullptr ? kW_BITS_IN : 0);
+  const int nthr = 64 + 32 * p.epi_warps;
+  switch (flags) {
+    case 0: B2U_LAUNCH(tc_conv3w_kernel<0>, grid, nthr, smem, stream, maps, p); break;
+    case 1: B2U_LAUNCH(tc_conv3w_kernel<1>, grid, nthr, smem, stream, maps, p); break;
+    case 2: B2U_LAUNCH(tc_conv3w_kernel<2>, grid, nthr, smem, stream, maps, p); break;
+    case 3: B2U_LAUNCH(tc_conv3w_kernel<3>, grid, nthr, smem, stream, maps, p); break;
+    case 4: B2U_LAUNCH(tc_conv3w_kernel<4>, grid, nthr, smem, stream, maps, p); break;      // forward + bit mask
+    case 6: B2U_LAUNCH(tc_conv3w_kernel<6>, grid, nthr, smem, stream, maps, p); break;      // ... + statistics
+    case 8: B2U_LAUNCH(tc_conv3w_kernel<8>, grid, nthr, smem, stream, maps, p); break;      // data gradient, 1-bit mask
+    case 10: B2U_LAUNCH(tc_conv3w_kernel<10>, grid, nthr, smem, stream, maps, p); break;    // ... + column sums
+    default:
+      b2u_set_error("tc_conv3w: unsupported feature combination %d (1-bit masks do not combine with accumulate / fp16 masks)", flags);
+      return B2U_ERR_ARG;
+  }
   return B2U_OK;
 }

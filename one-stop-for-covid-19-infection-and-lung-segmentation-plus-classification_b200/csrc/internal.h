@@ -5,7 +5,8 @@
 // exact CUDA-core path (conv_direct.cu)
 int b2u_direct_conv3x3(int dt, const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act,
                        void* y, int ldy, int J, double* stats, const void* mask, int ldmask, int mask_act,
-                       int accumulate, int n, int h, int wd, void* stream);
+                       int accumulate, int n, int h, int wd, void* stream, void* relu_bits = nullptr,
+                       int* bits_done = nullptr);     // relu_bits: written in the same pass where the kernel can (*bits_done)
 int b2u_direct_conv3x3_wgrad(int dt, const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw,
                              float* db, int n, int h, int wd, void* stream);
 int b2u_direct_convt_fwd(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, void* y, int ldy,
@@ -60,10 +61,10 @@ int b2u_tc_convt_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy
 int b2u_head_bwd_cs(int dt, const float* prob, const float* target, const double* sums, long long count,
                     const struct b2u_step_state* d_state, const void* x, int ldx, int cin, const float* w, void* dx,
                     int lddx, int x_act, float* dw, float* db, long long npix, float* colsum, void* stream);
-// thin layers (Cout <= 64) with the three dw taps side by side in N (conv_tc3w.cu): NOT yet validated on a GPU,
-// reached only with b2u_set_option("tc_dwmerge", 1)
+// thin layers (Cout <= 64) with the three dw taps side by side in N (conv_tc3w.cu); b2u_set_option("tc_dwmerge", 0|1|2)
 extern int g_b2u_tc_dwmerge;
 int b2u_tc_conv3x3_dwmerge_ok(int K, int J);
 int b2u_tc_conv3x3_dwmerge(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                            int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
-                           int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
+                           int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream,
+                           void* relu_bits_out);

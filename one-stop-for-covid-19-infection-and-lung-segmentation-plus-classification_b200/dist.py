@@ -16,6 +16,45 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def epoch_batches(perm, batch_size, rank=0, world=1):
+    """This rank's mini-batches (index arrays) of one epoch over the permutation `perm` of the whole dataset.
+
+    Every rank must issue the SAME number of steps with the SAME batch sizes (the gradient all-reduce is part of the
+    captured step, so a missing step on one rank deadlocks the others): the permutation -- identical on every rank,
+    they share the shuffle seed -- is padded by wrapping around to a multiple of the world size and dealt out
+    round-robin (rank r takes perm[r::world]), then cut into batches of `batch_size` per rank; the last batch of the
+    epoch is partial on all ranks alike.  world = 1 is the reference's single-device epoch (T1H:1059-1061)."""
+    import numpy as np
+    perm = np.asarray(perm)
+    if world > 1:
+        if not 0 <= rank < world:
+            raise ValueError("rank %d outside world of %d" % (rank, world))
+        pad = (-len(perm)) % world
+        if pad:
+            perm = np.concatenate([perm, perm[:pad]])
+        perm = perm[rank::world]
+    return [perm[lo:lo + batch_size] for lo in range(0, len(perm), batch_size)]
+
+
+def mean_over_ranks(value, world):
+    """mean of a host scalar over the ranks of the default torch.distributed group (training logs of model.fit)"""
+    import torch
+    import torch.distributed as dist
+    if world == 1 or not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t)
+    return float(t.item()) / world
+
+
+def barrier(world):
+    import torch.distributed as dist
+    if world > 1 and dist.is_initialized():
+        dist.barrier()
+
+
 def env_rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 

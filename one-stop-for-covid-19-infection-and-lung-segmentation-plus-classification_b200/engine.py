@@ -112,7 +112,8 @@ class Engine:
             self.adam_v = torch.zeros(npar, dtype=torch.float32, device=dev)
             self.step_dev = torch.zeros(P.STEP_STATE_BYTES, dtype=torch.uint8, device=dev)
             self.ws = torch.empty(int(self.lib.b2u_ws_bytes()), dtype=torch.uint8, device=dev)
-        self.host_state = _lib.StepState(seed=dropout_seed, step=0, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-7,
+        # data parallel: every rank draws its own dropout masks (same counters, rank-specific key)
+        self.host_state = _lib.StepState(seed=dropout_seed + 7919 * self.rank, step=0, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-7,
                                          beta1_pow=0.9, beta2_pow=0.999, loss_scale=1.0,
                                          grad_div=1.0 if self.sync_stats else float(self.world), overflow=0, pad_=0)
         self._arenas = {}        # name -> torch uint8 tensor (grown on demand, shared between plans)

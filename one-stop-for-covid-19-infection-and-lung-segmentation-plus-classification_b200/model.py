@@ -17,6 +17,7 @@ import time
 import numpy as np
 import torch
 
+from . import dist as D
 from . import engine as E
 from . import layers as L
 from . import losses as LS
@@ -256,11 +257,14 @@ class Model:
         self.engine.set_weights(d)
 
     def save_weights(self, path):
+        if self.engine.rank != 0:           # data parallel: replicas are identical, rank 0 owns the file
+            return
         d = self.engine.get_weights()
         with open(path, "wb") as f:
             np.savez(f, **{k.replace("/", "__"): v for k, v in d.items()})
 
     def load_weights(self, path):
+        D.barrier(self.engine.world)        # data parallel: rank 0 may still be writing the file
         with np.load(path) as z:
             self.engine.set_weights({k.replace("__", "/"): z[k] for k in z.files})
 
@@ -475,17 +479,22 @@ class Model:
             for cb in cbs:
                 cb.on_epoch_begin(epoch, logs)
             t0 = time.time()
+            # the shuffle stream is seeded identically on every rank, so all ranks see the same permutation and take
+            # disjoint, equally sized shares of it (dist.epoch_batches): same step count and batch sizes everywhere
             perm = self._shuffle_rng.permutation(n_tot) if shuffle else np.arange(n_tot)
-            starts = list(range(0, n_tot, batch_size))
+            batches = D.epoch_batches(perm, batch_size, rank, world)
             with torch.cuda.stream(eng.stream):
-                perm_d = torch.from_numpy(perm.astype(np.int32)).to(eng.device)
-                lossbuf = torch.zeros(len(starts), 2, dtype=torch.float32, device=eng.device)
+                lossbuf = torch.zeros(len(batches), 2, dtype=torch.float32, device=eng.device)
                 sizes = []
-                for bi, lo in enumerate(starts):
-                    n = min(batch_size, n_tot - lo)
+                lo = 0
+                mine = np.concatenate(batches) if batches else np.zeros(0, np.int64)
+                perm_d = torch.from_numpy(mine.astype(np.int32)).to(eng.device)
+                for bi, idx in enumerate(batches):
+                    n = len(idx)
                     sizes.append(n)
                     b = eng.train_batch(xd, yd, perm_d[lo:lo + n], n, dropout=dropout, sw_src=swd)
                     lossbuf[bi].copy_(eng.loss_dev(b))
+                    lo += n
             eng.stream.synchronize()
             if eng.overflowed():
                 print("warning: non-finite gradients were skipped this epoch (loss scale %g)" % eng._cur_ls)
@@ -495,6 +504,10 @@ class Model:
             logs["loss"] = float((lb[:, 0] * w).sum() / w.sum())
             if "dice_coeff" in metric_names:
                 logs["dice_coeff"] = float((lb[:, 1] * w).sum() / w.sum())
+            if world > 1:                      # epoch means over all ranks (equal sample counts per rank)
+                for k in ("loss", "dice_coeff"):
+                    if k in logs:
+                        logs[k] = D.mean_over_ranks(logs[k], world)
             if validation_data is not None:
                 xv, yv = validation_data[0], validation_data[1]
                 vals = self._run_eval(xv, yv, batch_size, self.metrics)

@@ -130,7 +130,7 @@ class Plan:
 
     def __init__(self, graph, n, dt=F32, training=True, dropout=True, loss="bce_dice", world=1,
                  sync_stats=False, layout=None, rank=0, fuse_bn_bwd=True, fuse_bn_stats=True, fuse_bias_grad=True,
-                 prepack=True, fuse_bn_bwd_wgrad=True, fuse_bn_pool=True, relu_bits=False):
+                 prepack=True, fuse_bn_bwd_wgrad=True, fuse_bn_pool=True, relu_bits=None):
         self.graph, self.n, self.dt, self.training = graph, int(n), dt, training
         self.dropout = dropout and training
         self.loss, self.world, self.sync_stats = loss, int(world), bool(sync_stats) and world > 1
@@ -142,8 +142,10 @@ class Plan:
         self.fuse_bn_pool = bool(fuse_bn_pool)
         # 1-bit ReLU masks: a ReLU conv whose only consumer is another 3x3 conv also writes (y > 0) as packed bits, and
         # that consumer's data gradient reads 1 bit instead of 16 per element (and one word per thread and tile, issued
-        # before the accumulator wait).  Built and emulated in round 1, NOT yet validated on the GPU: off by default.
-        self.relu_bits = bool(relu_bits) and self.training
+        # before the accumulator wait).  Default: on with fp16 storage, where the tensor-core epilogues write / read the
+        # bits in place (measured on B200, U-Net 512^2 batch 8: data gradients 1.30 -> 1.07 ms per step); the exact fp32
+        # path would need an extra pass per tensor, so it keeps the activation tensor as its mask.
+        self.relu_bits = (dt == F16 if relu_bits is None else bool(relu_bits)) and self.training
         self._bits = {}                  # id(tensor) -> Ref of its packed ReLU mask
         self._bias_done = set()          # id(conv layer) whose bias gradient is produced by another backward op
         # fp16 operand copies of the conv kernels: ONE pack launch per step for the whole model (OP_PACK_WEIGHTS)

@@ -28,6 +28,16 @@ class Emulator:
             self.mem.update(extra)
         self.state = dict(seed=0, step=0, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-7, beta1_pow=0.9,
                           beta2_pow=0.999, loss_scale=1.0, grad_div=1.0, overflow=0)
+        # True: conv / transposed-conv kernels whose channel counts the tcgen05 path takes (multiples of 16) are
+        # rounded to fp16 first, as the GPU's packed operand copies are -- the emulator then has the SAME rounding
+        # points as the fp16 engine (fp16 operands, fp32 accumulation, fp16 stores)
+        self.fp16_weights = False
+
+    def _kernel(self, ref, count, cin, cout, dt):
+        w = self.f32(ref, count)
+        if self.fp16_weights and dt == P.F16 and cin % 16 == 0 and cout % 16 == 0:
+            w = w.astype(np.float16).astype(np.float32)
+        return w
 
     # ---- raw access ------------------------------------------------------------------------
     def arr(self, ref, count, dtype):
@@ -84,7 +94,7 @@ class Emulator:
     def op_conv3x3_fwd(self, o):
         ldx, cin, act, ldy, cout, n, h, w = o.i[:8]
         x = self.view(o.p[0], ldx, cin, n * h * w, o.dt).astype(np.float32).reshape(n, h, w, cin)
-        wt = self.f32(o.p[1], 9 * cin * cout).reshape(3, 3, cin, cout)
+        wt = self._kernel(o.p[1], 9 * cin * cout, cin, cout, o.dt).reshape(3, 3, cin, cout)
         b = self.f32(o.p[2], cout)
         y = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(wt.copy()).permute(3, 2, 0, 1),
                      torch.from_numpy(b.copy()), padding=1).permute(0, 2, 3, 1).numpy()
@@ -103,7 +113,7 @@ class Emulator:
     def op_conv3x3_dgrad(self, o):
         lddy, cout, lddx, cin, ldm, mact, acc, n, h, w = o.i[:10]
         dy = self.view(o.p[0], lddy, cout, n * h * w, o.dt).astype(np.float32).reshape(n, h, w, cout)
-        wt = self.f32(o.p[1], 9 * cin * cout).reshape(3, 3, cin, cout)
+        wt = self._kernel(o.p[1], 9 * cin * cout, cin, cout, o.dt).reshape(3, 3, cin, cout)
         wo = torch.from_numpy(wt.copy()).permute(3, 2, 0, 1)           # (cout, cin, 3, 3)
         dx = F.conv_transpose2d(torch.from_numpy(dy).permute(0, 3, 1, 2), wo, padding=1).permute(0, 2, 3, 1).numpy()
         dx = dx.reshape(-1, cin)
@@ -139,7 +149,7 @@ class Emulator:
     def op_convt_fwd(self, o):
         ldx, cin, ldy, cout, n, h, w = o.i[:7]
         x = self.view(o.p[0], ldx, cin, n * h * w, o.dt).astype(np.float32).reshape(n, h, w, cin)
-        wt = self.f32(o.p[1], 4 * cout * cin).reshape(2, 2, cout, cin)
+        wt = self._kernel(o.p[1], 4 * cout * cin, cin, cout, o.dt).reshape(2, 2, cout, cin)
         b = self.f32(o.p[2], cout)
         y = F.conv_transpose2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(wt.copy()).permute(3, 2, 0, 1),
                                torch.from_numpy(b.copy()), stride=2).permute(0, 2, 3, 1).numpy()
@@ -155,7 +165,7 @@ class Emulator:
     def op_convt_dgrad(self, o):
         lddy, cout, lddx, cin, ldm, mact, acc, n, h, w = o.i[:10]
         dy = self.view(o.p[0], lddy, cout, n * 4 * h * w, o.dt).astype(np.float32).reshape(n, 2 * h, 2 * w, cout)
-        wt = self.f32(o.p[1], 4 * cout * cin).reshape(2, 2, cout, cin)
+        wt = self._kernel(o.p[1], 4 * cout * cin, cin, cout, o.dt).reshape(2, 2, cout, cin)
         dx = F.conv2d(torch.from_numpy(dy).permute(0, 3, 1, 2), torch.from_numpy(wt.copy()).permute(3, 2, 0, 1),
                       stride=2).permute(0, 2, 3, 1).numpy().reshape(-1, cin)
         if o.p[3] is not None:

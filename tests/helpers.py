@@ -51,3 +51,16 @@ def grad_errors(got, want, skip_zero_bias=True, norm="max"):
         if d > worst:
             worst, who = d, k
     return worst, who
+
+
+def load_emulator(em, plan, params, x, t):
+    """weights, inputs, targets and unit sample weights into a tests/emulator.py memory image laid out by `plan`"""
+    import emulator as E
+    fp, fs = plan.layout.pack(params)
+    em.f32(P.Ref("params", 0), fp.size)[:] = fp
+    em.f32(P.Ref("state", 0), fs.size)[:] = fs
+    xv = plan.x_view
+    em.view(xv.ref, xv.ld, xv.c, x.shape[0] * xv.h * xv.w, xv.dt)[:] = x.reshape(-1, xv.c).astype(E.NPDT[xv.dt])
+    em.f32(plan.target, t.size)[:] = t.reshape(-1)
+    em.f32(plan.sample_w, x.shape[0])[:] = 1.0
+    return fp, fs

@@ -101,3 +101,26 @@ def test_shard_helpers():
     assert D.shard_range(3, 3, 4) == (3, 3)           # empty shard is legal
     with pytest.raises(ValueError):
         D.shard_range(4, 4, 4)
+
+
+def test_epoch_batches_equal_steps_and_cover_everything():
+    """Model.fit under data parallelism (every rank trained the full set): ranks take disjoint, equally
+    sized shares of the shared permutation -- same number of steps and the same batch sizes on every rank (the
+    gradient all-reduce is part of the step), every sample seen at least once per epoch, at most world-1 repeats."""
+    import importlib
+    from conftest import PKG
+    D = importlib.import_module(PKG + ".dist")
+    rng = np.random.RandomState(0)
+    for n_tot, bs, world in ((11, 8, 1), (11, 8, 2), (1129, 32, 8), (16, 8, 4), (5, 8, 4), (7, 2, 3)):
+        perm = rng.permutation(n_tot)
+        per_rank = [D.epoch_batches(perm, bs, r, world) for r in range(world)]
+        shapes = [[len(b) for b in br] for br in per_rank]
+        assert all(s == shapes[0] for s in shapes), (n_tot, bs, world, shapes)
+        assert all(0 < len(b) <= bs for b in per_rank[0])
+        seen = np.concatenate([np.concatenate(br) for br in per_rank])
+        assert set(seen.tolist()) == set(range(n_tot))
+        assert len(seen) - n_tot == (-n_tot) % world
+        if world == 1:
+            assert [b.tolist() for b in per_rank[0]] == [perm[lo:lo + bs].tolist() for lo in range(0, n_tot, bs)]
+    with pytest.raises(ValueError):
+        D.epoch_batches(np.arange(4), 2, 2, 2)

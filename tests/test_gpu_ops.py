@@ -27,7 +27,10 @@ class Img:
         ref = self.act.alloc(n * h * w * ld * P.ELEM[dt])
         v = P.View(ref + c0 * P.ELEM[dt], ld, c, h, w, dt)
         if fill is not None:
-            full = self.rng.standard_normal((n * h * w, ld)) * scale if fill == "normal" else self.rng.random((n * h * w, ld))
+            if fill == "int":            # small integers: sums of products stay exact in fp32 whatever the order
+                full = self.rng.integers(-3, 4, (n * h * w, ld)).astype(np.float64) * scale
+            else:
+                full = self.rng.standard_normal((n * h * w, ld)) * scale if fill == "normal" else self.rng.random((n * h * w, ld))
             self.init.append((ref, full.astype(NPDT[dt])))
         return v
 
@@ -37,6 +40,8 @@ class Img:
             a = (self.rng.standard_normal(count) * scale).astype(dtype)
         elif fill == "uniform":
             a = self.rng.random(count).astype(dtype)
+        elif fill == "int":              # multiples of `scale` (a power of two): exact in fp16 and in fp32 sums
+            a = (self.rng.integers(-4, 5, count) * scale).astype(dtype)
         elif fill == "pos":
             a = (0.5 + self.rng.random(count)).astype(dtype)
         else:
@@ -97,6 +102,27 @@ def test_conv3x3_fwd(dt, n, h, w, cin, cout):
     for act in (1, 2):
         ops = [P.Op(P.OP_CONV3X3_FWD, dt, [x.ref, wt, b, y.ref, stats], [x.ld, cin, act, y.ld, cout, n, h, w])]
         compare(ops, img, dt, tol=3e-3 if dt == P.F16 else 2e-5)
+
+
+@pytest.mark.parametrize("dt", [P.F32, P.F16])
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 1, 32), (1, 20, 12, 1, 16), (1, 16, 16, 8, 32), (1, 12, 20, 32, 48)])
+def test_conv3x3_relu_bits_generic_paths(dt, n, h, w, cin, cout):
+    """packed 1-bit ReLU masks outside the tensor-core epilogues: written by the Cin = 1 kernel in the same pass
+    (conv2d_1 of every network) or by one extra pass (exact path), applied to a data gradient by one extra pass.
+    Integer data: exact sums, so the bits must equal the emulator's bit for bit."""
+    img = Img(83)
+    x = img.view(n, h, w, cin, dt, ld=cin + (8 if cin % 8 == 0 else 0), fill="int")
+    y = img.view(n, h, w, cout, dt, ld=cout + 16, c0=8, fill=None)
+    wt = img.farr(img.par, 9 * cin * cout, fill="int", scale=0.125)
+    b = img.farr(img.par, cout, fill="int", scale=0.125)
+    bits = img.act.alloc(n * h * w * cout // 8)
+    dy = img.view(n, h, w, 16, dt, fill="int")
+    wt2 = img.farr(img.par, 9 * cout * 16, fill="int", scale=0.125)
+    dx = img.view(n, h, w, cout, dt, fill=None)
+    ops = [P.Op(P.OP_CONV3X3_FWD, dt, [x.ref, wt, b, y.ref, None, None, bits], [x.ld, cin, 1, y.ld, cout, n, h, w]),
+           P.Op(P.OP_CONV3X3_DGRAD, dt, [dy.ref, wt2, dx.ref, bits, None],
+                [dy.ld, 16, dx.ld, cout, cout, P.ACT_RELU_BITS, 0, n, h, w])]
+    compare(ops, img, dt, tol=1e-6)
 
 
 @pytest.mark.parametrize("dt", [P.F32, P.F16])

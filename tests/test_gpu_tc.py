@@ -281,41 +281,43 @@ def test_bn_bwd_sums_from_wgrad(c, cout):
     compare(ops, img, P.F32, tol=1e-5)
 
 
-# ---- 1-bit ReLU masks (planner option relu_bits, B2U_ACT_RELU_BITS): built in round 1 together with the emulator, the
-# ---- kernels have not run on a GPU yet -> enable these when the first GPU session of round 2 has validated them
-RELU_BITS_PENDING = pytest.mark.skip(reason="1-bit ReLU mask kernels: first GPU validation pending (round 2)")
-
-
-@RELU_BITS_PENDING
+# ---- 1-bit ReLU masks (planner option relu_bits, B2U_ACT_RELU_BITS)
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 32, 32, 32), (1, 32, 40, 32, 64), (1, 16, 16, 64, 64), (2, 24, 40, 128, 128),
                                             (1, 16, 16, 256, 512), (1, 56, 56, 16, 16), (1, 16, 16, 32, 80)])
-def test_tc_conv3x3_relu_bits_roundtrip(n, h, w, cin, cout):
+@pytest.mark.parametrize("dwmerge", [0, 1])
+def test_tc_conv3x3_relu_bits_roundtrip(n, h, w, cin, cout, dwmerge):
     """forward writes the packed mask of y > 0 (epilogue variant kF_BITS_OUT), the data gradient of the next conv reads
-    it (kF_BITS_IN) with and without column sums"""
+    it (kF_BITS_IN) with and without column sums.  A mask bit flips with the sign of a near-zero pre-activation, so the
+    inputs are small integers and the weights multiples of 1/8: every partial sum is exact in fp32 in any order and
+    the GPU must reproduce the emulator's bits, outputs and gradients EXACTLY (tolerance 0 up to fp16 storage)."""
+    lib = importlib.import_module(PKG + "._lib").lib()
+    old = lib.b2u_set_option(b"tc_dwmerge", dwmerge)       # 1: thin layers through conv_tc3w.cu (same bits, same sums)
+    try:
+        _relu_bits_roundtrip(n, h, w, cin, cout)
+    finally:
+        lib.b2u_set_option(b"tc_dwmerge", old)
+
+
+def _relu_bits_roundtrip(n, h, w, cin, cout):
     img = Img(81)
-    x = img.view(n, h, w, cin, dt, fill="normal")
+    x = img.view(n, h, w, cin, dt, fill="int")
     y = img.view(n, h, w, cout, dt, ld=cout + 16, c0=8, fill=None)
-    wt = img.farr(img.par, 9 * cin * cout, scale=(2.0 / (9 * cin)) ** 0.5)
-    b = img.farr(img.par, cout, scale=0.1)
+    wt = img.farr(img.par, 9 * cin * cout, fill="int", scale=0.125)
+    b = img.farr(img.par, cout, fill="int", scale=0.125)
     bits = img.act.alloc(n * h * w * cout // 8)
     stats = img.zero.alloc(2 * cout * 8)
-    dy = img.view(n, h, w, cin, dt, scale=0.5)                 # gradient of a following conv's output (cin channels again)
-    wt2 = img.farr(img.par, 9 * cout * cin, scale=(2.0 / (9 * cout)) ** 0.5)
+    dy = img.view(n, h, w, cin, dt, fill="int")                # gradient of a following conv's output (cin channels again)
+    wt2 = img.farr(img.par, 9 * cout * cin, fill="int", scale=0.125)
     dx = img.view(n, h, w, cout, dt, ld=2 * cout, c0=cout, fill=None)
-    db = img.farr(img.gr, cout, scale=0.01)
+    db = img.farr(img.gr, cout, fill="int", scale=1.0)
     for st, cs in ((None, None), (stats, db)):
         ops = [P.Op(P.OP_CONV3X3_FWD, dt, [x.ref, wt, b, y.ref, st, None, bits], [x.ld, cin, 1, y.ld, cout, n, h, w]),
                P.Op(P.OP_CONV3X3_DGRAD, dt, [dy.ref, wt2, dx.ref, bits, cs],
                     [dy.ld, cin, dx.ld, cout, cout, P.ACT_RELU_BITS, 0, n, h, w])]
-        compare(ops, img, dt, tol=4e-3)
+        compare(ops, img, dt, tol=1e-6)
 
 
-# ---- dw-merged thin-layer kernel (conv_tc3w.cu, b2u_set_option("tc_dwmerge", 1)): written after the round-1 GPU budget
-# ---- was spent -> these run it against the emulator once a GPU is available again
-DWMERGE_PENDING = pytest.mark.skip(reason="conv_tc3w.cu (dw taps merged into N): first GPU validation pending (round 2)")
-
-
-@DWMERGE_PENDING
+# ---- dw-merged thin-layer kernel (conv_tc3w.cu, b2u_set_option("tc_dwmerge", 1))
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 32, 32, 32), (1, 24, 40, 64, 32), (1, 16, 30, 64, 64), (1, 56, 56, 16, 16),
                                             (1, 8, 14, 32, 48), (2, 64, 64, 32, 64), (4, 128, 128, 32, 32)])
 def test_tc_conv3x3_dwmerge_fwd_and_dgrad(n, h, w, cin, cout):

@@ -136,10 +136,11 @@ def test_every_fusion_can_be_switched_off(flags):
 
 
 def test_relu_bits_plan_structure():
-    """relu_bits=True (built in round 1, GPU validation pending, off by default): the nine `a` convs of the U-Net write a
-    packed ReLU mask and the data gradients of the nine `b` convs read it; the default plan is unchanged"""
-    on = P.Plan(G.unet(32, 1), 2, dt=P.F16, training=True, relu_bits=True)
-    off = P.Plan(G.unet(32, 1), 2, dt=P.F16, training=True)
+    """relu_bits (default with fp16 storage, off in the exact fp32 mode): the nine `a` convs of the U-Net write a
+    packed ReLU mask and the data gradients of the nine `b` convs read it"""
+    on = P.Plan(G.unet(32, 1), 2, dt=P.F16, training=True)
+    off = P.Plan(G.unet(32, 1), 2, dt=P.F16, training=True, relu_bits=False)
+    assert not P.Plan(G.unet(32, 1), 2, dt=P.F32, training=True).relu_bits and not P.Plan(G.unet(32, 1), 2, dt=P.F16, training=False).relu_bits
     assert sum(1 for o in on.fwd if o.kind == P.OP_CONV3X3_FWD and len(o.p) > 6 and o.p[6] is not None) == 9
     assert sum(1 for o in on.bwd if o.kind == P.OP_CONV3X3_DGRAD and o.i[5] == P.ACT_RELU_BITS) == 9
     assert all(o.p[6] is None for o in off.fwd if o.kind == P.OP_CONV3X3_FWD)

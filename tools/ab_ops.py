@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--opt", default="")
     ap.add_argument("--kinds", default="")
     ap.add_argument("--workload", default="unet512")
+    ap.add_argument("--plan", default="", help="planner options, e.g. relu_bits=1,fuse_bn_pool=0")
     args = ap.parse_args()
     name, vals = (args.opt.split("=") + [""])[:2] if args.opt else ("", "")
     vals = [int(v) for v in vals.split(",")] if vals else [None]
@@ -32,7 +33,9 @@ def main():
     S = importlib.import_module(PKG + ".synthetic")
     graph, size, batch = WL[args.workload]
     torch.cuda.set_device(0)
-    eng = E.Engine(G.GRAPHS[graph](size, 1), precision="float16", use_graph=False, dropout_seed=7)
+    plan_options = {k: bool(int(v)) for k, v in (kv.split("=") for kv in args.plan.split(",") if kv)}
+    eng = E.Engine(G.GRAPHS[graph](size, 1), precision="float16", use_graph=False, dropout_seed=7,
+                   plan_options=plan_options)
     x, t = S.make_slices(batch, size, seed=1234)
     xd = torch.from_numpy(x).cuda()
     td = torch.from_numpy(t.reshape(batch, -1)).cuda()
