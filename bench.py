@@ -39,6 +39,10 @@ WORKLOADS = {
                     name="Task-3 lung U-Net 256x256x1 train step, batch 32 per GPU (BASELINE configs[2])"),
     "unetpp512": dict(graph="unetpp", size=512, batch=4, flop=418306326528, metric="CT-slices/sec U-Net++ 512x512 train step",
                       name="Task-1 U-Net++ 512x512x1 train step, batch 4 per GPU (BASELINE configs[3])"),
+    # inference workload (forward only, BN moving statistics, no dropout): handled by run_classifier()
+    "classifier224x3": dict(graph="classifier", size=224, batch=64, flop=971407424, cin=3,
+                            metric="CT-slices/sec Task-2 classifier 224x224x3 inference",
+                            name="Task-2 classifier 224x224x3 inference, batch 64 per GPU (BASELINE configs[4])"),
 }
 
 
@@ -101,6 +105,7 @@ def cpu_port_rate(steps, warmup, budget_s, batch):
     params, _ = K.init_params(GRAPH, (SIZE, SIZE, 1), seed=42)
     opt = K.Adam(lr=5e-4)
     times = []
+    extrapolated = 0
     t_begin = time.perf_counter()
     for s in range(warmup + steps):
         t0 = time.perf_counter()
@@ -110,11 +115,14 @@ def cpu_port_rate(steps, warmup, budget_s, batch):
             times.append(dt)
         if time.perf_counter() - t_begin > budget_s and len(times) >= 1 and s < warmup + steps - 1:
             # keep the run bounded: extrapolate the remaining (identical) steps from the measured ones
+            extrapolated = len(times)
             times += [sum(times) / len(times)] * (warmup + steps - 1 - s)
             break
     total = sum(times)
+    measured = len([1 for _ in times]) if not extrapolated else extrapolated
     sample = ("%d of the %d slices per step at %dx%d, fp32 torch-CPU restatement of the Keras path "
-              "(Keras/TF unavailable offline), %d threads, %d measured step(s)" % (batch, BATCH, SIZE, SIZE, cores, len(times)))
+              "(Keras/TF unavailable offline), %d threads, %d measured step(s)%s"
+              % (batch, BATCH, SIZE, SIZE, cores, measured, " (the rest extrapolated: time budget)" if extrapolated else ""))
     return batch * len(times) / total, cores, sample, 1000.0 * total / len(times)
 
 
@@ -122,17 +130,207 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 1 if args.steps * 1 > 8 else 2
-    rate, cores, sample, ms = cpu_port_rate(args.steps, min(args.warmup, 1), budget_s=200.0, batch=batch)
+    if args.workload == "classifier224x3":
+        return run_reference_classifier(args)
+    # the SAME step as the engine arm: the full batch (8 slices at 512x512) per step.  A step takes ~10 s on 16 host
+    # cores, so the run is bounded by a time budget: once it is spent the remaining (identical) steps are extrapolated
+    # from the measured ones (the count of really measured steps is part of `sample`)
+    batch = BATCH
+    rate, cores, sample, ms = cpu_port_rate(args.steps, min(args.warmup, 1), budget_s=150.0, batch=batch)
     line = {"metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "Task-1 U-Net 512x512x1 train step (reference CPU path, oracle port)",
-                       "slices_per_step": batch},
+            "config": {"workload": WORKLOADS[args.workload]["name"], "global_batch": batch, "slices_per_step": batch,
+                       "implementation": "reference CPU path: torch-CPU restatement of the Keras graph (oracle port; "
+                                         "Keras/TF are not installable offline)"},
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def _classifier_data(n, size, cin, seed):
+    """smooth synthetic slices with a class-conditional texture, gray replicated to `cin` channels,
+    labels Bernoulli(0.765)"""
+    import numpy as np
+    S = importlib.import_module(PKG + ".synthetic")
+    x1, y = S.make_slices(n, size, seed=seed, task="class")
+    return np.ascontiguousarray(np.repeat(x1, cin, axis=3), dtype=np.float32), y.astype(np.float32)
+
+
+def run_reference_classifier(args):
+    """reference arm of the classifier workload: the oracle port's inference forward on the host cores"""
+    import numpy as np
+    import torch
+    from oracle import keras_ref as K
+    wl = WORKLOADS["classifier224x3"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x, _ = _classifier_data(wl["batch"], wl["size"], wl["cin"], 1234)
+    params, _ = K.init_params("classifier", (wl["size"], wl["size"], wl["cin"]), seed=42)
+    times = []
+    for s in range(min(args.warmup, 2) + args.steps):
+        t0 = time.perf_counter()
+        K.forward("classifier", params, x, training=False, dtype=torch.float32)
+        if s >= min(args.warmup, 2):
+            times.append(time.perf_counter() - t0)
+    rate = wl["batch"] * len(times) / sum(times)
+    sample = "%d-image batches at %dx%dx%d, fp32 torch-CPU restatement of the Keras path, %d threads, %d measured steps" % (
+        wl["batch"], wl["size"], wl["size"], wl["cin"], cores, len(times))
+    print(json.dumps({"metric": wl["metric"], "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times), "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+                      "config": {"workload": wl["name"], "global_batch": wl["batch"]},
+                      "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
+
+
+def run_classifier(args):
+    """BASELINE configs[4]: Task-2 classifier, 224x224x3, batch 64, INFERENCE (model.predict, T2:919), slices/s, plus the
+    AUROC of the engine's probabilities against the oracle's on synthetic labels.  HBM-bound: the roofline is
+    the layer-boundary byte count of the forward over the measured HBM bandwidth."""
+    import numpy as np
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    G = importlib.import_module(PKG + ".graphs")
+    M = importlib.import_module(PKG + ".model")
+    P = importlib.import_module(PKG + ".plan")
+    wl = WORKLOADS["classifier224x3"]
+    size, batch, cin = wl["size"], wl["batch"], wl["cin"]
+    if world > 1:                       # inference shards over images with no exchange step: independent replicas
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = load_peaks()
+    for kv in args.opt:
+        k, v = kv.split("=")
+        importlib.import_module(PKG + "._lib").lib().b2u_set_option(k.encode(), int(v))
+    model = M.Model(graph=G.classifier(size, cin), precision=args.precision, use_graph=not args.no_graph, seed=42)
+    model.compile(loss='binary_crossentropy', optimizer=M.Adam(lr=0.0005), metrics=[])
+    eng = model.engine
+    nres = 4 * batch
+    x, y = _classifier_data(nres, size, cin, 1234 + rank)
+    with torch.cuda.stream(eng.stream):
+        xd = torch.from_numpy(x).to(eng.device)
+        idx = [torch.arange(k * batch, (k + 1) * batch, dtype=torch.int32, device=eng.device) for k in range(4)]
+    eng.stream.synchronize()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def maxms(ms):
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda")
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            return float(tt.item())
+        return ms
+
+    lib = eng.lib
+    sampler = ClockSampler(local)
+    sampler.start()
+    for s in range(args.warmup):
+        eng.forward_batch(xd, idx[s % 4], batch)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(eng.stream)
+    for s in range(args.steps):
+        b = eng.forward_batch(xd, idx[s % 4], batch)
+    ev1.record(eng.stream)
+    barrier()
+    ms_total = maxms(ev0.elapsed_time(ev1))
+    value = world * batch * args.steps / (ms_total / 1000.0)
+    l1 = lib.b2u_launch_count()
+    eng.use_graph = False
+    eng.forward_batch(xd, idx[0], batch)
+    eng.stream.synchronize()
+    launches = (lib.b2u_launch_count() - l1) * args.steps
+    eng.use_graph = not args.no_graph
+    # ---- end to end: model.predict on a pinned HOST batch, probabilities back on the host, every step ----
+    xh = [torch.from_numpy(x[k * batch:(k + 1) * batch]).pin_memory() for k in range(4)]
+    for s in range(3):
+        model.predict(xh[s % 4], batch_size=batch)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        pr = model.predict(xh[s % 4], batch_size=batch)
+    torch.cuda.synchronize()
+    e2e_ms = maxms((time.perf_counter() - t0) * 1000.0)
+    clocks = sampler.finish()
+    e2e_value = world * batch * args.steps / (e2e_ms / 1000.0)
+    # ---- roofline: layer-boundary bytes of the forward (each op reads its input and writes its output once) ----
+    bplan = eng._get_bound(batch, False, False)
+    prof_ms, by = {}, 0
+    arr, cnt = eng._ops(bplan, "forward")
+    import ctypes as C
+    msb = (C.c_float * cnt)()
+    for rep in range(3):
+        importlib.import_module(PKG + "._lib").check(lib.b2u_run_ops_timed(arr, cnt, C.c_void_p(eng.ws.data_ptr()), eng.ws.numel(), None,
+                                                                          C.c_void_p(eng.stream.cuda_stream), msb), "run_ops_timed")
+    ops = bplan.plan.forward_ops()
+    es = 2 if args.precision == "float16" else 4
+    for op, ms in zip(ops, msb):
+        nm = P.OP_NAMES[op.kind][3:].lower()
+        prof_ms[nm] = prof_ms.get(nm, 0.0) + float(ms)
+        i = op.i
+        if op.kind == P.OP_CONV3X3_FWD:
+            by += i[5] * i[6] * i[7] * (i[1] + i[4]) * es
+        elif op.kind == P.OP_BN_APPLY:
+            by += 2 * i[3] * i[2] * es
+        elif op.kind == P.OP_MAXPOOL_FWD:
+            by += i[3] * i[4] * i[5] * i[2] * es * 5 // 4
+        elif op.kind == P.OP_BN_APPLY_POOL:
+            by += i[5] * i[6] * i[7] * i[2] * es * 9 // 4
+        elif op.kind == P.OP_DENSE_FWD:
+            by += i[3] * i[0] * es + i[0] * i[2] * 4
+    step_ms = ms_total / args.steps
+    ach = by / (step_ms / 1000.0) / 1e9
+    # ---- AUROC against the oracle on synthetic labels (T2:919-926), same weights, a bounded sample ----
+    auroc = None
+    if rank == 0 and not args.no_cpu:
+        from sklearn.metrics import roc_auc_score
+        from oracle import keras_ref as K
+        ns = 128
+        t0 = time.perf_counter()
+        want, _ = K.forward("classifier", model.get_weights_dict(), x[:ns], training=False, dtype=torch.float32)
+        cpu_s = time.perf_counter() - t0
+        got = model.predict(x[:ns], batch_size=batch)
+        yy = y[:ns].ravel()
+        auroc = {"engine": float(roc_auc_score(yy, got.ravel())), "oracle": float(roc_auc_score(yy, want.ravel())),
+                 "max_abs_prob_diff": float(np.abs(got - want).max()), "images": ns,
+                 "note": "random-init weights (no dataset offline): the two AUROCs must agree, their level is arbitrary"}
+        cores = os.cpu_count() or 1
+        cpu = {"value": ns / cpu_s, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d images at %dx%dx%d, one forward of the fp32 torch-CPU restatement, %d threads" % (ns, size, size, cin, cores)}
+    else:
+        cpu = None
+    if rank == 0:
+        print(json.dumps({
+            "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16" if args.precision == "float16" else "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "global_batch": batch * world, "parallelism": "replicas%d" % world,
+                       "l2": "4 resident batches of 38.5 MB (fp32 inputs) cycle through; activations of one batch (~1 GB) exceed the 126 MB L2",
+                       "cuda_graph": not args.no_graph, "fwd_flop_per_slice": wl["flop"],
+                       "baseline_md_roofline_slices_per_s": 270000},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(xh[0].numel() * 4), "d2h_bytes_per_step": batch * 4,
+                    "ms_per_step": e2e_ms / args.steps, "api": "Model.predict(pinned host batch) -> host probabilities"},
+            "roofline": {"bound": "hbm", "kernel": "whole forward (every kernel is HBM-bound: SURVEY 8d)", "achieved": ach,
+                         "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
+                         "algorithmic_bytes_per_step": by, "peak_source": peaks["src"]},
+            "cpu_baseline": cpu, "auroc_vs_oracle": auroc,
+            "op_breakdown_ms": {k: round(v, 4) for k, v in sorted(prof_ms.items(), key=lambda kv: -kv[1])}}))
+    if world > 1:
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -317,16 +515,26 @@ def run_engine(args):
             d[1] += 1
             d[2] += conv_flops(op, P)
         step_ms = sum(ms for _, ms in prof)
-        tc_names = ("conv3x3_fwd", "conv3x3_dgrad") if precision == "float16" else ()
-        tc_ms = sum(kinds[k][0] for k in tc_names if k in kinds)
-        tc_fl = sum(kinds[k][2] for k in tc_names if k in kinds)
-        tc_n = sum(kinds[k][1] for k in tc_names if k in kinds)
-        tc_by = sum(conv_bytes(op, P) for op, _ in prof)
+
+        def is_tc(op):
+            """launches of the tcgen05 3x3 kernels (tc_conv3_kernel / tc_conv3w_kernel): forward + data gradient ops
+            whose channel counts the tensor path takes; conv2d_1 (Cin = 1) runs the CUDA-core kernel and is NOT counted"""
+            if precision != "float16" or op.kind not in (P.OP_CONV3X3_FWD, P.OP_CONV3X3_DGRAD):
+                return False
+            return op.i[1] % 16 == 0 and (op.i[4] if op.kind == P.OP_CONV3X3_FWD else op.i[3]) % 16 == 0
+
+        tc_ops = [(op, ms) for op, ms in prof if is_tc(op)]
+        tc_ms = sum(ms for _, ms in tc_ops)
+        tc_fl = sum(conv_flops(op, P) for op, _ in tc_ops)
+        tc_n = len(tc_ops)
+        tc_by = sum(conv_bytes(op, P) for op, _ in tc_ops)
         if tc_ms > 0:
             ach = tc_fl / (tc_ms / 1000.0) / 1e12
-            traffic, tsrc = ncu_traffic("tc_conv3_kernel")
-            roof = {"bound": "tensor", "kernel": "tc_conv3_kernel (3x3 conv forward + data gradient, tcgen05 halo-tile)",
+            traffic, tsrc = ncu_traffic("tc_conv3")
+            roof = {"bound": "tensor", "kernel": "tc_conv3_kernel / tc_conv3w_kernel (3x3 conv forward + data gradient, tcgen05 "
+                                                 "halo-tile and dw-merged thin-layer variants)",
                     "achieved": ach, "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sus"],
+                    "frac_of_burst_peak": ach / peaks["tf_burst"],
                     "traffic": traffic, "traffic_source": tsrc,
                     "launches_per_step": tc_n, "avg_launch_ms": tc_ms / max(tc_n, 1), "share_of_step": tc_ms / step_ms,
                     "flop_per_launch": tc_fl / max(tc_n, 1), "algorithmic_bytes_per_launch": tc_by / max(tc_n, 1),
@@ -352,7 +560,7 @@ def run_engine(args):
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rate, cores, sample, _ = cpu_port_rate(1, 1, budget_s=120.0, batch=2)
+        rate, cores, sample, _ = cpu_port_rate(1, 1, budget_s=120.0, batch=BATCH)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
@@ -409,6 +617,8 @@ def main():
     METRIC, SIZE, BATCH, TRAIN_FLOP_PER_SLICE, GRAPH = wl["metric"], wl["size"], wl["batch"], wl["flop"], wl["graph"]
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "classifier224x3":
+        run_classifier(args)
     else:
         run_engine(args)
 

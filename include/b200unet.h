@@ -238,6 +238,7 @@ enum {
 /* executor flags, OR-ed into b2u_op.dt above the storage type (dt & 0xff): */
 #define B2U_OPF_SIDE 0x100 /* may run on the executor's side stream (forked / joined with events; weight gradients) */
 #define B2U_OPF_JOIN 0x200 /* reads what earlier B2U_OPF_SIDE ops wrote: wait for the side stream first            */
+#define B2U_OPF_COMM 0x400 /* gradient-bucket all-reduce: ALWAYS on the side stream (overlaps the rest of the backward) */
 typedef struct b2u_op {
   int32_t kind;
   int32_t dt;

@@ -38,6 +38,7 @@ extern "C" int b2u_tensor_path_available(void) {
 }
 
 extern int g_b2u_side_stream;
+extern int g_b2u_comm_overlap;
 static int side_init();
 extern "C" int b2u_set_option(const char* name, int value) {
   if (name == nullptr) return -1;
@@ -56,6 +57,11 @@ extern "C" int b2u_set_option(const char* name, int value) {
     g_b2u_tc_dwmerge = value;
     return old;
   }
+  if (strcmp(name, "tc_dw_epi8") == 0) {
+    int old = g_b2u_tc_dw_epi8;
+    g_b2u_tc_dw_epi8 = value ? 1 : 0;
+    return old;
+  }
   if (strcmp(name, "tc_2sm_max_j") == 0) {
     int old = g_b2u_tc_2sm_max_j;
     g_b2u_tc_2sm_max_j = value;
@@ -70,6 +76,12 @@ extern "C" int b2u_set_option(const char* name, int value) {
     int old = g_b2u_side_stream;
     if (value && side_init() != B2U_OK) return -1;        // create the stream / events outside any stream capture
     g_b2u_side_stream = value ? 1 : 0;
+    return old;
+  }
+  if (strcmp(name, "comm_overlap") == 0) {
+    int old = g_b2u_comm_overlap;
+    if (value && side_init() != B2U_OK) return -1;
+    g_b2u_comm_overlap = value ? 1 : 0;
     return old;
   }
   if (strcmp(name, "wgrad_halo") == 0) {
@@ -112,7 +124,7 @@ extern "C" int b2u_debug_read(long long* h_out, int count) {
 static bool use_dwmerge(int K, int J, int h, int wd) {
   if (g_b2u_tc_dwmerge == 0 || !b2u_tc_conv3x3_dwmerge_ok(K, J)) return false;
   if (g_b2u_tc_dwmerge == 1) return true;
-  return K >= 128 && J == 64 && (long long)h * wd >= 128 * 128;
+  return K >= 128 && (long long)h * wd >= 128 * 128;
 }
 
 // `relu_bits` (optional, op lists only): packed 1-bit mask of y > 0, written by the halo kernel's epilogue or, on the
@@ -308,7 +320,7 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
                              (const b2u_step_state*)p[3], p[4], I(1), I(2), (const float*)p[5], p[6], I(3), I(4),
                              (float*)p[7], (float*)p[8], i[5], (float*)p[9], s);
     case B2U_OP_DENSE_FWD:
-      return b2u_dense_fwd(dt, p[0], I(0), (const float*)p[1], (const float*)p[2], I(1), p[3], I(2), I(3), s);
+      return b2u_dense_fwd_ws(dt, p[0], I(0), (const float*)p[1], (const float*)p[2], I(1), p[3], I(2), I(3), ws, wsb, s);
     case B2U_OP_DENSE_BWD:
       return b2u_dense_bwd(dt, p[0], I(0), (const float*)p[1], p[2], I(1), p[3], p[4], p[5], I(2), (float*)p[6],
                            (float*)p[7], I(3), I(4), s);
@@ -351,6 +363,10 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
 // list, wait for everything issued there.  Works unchanged under stream capture (the side stream joins the capture
 // through the fork event and is joined back before the list ends).
 int g_b2u_side_stream = 0;             // b2u_set_option("side_stream", 0/1); side_init() runs when it is enabled
+// ops flagged B2U_OPF_COMM (the planner's gradient-bucket all-reduces) are forked to the same side stream: a bucket's
+// exchange over NVLink runs while the main stream computes the gradients of the layers below it
+// (b2u_set_option("comm_overlap", 0) serialises them on the main stream for A/B runs)
+int g_b2u_comm_overlap = 1;
 static cudaStream_t g_side = nullptr;
 static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
 
@@ -369,7 +385,7 @@ extern "C" int b2u_run_ops(const b2u_op* h_ops, int n_ops, void* ws, size_t ws_b
   int rc = B2U_OK;
   for (int k = 0; k < n_ops && rc == B2U_OK; ++k) {
     const int flags = h_ops[k].dt >> 8;
-    if (g_b2u_side_stream && (flags & (B2U_OPF_SIDE >> 8))) {
+    if ((g_b2u_side_stream && (flags & (B2U_OPF_SIDE >> 8))) || (g_b2u_comm_overlap && (flags & (B2U_OPF_COMM >> 8)))) {
       rc = side_init();
       if (rc != B2U_OK) break;
       B2U_CHECK_CUDA(cudaEventRecord(g_ev_fork, main_s));

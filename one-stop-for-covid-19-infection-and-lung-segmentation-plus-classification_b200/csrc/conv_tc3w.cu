@@ -50,6 +50,7 @@ struct W3Params {
   float* colsum;          // per-channel sums of the stored values (fp32 atomics)
   uint8_t* bits_out;      // kW_BITS_OUT: packed 1-bit ReLU mask of the values stored (bit pix*J + column)
   const uint8_t* bits_in; // kW_BITS_IN : packed 1-bit ReLU mask applied to the values written (data gradient)
+  long long* dbg;         // optional timeline buffer (CTA 0): [iter][8] clock64 stamps (b2u_set_option("tc_debug", 1))
 };
 
 struct W3Maps {
@@ -78,8 +79,9 @@ __device__ __forceinline__ float transpose_reduce16w(float v[16], int lane) {
 // bit 1 = BatchNorm statistics and/or column sums, bit 2 = write a 1-bit ReLU mask, bit 3 = read one
 constexpr int kW_MASKACC = 1, kW_SUMS = 2, kW_BITS_OUT = 4, kW_BITS_IN = 8;
 
+// variants without register statistics are capped at 102 registers: two CTAs of 320 threads then share an SM
 template <int kFlags>
-__global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_constant__ W3Maps maps,
+__global__ void __launch_bounds__(kThreadsW3, (kFlags & 2) ? 1 : 2) tc_conv3w_kernel(const __grid_constant__ W3Maps maps,
                                                                    const __grid_constant__ W3Params prm) {
   constexpr bool kMaskAcc = (kFlags & kW_MASKACC) != 0, kSums = (kFlags & kW_SUMS) != 0;
   B2U_PDL_LAUNCH_DEPENDENTS();
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_c
         const int th = (int)(r % (unsigned)tiles_h), n = (int)(r / (unsigned)tiles_h);
         for (int ks = 0; ks < kslabs; ++ks) {
           tc::mbar_wait(&a_empty[sa], pa ^ 1);
+          if (prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64) prm.dbg[(tile / gridDim.x) * 8 + 0] = clock64();
           tc::mbar_expect_tx(&a_full[sa], a_tx);
           // out-of-image rows / columns are zero-filled by TMA = the conv padding
           tc::tma_load_4d(a_ring + (size_t)sa * prm.a_stage, &maps.a, &a_full[sa], ks * KS, tw * kOW - 1, th * kBH - 1, n);
@@ -166,10 +169,13 @@ __global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_c
     for (unsigned tile = blockIdx.x; tile < (unsigned)ntiles; tile += gridDim.x) {
       tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc::fence_after_sync();
+      const bool dbg_on = prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64;
+      if (dbg_on && lane == 0) prm.dbg[(tile / gridDim.x) * 8 + 2] = clock64();
       const uint32_t d_tmem = tmem_base + acc * NT;
       for (int ks = 0; ks < kslabs; ++ks) {
         tc::mbar_wait(&a_full[sa], pa);
         tc::fence_after_sync();
+        if (dbg_on && ks == 0 && lane == 0) prm.dbg[(tile / gridDim.x) * 8 + 3] = clock64();
         const uint32_t a_lo = a_ring_lo + (uint32_t)sa * a_stage16;
 #pragma unroll
         for (int dh = 0; dh < 3; ++dh) {
@@ -185,6 +191,7 @@ __global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_c
         if (++sa == SA) { sa = 0; pa ^= 1; }
       }
       tc::mma_commit_elect(&tfull[acc]);
+      if (dbg_on && lane == 0) prm.dbg[(tile / gridDim.x) * 8 + 4] = clock64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
@@ -210,10 +217,15 @@ __global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_c
     for (int i = 0; i < kRS; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
     int acc = 0;
     uint32_t acc_phase = 0;
+    // tile coordinates advance incrementally (gridDim.x = d2 * tiles_h * tiles_w + d1 * tiles_w + d0): the three
+    // integer divisions per tile were a fifth of this warp's stall samples (ncu source view, round 2)
+    const int d0 = (int)(gridDim.x % (unsigned)tiles_w);
+    const int d1 = (int)((gridDim.x / (unsigned)tiles_w) % (unsigned)tiles_h);
+    const int d2 = (int)(gridDim.x / (unsigned)(tiles_w * tiles_h));
+    int tw = (int)(blockIdx.x % (unsigned)tiles_w);
+    int th = (int)((blockIdx.x / (unsigned)tiles_w) % (unsigned)tiles_h);
+    int n = (int)(blockIdx.x / (unsigned)(tiles_w * tiles_h));
     for (unsigned tile = blockIdx.x; tile < (unsigned)ntiles; tile += gridDim.x) {
-      const int tw = (int)(tile % (unsigned)tiles_w);
-      const unsigned rr = tile / (unsigned)tiles_w;
-      const int th = (int)(rr % (unsigned)tiles_h), n = (int)(rr / (unsigned)tiles_h);
       const int h = th * kBH + r, w = tw * kOW + cp;
       const bool valid = cp < kOW && h < prm.H && w < prm.W;
       const long long pix = ((long long)n * prm.H + (h < prm.H ? h : 0)) * prm.W + (w < prm.W ? w : 0);
@@ -235,6 +247,8 @@ __global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_c
       }
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::fence_after_sync();
+      const bool dbg_e = prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64 && threadIdx.x == 64;
+      if (dbg_e) prm.dbg[(tile / gridDim.x) * 8 + 5] = clock64();
       if (has_cols) {
 #pragma unroll 1
         for (int cc = 0; cc < ccols; cc += 16) {
@@ -248,6 +262,7 @@ __global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_c
           tc::reg_fence16(a0);
           tc::reg_fence16(a1);
           tc::reg_fence16(a2);
+          if (dbg_e && cc == 0) prm.dbg[(tile / gridDim.x) * 8 + 7] = clock64();
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i)
@@ -331,10 +346,16 @@ __global__ void __launch_bounds__(kThreadsW3, 1) tc_conv3w_kernel(const __grid_c
           }
         }
       }
+      if (dbg_e) prm.dbg[(tile / gridDim.x) * 8 + 6] = clock64();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      tw += d0;
+      th += d1;
+      n += d2;
+      if (tw >= tiles_w) { tw -= tiles_w; ++th; }
+      if (th >= tiles_h) { th -= tiles_h; ++n; }
     }
     if (reg_stats && has_cols) {
       for (int cc = 0; cc < ccols; cc += 16) {
@@ -413,7 +434,8 @@ int get_encw() {
 }  // namespace
 
 // 0: never, 1: every layer the kernel takes (A/B runs), 2: the layers where it measured faster than the halo kernel
-int g_b2u_tc_dwmerge = 0;
+int g_b2u_tc_dwmerge = 2;
+int g_b2u_tc_dw_epi8 = 1;      // 8 epilogue warps also in the two-CTAs-per-SM configuration (variants without statistics)
 
 // shapes this kernel takes: resident weights and the A ring must fit shared memory
 int b2u_tc_conv3x3_dwmerge_ok(int K, int J) {
@@ -441,6 +463,7 @@ int b2u_tc_conv3x3_dwmerge(const void* x, int ldx, int K, const float* w, int dg
   p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate;
   p.stats = stats; p.colsum = colsum;
   p.bits_out = (uint8_t*)relu_bits_out;
+  p.dbg = g_b2u_dbg;
   if (mask != nullptr && mask_act == B2U_ACT_RELU_BITS) {          // packed 1-bit mask instead of the activation tensor
     p.bits_in = (const uint8_t*)mask;
     p.mask = nullptr;
@@ -460,7 +483,11 @@ int b2u_tc_conv3x3_dwmerge(const void* x, int ldx, int K, const float* w, int dg
   p.SA = (int)((cap - 1024 - wres - tail) / p.a_stage);
   if (p.SA > kMaxSAw) p.SA = kMaxSAw;
   B2U_REQUIRE(p.SA >= 2, "tc_conv3w: tiles do not fit shared memory (K=%d J=%d)", K, J);
-  p.epi_warps = two ? 4 : 8;
+  // two CTAs per SM: 4 epilogue warps each -- or 8 for the variants without register statistics (96 registers:
+  // 2 x 320 threads fit the register file), whose epilogue is bound by the latency of its shuffles (ncu: the FADDs
+  // behind the SHFLs hold most stall samples), so twice the warps hide twice the latency
+  const bool has_sums = stats != nullptr || colsum != nullptr;
+  p.epi_warps = (two && !(g_b2u_tc_dw_epi8 && !has_sums)) ? 4 : 8;
   const size_t smem = 1024 + (size_t)p.SA * p.a_stage + wres + tail;
 
   if (wp == nullptr) {                     // no prepacked bank from the caller: pack into the workspace

@@ -63,8 +63,11 @@ int b2u_head_bwd_cs(int dt, const float* prob, const float* target, const double
                     int lddx, int x_act, float* dw, float* db, long long npix, float* colsum, void* stream);
 // thin layers (Cout <= 64) with the three dw taps side by side in N (conv_tc3w.cu); b2u_set_option("tc_dwmerge", 0|1|2)
 extern int g_b2u_tc_dwmerge;
+extern int g_b2u_tc_dw_epi8;
 int b2u_tc_conv3x3_dwmerge_ok(int K, int J);
 int b2u_tc_conv3x3_dwmerge(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                            int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
                            int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream,
                            void* relu_bits_out);
+int b2u_dense_fwd_ws(int dt, const void* x, int k, const float* w, const float* bias, int act, void* y, int m, int n,
+                     void* ws, size_t ws_bytes, void* stream);

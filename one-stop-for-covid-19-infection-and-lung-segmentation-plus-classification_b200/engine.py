@@ -121,6 +121,12 @@ class Engine:
         self._push_state()
         self.set_weights(init_weights(graph, seed))
         if self.comm is not None:
+            # the gradient-bucket all-reduces run on the executor's side stream: create it now (not inside a capture)
+            was = self.lib.b2u_set_option(b"comm_overlap", 1)
+            if was < 0:
+                raise _lib.B2UError("cannot create the communication stream: " + self.lib.b2u_last_error().decode())
+            if was == 0:                 # switched off by the caller (A/B runs): keep it off, the stream exists now
+                self.lib.b2u_set_option(b"comm_overlap", 0)
             self.broadcast_weights()
             # NCCL connects its transports lazily at the first collective; that must not happen inside a CUDA
             # graph capture, so run one eager all-reduce of the real gradient buffer (zeros) now

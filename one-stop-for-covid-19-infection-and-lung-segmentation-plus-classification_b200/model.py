@@ -270,13 +270,17 @@ class Model:
 
     # ---- data --------------------------------------------------------------------------------
     def _to_dev(self, a, flat_out=False):
-        a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
         eng = self.engine
+        if isinstance(a, torch.Tensor):           # e.g. a pinned host batch: asynchronous copy on the engine's stream
+            with torch.cuda.stream(eng.stream):
+                return a.to(eng.device, dtype=torch.float32, non_blocking=True).contiguous()
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
         with torch.cuda.stream(eng.stream):
             return torch.from_numpy(a).to(eng.device, non_blocking=False)
 
     def _check_x(self, x):
-        x = np.asarray(x)
+        if not isinstance(x, torch.Tensor):
+            x = np.asarray(x)
         if tuple(x.shape[1:]) != tuple(self.graph.input.shape):
             raise ValueError("expected input of shape (N,%s), got %s" % (",".join(map(str, self.graph.input.shape)), x.shape))
         return x
@@ -536,14 +540,16 @@ class Sequential(Model):
     def __init__(self, **kw):
         self._seq_layers, self._seq_out, self._kw = [], None, kw
         self._built = False
+        L.reset_names()          # a fresh model: the layers created for the add() calls are conv2d_1, ... as in Keras
 
     def add(self, layer):
         if self._seq_out is None:
             shape = getattr(layer, "input_shape", None)
             if shape is None:
                 raise ValueError("the first layer of a Sequential model needs input_shape=")
-            L.reset_names()
             self._seq_in = L.Input(shape)
+            # the input layer is created after the first layer object: order it in front (Graph sorts by creation)
+            self._seq_in.producer._seq = layer._seq - 0.5
             self._seq_out = layer(self._seq_in)
         else:
             self._seq_out = layer(self._seq_out)

@@ -1,0 +1,127 @@
+"""Worker of tests/test_gpu_multi.py (one process per GPU under torchrun, NCCL): asserts the data-parallel path and
+exits non-zero on any failure.
+
+  A  local statistics (the bench's weak-scaling mode): after three steps on per-rank data every rank holds the same
+     weights, with the bucketed + overlapped gradient exchange and with the single serial all-reduce alike;
+  B  sync_stats=True: a global batch split over the ranks reproduces the single-GPU step on the full batch
+     (BatchNorm / Dice sums and gradients all-reduced) -- parameters and loss;
+  C  Model.fit under data parallelism: ranks train disjoint shares of every epoch (dist.epoch_batches), report the same
+     epoch logs and end with identical weights; only rank 0 writes the checkpoint.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+PKG = "one-stop-for-covid-19-infection-and-lung-segmentation-plus-classification_b200"
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    E = importlib.import_module(PKG + ".engine")
+    G = importlib.import_module(PKG + ".graphs")
+    M = importlib.import_module(PKG + ".model")
+    LS = importlib.import_module(PKG + ".losses")
+    S = importlib.import_module(PKG + ".synthetic")
+    from helpers import perturbed_params
+    comm = E.Comm(rank, world)
+    hw, nl = 64, 4
+
+    def same_everywhere(w, what, tol=0.0):
+        flat = torch.from_numpy(np.concatenate([np.asarray(v, np.float64).ravel() for v in w.values()])).cuda()
+        ref = flat.clone()
+        dist.broadcast(ref, src=0)
+        d = (flat - ref).abs().max()
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        assert float(d) <= tol, "%s: ranks differ by %g" % (what, float(d))
+
+    # ---- A: local statistics, bucketed / overlapped exchange and the single all-reduce -------------------------------
+    params = perturbed_params("unet", hw)
+    x, t = S.make_slices(nl, hw, seed=10 + rank)
+    xd, td = torch.from_numpy(x).cuda(), torch.from_numpy(t.reshape(nl, -1)).cuda()
+    finals = {}
+    for name, opts, precision, graph in (("buckets", dict(grad_bucket_bytes=64 << 10), "float32", True),
+                                         ("single", dict(grad_bucket_bytes=0), "float32", False),
+                                         ("buckets-fp16", dict(grad_bucket_bytes=64 << 10), "float16", True)):
+        eng = E.Engine(G.unet(hw, 1), precision=precision, comm=comm, use_graph=graph, plan_options=opts)
+        eng.set_weights(params)
+        eng.broadcast_weights()
+        for s in range(3):
+            b = eng.train_batch(xd, td, None, nl, dropout=False)
+        eng.stream.synchronize()
+        nb = sum(1 for o in b.plan.bwd if o.kind == E.P.OP_ALLREDUCE_F32)
+        assert (nb >= 3) == (name != "single"), (name, nb)
+        w = eng.get_weights()
+        same_everywhere(w, "A/" + name)               # every rank applied the same all-reduced gradient: bit-identical
+        finals[name] = w
+        eng.close()
+    for k in finals["single"]:                        # both exchange schedules compute the same step (atomics-order noise)
+        assert np.abs(finals["buckets"][k] - finals["single"][k]).max() < 2e-4 * max(1.0, float(np.abs(finals["single"][k]).max())), k
+
+    # ---- B: sync_stats reproduces the single-GPU step on the full global batch ------------------------------------------
+    xg, tg = S.make_slices(nl * world, hw, seed=77)
+    lo = rank * nl
+    eng = E.Engine(G.unet(hw, 1), precision="float32", comm=comm, sync_stats=True, use_graph=False)
+    eng.set_weights(params)
+    b = eng.train_batch(torch.from_numpy(xg[lo:lo + nl]).cuda(), torch.from_numpy(tg[lo:lo + nl].reshape(nl, -1)).cuda(), None, nl,
+                        dropout=False)
+    eng.stream.synchronize()
+    loss_sync = eng.loss_dev(b).cpu().numpy().copy()
+    w_sync = eng.get_weights()
+    eng.close()
+    same_everywhere(w_sync, "B/sync", tol=1e-6)
+    if rank == 0:
+        one = E.Engine(G.unet(hw, 1), precision="float32", use_graph=False)
+        one.set_weights(params)
+        b1 = one.train_batch(torch.from_numpy(xg).cuda(), torch.from_numpy(tg.reshape(nl * world, -1)).cuda(), None, nl * world,
+                             dropout=False)
+        one.stream.synchronize()
+        loss_one = one.loss_dev(b1).cpu().numpy()
+        w_one = one.get_weights()
+        one.close()
+        assert np.allclose(loss_sync, loss_one, rtol=1e-5, atol=1e-6), (loss_sync, loss_one)
+        worst = max(float(np.abs(w_sync[k] - w_one[k]).max()) for k in w_one)
+        assert worst < 5e-5, "sync_stats step differs from the single-GPU full batch by %g" % worst
+        print("B: sync_stats vs single GPU full batch: max |dw| = %.2e, loss %s vs %s" % (worst, loss_sync, loss_one), flush=True)
+
+    # ---- C: Model.fit shards every epoch over the ranks -----------------------------------------------------------------
+    xs, ts = S.make_slices(22, 32, seed=5)                       # 22 samples over 2 ranks, batch 4: 3 steps per rank and epoch
+    ck = "/tmp/b2u_dp_ckpt_%d.npz" % os.getppid()
+    if rank == 0 and os.path.exists(ck):
+        os.remove(ck)
+    m = M.Model(graph=G.unet(32, 1), precision="float32", comm=comm, seed=42)
+    m.compile(optimizer=M.Adam(lr=0.0005), loss=LS.bce_dice_loss, metrics=[LS.dice_coeff])
+    h = m.fit(xs, ts, batch_size=4, epochs=2, validation_data=(xs[:6], ts[:6]), verbose=0,
+              callbacks=[M.ModelCheckpoint(ck, monitor="val_dice_coeff", mode="max", save_best_only=True)])
+    same_everywhere(m.get_weights_dict(), "C/fit")
+    logs = torch.tensor([h.history["loss"][-1], h.history["val_loss"][-1]], dtype=torch.float64).cuda()
+    ref = logs.clone()
+    dist.broadcast(ref, src=0)
+    assert float((logs - ref).abs().max()) < 1e-9, "epoch logs differ between ranks"
+    dist.barrier()
+    assert os.path.exists(ck) or rank != 0
+    m.load_weights(ck)                                          # (barrier inside: rank 0 wrote it)
+    same_everywhere(m.get_weights_dict(), "C/load")
+    m.engine.close()
+    dist.barrier()
+    if rank == 0:
+        os.remove(ck)
+        print("dp_worker ok (world %d)" % world, flush=True)
+    comm.close()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,16 @@ class Emulator:
         # rounded to fp16 first, as the GPU's packed operand copies are -- the emulator then has the SAME rounding
         # points as the fp16 engine (fp16 operands, fp32 accumulation, fp16 stores)
         self.fp16_weights = False
+        # numpy Generator or None: multiplies every conv / transposed-conv accumulator by (1 + 2^-22 * N(0,1)) before it
+        # is rounded to the storage type -- the size of fp32 summation-ORDER noise.  Two jittered runs differ by what
+        # ANY correct fp16 implementation may differ by (rounding decisions, ReLU / max-pool flips, amplified through
+        # the BatchNorm chain): the measured noise floor the GPU-vs-emulator comparison is judged against.
+        self.jitter = None
+
+    def _jit(self, a):
+        if self.jitter is None:
+            return a
+        return (a * (1.0 + 2.384185791015625e-07 * self.jitter.standard_normal(a.shape).astype(np.float32))).astype(np.float32)
 
     def _kernel(self, ref, count, cin, cout, dt):
         w = self.f32(ref, count)
@@ -98,7 +108,7 @@ class Emulator:
         b = self.f32(o.p[2], cout)
         y = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(wt.copy()).permute(3, 2, 0, 1),
                      torch.from_numpy(b.copy()), padding=1).permute(0, 2, 3, 1).numpy()
-        y = self._act(y, act).reshape(-1, cout)
+        y = self._act(self._jit(y), act).reshape(-1, cout)
         yv = self.view(o.p[3], ldy, cout, n * h * w, o.dt)
         yv[:] = y.astype(yv.dtype)
         if o.p[4] is not None:
@@ -116,7 +126,7 @@ class Emulator:
         wt = self._kernel(o.p[1], 9 * cin * cout, cin, cout, o.dt).reshape(3, 3, cin, cout)
         wo = torch.from_numpy(wt.copy()).permute(3, 2, 0, 1)           # (cout, cin, 3, 3)
         dx = F.conv_transpose2d(torch.from_numpy(dy).permute(0, 3, 1, 2), wo, padding=1).permute(0, 2, 3, 1).numpy()
-        dx = dx.reshape(-1, cin)
+        dx = self._jit(dx.reshape(-1, cin))
         if o.p[3] is not None and mact == 4:             # B2U_ACT_RELU_BITS: bit pix*cin + c
             nbits = n * h * w * cin
             bits = np.unpackbits(self.arr(o.p[3], nbits // 8, np.uint8), bitorder="little")[:nbits]
@@ -154,7 +164,7 @@ class Emulator:
         y = F.conv_transpose2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(wt.copy()).permute(3, 2, 0, 1),
                                torch.from_numpy(b.copy()), stride=2).permute(0, 2, 3, 1).numpy()
         yv = self.view(o.p[3], ldy, cout, n * 4 * h * w, o.dt)
-        yv[:] = y.reshape(-1, cout).astype(yv.dtype)
+        yv[:] = self._jit(y.reshape(-1, cout)).astype(yv.dtype)
         if len(o.p) > 4 and o.p[4] is not None:          # statistics for a following BN over the concat buffer
             sq = o.i[7]
             s = self.f64(o.p[4], sq + cout)
@@ -168,6 +178,7 @@ class Emulator:
         wt = self._kernel(o.p[1], 4 * cout * cin, cin, cout, o.dt).reshape(2, 2, cout, cin)
         dx = F.conv2d(torch.from_numpy(dy).permute(0, 3, 1, 2), torch.from_numpy(wt.copy()).permute(3, 2, 0, 1),
                       stride=2).permute(0, 2, 3, 1).numpy().reshape(-1, cin)
+        dx = self._jit(dx)
         if o.p[3] is not None:
             dx = dx * self._dact(self.view(o.p[3], ldm, cin, n * h * w, o.dt), mact)
         dv = self.view(o.p[2], lddx, cin, n * h * w, o.dt)

@@ -274,9 +274,10 @@ def test_adam_flags_non_finite_gradients():
     assert newp[5] == oldp[5] and np.isfinite(newp).all() and (newp[:5] != oldp[:5]).all()
 
 
+@pytest.mark.parametrize("n", [6, 70])                      # split-K Dense(32): a partial and several ragged sample groups
 @pytest.mark.parametrize("dt", [P.F32, P.F16])
-def test_dense_and_bce(dt):
-    n, k = 6, 28 * 28 * 64
+def test_dense_and_bce(dt, n):
+    k = 28 * 28 * 64
     img = Img(10)
     x = img.view(n, 1, 1, k, dt, fill="uniform")
     dxv = img.view(n, 1, 1, k, dt, fill=None)

@@ -1,0 +1,169 @@
+"""The reference's runner surface on the GPU: the six public runner names
+(/root/reference/Scripts/app.py:36-57) on tiny synthetic data, and the Keras calls around them that no other test
+exercises -- Sequential().add(...), class_weight, RocCallback, ModelCheckpoint (best-only save, then load_weights),
+CosineAnnealingScheduler inside fit, get_layer(name).output taps, a C_in = 3 classifier (Task-2's real input depth,
+BASELINE configs[4]) with AUROC against the oracle on synthetic labels."""
+import importlib
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG
+from helpers import K
+
+pytestmark = pytest.mark.gpu
+
+R = importlib.import_module(PKG + ".runners")
+M = importlib.import_module(PKG + ".model")
+L = importlib.import_module(PKG + ".layers")
+LS = importlib.import_module(PKG + ".losses")
+S = importlib.import_module(PKG + ".synthetic")
+G = importlib.import_module(PKG + ".graphs")
+
+TINY = dict(new_dim=32, n_synthetic=24, batch_size=8, verbose=0)
+
+
+@pytest.mark.parametrize("name", ["holdout_runner_unet_infection_segmentation",
+                                  "holdout_runner_unetplusplus_infection_segmentation", "runner_lung_segmentation"])
+def test_segmentation_holdout_runners(name, tmp_path):
+    """T1H:6 / UPP / T3:6 -- split 70/30 (seed 42), compile, fit with best-val-Dice checkpoint, reload, evaluate,
+    threshold sweep."""
+    out = getattr(R, name)(epochs=3, checkpoint_path=str(tmp_path / "best.h5"), cosine=True, **TINY)
+    h = out["history"]
+    assert len(h["loss"]) == 3 and len(h["val_dice_coeff"]) == 3 and all(np.isfinite(h["loss"]))
+    assert h["lr"][0] == pytest.approx(0.0005) and h["lr"][1] == pytest.approx(K.cosine_annealing_lr(1), rel=1e-6)
+    assert h["loss"][-1] < h["loss"][0]                                   # it trains
+    assert out["x_valid"].shape == (8, 32, 32, 1)                         # sklearn: ceil(0.3 * 24) = 8 held out
+    # the checkpoint holds the best epoch: evaluating the reloaded weights reproduces that epoch's validation Dice
+    assert out["val_dice_coeff"] == pytest.approx(max(h["val_dice_coeff"]), rel=1e-4)
+    sw = out["sweep"]
+    assert len(sw["f1"]) == 9 and np.all((sw["iou"] >= 0) & (sw["iou"] <= 1)) and np.all(sw["f1"] >= sw["iou"] - 1e-9)
+    assert out["best_dice"] == pytest.approx(float(np.max(sw["f1"])))
+    out["model"].engine.close()
+
+
+@pytest.mark.parametrize("name,folds,epochs", [("three_fold_runner_unet_infection_segmentation", 3, (2, 1, 1)),
+                                               ("four_fold_runner_unet_infection_segmentation", 4, 1)])
+def test_cross_validation_runners(name, folds, epochs):
+    """CV3:6 / CV4:6 -- KFold(shuffle, seed 42), one model per fold, per-fold threshold sweeps, report tables."""
+    out = getattr(R, name)(epochs=epochs, thresholds=[0.3, 0.5, 0.7], **TINY)
+    assert len(out["folds"]) == folds
+    assert out["tables"]["dice"].shape == (3, folds) and list(out["tables"]["iou"].columns) == list(range(1, folds + 1))
+    if folds == 3:
+        assert [len(f["history"]["loss"]) for f in out["folds"]] == [2, 1, 1]          # CV3: 80 + 20 + 20 epochs pattern
+    assert 0.0 <= out["mean"]["dice"] <= 1.0 and out["maximum"]["dice"] >= out["mean"]["dice"]
+
+
+def test_runner_classification():
+    """T2:6 -- stratified split, balanced class weights, bce + f1 metric, RocCallback, AUROC and thresholded metrics."""
+    out = R.runner_classification(new_dim=32, n_synthetic=64, epochs=3, batch_size=16, verbose=0)
+    h = out["history"]
+    assert len(h["loss"]) == 3 and "val_f1" in h and "val_roc_auc" in h and "roc_auc" in h
+    assert out["probs"].shape == (20, 1) and np.all((out["probs"] >= 0) & (out["probs"] <= 1))      # ceil(0.3 * 64)
+    assert 0.0 <= out["auroc"] <= 1.0 and out["auroc"] == pytest.approx(h["val_roc_auc"][-1], abs=1e-6)
+    assert set(out["metrics@0.81"]) == {"accuracy", "precision", "recall", "f1"}
+    assert len(out["class_weight"]) == 2 and out["class_weight"][0] > out["class_weight"][1]        # minority class 0 weighs more
+    out["model"].engine.close()
+
+
+def _task2_sequential(hw, cin, **kw):
+    """the reference's declaration, T2:747-778, statement for statement"""
+    model = M.Sequential(**kw)
+    model.add(L.Conv2D(16, (3, 3), activation='relu', padding="same", kernel_initializer="he_normal", input_shape=(hw, hw, cin)))
+    model.add(L.BatchNormalization())
+    model.add(L.Conv2D(16, (3, 3), padding="same", activation='relu', kernel_initializer="he_normal"))
+    model.add(L.BatchNormalization())
+    model.add(L.MaxPooling2D(pool_size=(2, 2)))
+    model.add(L.Conv2D(32, (3, 3), padding="same", activation='relu', kernel_initializer="he_normal"))
+    model.add(L.BatchNormalization())
+    model.add(L.Conv2D(32, (3, 3), padding="same", activation='relu', kernel_initializer="he_normal"))
+    model.add(L.BatchNormalization())
+    model.add(L.MaxPooling2D(pool_size=(2, 2)))
+    model.add(L.Conv2D(64, (3, 3), padding="same", activation='relu', kernel_initializer="he_normal"))
+    model.add(L.BatchNormalization())
+    model.add(L.Conv2D(64, (3, 3), padding="same", activation='relu', kernel_initializer="he_normal"))
+    model.add(L.BatchNormalization())
+    model.add(L.MaxPooling2D(pool_size=(2, 2)))
+    model.add(L.Flatten())
+    model.add(L.Dense(32, activation='relu'))
+    model.add(L.Dropout(0.4))
+    model.add(L.Dense(1, activation='sigmoid'))
+    return model
+
+
+def _class_data(n, hw, cin, seed):
+    x1, y = S.make_slices(n, hw, seed=seed, task="class")
+    return np.repeat(x1, cin, axis=3).astype(np.float64), y.astype(np.float64)      # gray replicated
+
+
+@pytest.mark.parametrize("precision", ["float32", "float16"])
+def test_sequential_cin3_classifier_fit_predict_auroc_vs_oracle(precision, tmp_path):
+    """Sequential API + class_weight + RocCallback + ModelCheckpoint on a C_in = 3 classifier; afterwards the
+    inference-mode probabilities and the AUROC on synthetic labels against the oracle run on the SAME trained
+    weights (T2:919-926): 1e-3 max-abs on probabilities, AUROC within 1e-3."""
+    from sklearn.metrics import roc_auc_score
+    hw, cin, n = 32, 3, 96
+    x, y = _class_data(n, hw, cin, seed=5)
+    xv, yv = _class_data(64, hw, cin, seed=6)
+    model = _task2_sequential(hw, cin, precision=precision, dropout_seed=7)
+    assert model.count_params() == sum(v.size for v in K.init_params("classifier", (hw, hw, cin))[0].values())
+    model.compile(loss='binary_crossentropy', optimizer=M.Adam(lr=0.0005), metrics=[LS.f1, LS.precision, LS.recall])   # T2:828
+    cw = np.array([2.0, 0.65])                                                       # ndarray as in T2:801-803
+    ck = str(tmp_path / "cls_best.h5")
+    roc = M.RocCallback(training_data=(x, y), validation_data=(xv, yv), filepath=str(tmp_path / "best_val_auc_weights.h5"))
+    h = model.fit(x, y, batch_size=32, epochs=3, validation_data=(xv, yv), class_weight=cw, verbose=0,
+                  callbacks=[roc, M.ModelCheckpoint(ck, monitor="val_loss", save_best_only=True)])              # T2:834-836
+    assert set(["loss", "f1", "val_loss", "val_f1", "val_precision", "val_recall", "roc_auc", "val_roc_auc"]) <= set(h.history) or \
+        set(["loss", "val_loss", "val_f1", "val_precision", "val_recall", "roc_auc", "val_roc_auc"]) <= set(h.history)
+    # inference parity on the trained weights
+    w = model.get_weights_dict()
+    want, _ = K.forward("classifier", w, xv.astype(np.float32), training=False, dtype=torch.float32)
+    got = model.predict_proba(xv)                                                    # T2:726-728
+    assert got.shape == (64, 1)
+    assert np.abs(got - want).max() < (2e-5 if precision == "float32" else 1e-3)
+    # AUROC moves in steps of 1 / (positives * negatives): allow three swapped pairs on top of the 1e-3 of the north star
+    pairs = float(yv.sum() * (len(yv) - yv.sum()))
+    assert pairs > 0 and abs(roc_auc_score(yv, got) - roc_auc_score(yv, want)) <= 1e-3 + 3.0 / pairs
+    ev = model.evaluate(xv, yv, batch_size=32)
+    assert len(ev) == 4 and ev[0] == pytest.approx(h.history["val_loss"][-1], rel=1e-5)
+    # checkpoint round trip: best-val-loss weights come back and reproduce that epoch's validation loss
+    model.load_weights(ck)
+    assert model.evaluate(xv, yv, batch_size=32)[0] == pytest.approx(min(h.history["val_loss"]), rel=1e-4)
+    model.engine.close()
+
+
+def test_class_weight_scales_the_loss_like_keras():
+    """fit(class_weight=...) multiplies every sample's cross-entropy by the weight of its class and divides by the
+    batch size (Keras weighted mean, T2:836): one step with lr = 0 against the oracle's weighted_bce."""
+    hw, n = 32, 16
+    x, y = _class_data(n, hw, 1, seed=9)
+    params, _ = K.init_params("classifier", (hw, hw, 1), seed=3)
+    model = M.Model(graph=G.classifier(hw, 1), precision="float32", dropout_seed=7)
+    model.set_weights_dict(params)
+    model.compile(loss='binary_crossentropy', optimizer=M.Adam(lr=0.0), metrics=[])
+    cw = {0: 3.0, 1: 0.5}
+    h = model.fit(x, y, batch_size=n, epochs=1, class_weight=cw, shuffle=False, verbose=0)
+    sw = np.array([cw[int(v)] for v in y.ravel()], np.float32)
+    r = K.loss_and_grads("classifier", params, x.astype(np.float32), y.astype(np.float32), dtype=torch.float64,
+                         dropout=dict(seed=7, step=0), loss="bce", sample_weight=sw)
+    assert h.history["loss"][0] == pytest.approx(r["loss"], rel=1e-5)
+    model.engine.close()
+
+
+def test_intermediate_layer_outputs_match_oracle_taps():
+    """Model(inputs=model.input, outputs=model.get_layer(name).output).predict(x) (T1H:1386-1405)"""
+    hw, n = 32, 3
+    x, _ = S.make_slices(n, hw, seed=2)
+    params, _ = K.init_params("unet", (hw, hw, 1), seed=4)
+    model = M.Model(graph=G.unet(hw, 1), precision="float32")
+    model.set_weights_dict(params)
+    taps = {}
+    K.forward("unet", params, x, training=False, dtype=torch.float32, taps=taps)
+    for name in ("conv2d_2", "batch_normalization_1", "max_pooling2d_2", "conv2d_10", "conv2d_transpose_1", "conv2d_18"):
+        got = model.intermediate(x, name)
+        assert got.shape == taps[name].shape, name
+        assert np.abs(got - taps[name]).max() < 1e-4 * max(1.0, float(np.abs(taps[name]).max())), name
+    assert model.get_layer("conv2d_10").output.shape == (2, 2, 512)
+    model.engine.close()

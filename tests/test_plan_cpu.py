@@ -146,3 +146,26 @@ def test_relu_bits_plan_structure():
     assert all(o.p[6] is None for o in off.fwd if o.kind == P.OP_CONV3X3_FWD)
     assert not any(o.kind == P.OP_CONV3X3_DGRAD and o.i[5] == P.ACT_RELU_BITS for o in off.bwd)
     assert on.act.size > off.act.size
+
+
+@pytest.mark.parametrize("gname,hw", [("unet", 64), ("unetpp", 32), ("classifier", 32)])
+def test_gradient_buckets_cover_the_buffer_and_follow_their_last_writer(gname, hw):
+    """data parallel: the flat gradient buffer is all-reduced in contiguous buckets, each placed right behind the last
+    backward op that writes into it (executor flag OPF_COMM = side stream), the union is the whole buffer exactly once,
+    nothing but Adam reads a bucket after its exchange, and grad_bucket_bytes=0 restores the single all-reduce"""
+    loss = "bce" if gname == "classifier" else "bce_dice"
+    plan = P.Plan(G.GRAPHS[gname](hw, 1), 4, dt=P.F16, training=True, world=4, loss=loss, grad_bucket_bytes=256 << 10)
+    ars = [(k, o) for k, o in enumerate(plan.bwd) if o.kind == P.OP_ALLREDUCE_F32]
+    assert len(ars) >= 2 and all(o.dt & P.OPF_COMM for _, o in ars) and not any(o.kind == P.OP_ALLREDUCE_F32 for o in plan.opt)
+    spans = sorted((o.p[0].off // 4, o.p[0].off // 4 + o.i[0]) for _, o in ars)
+    assert spans[0][0] == 0 and spans[-1][1] == plan.layout.n_params
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))                      # contiguous, no overlap
+    for k, o in ars:
+        lo, hi = o.p[0].off, o.p[0].off + 4 * o.i[0]
+        for later in plan.bwd[k + 1:]:          # nothing touches the bucket after its exchange: no gradient write, and
+            for ref in later.p:                 # no read either (BN_BWD_SUMS_WGRAD reads a conv's LOCAL weight gradient)
+                if isinstance(ref, P.Ref) and ref.arena == "grads" and later.kind != P.OP_ALLREDUCE_F32:
+                    assert not (lo <= ref.off < hi), (o.tag, later)
+    assert plan.opt[0].kind == P.OP_ADAM and plan.opt[0].dt & P.OPF_JOIN
+    one = P.Plan(G.GRAPHS[gname](hw, 1), 4, dt=P.F16, training=True, world=4, loss=loss, grad_bucket_bytes=0)
+    assert [o.kind for o in one.opt][:2] == [P.OP_ALLREDUCE_F32, P.OP_ADAM] and not any(o.kind == P.OP_ALLREDUCE_F32 for o in one.bwd)

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--kinds", default="")
     ap.add_argument("--workload", default="unet512")
     ap.add_argument("--plan", default="", help="planner options, e.g. relu_bits=1,fuse_bn_pool=0")
+    ap.add_argument("--set", default="", help="library options held fixed for the whole run, e.g. tc_dw_epi8=0,pdl=0")
     args = ap.parse_args()
     name, vals = (args.opt.split("=") + [""])[:2] if args.opt else ("", "")
     vals = [int(v) for v in vals.split(",")] if vals else [None]
@@ -39,6 +40,8 @@ def main():
     x, t = S.make_slices(batch, size, seed=1234)
     xd = torch.from_numpy(x).cuda()
     td = torch.from_numpy(t.reshape(batch, -1)).cuda()
+    for kv in (kv for kv in args.set.split(",") if kv):
+        eng.lib.b2u_set_option(kv.split("=")[0].encode(), int(kv.split("=")[1]))
     cols = []
     for v in vals:
         if name:
