@@ -182,9 +182,15 @@ int b2u_threshold_counts(const float* prob, const float* target, long long count
 int b2u_clahe_u8(const uint8_t* in, uint8_t* out, int n, int h, int wd, float clip_limit, int tiles,
                  void* ws, size_t ws_bytes, void* stream);
 /* per image: crop two boxes (x,y,w,h int32 x8), cv2.resize INTER_AREA to (half_w x out_h) each, hconcat,
- * cv2.resize INTER_LINEAR (u8 fixed point) to final x final, /255 -> float32 (n,final,final) */
+ * cv2.resize INTER_LINEAR (u8 fixed point) to final x final, /255 -> float32 (n,final,final); both stages are
+ * bit-exact against OpenCV (mid_u8 = the 250 x 250 stage, out = np.uint8(.)/255) */
 int b2u_crop_resize(const uint8_t* in, int n, int h, int wd, const int* boxes, int half_w, int out_h,
                     int final_dim, uint8_t* mid_u8, float* out, void* stream);
+/* cv2.resize(img, (dst_w, dst_h), interpolation) on n uint8 images (T1H:335 the 512 x 512 INTER_AREA stage of the
+ * NIfTI ingest; T1H:485-488 INTER_LINEAR to new_dim): interpolation = OpenCV's enum, 1 INTER_LINEAR (square targets),
+ * 3 INTER_AREA.  Bit-exact against OpenCV's CV_8UC1 arithmetic (area tables / 11-bit fixed point). */
+int b2u_resize_u8(const uint8_t* in, int n, int src_h, int src_w, uint8_t* out, int dst_h, int dst_w,
+                  int interpolation, void* stream);
 
 /* ---- BatchNormalization apply + MaxPooling2D((2,2)) + Dropout in one pass (encoder level, T1H:861-863) ---- */
 /* y = x * scale + shift is written at full resolution (the skip tensor, possibly a concat slice) and its 2x2 max,

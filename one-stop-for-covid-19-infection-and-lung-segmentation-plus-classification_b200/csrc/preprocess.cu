@@ -99,16 +99,112 @@ __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __rest
   }
 }
 
-// ---- P2 + P3 ---------------------------------------------------------------------------------------
-// Stage 1: for each image and each of its two boxes (x,y,w,h): cv2.resize(crop, (half_w, out_h), INTER_AREA)
-// written side by side into mid (out_h x 2*half_w) -- the reference's `cropper` (T1H:236-241) / box
-// re-application (T1H:347-368).  INTER_AREA = exact box filter with fractional pixel coverage (float
-// accumulation like OpenCV's resizeArea_; integer scale factors reduce to plain averaging), rounded to uint8.
-// When a crop is SMALLER than the target in a dimension OpenCV switches that call to its bilinear path; the
-// same rule is applied here per call (area coefficients: fx = (dx+1) - (sx+1)/scale, clamped).
-__device__ __forceinline__ float area_axis_weight(int s, float lo, float hi) {
-  float a = fmaxf((float)s, lo), b = fminf((float)(s + 1), hi);
-  return fmaxf(b - a, 0.f);
+// ---- P2 + P3: OpenCV's uint8 resize arithmetic, bit for bit ---------------------------------------------
+// (modules/imgproc/src/resize.cpp, CV_8UC1; restated in numpy by oracle/cv_resize.py, which tests/ pin against cv2)
+//
+// Stage 1: for each image and each of its two boxes (x,y,w,h): cv2.resize(crop, (half_w, out_h), INTER_AREA) written side
+// by side into mid (out_h x 2*half_w) -- the reference's `cropper` (T1H:236-241) / box re-application (T1H:347-368).
+//   both scales >= 1, both integer : resizeAreaFast_   2x2: (a+b+c+d+2) >> 2, else cvRound(sum * (1.f / area))
+//   both scales >= 1               : resizeArea_        DecimateAlpha tables, float accumulation IN TABLE ORDER with
+//                                                       separate multiply / add roundings (no FMA), cvRound at the end
+//   otherwise (a crop smaller than the target in a dimension): the fixed-point bilinear path below with the "area"
+//   coefficients  sx = floor(dx*scale), fx = (dx+1) - (sx+1)*inv_scale  (fx <= 0 ? 0 : fx - floor(fx))
+// scale = 1. / ((double)dst / src) exactly as cv::resize derives it.
+struct AreaTab {            // the DecimateAlpha entries of ONE destination index (computeResizeAreaTab)
+  int s_first;              // source index of the first entry
+  int n;                    // number of entries (consecutive source indices)
+  float a_first, a_mid, a_last;
+  bool has_first, has_last;
+};
+
+__device__ __forceinline__ AreaTab area_tab(int d, int ssize, double scale) {
+  AreaTab t;
+  const double fsx1 = d * scale, fsx2 = fsx1 + scale;
+  const double cell = fmin(scale, (double)ssize - fsx1);
+  int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+  sx2 = min(sx2, ssize - 1);
+  sx1 = min(sx1, sx2);
+  t.has_first = (double)sx1 - fsx1 > 1e-3;
+  t.has_last = fsx2 - (double)sx2 > 1e-3;
+  t.a_first = (float)(((double)sx1 - fsx1) / cell);
+  t.a_mid = (float)(1.0 / cell);
+  t.a_last = (float)(fmin(fmin(fsx2 - (double)sx2, 1.0), cell) / cell);
+  t.s_first = t.has_first ? sx1 - 1 : sx1;
+  t.n = (sx2 - sx1) + (t.has_first ? 1 : 0) + (t.has_last ? 1 : 0);
+  return t;
+}
+
+__device__ __forceinline__ float area_alpha(const AreaTab& t, int k) {
+  if (k == 0 && t.has_first) return t.a_first;
+  if (k == t.n - 1 && t.has_last) return t.a_last;
+  return t.a_mid;
+}
+
+// 11-bit bilinear coefficients of cv::resize's generic path (ksize 2): source index and the two short weights
+__device__ __forceinline__ void linear_coeff(int d, double scale, double inv_scale, bool area_mode, int* s, int* a0, int* a1) {
+  float f;
+  int si;
+  if (!area_mode) {
+    f = (float)(((double)d + 0.5) * scale - 0.5);
+    si = (int)floorf(f);
+    f -= (float)si;
+  } else {
+    si = (int)floor((double)d * scale);
+    f = (float)((double)(d + 1) - (double)(si + 1) * inv_scale);
+    f = f <= 0.f ? 0.f : f - floorf(f);
+  }
+  *s = si;
+  *a0 = __float2int_rn(__fmul_rn(1.f - f, 2048.f));       // saturate_cast<short>: cvRound, half to even
+  *a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+// horizontal pass of one source row at destination column coefficients (sx, a0, a1): HResizeLinear incl. its borders
+__device__ __forceinline__ int linear_row(const uint8_t* row, int sw, int sx, int a0, int a1) {
+  if (sx < 0) return (int)row[0] * 2048;
+  if (sx >= sw - 1) return (int)row[sw - 1] * 2048;
+  return (int)row[sx] * a0 + (int)row[sx + 1] * a1;
+}
+
+__device__ __forceinline__ uint8_t linear_fixed_pixel(const uint8_t* src, long long pitch, int sw, int sh, int dx, int dy,
+                                                      double scale_x, double inv_x, double scale_y, double inv_y,
+                                                      bool area_mode) {
+  int sx, ax0, ax1, sy, ay0, ay1;
+  linear_coeff(dx, scale_x, inv_x, area_mode, &sx, &ax0, &ax1);
+  linear_coeff(dy, scale_y, inv_y, area_mode, &sy, &ay0, &ay1);
+  const int y0 = min(max(sy, 0), sh - 1), y1 = min(max(sy + 1, 0), sh - 1);      // rows are clamped, the weights are not
+  const int r0 = linear_row(src + (long long)y0 * pitch, sw, sx, ax0, ax1);
+  const int r1 = linear_row(src + (long long)y1 * pitch, sw, sx, ax0, ax1);
+  const int v = (((ay0 * (r0 >> 4)) >> 16) + ((ay1 * (r1 >> 4)) >> 16) + 2) >> 2;   // VResizeLinear, 8-bit
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+__device__ __forceinline__ uint8_t area_pixel(const uint8_t* src, long long pitch, int sw, int sh, int dw, int dh, int dx,
+                                              int dy) {
+  const double inv_x = (double)dw / (double)sw, inv_y = (double)dh / (double)sh;
+  const double scale_x = 1.0 / inv_x, scale_y = 1.0 / inv_y;
+  if (!(scale_x >= 1.0 && scale_y >= 1.0))
+    return linear_fixed_pixel(src, pitch, sw, sh, dx, dy, scale_x, inv_x, scale_y, inv_y, true);
+  const int ix = __double2int_rn(scale_x), iy = __double2int_rn(scale_y);
+  if (fabs(scale_x - ix) < 2.220446049250313e-16 && fabs(scale_y - iy) < 2.220446049250313e-16) {
+    int sum = 0;
+    for (int yy = 0; yy < iy; ++yy)
+      for (int xx = 0; xx < ix; ++xx) sum += src[(long long)(dy * iy + yy) * pitch + dx * ix + xx];
+    if (ix == 2 && iy == 2) return (uint8_t)((sum + 2) >> 2);
+    const float sc = __fdiv_rn(1.f, (float)(ix * iy));
+    const int q = __float2int_rn(__fmul_rn((float)sum, sc));
+    return (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+  }
+  const AreaTab tx = area_tab(dx, sw, scale_x), ty = area_tab(dy, sh, scale_y);
+  float sum = 0.f;
+  for (int j = 0; j < ty.n; ++j) {
+    const uint8_t* row = src + (long long)(ty.s_first + j) * pitch;
+    float buf = 0.f;
+    for (int k = 0; k < tx.n; ++k) buf = __fadd_rn(buf, __fmul_rn((float)row[tx.s_first + k], area_alpha(tx, k)));
+    const float term = __fmul_rn(area_alpha(ty, j), buf);
+    sum = j == 0 ? term : __fadd_rn(sum, term);
+  }
+  const int q = __float2int_rn(sum);
+  return (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
 }
 
 __global__ void __launch_bounds__(256) crop_area_resize_kernel(const uint8_t* __restrict__ in, int H, int W,
@@ -127,84 +223,46 @@ __global__ void __launch_bounds__(256) crop_area_resize_kernel(const uint8_t* __
     const int dx = ox - side * half_w;
     const int* bx = boxes + (long long)n * 8 + side * 4;
     const int x0 = bx[0], y0 = bx[1], bw = bx[2], bh = bx[3];
-    const uint8_t* src = in + (long long)n * H * W;
-    float val;
-    if (bw <= 0 || bh <= 0) {
-      val = 0.f;
-    } else {
-      const float sx = (float)bw / (float)half_w, sy = (float)bh / (float)out_h;
-      if (sx >= 1.f && sy >= 1.f) {
-        // area (box) filter with fractional coverage
-        const float fx0 = dx * sx, fx1 = fx0 + sx, fy0 = oy * sy, fy1 = fy0 + sy;
-        int ix0 = (int)floorf(fx0), ix1 = min((int)ceilf(fx1), bw), iy0 = (int)floorf(fy0), iy1 = min((int)ceilf(fy1), bh);
-        float acc = 0.f, wsum = 0.f;
-        for (int yy = iy0; yy < iy1; ++yy) {
-          const float wy = area_axis_weight(yy, fy0, fy1);
-          if (wy <= 0.f) continue;
-          float row = 0.f, wrow = 0.f;
-          for (int xx = ix0; xx < ix1; ++xx) {
-            const float wx = area_axis_weight(xx, fx0, fx1);
-            row += wx * (float)src[(long long)(y0 + yy) * W + x0 + xx];
-            wrow += wx;
-          }
-          acc += wy * row;
-          wsum += wy * wrow;
-        }
-        val = wsum > 0.f ? acc / wsum : 0.f;
-      } else {
-        // OpenCV's INTER_AREA up-scaling rule: bilinear with area-style coefficients
-        int sx0 = (int)floorf(dx * sx);
-        float fx = (float)(dx + 1) - (float)(sx0 + 1) / sx;
-        fx = fx <= 0.f ? 0.f : fx - floorf(fx);
-        int sy0 = (int)floorf(oy * sy);
-        float fy = (float)(oy + 1) - (float)(sy0 + 1) / sy;
-        fy = fy <= 0.f ? 0.f : fy - floorf(fy);
-        int sx1 = min(sx0 + 1, bw - 1), sy1 = min(sy0 + 1, bh - 1);
-        sx0 = min(sx0, bw - 1);
-        sy0 = min(sy0, bh - 1);
-        const float p00 = src[(long long)(y0 + sy0) * W + x0 + sx0], p01 = src[(long long)(y0 + sy0) * W + x0 + sx1];
-        const float p10 = src[(long long)(y0 + sy1) * W + x0 + sx0], p11 = src[(long long)(y0 + sy1) * W + x0 + sx1];
-        val = (p00 * (1.f - fx) + p01 * fx) * (1.f - fy) + (p10 * (1.f - fx) + p11 * fx) * fy;
-      }
-    }
-    int q = __float2int_rn(val);
-    mid[idx] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+    uint8_t v = 0;
+    if (bw > 0 && bh > 0)
+      v = area_pixel(in + (long long)n * H * W + (long long)y0 * W + x0, W, bw, bh, half_w, out_h, dx, oy);
+    mid[idx] = v;
   }
 }
 
-// Stage 2: cv2.resize(mid, (final, final), INTER_LINEAR) for uint8 (OpenCV fixed point: 11-bit
-// coefficients, two-pass with the (>>4, >>16, +2 >>2) rounding of its 8-bit VResizeLinear) then /255.
+// whole images: cv2.resize(img, (dw, dh), INTER_AREA) -- the NIfTI ingest's 512 x 512 stage (T1H:335)
+__global__ void __launch_bounds__(256) area_resize_kernel(const uint8_t* __restrict__ in, int sh, int sw,
+                                                          uint8_t* __restrict__ out, int dh, int dw, int N) {
+  B2U_PDL_PROLOGUE();
+  const long long total = (long long)N * dh * dw;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int dx = (int)(idx % dw);
+    const long long t = idx / dw;
+    const int dy = (int)(t % dh);
+    const int n = (int)(t / dh);
+    out[idx] = area_pixel(in + (long long)n * sh * sw, sw, sw, sh, dw, dh, dx, dy);
+  }
+}
+
+// Stage 2: cv2.resize(mid, (final, final), INTER_LINEAR) for uint8 (OpenCV fixed point: 11-bit coefficients, two-pass
+// with the (>>4, >>16, +2 >>2) rounding of its 8-bit VResizeLinear), then np.uint8(.) / 255 (T1H:485-488).
 __global__ void __launch_bounds__(256) linear_resize_scale_kernel(const uint8_t* __restrict__ mid, int mh, int mw, int fd,
-                                                                  float* __restrict__ out, int N) {
+                                                                  float* __restrict__ out, uint8_t* __restrict__ out_u8,
+                                                                  int N) {
   B2U_PDL_PROLOGUE();
   const long long total = (long long)N * fd * fd;
-  const float scx = (float)mw / (float)fd, scy = (float)mh / (float)fd;
+  const double inv_x = (double)fd / (double)mw, inv_y = (double)fd / (double)mh;
+  const double scale_x = 1.0 / inv_x, scale_y = 1.0 / inv_y;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int dx = (int)(idx % fd);
     const long long t = idx / fd;
     const int dy = (int)(t % fd);
     const int n = (int)(t / fd);
-    float fx = (float)((dx + 0.5) * (double)scx - 0.5);
-    int sx = (int)floorf(fx);
-    fx -= sx;
-    if (sx < 0) { fx = 0.f; sx = 0; }
-    if (sx >= mw - 1) { fx = 0.f; sx = mw - 1; }
-    float fy = (float)((dy + 0.5) * (double)scy - 0.5);
-    int sy = (int)floorf(fy);
-    fy -= sy;
-    if (sy < 0) { fy = 0.f; sy = 0; }
-    if (sy >= mh - 1) { fy = 0.f; sy = mh - 1; }
-    const int sx1 = min(sx + 1, mw - 1), sy1 = min(sy + 1, mh - 1);
-    // saturate_cast<short>(f * 2048): round to nearest even
-    const int ax1 = __float2int_rn(fx * 2048.f), ax0 = __float2int_rn((1.f - fx) * 2048.f);
-    const int ay1 = __float2int_rn(fy * 2048.f), ay0 = __float2int_rn((1.f - fy) * 2048.f);
-    const uint8_t* src = mid + (long long)n * mh * mw;
-    const int r0 = src[(long long)sy * mw + sx] * ax0 + src[(long long)sy * mw + sx1] * ax1;     // horizontal pass
-    const int r1 = src[(long long)sy1 * mw + sx] * ax0 + src[(long long)sy1 * mw + sx1] * ax1;
-    const int v = ((((ay0 * (r0 >> 4)) >> 16) + ((ay1 * (r1 >> 4)) >> 16) + 2) >> 2);
-    const int q = v < 0 ? 0 : (v > 255 ? 255 : v);
-    out[idx] = (float)q / 255.0f;
+    const uint8_t q = linear_fixed_pixel(mid + (long long)n * mh * mw, mw, mw, mh, dx, dy, scale_x, inv_x, scale_y, inv_y, false);
+    if (out != nullptr) out[idx] = __fdiv_rn((float)q, 255.0f);
+    if (out_u8 != nullptr) out_u8[idx] = q;
   }
 }
 
@@ -240,6 +298,27 @@ extern "C" int b2u_crop_resize(const uint8_t* in, int n, int h, int wd, const in
   if (g1 > 16 * B2U_NUM_SMS) g1 = 16 * B2U_NUM_SMS;
   if (g2 > 16 * B2U_NUM_SMS) g2 = 16 * B2U_NUM_SMS;
   B2U_LAUNCH(crop_area_resize_kernel, g1, 256, 0, stream, in, h, wd, boxes, half_w, out_h, mid_u8, n);
-  B2U_LAUNCH(linear_resize_scale_kernel, g2, 256, 0, stream, (const uint8_t*)mid_u8, out_h, 2 * half_w, final_dim, out, n);
+  B2U_LAUNCH(linear_resize_scale_kernel, g2, 256, 0, stream, (const uint8_t*)mid_u8, out_h, 2 * half_w, final_dim, out,
+             (uint8_t*)nullptr, n);
+  return B2U_OK;
+}
+
+// cv2.resize(img, (dst_w, dst_h), interpolation) for n uint8 images of src_h x src_w; interpolation 1 = INTER_LINEAR,
+// 3 = INTER_AREA (OpenCV's enum values), bit-exact against OpenCV (tests/test_gpu_preprocess.py)
+extern "C" int b2u_resize_u8(const uint8_t* in, int n, int src_h, int src_w, uint8_t* out, int dst_h, int dst_w,
+                             int interpolation, void* stream) {
+  B2U_REQUIRE(in != nullptr && out != nullptr && n > 0 && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "resize_u8: args");
+  long long total = (long long)n * dst_h * dst_w;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 16 * B2U_NUM_SMS) grid = 16 * B2U_NUM_SMS;
+  if (interpolation == 3) {
+    B2U_LAUNCH(area_resize_kernel, grid, 256, 0, stream, in, src_h, src_w, out, dst_h, dst_w, n);
+  } else if (interpolation == 1) {
+    B2U_REQUIRE(dst_h == dst_w, "resize_u8: INTER_LINEAR is implemented for square targets (the reference's new_dim)");
+    B2U_LAUNCH(linear_resize_scale_kernel, grid, 256, 0, stream, in, src_h, src_w, dst_h, (float*)nullptr, out, n);
+  } else {
+    b2u_set_error("resize_u8: interpolation %d not supported (1 = INTER_LINEAR, 3 = INTER_AREA)", interpolation);
+    return B2U_ERR_ARG;
+  }
   return B2U_OK;
 }

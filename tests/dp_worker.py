@@ -36,8 +36,11 @@ def main():
     comm = E.Comm(rank, world)
     hw, nl = 64, 4
 
-    def same_everywhere(w, what, tol=0.0):
-        flat = torch.from_numpy(np.concatenate([np.asarray(v, np.float64).ravel() for v in w.values()])).cuda()
+    def same_everywhere(w, what, tol=0.0, moving=False):
+        # with LOCAL BatchNorm statistics every rank keeps the moving statistics of its own shard (as framework DDP
+        # does with unsynchronised BN buffers): only the trainable parameters must be identical then
+        flat = torch.from_numpy(np.concatenate([np.asarray(v, np.float64).ravel() for k, v in w.items()
+                                                if moving or "moving_" not in k])).cuda()
         ref = flat.clone()
         dist.broadcast(ref, src=0)
         d = (flat - ref).abs().max()
@@ -65,6 +68,8 @@ def main():
         finals[name] = w
         eng.close()
     for k in finals["single"]:                        # both exchange schedules compute the same step (atomics-order noise)
+        if "moving_" in k:
+            continue
         assert np.abs(finals["buckets"][k] - finals["single"][k]).max() < 2e-4 * max(1.0, float(np.abs(finals["single"][k]).max())), k
 
     # ---- B: sync_stats reproduces the single-GPU step on the full global batch ------------------------------------------
@@ -78,7 +83,7 @@ def main():
     loss_sync = eng.loss_dev(b).cpu().numpy().copy()
     w_sync = eng.get_weights()
     eng.close()
-    same_everywhere(w_sync, "B/sync", tol=1e-6)
+    same_everywhere(w_sync, "B/sync", tol=1e-6, moving=True)
     if rank == 0:
         one = E.Engine(G.unet(hw, 1), precision="float32", use_graph=False)
         one.set_weights(params)

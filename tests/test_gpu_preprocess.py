@@ -57,10 +57,9 @@ def test_crop_resize_vs_cv2():
         c1 = cv2.resize(cts[k][y0:y0 + h, x0:x0 + w], dsize=(125, 250), interpolation=cv2.INTER_AREA)
         c2 = cv2.resize(cts[k][q:q + s, p:p + r], dsize=(125, 250), interpolation=cv2.INTER_AREA)
         fused = np.concatenate((c1, c2), axis=1)
-        d = np.abs(mid[k].astype(int) - fused.astype(int))
-        assert d.max() <= 1, "250x250 stage differs by %d" % d.max()
-        final = np.uint8(cv2.resize(mid[k], dsize=(224, 224), interpolation=cv2.INTER_LINEAR)) / 255.0
-        assert np.abs(got[k, :, :, 0] - final).max() <= 1.0 / 255 + 1e-6
+        assert np.array_equal(mid[k], fused), "250x250 stage: %d pixels differ" % int((mid[k] != fused).sum())   # integer work: bit-exact
+        final = (np.uint8(cv2.resize(fused, dsize=(224, 224), interpolation=cv2.INTER_LINEAR)) / 255.0).astype(np.float32)
+        assert np.array_equal(got[k, :, :, 0], final)
 
 
 def test_nifti_case_to_network_input_vs_reference_lines(tmp_path):
@@ -90,5 +89,32 @@ def test_nifti_case_to_network_input_vs_reference_lines(tmp_path):
             i2 = cv2.resize(src[f:f + h, e:e + g], dsize=(125, 250), interpolation=cv2.INTER_AREA)
             fused = np.concatenate((i1, i2), axis=1)
             final = np.uint8(cv2.resize(fused, dsize=(224, 224), interpolation=cv2.INTER_LINEAR)) / 255.0
-            # the device area resize is within 1 LSB of cv2 at the 250 x 250 stage (test_crop_resize_vs_cv2): 2 LSB here
-            assert np.abs(got[k, :, :, 0] - final).max() <= 2.0 / 255 + 1e-6
+            assert np.array_equal(got[k, :, :, 0], final.astype(np.float32))       # both resize stages are bit-exact
+
+
+AREA_CASES = [(300, 200), (250, 125), (500, 250), (750, 375), (500, 375), (251, 126), (333, 177), (512, 512), (260, 140),
+              (249, 124), (100, 60), (400, 90), (120, 300), (20, 9), (250, 126), (501, 251), (1000, 250)]
+
+
+def test_resize_u8_is_bit_exact_against_cv2():
+    """b2u_resize_u8 against cv2.resize over OpenCV's three INTER_AREA regimes (integer scales incl. 2x2, fractional
+    shrinking, up-sampling in one or both dimensions) and the fixed-point INTER_LINEAR, on noise and on smooth images"""
+    PP = importlib.import_module(PKG + ".preprocess")
+    for sh, sw in AREA_CASES:
+        rng = np.random.default_rng(sh * 1000 + sw)
+        src = rng.integers(0, 256, (2, sh, sw)).astype(np.uint8)
+        src[1] = cv2.GaussianBlur(src[1], (0, 0), 2.0)
+        got = PP.resize(src, (125, 250), PP.INTER_AREA)
+        for k in range(2):
+            want = cv2.resize(src[k], dsize=(125, 250), interpolation=cv2.INTER_AREA)
+            assert np.array_equal(got[k], want), ("area", sh, sw, k, int((got[k] != want).sum()))
+    got = PP.resize(np.full((630, 630), 7, np.uint8), (512, 512), PP.INTER_AREA)
+    assert got.shape == (512, 512) and (got == 7).all()
+    for s_, d_ in ((250, 224), (250, 256), (250, 512), (250, 96), (37, 224), (512, 224)):
+        rng = np.random.default_rng(s_ * 1000 + d_)
+        src = rng.integers(0, 256, (s_, s_)).astype(np.uint8)
+        want = cv2.resize(src, dsize=(d_, d_), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(PP.resize(src, (d_, d_), PP.INTER_LINEAR), want), ("linear", s_, d_)
+    lib = importlib.import_module(PKG + "._lib")
+    with pytest.raises(lib.B2UError):
+        PP.resize(np.zeros((8, 8), np.uint8), (4, 4), 2)          # INTER_CUBIC: not part of the reference's path
