@@ -24,6 +24,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PKG = "one-stop-for-covid-19-infection-and-lung-segmentation-plus-classification_b200"
+_restore_stdout = lambda: None
 
 METRIC = "CT-slices/sec U-Net 512x512 train step"
 UNIT = "slices/s"
@@ -146,6 +147,7 @@ def run_reference(args):
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    _restore_stdout()
     print(json.dumps(line))
 
 
@@ -177,6 +179,7 @@ def run_reference_classifier(args):
     rate = wl["batch"] * len(times) / sum(times)
     sample = "%d-image batches at %dx%dx%d, fp32 torch-CPU restatement of the Keras path, %d threads, %d measured steps" % (
         wl["batch"], wl["size"], wl["size"], wl["cin"], cores, len(times))
+    _restore_stdout()
     print(json.dumps({"metric": wl["metric"], "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times), "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
@@ -274,9 +277,11 @@ def run_classifier(args):
                                                                           C.c_void_p(eng.stream.cuda_stream), msb), "run_ops_timed")
     ops = bplan.plan.forward_ops()
     es = 2 if args.precision == "float16" else 4
+    per_op = []
     for op, ms in zip(ops, msb):
         nm = P.OP_NAMES[op.kind][3:].lower()
         prof_ms[nm] = prof_ms.get(nm, 0.0) + float(ms)
+        per_op.append({"op": nm, "layer": op.tag, "ms": round(float(ms), 4), "i": op.i[:8]})
         i = op.i
         if op.kind == P.OP_CONV3X3_FWD:
             by += i[5] * i[6] * i[7] * (i[1] + i[4]) * es
@@ -310,6 +315,7 @@ def run_classifier(args):
     else:
         cpu = None
     if rank == 0:
+        _restore_stdout()
         print(json.dumps({
             "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -325,7 +331,8 @@ def run_classifier(args):
                          "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
                          "algorithmic_bytes_per_step": by, "peak_source": peaks["src"]},
             "cpu_baseline": cpu, "auroc_vs_oracle": auroc,
-            "op_breakdown_ms": {k: round(v, 4) for k, v in sorted(prof_ms.items(), key=lambda kv: -kv[1])}}))
+            "op_breakdown_ms": dict({k: round(v, 4) for k, v in sorted(prof_ms.items(), key=lambda kv: -kv[1])},
+                                    **({"_per_op": per_op} if args.per_op else {}))}))
     if world > 1:
         torch.cuda.synchronize()
         torch.distributed.barrier()
@@ -406,7 +413,9 @@ def run_engine(args):
         k, v = kv.split("=")
         importlib.import_module(PKG + "._lib").lib().b2u_set_option(k.encode(), int(v))
     precision = args.precision
-    model = M.Model(graph=G.GRAPHS[GRAPH](SIZE, 1), precision=precision, comm=comm, use_graph=not args.no_graph, seed=42)
+    plan_options = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.plan}
+    model = M.Model(graph=G.GRAPHS[GRAPH](SIZE, 1), precision=precision, comm=comm, use_graph=not args.no_graph, seed=42,
+                    plan_options=plan_options)
     model.compile(optimizer=M.Adam(lr=0.0005), loss=LS.bce_dice_loss, metrics=[LS.dice_coeff])
     eng = model.engine
     # device-resident synthetic dataset: 4 batches per rank, per-rank seed
@@ -587,7 +596,8 @@ def run_engine(args):
                     "blocking_api": "Model.train_on_batch(pinned host x, y) -> [loss, dice]"},
             "roofline": roof, "cpu_baseline": cpu, "op_breakdown_ms": breakdown,
         }
-        print(json.dumps(line))
+        _restore_stdout()
+    print(json.dumps(line))
     if world > 1:
         # leave together and without running NCCL / process-group destructors (a rank that tears its communicator
         # down while a peer is still inside one would hang the launcher until its timeout)
@@ -596,6 +606,20 @@ def run_engine(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def _quiet_stdout():
+    """NCCL prints its version banner to stdout when the first communicator is created; the contract is ONE JSON line
+    on stdout, so file descriptor 1 points at stderr until the result line is printed (returns the restore function)."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+
+    def restore():
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    return restore
 
 
 def main():
@@ -610,11 +634,14 @@ def main():
     ap.add_argument("--per-op", action="store_true", help="add per-op device times to op_breakdown_ms")
     ap.add_argument("--workload", default="unet512", choices=sorted(WORKLOADS))
     ap.add_argument("--opt", action="append", default=[], help="library option name=int (b2u_set_option), repeatable")
+    ap.add_argument("--plan", action="append", default=[], help="planner option name=int (plan.Plan keyword), repeatable")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     global METRIC, SIZE, BATCH, TRAIN_FLOP_PER_SLICE, GRAPH
     wl = WORKLOADS[args.workload]
     METRIC, SIZE, BATCH, TRAIN_FLOP_PER_SLICE, GRAPH = wl["metric"], wl["size"], wl["batch"], wl["flop"], wl["graph"]
+    global _restore_stdout
+    _restore_stdout = _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "classifier224x3":

@@ -50,8 +50,9 @@ typedef struct b2u_step_state {
   float beta2_pow;
   float loss_scale;     /* gradients are multiplied by this in the loss backward (fp16 range) */
   float grad_div;       /* Adam divides gradients by loss_scale*grad_div (grad_div = world size) */
-  uint32_t overflow;    /* set !=0 by Adam if a non-finite gradient was seen (step skipped)   */
-  uint32_t pad_;
+  uint32_t overflow;    /* sticky: != 0 once a step was skipped because of a non-finite gradient (host resets) */
+  uint32_t skip_step;   /* set by b2u_adam's check pass when the CURRENT step's gradient is non-finite: Adam then
+                         * changes nothing, b2u_state_advance halves loss_scale and does not advance step / beta powers */
 } b2u_step_state;
 
 int b2u_version(void);
@@ -191,6 +192,11 @@ int b2u_crop_resize(const uint8_t* in, int n, int h, int wd, const int* boxes, i
  * 3 INTER_AREA.  Bit-exact against OpenCV's CV_8UC1 arithmetic (area tables / 11-bit fixed point). */
 int b2u_resize_u8(const uint8_t* in, int n, int src_h, int src_w, uint8_t* out, int dst_h, int dst_w,
                   int interpolation, void* stream);
+/* read_nii's slice stage (T1H:288-297, 335-337): cv2.resize(slice, (dst_w, dst_h), INTER_AREA) on n float64 slices
+ * (get_fdata() values), bit-exact against OpenCV's CV_64F path, then -- minmax_normalize != 0 -- (img - min) / (max - min)
+ * per slice in double (a constant slice becomes NaN like the reference's 0/0) */
+int b2u_resize_area_f64(const double* in, int n, int src_h, int src_w, double* out, int dst_h, int dst_w,
+                        int minmax_normalize, void* stream);
 
 /* ---- BatchNormalization apply + MaxPooling2D((2,2)) + Dropout in one pass (encoder level, T1H:861-863) ---- */
 /* y = x * scale + shift is written at full resolution (the skip tensor, possibly a concat slice) and its 2x2 max,

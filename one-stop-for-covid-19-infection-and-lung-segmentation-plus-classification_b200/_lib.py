@@ -18,7 +18,7 @@ class StepState(C.Structure):
     """mirror of b2u_step_state (include/b200unet.h)"""
     _fields_ = [("seed", C.c_uint64), ("step", C.c_uint64), ("lr", C.c_float), ("beta1", C.c_float),
                 ("beta2", C.c_float), ("eps", C.c_float), ("beta1_pow", C.c_float), ("beta2_pow", C.c_float),
-                ("loss_scale", C.c_float), ("grad_div", C.c_float), ("overflow", C.c_uint32), ("pad_", C.c_uint32)]
+                ("loss_scale", C.c_float), ("grad_div", C.c_float), ("overflow", C.c_uint32), ("skip_step", C.c_uint32)]
 
 
 class Op(C.Structure):
@@ -37,7 +37,7 @@ SYMBOLS = [
     "b2u_bn_bwd_apply", "b2u_maxpool_fwd", "b2u_maxpool_bwd", "b2u_dropout_fwd", "b2u_dropout_bwd",
     "b2u_copy_slice", "b2u_head_fwd", "b2u_bce_dice_sums", "b2u_bce_dice_finalize", "b2u_head_bwd",
     "b2u_dense_fwd", "b2u_dense_bwd", "b2u_bce_fwd", "b2u_bce_sigmoid_bwd", "b2u_adam", "b2u_gather_batch",
-    "b2u_threshold_counts", "b2u_clahe_u8", "b2u_crop_resize", "b2u_resize_u8", "b2u_run_ops", "b2u_run_ops_timed", "b2u_graph_create",
+    "b2u_threshold_counts", "b2u_clahe_u8", "b2u_crop_resize", "b2u_resize_u8", "b2u_resize_area_f64", "b2u_run_ops", "b2u_run_ops_timed", "b2u_graph_create",
     "b2u_graph_launch", "b2u_graph_destroy", "b2u_launch_count", "b2u_comm_unique_id", "b2u_comm_create",
     "b2u_comm_destroy", "b2u_allreduce", "b2u_pack_weights", "b2u_bn_bwd_sums_from_wgrad", "b2u_bn_apply_pool",
 ]
@@ -73,6 +73,7 @@ def lib():
     l.b2u_clahe_u8.argtypes = [vp, vp, i32, i32, i32, f32, i32, vp, sz, vp]
     l.b2u_crop_resize.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp]
     l.b2u_resize_u8.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp]
+    l.b2u_resize_area_f64.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp]
     # per-op entry points (used directly by the per-kernel parity tests)
     l.b2u_conv3x3_fwd.argtypes = [i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, vp, i32, i32, i32, vp, sz, vp]
     l.b2u_conv3x3_dgrad.argtypes = [i32, vp, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]

@@ -9,7 +9,11 @@ pids=()
 for f in csrc/*.cu; do
   o=build/$(basename "${f%.cu}").o
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ csrc/common.cuh -nt "$o" ] || [ csrc/launch.cuh -nt "$o" ] || [ csrc/internal.h -nt "$o" ] || [ ../include/b200unet.h -nt "$o" ] || [ csrc/tc_common.cuh -nt "$o" ]; then
-    $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c "$f" -o "$o" &
+    # preprocess.cu restates OpenCV's CPU arithmetic bit for bit: no fused multiply-add contraction there (the CV_64F
+    # resize compares equal to cv2 only with separately rounded products and sums)
+    EXTRA=""
+    [ "$(basename "$f")" = "preprocess.cu" ] && EXTRA="--fmad=false"
+    $NVCC $FLAGS $EXTRA ${PTXAS_V:+-Xptxas -v} -c "$f" -o "$o" &
     pids+=($!)
   fi
 done

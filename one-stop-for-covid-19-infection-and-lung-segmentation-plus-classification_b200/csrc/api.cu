@@ -57,6 +57,11 @@ extern "C" int b2u_set_option(const char* name, int value) {
     g_b2u_tc_dwmerge = value;
     return old;
   }
+  if (strcmp(name, "tc_dw_packed") == 0) {
+    int old = g_b2u_tc_dw_packed;
+    g_b2u_tc_dw_packed = value ? 1 : 0;
+    return old;
+  }
   if (strcmp(name, "tc_dw_epi8") == 0) {
     int old = g_b2u_tc_dw_epi8;
     g_b2u_tc_dw_epi8 = value ? 1 : 0;
@@ -121,22 +126,26 @@ extern "C" int b2u_debug_read(long long* h_out, int count) {
 // Thin layers (N = Cout <= 64): the dw-merged kernel (conv_tc3w.cu) reads the A operand a third as often as the halo
 // kernel.  tc_dwmerge = 1 takes every shape the kernel supports (A/B runs, tests), 2 only the shapes where it measured
 // faster on B200 (tools/ab_ops.py --opt tc_dwmerge=0,1; profiles/).
-static bool use_dwmerge(int K, int J, int h, int wd) {
+// tc_dwmerge = 3: additionally every eligible layer of a TRAINING op list (forward ops flagged by the planner, all data
+// gradients), whose epilogue may shuffle its shifted partial sums as fp16 pairs ("tc_dw_packed", conv_tc3w.cu).
+int g_b2u_tc_dw_packed = 1;
+static bool use_dwmerge(int K, int J, int h, int wd, int training) {
   if (g_b2u_tc_dwmerge == 0 || !b2u_tc_conv3x3_dwmerge_ok(K, J)) return false;
   if (g_b2u_tc_dwmerge == 1) return true;
-  return K >= 128 && (long long)h * wd >= 128 * 128;
+  if (K >= 128 && (long long)h * wd >= 128 * 128) return true;
+  return g_b2u_tc_dwmerge == 3 && training && (long long)h * wd >= 128 * 128;
 }
 
 // `relu_bits` (optional, op lists only): packed 1-bit mask of y > 0, written by the halo kernel's epilogue or, on the
 // other paths, by one extra pass over y
 static int conv3x3_fwd_wp(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, int act, void* y,
                           int ldy, int cout, double* stats, int n, int h, int wd, void* ws, size_t ws_bytes,
-                          const void* wp, void* relu_bits, void* stream) {
+                          const void* wp, void* relu_bits, void* stream, int training = 0) {
   int rc;
   if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy)) {
-    if (use_dwmerge(cin, cout, h, wd))
+    if (use_dwmerge(cin, cout, h, wd, training))
       return b2u_tc_conv3x3_dwmerge(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, nullptr, 0, 0, 0, n, h, wd,
-                                    ws, ws_bytes, wp, stream, relu_bits);
+                                    ws, ws_bytes, wp, stream, relu_bits, training && g_b2u_tc_dw_packed);
     if (g_b2u_tc_halo)
       return b2u_tc_conv3x3_halo(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, nullptr, 0, 0, 0, n, h, wd,
                                  ws, ws_bytes, wp, stream, relu_bits);
@@ -166,9 +175,9 @@ static int conv3x3_dgrad_cs(int dt, const void* dy, int lddy, int cout, const fl
                             int wd, void* ws, size_t ws_bytes, const void* wp, void* stream) {
   const bool tc = dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cout, cin, lddy, lddx);
   const bool bits = mask != nullptr && mask_act == B2U_ACT_RELU_BITS;
-  if (tc && !(bits && accumulate) && use_dwmerge(cout, cin, h, wd))
+  if (tc && !(bits && accumulate) && use_dwmerge(cout, cin, h, wd, 1))
     return b2u_tc_conv3x3_dwmerge(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, colsum, mask, ldmask,
-                                  mask_act, accumulate, n, h, wd, ws, ws_bytes, wp, stream, nullptr);
+                                  mask_act, accumulate, n, h, wd, ws, ws_bytes, wp, stream, nullptr, g_b2u_tc_dw_packed);
   if (tc && (!bits || g_b2u_tc_halo))
     return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx,
                                                                   cin, nullptr, colsum, mask, ldmask, mask_act,
@@ -264,7 +273,8 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
   switch (o.kind) {
     case B2U_OP_CONV3X3_FWD:         // p[5] (optional): packed weights
       return conv3x3_fwd_wp(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], I(2), p[3], I(3), I(4),
-                            (double*)p[4], I(5), I(6), I(7), ws, wsb, p[5], p[6], s);     // p[6] (optional): 1-bit ReLU mask out
+                            (double*)p[4], I(5), I(6), I(7), ws, wsb, p[5], p[6], s,      // p[6] (optional): 1-bit ReLU mask out
+                            I(8));                                                       // i[8]: op of a training-mode plan
     case B2U_OP_CONV3X3_DGRAD:       // p[4] (optional): colsum
       return conv3x3_dgrad_cs(dt, p[0], I(0), I(1), (const float*)p[1], p[2], I(2), I(3), p[3], I(4), I(5), I(6),
                               (float*)p[4], I(7), I(8), I(9), ws, wsb, p[5], s);

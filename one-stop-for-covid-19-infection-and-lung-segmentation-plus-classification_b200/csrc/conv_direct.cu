@@ -601,6 +601,96 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ 
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&db[i], sacc[i]);
 }
 
+// ==========================================================================================
+// 2 <= Cin <= 4 first layer (Task-2 classifier on 224 x 224 x 3 slices, T2:748: Conv2D(16,(3,3)) -- BASELINE configs[4]).
+// K = 9 * Cin = 27 is no tensor-core shape either; the generic direct kernel spent 0.46 ms of the classifier's 0.83 ms
+// forward here (B200, batch 64).  Same scheme as the Cin == 1 kernel: thread = (pixel pair, 2-channel group), the
+// 9 * Cin * 2 weights of the group live in registers, the halo tile (all Cin channels, NHWC = contiguous) is staged in
+// shared memory, a thread computes two horizontally adjacent pixels so that the 3 x 4 input window is read once for both.
+// ==========================================================================================
+template <typename T> __device__ __forceinline__ void store4(T* p, const float v[4]);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float v[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void store4<__half>(__half* p, const float v[4]) {
+  const __half2 lo = __floats2half2_rn(v[0], v[1]), hi = __floats2half2_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
+}
+
+template <typename T> __device__ __forceinline__ void store2(T* p, const float v[2]);
+template <> __device__ __forceinline__ void store2<float>(float* p, const float v[2]) {
+  *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+}
+template <> __device__ __forceinline__ void store2<__half>(__half* p, const float v[2]) {
+  *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v[0], v[1]);
+}
+
+template <typename T, int CIN, int COUT>
+__global__ void __launch_bounds__(256, 2) conv3x3_smallcin_fwd_kernel(const T* __restrict__ x, int ldx,
+                                                                   const float* __restrict__ w,
+                                                                   const float* __restrict__ bias, int act,
+                                                                   T* __restrict__ y, int ldy, int N, int H, int W) {
+  B2U_PDL_PROLOGUE();
+  // 2 channels per thread: 54 weight registers, two blocks per SM (with 4 channels the 108 weight registers allowed one
+  // block of 8 warps per SM and the kernel was latency-bound: 0.27 ms for the classifier's first conv at batch 64)
+  constexpr int CPT = 2, CG = COUT / CPT, LANES = 256 / CG;
+  constexpr int HW2 = C1_TW + 2, HALO = (C1_TH + 2) * HW2;
+  __shared__ float xs[HALO * CIN];
+  const int g = threadIdx.x % CG, lane = threadIdx.x / CG;
+  float wr[9 * CIN][CPT], br[CPT];
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) {
+    br[k] = bias ? bias[g * CPT + k] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9 * CIN; ++t) wr[t][k] = w[t * COUT + g * CPT + k];       // HWIO: [tap][ci][co]
+  }
+  const int tiles_w = (W + C1_TW - 1) / C1_TW, tiles_h = (H + C1_TH - 1) / C1_TH;
+  const int ntiles = N * tiles_h * tiles_w;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int h0 = th * C1_TH, w0 = tw * C1_TW;
+    __syncthreads();                                         // the previous tile's readers are done
+    for (int i = threadIdx.x; i < HALO * CIN; i += 256) {
+      const int pix = i / CIN, ci = i % CIN;
+      const int hh = h0 - 1 + pix / HW2, ww = w0 - 1 + pix % HW2;
+      float v = 0.f;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = ldf<T>(x + (((long long)n * H + hh) * W + ww) * ldx + ci);
+      xs[i] = v;
+    }
+    __syncthreads();
+    for (int pp = lane; pp < C1_TH * C1_TW / 2; pp += LANES) {
+      const int r = pp / (C1_TW / 2), c = (pp % (C1_TW / 2)) * 2;
+      float a0[CPT], a1[CPT];
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) { a0[k] = br[k]; a1[k] = br[k]; }
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh) {
+        float xv[4][CIN];                                    // the row's four columns c-1 .. c+2 (halo coordinates c .. c+3)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) xv[q][ci] = xs[((r + dh) * HW2 + c + q) * CIN + ci];
+#pragma unroll
+        for (int dw = 0; dw < 3; ++dw)
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+              a0[k] = fmaf(xv[dw][ci], wr[(dh * 3 + dw) * CIN + ci][k], a0[k]);
+              a1[k] = fmaf(xv[dw + 1][ci], wr[(dh * 3 + dw) * CIN + ci][k], a1[k]);
+            }
+      }
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) { a0[k] = act_fwd(a0[k], act); a1[k] = act_fwd(a1[k], act); }
+      if (h0 + r < H) {
+        T* yp = y + (((long long)n * H + h0 + r) * W + w0 + c) * ldy + g * CPT;
+        if (w0 + c < W) store2<T>(yp, a0);                   // a pixel's COUT channels = one contiguous 32 / 64-byte span
+        if (w0 + c + 1 < W) store2<T>(yp + ldy, a1);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -624,6 +714,14 @@ int b2u_direct_conv3x3(int dt, const void* x, int ldx, int K, const float* w, in
     if (J == 32) { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_fwd_kernel<T, 32>), grid1, 256, 0, stream, (const T*)x, ldx, w, bias, act, (T*)y, ldy, n, h, wd, (uint8_t*)relu_bits)); }
     else { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_c1_fwd_kernel<T, 16>), grid1, 256, 0, stream, (const T*)x, ldx, w, bias, act, (T*)y, ldy, n, h, wd, (uint8_t*)relu_bits)); }
     if (bits_done != nullptr && relu_bits != nullptr) *bits_done = 1;
+    return B2U_OK;
+  }
+  if (K == 3 && !dgrad && stats == nullptr && mask == nullptr && !accumulate && (J == 16 || J == 32) && ldy % 4 == 0 &&
+      ((uintptr_t)y & 15) == 0) {
+    long long gl = (long long)n * b2u_cdiv(h, C1_TH) * b2u_cdiv(wd, C1_TW);
+    int grid3 = (int)(gl < 2 * B2U_NUM_SMS ? gl : 2 * B2U_NUM_SMS);       // two persistent blocks per SM
+    if (J == 16) { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_smallcin_fwd_kernel<T, 3, 16>), grid3, 256, 0, stream, (const T*)x, ldx, w, bias, act, (T*)y, ldy, n, h, wd)); }
+    else { DISPATCH_T(dt, B2U_LAUNCH((conv3x3_smallcin_fwd_kernel<T, 3, 32>), grid3, 256, 0, stream, (const T*)x, ldx, w, bias, act, (T*)y, ldy, n, h, wd)); }
     return B2U_OK;
   }
   if (J > 32) {

@@ -77,7 +77,7 @@ __device__ __forceinline__ float transpose_reduce16w(float v[16], int lane) {
 
 // epilogue features as compile-time variants (see conv_tc3.cu): bit 0 = fp16 activation mask and/or accumulate,
 // bit 1 = BatchNorm statistics and/or column sums, bit 2 = write a 1-bit ReLU mask, bit 3 = read one
-constexpr int kW_MASKACC = 1, kW_SUMS = 2, kW_BITS_OUT = 4, kW_BITS_IN = 8;
+constexpr int kW_MASKACC = 1, kW_SUMS = 2, kW_BITS_OUT = 4, kW_BITS_IN = 8, kW_PACKED = 16;
 
 // variants without register statistics are capped at 102 registers: two CTAs of 320 threads then share an SM
 template <int kFlags>
@@ -264,10 +264,27 @@ __global__ void __launch_bounds__(kThreadsW3, (kFlags & 2) ? 1 : 2) tc_conv3w_ke
           tc::reg_fence16(a2);
           if (dbg_e && cc == 0) prm.dbg[(tile / gridDim.x) * 8 + 7] = clock64();
           float v[16];
+          if constexpr ((kFlags & kW_PACKED) != 0) {
+            // training-mode ops: the two shifted partial sums travel as fp16 pairs -- 16 shuffles per chunk instead of 32
+            // (the epilogue is bound by the SHFL rate of the SM's MIO pipe: ncu source view, profiles/).  The partials
+            // are rounded to fp16 once more than the stored result is; inference ops keep the exact fp32 shuffles.
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            v[i] = (__uint_as_float(a0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(a1[i]), 1)) +
-                   __shfl_down_sync(0xffffffffu, __uint_as_float(a2[i]), 2);
+            for (int j = 0; j < 8; ++j) {
+              __half2 h1 = __floats2half2_rn(__uint_as_float(a1[2 * j]), __uint_as_float(a1[2 * j + 1]));
+              __half2 h2 = __floats2half2_rn(__uint_as_float(a2[2 * j]), __uint_as_float(a2[2 * j + 1]));
+              const unsigned u1 = __shfl_down_sync(0xffffffffu, *reinterpret_cast<unsigned*>(&h1), 1);
+              const unsigned u2 = __shfl_down_sync(0xffffffffu, *reinterpret_cast<unsigned*>(&h2), 2);
+              const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&u1));
+              const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&u2));
+              v[2 * j] = (__uint_as_float(a0[2 * j]) + f1.x) + f2.x;
+              v[2 * j + 1] = (__uint_as_float(a0[2 * j + 1]) + f1.y) + f2.y;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              v[i] = (__uint_as_float(a0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(a1[i]), 1)) +
+                     __shfl_down_sync(0xffffffffu, __uint_as_float(a2[i]), 2);
+          }
           const float4* bp = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -452,7 +469,7 @@ int b2u_tc_conv3x3_dwmerge_ok(int K, int J) {
 int b2u_tc_conv3x3_dwmerge(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                            int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
                            int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream,
-                           void* relu_bits_out) {
+                           void* relu_bits_out, int packed_shift) {
   int rc = get_encw();
   if (rc != B2U_OK) return rc;
   B2U_REQUIRE(b2u_tc_conv3x3_dwmerge_ok(K, J), "tc_conv3w: unsupported channel counts K=%d J=%d", K, J);
@@ -520,7 +537,9 @@ int b2u_tc_conv3x3_dwmerge(const void* x, int ldx, int K, const float* w, int dg
     if (r != CUDA_SUCCESS) { b2u_set_error("tc_conv3w: weight tensor map failed (%d)", (int)r); return B2U_ERR_CUDA; }
   }
   if (!g_attrw) {
-#define B2U_W3_ATTR(F) B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3w_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+#define B2U_W3_ATTR(F)                                                                                                   \
+  B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3w_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));     \
+  B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3w_kernel<F | kW_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
     B2U_W3_ATTR(0); B2U_W3_ATTR(1); B2U_W3_ATTR(2); B2U_W3_ATTR(3); B2U_W3_ATTR(4); B2U_W3_ATTR(6); B2U_W3_ATTR(8); B2U_W3_ATTR(10);
 #undef B2U_W3_ATTR
     g_attrw = true;
@@ -533,18 +552,21 @@ int b2u_tc_conv3x3_dwmerge(const void* x, int ldx, int K, const float* w, int dg
   const int flags = ((mask != nullptr || accumulate) ? kW_MASKACC : 0) | ((stats != nullptr || colsum != nullptr) ? kW_SUMS : 0) |
                     (p.bits_out != nullptr ? kW_BITS_OUT : 0) | (p.bits_in != nullptr ? kW_BITS_IN : 0);
   const int nthr = 64 + 32 * p.epi_warps;
+#define B2U_W3_CASE(F)                                                                                     \
+  case F:                                                                                                  \
+    if (packed_shift) B2U_LAUNCH(tc_conv3w_kernel<F | kW_PACKED>, grid, nthr, smem, stream, maps, p);      \
+    else B2U_LAUNCH(tc_conv3w_kernel<F>, grid, nthr, smem, stream, maps, p);                               \
+    break
   switch (flags) {
-    case 0: B2U_LAUNCH(tc_conv3w_kernel<0>, grid, nthr, smem, stream, maps, p); break;
-    case 1: B2U_LAUNCH(tc_conv3w_kernel<1>, grid, nthr, smem, stream, maps, p); break;
-    case 2: B2U_LAUNCH(tc_conv3w_kernel<2>, grid, nthr, smem, stream, maps, p); break;
-    case 3: B2U_LAUNCH(tc_conv3w_kernel<3>, grid, nthr, smem, stream, maps, p); break;
-    case 4: B2U_LAUNCH(tc_conv3w_kernel<4>, grid, nthr, smem, stream, maps, p); break;      // forward + bit mask
-    case 6: B2U_LAUNCH(tc_conv3w_kernel<6>, grid, nthr, smem, stream, maps, p); break;      // ... + statistics
-    case 8: B2U_LAUNCH(tc_conv3w_kernel<8>, grid, nthr, smem, stream, maps, p); break;      // data gradient, 1-bit mask
-    case 10: B2U_LAUNCH(tc_conv3w_kernel<10>, grid, nthr, smem, stream, maps, p); break;    // ... + column sums
+    B2U_W3_CASE(0); B2U_W3_CASE(1); B2U_W3_CASE(2); B2U_W3_CASE(3);
+    B2U_W3_CASE(4);        // forward + bit mask
+    B2U_W3_CASE(6);        // ... + statistics
+    B2U_W3_CASE(8);        // data gradient, 1-bit mask
+    B2U_W3_CASE(10);       // ... + column sums
     default:
       b2u_set_error("tc_conv3w: unsupported feature combination %d (1-bit masks do not combine with accumulate / fp16 masks)", flags);
       return B2U_ERR_ARG;
   }
+#undef B2U_W3_CASE
   return B2U_OK;
 }

@@ -749,10 +749,28 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(
 // ------------------------------------------------------------------------------------------
 // Adam over the flat parameter buffer; step-state bookkeeping; batch gather
 // ------------------------------------------------------------------------------------------
+// One pass over the (all-reduced) gradient buffer before the update: ANY non-finite value (fp16 overflow of an activation
+// gradient under the static loss scale) marks the whole step as skipped -- Adam then leaves parameters and moments
+// alone, the step / beta powers do not advance and the loss scale is halved (state_advance_kernel), as dynamic loss
+// scaling does; a per-element skip would apply the finite part of a corrupted gradient.  31 MB: ~7 us.
+__global__ void __launch_bounds__(kThreads) grad_finite_check_kernel(const float* __restrict__ g, long long n,
+                                                                     b2u_step_state* __restrict__ st) {
+  B2U_PDL_PROLOGUE();
+  bool bad = false;
+  const long long nq = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+    const float4 a = reinterpret_cast<const float4*>(g)[q];
+    bad |= !(isfinite(a.x) && isfinite(a.y) && isfinite(a.z) && isfinite(a.w));
+  }
+  for (long long i = (nq << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) bad |= !isfinite(g[i]);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&st->skip_step, 1u);
+}
+
 __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, long long n,
                                                         b2u_step_state* __restrict__ st) {
   B2U_PDL_PROLOGUE();
+  if (*reinterpret_cast<volatile const uint32_t*>(&st->skip_step) != 0u) return;     // whole step skipped (set by the check pass)
   // 16-byte accesses (the flat buffers are 16-byte aligned and every tensor is padded to 4 elements), two
   // quads per trip so that eight independent loads are in flight per thread
   const float b1 = st->beta1, b2 = st->beta2, eps = st->eps;
@@ -801,6 +819,12 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, c
 }
 __global__ void state_advance_kernel(b2u_step_state* st) {
   B2U_PDL_PROLOGUE();
+  if (st->skip_step != 0u) {              // skipped step: nothing advances, the loss scale backs off, the host is told
+    st->skip_step = 0u;
+    st->overflow = 1u;
+    st->loss_scale = fmaxf(st->loss_scale * 0.5f, 1.f);
+    return;
+  }
   st->step += 1;
   st->beta1_pow *= st->beta1;
   st->beta2_pow *= st->beta2;
@@ -1276,6 +1300,7 @@ extern "C" int b2u_adam(float* params, const float* grads, float* m, float* v, l
   B2U_REQUIRE(n >= 0 && d_state != nullptr, "adam: args");
   if (n == 0) return B2U_OK;
   B2U_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam: buffers must be 16-byte aligned");
+  B2U_LAUNCH(grad_finite_check_kernel, stream_grid((n + 7) / 8), kThreads, 0, stream, grads, n, d_state);
   B2U_LAUNCH(adam_kernel, stream_grid((n + 7) / 8), kThreads, 0, stream, params, grads, m, v, n, d_state);
   return B2U_OK;
 }

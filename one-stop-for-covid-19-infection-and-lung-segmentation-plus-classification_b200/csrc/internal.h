@@ -68,6 +68,7 @@ int b2u_tc_conv3x3_dwmerge_ok(int K, int J);
 int b2u_tc_conv3x3_dwmerge(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                            int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
                            int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream,
-                           void* relu_bits_out);
+                           void* relu_bits_out, int packed_shift);
+extern int g_b2u_tc_dw_packed;
 int b2u_dense_fwd_ws(int dt, const void* x, int k, const float* w, const float* bias, int act, void* y, int m, int n,
                      void* ws, size_t ws_bytes, void* stream);

@@ -245,6 +245,110 @@ __global__ void __launch_bounds__(256) area_resize_kernel(const uint8_t* __restr
   }
 }
 
+// ---- CV_64F INTER_AREA + per-slice min-max (the first stage of the NIfTI ingest, T1H:288-297 / 335-337) -----------
+// the same three regimes with double accumulators, float32 coefficients promoted to double, separate multiply / add
+// roundings, the fast path summing in groups of four like OpenCV's unrolled loop; no rounding at the end
+__device__ __forceinline__ double area_pixel_f64(const double* src, long long pitch, int sw, int sh, int dw, int dh, int dx,
+                                                 int dy) {
+  const double inv_x = (double)dw / (double)sw, inv_y = (double)dh / (double)sh;
+  const double scale_x = 1.0 / inv_x, scale_y = 1.0 / inv_y;
+  if (scale_x >= 1.0 && scale_y >= 1.0) {
+    const int ix = __double2int_rn(scale_x), iy = __double2int_rn(scale_y);
+    if (fabs(scale_x - ix) < 2.220446049250313e-16 && fabs(scale_y - iy) < 2.220446049250313e-16) {
+      const int area = ix * iy;
+      const double sc = (double)__fdiv_rn(1.f, (float)area);
+      double sum = 0.0, grp = 0.0;
+      int k = 0;
+      const int full = area & ~3;
+      for (int yy = 0; yy < iy; ++yy)
+        for (int xx = 0; xx < ix; ++xx, ++k) {
+          const double v = src[(long long)(dy * iy + yy) * pitch + dx * ix + xx];
+          if (k < full) {
+            grp = (k & 3) == 0 ? v : __dadd_rn(grp, v);
+            if ((k & 3) == 3) sum = __dadd_rn(sum, grp);
+          } else {
+            sum = __dadd_rn(sum, v);
+          }
+        }
+      return __dmul_rn(sum, sc);
+    }
+    const AreaTab tx = area_tab(dx, sw, scale_x), ty = area_tab(dy, sh, scale_y);
+    double sum = 0.0;
+    for (int j = 0; j < ty.n; ++j) {
+      const double* row = src + (long long)(ty.s_first + j) * pitch;
+      double buf = 0.0;
+      for (int k = 0; k < tx.n; ++k) buf = __dadd_rn(buf, __dmul_rn(row[tx.s_first + k], (double)area_alpha(tx, k)));
+      const double term = __dmul_rn((double)area_alpha(ty, j), buf);
+      sum = j == 0 ? term : __dadd_rn(sum, term);
+    }
+    return sum;
+  }
+  // up-sampling in a dimension: bilinear, "area" coefficients in float32, arithmetic in double
+  int sx = (int)floor((double)dx * scale_x);
+  float fx = (float)((double)(dx + 1) - (double)(sx + 1) * inv_x);
+  fx = fx <= 0.f ? 0.f : fx - floorf(fx);
+  if (sx < 0) { fx = 0.f; sx = 0; }
+  if (sx >= sw - 1) { fx = 0.f; sx = sw - 1; }
+  int sy = (int)floor((double)dy * scale_y);
+  float fy = (float)((double)(dy + 1) - (double)(sy + 1) * inv_y);
+  fy = fy <= 0.f ? 0.f : fy - floorf(fy);
+  if (sy < 0) { fy = 0.f; sy = 0; }
+  if (sy >= sh - 1) { fy = 0.f; sy = sh - 1; }
+  const int sx1 = min(sx + 1, sw - 1), sy1 = min(sy + 1, sh - 1);
+  const double a0 = (double)(1.f - fx), a1 = (double)fx, b0 = (double)(1.f - fy), b1 = (double)fy;
+  const double* r0 = src + (long long)sy * pitch;
+  const double* r1 = src + (long long)sy1 * pitch;
+  const bool edge = sx >= sw - 1;                                   // (dx >= xmax: D = S[sx] * ONE)
+  const double h0 = edge ? r0[sx] : __dadd_rn(__dmul_rn(r0[sx], a0), __dmul_rn(r0[sx1], a1));
+  const double h1 = edge ? r1[sx] : __dadd_rn(__dmul_rn(r1[sx], a0), __dmul_rn(r1[sx1], a1));
+  return __dadd_rn(__dmul_rn(h0, b0), __dmul_rn(h1, b1));
+}
+
+__global__ void __launch_bounds__(256) area_resize_f64_kernel(const double* __restrict__ in, int sh, int sw,
+                                                              double* __restrict__ out, int dh, int dw, int N) {
+  B2U_PDL_PROLOGUE();
+  const long long total = (long long)N * dh * dw;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int dx = (int)(idx % dw);
+    const long long t = idx / dw;
+    const int dy = (int)(t % dh);
+    const int n = (int)(t / dh);
+    const double* src = in + (long long)n * sh * sw;
+    out[idx] = (sh == dh && sw == dw) ? src[(long long)dy * sw + dx]          // cv::resize: same size = copy
+                                      : area_pixel_f64(src, sw, sw, sh, dw, dh, dx, dy);
+  }
+}
+
+// (img - min) / (max - min) per image in double, exactly numpy's two roundings; a constant image gives 0/0 = NaN like
+// the reference (T1H:337).  One block per image.
+__global__ void __launch_bounds__(1024) minmax_normalize_f64_kernel(double* __restrict__ img, long long count) {
+  B2U_PDL_PROLOGUE();
+  double* p = img + (long long)blockIdx.x * count;
+  __shared__ double smin[32], smax[32];
+  double lo = INFINITY, hi = -INFINITY;
+  bool nan = false;
+  for (long long i = threadIdx.x; i < count; i += blockDim.x) {
+    const double v = p[i];
+    nan |= v != v;
+    lo = fmin(lo, v);
+    hi = fmax(hi, v);
+  }
+  for (int o = 16; o >= 1; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  nan = __syncthreads_or(nan);
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  lo = smin[0];
+  hi = smax[0];
+  for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { lo = fmin(lo, smin[k]); hi = fmax(hi, smax[k]); }
+  if (nan) { lo = NAN; hi = NAN; }                                 // numpy's min / max propagate NaN
+  const double den = __dsub_rn(hi, lo);
+  for (long long i = threadIdx.x; i < count; i += blockDim.x) p[i] = __ddiv_rn(__dsub_rn(p[i], lo), den);
+}
+
 // Stage 2: cv2.resize(mid, (final, final), INTER_LINEAR) for uint8 (OpenCV fixed point: 11-bit coefficients, two-pass
 // with the (>>4, >>16, +2 >>2) rounding of its 8-bit VResizeLinear), then np.uint8(.) / 255 (T1H:485-488).
 __global__ void __launch_bounds__(256) linear_resize_scale_kernel(const uint8_t* __restrict__ mid, int mh, int mw, int fd,
@@ -320,5 +424,18 @@ extern "C" int b2u_resize_u8(const uint8_t* in, int n, int src_h, int src_w, uin
     b2u_set_error("resize_u8: interpolation %d not supported (1 = INTER_LINEAR, 3 = INTER_AREA)", interpolation);
     return B2U_ERR_ARG;
   }
+  return B2U_OK;
+}
+
+// the first stage of the NIfTI ingest on the device: cv2.resize(slice, (dst_w, dst_h), INTER_AREA) on float64 slices
+// (T1H:335), bit-exact against OpenCV's CV_64F arithmetic; then optionally (img - min) / (max - min) per slice (T1H:336-337)
+extern "C" int b2u_resize_area_f64(const double* in, int n, int src_h, int src_w, double* out, int dst_h, int dst_w,
+                                   int minmax_normalize, void* stream) {
+  B2U_REQUIRE(in != nullptr && out != nullptr && n > 0 && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "resize_area_f64: args");
+  long long total = (long long)n * dst_h * dst_w;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 32 * B2U_NUM_SMS) grid = 32 * B2U_NUM_SMS;
+  B2U_LAUNCH(area_resize_f64_kernel, grid, 256, 0, stream, in, src_h, src_w, out, dst_h, dst_w, n);
+  if (minmax_normalize) B2U_LAUNCH(minmax_normalize_f64_kernel, n, 1024, 0, stream, out, (long long)dst_h * dst_w);
   return B2U_OK;
 }

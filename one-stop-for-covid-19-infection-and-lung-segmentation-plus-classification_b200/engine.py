@@ -115,7 +115,7 @@ class Engine:
         # data parallel: every rank draws its own dropout masks (same counters, rank-specific key)
         self.host_state = _lib.StepState(seed=dropout_seed + 7919 * self.rank, step=0, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-7,
                                          beta1_pow=0.9, beta2_pow=0.999, loss_scale=1.0,
-                                         grad_div=1.0 if self.sync_stats else float(self.world), overflow=0, pad_=0)
+                                         grad_div=1.0 if self.sync_stats else float(self.world), overflow=0, skip_step=0)
         self._arenas = {}        # name -> torch uint8 tensor (grown on demand, shared between plans)
         self._bound = {}         # (n, training, dropout, loss) -> _Bound
         self._push_state()
@@ -181,7 +181,13 @@ class Engine:
         self._set_fields(lr=float(np.float32(v)))
 
     def overflowed(self):
+        """True once a step was skipped because its gradient was not finite (the device then halved the loss scale)"""
         return bool(self._pull_state().overflow)
+
+    @property
+    def loss_scale(self):
+        """the loss scale on the device: the static choice of train_batch, halved by every skipped step"""
+        return float(self._pull_state().loss_scale)
 
     # ---------------------------------------------------------------------------------------
     # weights

@@ -355,7 +355,9 @@ def _as_array(v):
         a = a.astype(np.uint8)
     if a.dtype.kind == "f" and a.dtype.itemsize == 2:
         a = a.astype(np.float32)
-    return np.ascontiguousarray(a.astype(a.dtype.newbyteorder("<")) if a.dtype.byteorder == ">" else a)
+    if a.dtype.byteorder == ">":
+        a = a.astype(a.dtype.newbyteorder("<"))
+    return a if a.flags.c_contiguous else np.array(a, order="C")     # (np.ascontiguousarray would turn scalars into 1-D)
 
 
 def _msg(mtype, body, flags=0):

@@ -19,6 +19,7 @@ import torch
 
 from . import dist as D
 from . import engine as E
+from . import hdf5 as H5
 from . import layers as L
 from . import losses as LS
 from . import plan as P
@@ -198,15 +199,10 @@ class Model:
         print_fn("Non-trainable params: {:,}".format(ntr))
 
     def to_json(self):
-        cfg = []
-        for l in self.graph.layers:
-            d = {"class_name": type(l).__name__, "name": l.name, "inbound": [t.producer.name for t in l.inputs],
-                 "output_shape": list(l.output.shape)}
-            for k in ("filters", "kernel_size", "activation", "rate", "units", "kernel_initializer", "momentum", "epsilon"):
-                if hasattr(l, k):
-                    d[k] = getattr(l, k)
-            cfg.append(d)
-        return json.dumps({"class_name": "Model", "config": {"layers": cfg}, "backend": "b200unet"})
+        """keras `model.to_json()` (T1H:1091, UPP:1113): the functional-API architecture description Keras 2.3 writes --
+        class_name Model, config.layers[{name, class_name, config, inbound_nodes}], input_layers, output_layers --
+        so `keras.models.model_from_json` can rebuild the network, and `model_from_json` below reads Keras' own files."""
+        return json.dumps(keras_config(self.graph))
 
     # ---- engine ------------------------------------------------------------------------------
     @property
@@ -256,15 +252,48 @@ class Model:
     def set_weights_dict(self, d):
         self.engine.set_weights(d)
 
+    def _keras_layers(self, d):
+        """[(layer name, [(weight name 'layer/kernel:0', array), ...])] in model.layers order (Keras' HDF5 layout)"""
+        out = []
+        for l in self.graph.layers:
+            out.append((l.name, [("%s/%s:0" % (l.name, k), d["%s/%s" % (l.name, k)]) for k in l.weights]))
+        return out
+
     def save_weights(self, path):
+        """keras `model.save_weights(path)` (T1H:1079, CV4:1105-1108): '.h5' / '.hdf5' / '.keras' paths are written as Keras
+        2.3 HDF5 weight files (hdf5.py: layer_names / weight_names attributes, <layer>/<layer>/kernel:0 datasets in Keras
+        layouts), anything else as a numpy .npz archive."""
         if self.engine.rank != 0:           # data parallel: replicas are identical, rank 0 owns the file
             return
         d = self.engine.get_weights()
+        if str(path).lower().endswith((".h5", ".hdf5", ".keras")):
+            H5.save_keras_weights(path, self._keras_layers(d))
+            return
         with open(path, "wb") as f:
             np.savez(f, **{k.replace("/", "__"): v for k, v in d.items()})
 
     def load_weights(self, path):
+        """keras `model.load_weights(path)` (T1H:1073, 1190): Keras HDF5 weight files -- also the full-model files
+        ModelCheckpoint writes (weights under /model_weights, T1H:1044-1047) -- or the .npz archives of save_weights.
+        Layers are matched by name like Keras' topological loading does for identical architectures; shapes are checked."""
         D.barrier(self.engine.world)        # data parallel: rank 0 may still be writing the file
+        with open(path, "rb") as f:
+            magic = f.read(8)
+        if magic == H5.SIGNATURE or str(path).lower().endswith((".h5", ".hdf5")):
+            layers = H5.load_keras_weights(path)
+            d = {}
+            for l in self.graph.layers:
+                if not l.weights:
+                    continue
+                if l.name not in layers:
+                    raise ValueError("weight file %s has no layer %r" % (path, l.name))
+                vals = list(layers[l.name].values())
+                if len(vals) != len(l.weights):
+                    raise ValueError("layer %s: file has %d weight tensors, the model %d" % (l.name, len(vals), len(l.weights)))
+                for k, v in zip(l.weights, vals):          # Keras order within a layer: kernel, bias / gamma, beta, mean, var
+                    d["%s/%s" % (l.name, k)] = v
+            self.engine.set_weights(d)
+            return
         with np.load(path) as z:
             self.engine.set_weights({k.replace("__", "/"): z[k] for k in z.files})
 
@@ -501,7 +530,7 @@ class Model:
                     lo += n
             eng.stream.synchronize()
             if eng.overflowed():
-                print("warning: non-finite gradients were skipped this epoch (loss scale %g)" % eng._cur_ls)
+                print("warning: steps with non-finite gradients were skipped this epoch (loss scale now %g)" % eng.loss_scale)
                 eng._set_fields(overflow=0)
             w = np.asarray(sizes, np.float64)
             lb = lossbuf.cpu().numpy().astype(np.float64)
@@ -568,3 +597,116 @@ class Sequential(Model):
             self._ensure()
             return getattr(self, name)
         raise AttributeError(name)
+
+
+# ---- Keras architecture JSON (model.to_json / model_from_json, T1H:1091) ------------------------------------------
+_INIT = {"he_normal": {"class_name": "VarianceScaling", "config": {"scale": 2.0, "mode": "fan_in", "distribution": "normal", "seed": None}},
+         "glorot_uniform": {"class_name": "VarianceScaling", "config": {"scale": 1.0, "mode": "fan_avg", "distribution": "uniform", "seed": None}}}
+_ZEROS, _ONES = {"class_name": "Zeros", "config": {}}, {"class_name": "Ones", "config": {}}
+
+
+def _layer_config(l):
+    base = {"name": l.name, "trainable": True, "dtype": "float32"}
+    reg = {"kernel_regularizer": None, "bias_regularizer": None, "activity_regularizer": None, "kernel_constraint": None,
+           "bias_constraint": None}
+    k = l.kind
+    if k == "input":
+        return "InputLayer", {"batch_input_shape": [None] + list(l.output.shape), "dtype": "float32", "sparse": False, "name": l.name}
+    if k == "conv2d":
+        return "Conv2D", dict(base, filters=l.filters, kernel_size=list(l.kernel_size), strides=[1, 1], padding=l.padding,
+                              data_format="channels_last", dilation_rate=[1, 1], activation=l.activation or "linear",
+                              use_bias=True, kernel_initializer=_INIT[l.kernel_initializer], bias_initializer=_ZEROS, **reg)
+    if k == "conv2d_transpose":
+        return "Conv2DTranspose", dict(base, filters=l.filters, kernel_size=[2, 2], strides=[2, 2], padding="same",
+                                       data_format="channels_last", dilation_rate=[1, 1], activation="linear", use_bias=True,
+                                       kernel_initializer=_INIT[l.kernel_initializer], bias_initializer=_ZEROS,
+                                       output_padding=None, **reg)
+    if k == "batch_normalization":
+        return "BatchNormalization", dict(base, axis=-1, momentum=l.momentum, epsilon=l.epsilon, center=True, scale=True,
+                                          beta_initializer=_ZEROS, gamma_initializer=_ONES, moving_mean_initializer=_ZEROS,
+                                          moving_variance_initializer=_ONES, beta_regularizer=None, gamma_regularizer=None,
+                                          beta_constraint=None, gamma_constraint=None)
+    if k == "max_pooling2d":
+        return "MaxPooling2D", dict(base, pool_size=[2, 2], padding="valid", strides=[2, 2], data_format="channels_last")
+    if k == "dropout":
+        return "Dropout", dict(base, rate=l.rate, noise_shape=None, seed=None)
+    if k == "concatenate":
+        return "Concatenate", dict(base, axis=3)
+    if k == "flatten":
+        return "Flatten", dict(base, data_format="channels_last")
+    if k == "dense":
+        return "Dense", dict(base, units=l.units, activation=l.activation or "linear", use_bias=True,
+                             kernel_initializer=_INIT[l.kernel_initializer], bias_initializer=_ZEROS, **reg)
+    raise ValueError("no Keras class for layer kind %r" % k)
+
+
+def keras_config(graph, name="model_1"):
+    layers = []
+    for l in graph.layers:
+        cls, cfg = _layer_config(l)
+        inbound = [[[t.producer.name, 0, 0, {}] for t in l.inputs]] if l.inputs else []
+        layers.append({"name": l.name, "class_name": cls, "config": cfg, "inbound_nodes": inbound})
+    return {"class_name": "Model", "config": {"name": name, "layers": layers,
+                                              "input_layers": [[graph.input.producer.name, 0, 0]],
+                                              "output_layers": [[graph.output.producer.name, 0, 0]]},
+            "keras_version": "2.3.1", "backend": "tensorflow"}
+
+
+def _init_name(spec):
+    if isinstance(spec, str):
+        return spec
+    c = (spec or {}).get("config", {})
+    if (spec or {}).get("class_name") == "VarianceScaling" and c.get("mode") == "fan_in" and c.get("scale") == 2.0:
+        return "he_normal"
+    return "glorot_uniform"
+
+
+def model_from_json(text, **model_kw):
+    """keras.models.model_from_json for the layer classes the reference uses: rebuilds the Graph from a Keras
+    functional-model ("Model") or Sequential JSON, keeping the layer names of the file."""
+    cfg = json.loads(text)
+    kind, conf = cfg["class_name"], cfg["config"]
+    L.reset_names()
+    tensors = {}
+    entries = conf["layers"] if isinstance(conf, dict) else conf
+    prev = None
+    for e in entries:
+        c, cls, name = e["config"], e["class_name"], e["config"].get("name", e.get("name"))
+        if cls == "InputLayer":
+            t = L.Input(tuple(c["batch_input_shape"][1:]), name=name)
+            tensors[name] = prev = t
+            continue
+        if kind == "Sequential" and prev is None:
+            prev = L.Input(tuple(c["batch_input_shape"][1:]))
+            tensors[prev.producer.name] = prev
+        if cls == "Conv2D":
+            layer = L.Conv2D(c["filters"], tuple(c["kernel_size"]), activation=None if c["activation"] == "linear" else c["activation"],
+                             padding=c["padding"], kernel_initializer=_init_name(c.get("kernel_initializer")), name=name)
+        elif cls == "Conv2DTranspose":
+            layer = L.Conv2DTranspose(c["filters"], tuple(c["kernel_size"]), strides=tuple(c["strides"]), padding=c["padding"],
+                                      kernel_initializer=_init_name(c.get("kernel_initializer")), name=name)
+        elif cls == "BatchNormalization":
+            layer = L.BatchNormalization(momentum=c.get("momentum", 0.99), epsilon=c.get("epsilon", 1e-3), name=name)
+        elif cls == "MaxPooling2D":
+            layer = L.MaxPooling2D(tuple(c["pool_size"]), name=name)
+        elif cls == "Dropout":
+            layer = L.Dropout(c["rate"], name=name)
+        elif cls == "Concatenate":
+            layer = L.Concatenate(axis=c.get("axis", -1), name=name)
+        elif cls == "Flatten":
+            layer = L.Flatten(name=name)
+        elif cls == "Dense":
+            layer = L.Dense(c["units"], activation=None if c["activation"] == "linear" else c["activation"],
+                            kernel_initializer=_init_name(c.get("kernel_initializer")), name=name)
+        else:
+            raise ValueError("model_from_json: layer class %r is outside the reference's layer set" % cls)
+        if kind == "Sequential":
+            ins = [prev]
+        else:
+            ins = [tensors[n[0]] for n in e["inbound_nodes"][0]]
+        out = layer(ins if cls == "Concatenate" else ins[0])
+        tensors[name] = prev = out
+    if kind == "Sequential":
+        first = next(t for t in tensors.values() if t.producer.kind == "input")
+        return Model(inputs=[first], outputs=[prev], **model_kw)
+    return Model(inputs=[tensors[conf["input_layers"][0][0]]], outputs=[tensors[conf["output_layers"][0][0]]], **model_kw)

@@ -91,14 +91,19 @@ def save_nii(path, array, scl_slope=0.0, scl_inter=0.0, byteorder="<"):
         f.write(blob)
 
 
-def volume_slices(array, img_size=IMG_SIZE):
+def volume_slices(array, img_size=IMG_SIZE, device=False):
     """T1H:288-297: rot90, keep slices [round(0.2 S), round(0.8 S)), resize each to img_size^2 with INTER_AREA and
     min-max normalise it.  Returns (S', img_size, img_size) float64; constant slices come out as NaN exactly like the
-    reference's 0/0 (read_nii skips them for the lung volume before this point matters)."""
-    import cv2
+    reference's 0/0 (read_nii skips them for the lung volume before this point matters).
+    device=True runs the resize + normalisation on the GPU (b2u_resize_area_f64, bit-exact against cv2 / numpy: this is
+    what preprocess_case uses); device=False is the reference's own cv2 call sequence on the host."""
     a = np.rot90(np.array(array))
     s = a.shape[2]
     a = a[:, :, round(s * 0.2):round(s * 0.8)]
+    if device:
+        from .preprocess import resize_area_normalize
+        return resize_area_normalize(np.ascontiguousarray(np.rollaxis(a, 2), dtype=np.float64), img_size)
+    import cv2
     a = np.reshape(np.rollaxis(a, 2), (a.shape[2], a.shape[0], a.shape[1], 1))
     out = np.empty((a.shape[0], img_size, img_size), np.float64)
     for k in range(a.shape[0]):
@@ -128,20 +133,21 @@ def lung_boxes(lung_slices):
 
 def preprocess_case(ct_path, lung_path, infection_path=None, new_dim=224, img_size=IMG_SIZE):
     """One patient, file to network input: what read_nii('lungs') / ('cts') / ('infections') followed by the final
-    resize and /255 produce (T1H:390-393, 485-488, 678-686).  CLAHE, crop, area / bilinear resize and scaling run on
-    the GPU (preprocess.py); contour tracing and the 512^2 area resize of the raw volume stay on the host with cv2.
+    resize and /255 produce (T1H:390-393, 485-488, 678-686).  The 512^2 area resize + min-max of the raw float64 slices,
+    CLAHE, crop, area / bilinear resize and scaling all run on the GPU (preprocess.py), bit-exact against the
+    reference's cv2 / numpy calls; only the contour tracing of `cropper` (cv2.findContours) stays on the host.
     Returns (x, y, boxes): x, y float32 (N, new_dim, new_dim, 1); y is None without an infection mask."""
     from . import preprocess as PP
     lung, _ = load_nii(lung_path)
     ct, _ = load_nii(ct_path)
-    _, boxes = lung_boxes(volume_slices(lung, img_size))
-    cts = volume_slices(ct, img_size)
+    _, boxes = lung_boxes(volume_slices(lung, img_size, device=True))
+    cts = volume_slices(ct, img_size, device=True)
     n = min(len(cts), len(boxes))                               # T1H:347: slice i uses box i while i < len(boxes)
     enhanced = PP.clahe_enhancer(np.nan_to_num(cts[:n]))        # np.uint8(img * 255) -> CLAHE, uint8 (T1H:169-170)
     x, _ = PP.crop_resize(enhanced, boxes[:n], new_dim=new_dim)
     y = None
     if infection_path is not None:
         inf, _ = load_nii(infection_path)
-        infs = np.uint8(np.nan_to_num(volume_slices(inf, img_size)[:n]) * 255)          # T1H:363
+        infs = np.uint8(np.nan_to_num(volume_slices(inf, img_size, device=True)[:n]) * 255)          # T1H:363
         y, _ = PP.crop_resize(infs, boxes[:n], new_dim=new_dim)
     return x, y, boxes[:n]

@@ -312,7 +312,8 @@ class Plan:
                     bits = self._bits[id(t)] = self.act.alloc(self._npix(yv) * yv.c // 8)
                 self.fwd.append(Op(OP_CONV3X3_FWD, dt, [xv.ref, self._w(l, "kernel"), self._w(l, "bias"), yv.ref, stats,
                                                         self._packed(l, 0, 9, yv.c, xv.c), bits],
-                                   [xv.ld, xv.c, ACT[l.activation], yv.ld, yv.c, n, xv.h, xv.w], tag=l.name))
+                                   [xv.ld, xv.c, ACT[l.activation], yv.ld, yv.c, n, xv.h, xv.w, 1 if self.training else 0],
+                                   tag=l.name))      # i[8]: training-mode op (kernel selection may trade a rounding for speed)
             elif l.kind == "conv2d":      # 1x1 output head
                 if l.activation != "sigmoid" or l.filters != 1 or t is not g.output:
                     raise NotImplementedError("1x1 conv is supported as the sigmoid output head only")

@@ -92,3 +92,17 @@ def resize(images_u8, dsize, interpolation=INTER_AREA):
                                         int(interpolation), _stream_ptr()), "resize_u8")
     out = d_out.cpu().numpy()
     return out[0] if single else out
+
+
+def resize_area_normalize(slices_f64, img_size=512, normalize=True):
+    """read_nii's first stage on the GPU (T1H:335-337): cv2.resize(img, (img_size, img_size), INTER_AREA) on float64
+    slices (S,H,W), then (img - min) / (max - min) per slice.  Bit-exact against cv2 + numpy; returns float64."""
+    a = np.ascontiguousarray(slices_f64, dtype=np.float64)
+    if a.ndim != 3:
+        raise ValueError("resize_area_normalize: (S,H,W) slices expected")
+    n, h, w = a.shape
+    d_in = torch.from_numpy(a).cuda()
+    d_out = torch.empty(n, img_size, img_size, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().b2u_resize_area_f64(C.c_void_p(d_in.data_ptr()), n, h, w, C.c_void_p(d_out.data_ptr()), img_size,
+                                              img_size, 1 if normalize else 0, _stream_ptr()), "resize_area_f64")
+    return d_out.cpu().numpy()

@@ -131,3 +131,66 @@ def resize_area_u8(src, dw, dh):
             acc = (beta * buf).astype(np.float32) if acc is None else (acc + (beta * buf).astype(np.float32)).astype(np.float32)
         out[dy] = np.clip(np.rint(acc), 0, 255).astype(np.uint8)
     return out
+
+
+# ---- CV_64F INTER_AREA (the 512 x 512 stage of the NIfTI ingest works on get_fdata() float64 slices, T1H:335) ------
+def resize_area_f64(src, dw, dh):
+    """cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA) for a 2-D float64 image: the same three regimes as uint8
+    with double accumulators (WT = double), float32 table / interpolation coefficients, and no rounding at the end."""
+    src = np.asarray(src, np.float64)
+    sh, sw = src.shape
+    if (sh, sw) == (dh, dw):
+        return src.copy()                                   # cv::resize: same size -> plain copy
+    inv_x, inv_y = dw / sw, dh / sh
+    scale_x, scale_y = 1.0 / inv_x, 1.0 / inv_y
+    out = np.empty((dh, dw), np.float64)
+    if scale_x >= 1 and scale_y >= 1:
+        ix, iy = _rint(scale_x), _rint(scale_y)
+        eps = np.finfo(np.float64).eps
+        if abs(scale_x - ix) < eps and abs(scale_y - iy) < eps:
+            sc = float(F(1.0) / F(ix * iy))                 # float scale, promoted to double in sum * scale
+            for dy in range(dh):
+                for dx in range(dw):
+                    # ofs[] order: row by row inside the cell; CV_ENABLE_UNROLLED adds the values in groups of four
+                    vals = [src[dy * iy + yy, dx * ix + xx] for yy in range(iy) for xx in range(ix)]
+                    s, k = 0.0, 0
+                    while k <= len(vals) - 4:
+                        s += ((vals[k] + vals[k + 1]) + vals[k + 2]) + vals[k + 3]
+                        k += 4
+                    for v in vals[k:]:
+                        s += v
+                    out[dy, dx] = s * sc
+            return out
+        xtab, ytab = _area_tab(sw, dw, scale_x), _area_tab(sh, dh, scale_y)
+        for dy in range(dh):
+            acc = None
+            for sy, beta in ytab[dy]:
+                buf = np.zeros(dw, np.float64)
+                for dx in range(dw):
+                    b = 0.0
+                    for sx, alpha in xtab[dx]:
+                        b = b + src[sy, sx] * float(alpha)
+                    buf[dx] = b
+                acc = float(beta) * buf if acc is None else acc + float(beta) * buf
+            out[dy] = acc
+        return out
+    # up-sampling in a dimension: bilinear with float32 "area" coefficients, double arithmetic
+    def coeffs(ssize, dsize, inv_scale, scale):
+        res = []
+        for d in range(dsize):
+            s = int(math.floor(d * scale))
+            f = F((d + 1) - (s + 1) * inv_scale)
+            f = F(0) if f <= 0 else F(f - F(math.floor(f)))
+            if s < 0:
+                f, s = F(0), 0
+            if s >= ssize - 1:
+                f, s = F(0), ssize - 1
+            res.append((s, float(F(1.0) - f), float(f)))
+        return res
+    cx, cy = coeffs(sw, dw, inv_x, scale_x), coeffs(sh, dh, inv_y, scale_y)
+    rows = np.empty((sh, dw), np.float64)
+    for dx, (sx, a0, a1) in enumerate(cx):
+        rows[:, dx] = src[:, sx] * a0 + src[:, min(sx + 1, sw - 1)] * a1 if sx < sw - 1 else src[:, sx] * 1.0
+    for dy, (sy, b0, b1) in enumerate(cy):
+        out[dy] = rows[sy] * b0 + rows[min(sy + 1, sh - 1)] * b1
+    return out

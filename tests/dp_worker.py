@@ -51,7 +51,7 @@ def main():
     params = perturbed_params("unet", hw)
     x, t = S.make_slices(nl, hw, seed=10 + rank)
     xd, td = torch.from_numpy(x).cuda(), torch.from_numpy(t.reshape(nl, -1)).cuda()
-    finals = {}
+    finals, first_grads = {}, {}
     for name, opts, precision, graph in (("buckets", dict(grad_bucket_bytes=64 << 10), "float32", True),
                                          ("single", dict(grad_bucket_bytes=0), "float32", False),
                                          ("buckets-fp16", dict(grad_bucket_bytes=64 << 10), "float16", True)):
@@ -60,6 +60,9 @@ def main():
         eng.broadcast_weights()
         for s in range(3):
             b = eng.train_batch(xd, td, None, nl, dropout=False)
+            if s == 0:
+                eng.stream.synchronize()
+                first_grads[name] = eng.get_grads()       # the all-reduced gradient of the first step
         eng.stream.synchronize()
         nb = sum(1 for o in b.plan.bwd if o.kind == E.P.OP_ALLREDUCE_F32)
         assert (nb >= 3) == (name != "single"), (name, nb)
@@ -67,10 +70,12 @@ def main():
         same_everywhere(w, "A/" + name)               # every rank applied the same all-reduced gradient: bit-identical
         finals[name] = w
         eng.close()
-    for k in finals["single"]:                        # both exchange schedules compute the same step (atomics-order noise)
-        if "moving_" in k:
-            continue
-        assert np.abs(finals["buckets"][k] - finals["single"][k]).max() < 2e-4 * max(1.0, float(np.abs(finals["single"][k]).max())), k
+    # both exchange schedules compute the same step: compare the first step's all-reduced gradients (after several Adam
+    # steps the +-lr updates of noise-level gradients have already pulled the two runs apart)
+    for k, g1 in first_grads["single"].items():
+        g0 = first_grads["buckets"][k]
+        rel = np.linalg.norm(g0.astype(np.float64) - g1) / (np.linalg.norm(g1.astype(np.float64)) + 1e-12)
+        assert rel < 2e-3, (k, rel)
 
     # ---- B: sync_stats reproduces the single-GPU step on the full global batch ------------------------------------------
     xg, tg = S.make_slices(nl * world, hw, seed=77)

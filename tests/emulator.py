@@ -433,6 +433,9 @@ class Emulator:
         n = o.i[0]
         st = self.state
         p, g, m, v = (self.f32(o.p[k], n) for k in range(4))
+        if not np.isfinite(g).all():              # whole step skipped (b2u_adam's check pass), see op_state_advance
+            st["skip_step"] = 1
+            return
         gi = g / np.float32(st["loss_scale"] * st["grad_div"])
         lr_t = np.float32(st["lr"] * np.sqrt(1 - st["beta2_pow"]) / (1 - st["beta1_pow"]))
         m[:] = np.float32(st["beta1"]) * m + np.float32(1 - st["beta1"]) * gi
@@ -440,6 +443,9 @@ class Emulator:
         p[:] = p - lr_t * m / (np.sqrt(v) + np.float32(st["eps"]))
 
     def op_state_advance(self, o):
+        if self.state.get("skip_step"):
+            self.state.update(skip_step=0, overflow=1, loss_scale=max(self.state["loss_scale"] * 0.5, 1.0))
+            return
         self.state["step"] += 1
         self.state["beta1_pow"] *= self.state["beta1"]
         self.state["beta2_pow"] *= self.state["beta2"]

@@ -18,7 +18,7 @@ def run_ops_gpu(ops, mem, state, graph=False):
     dev = {k: torch.from_numpy(v.copy()).cuda() for k, v in mem.items()}
     st = LIB.StepState(seed=state["seed"], step=state["step"], lr=state["lr"], beta1=state["beta1"], beta2=state["beta2"],
                        eps=state["eps"], beta1_pow=state["beta1_pow"], beta2_pow=state["beta2_pow"],
-                       loss_scale=state["loss_scale"], grad_div=state["grad_div"], overflow=0, pad_=0)
+                       loss_scale=state["loss_scale"], grad_div=state["grad_div"], overflow=0, skip_step=0)
     dev["step"] = torch.from_numpy(np.frombuffer(bytes(st), dtype=np.uint8).copy()).cuda()
     ws = torch.empty(int(l.b2u_ws_bytes()), dtype=torch.uint8, device="cuda")
     arr = LIB.make_ops(ops, lambda r: dev[r.arena].data_ptr() + r.off)

@@ -87,6 +87,7 @@ def compare(ops, img, dt, state=None, tol=None, graph=False, arenas=("act", "f32
 
 CONV_SHAPES = [  # n, h, w, cin, cout
     (2, 16, 16, 8, 32), (1, 20, 12, 32, 64), (2, 8, 8, 64, 16), (1, 33, 17, 16, 96), (2, 16, 16, 1, 32), (1, 16, 16, 3, 16),
+    (2, 21, 37, 3, 32), (3, 40, 70, 3, 16),          # Cin = 3 (Task-2 slices replicated to RGB): ragged tiles, several tiles
 ]
 
 
@@ -259,19 +260,29 @@ def test_adam_and_state_advance():
     assert st2.step == 3 and abs(st2.beta1_pow - 0.9 ** 4) < 1e-6 and st2.overflow == 0
 
 
-def test_adam_flags_non_finite_gradients():
+def test_adam_skips_the_whole_step_on_a_non_finite_gradient():
+    """one non-finite gradient value (fp16 overflow under the static loss scale): NOTHING is updated -- parameters and
+    both moments keep their values, the step counter and the beta powers do not advance -- the loss scale is halved and
+    the sticky overflow flag tells the host; the next (finite) step then runs normally with the smaller scale"""
+    n = 4099
     img = Img(9)
-    p = img.farr(img.par, 64)
-    g = img.farr(img.gr, 64)
-    img.init[-1][1][5] = np.inf
-    m, v = img.farr(img.f32, 64, fill="zero"), img.farr(img.f32, 64, fill="zero")
-    ops = [P.Op(P.OP_ADAM, 0, [p, g, m, v, P.Ref("step", 0)], [64])]
-    mem = img.mem()
-    out, st = run_ops_gpu(ops, mem, E.Emulator({"act": 0, "f32": 0, "zero": 0, "params": 0, "state": 0, "step": 0}).state)
-    assert st.overflow == 1
-    newp = np.frombuffer(out["params"], np.float32, 64)
-    oldp = np.frombuffer(mem["params"], np.float32, 64)
-    assert newp[5] == oldp[5] and np.isfinite(newp).all() and (newp[:5] != oldp[:5]).all()
+    p = img.farr(img.par, n)
+    g = img.farr(img.gr, n)
+    m, v = img.farr(img.f32, n, scale=0.1), img.farr(img.f32, n, fill="uniform")
+    step = P.Ref("step", 0)
+    ops = [P.Op(P.OP_ADAM, 0, [p, g, m, v, step], [n]), P.Op(P.OP_STATE_ADVANCE, 0, [step])]
+    st = dict(lr=5e-4, beta1_pow=0.9 ** 3, beta2_pow=0.999 ** 3, loss_scale=1024.0, grad_div=1.0, step=2)
+    for bad in (np.inf, np.nan):
+        img.init[1][1][n - 2] = bad                                   # (init[1] is the gradient buffer `g`)
+        mem = img.mem()
+        out, st2 = compare(ops, img, P.F32, state=st, tol=1e-6, arenas=("params", "f32"))
+        assert st2.overflow == 1 and st2.skip_step == 0 and st2.step == 2 and st2.loss_scale == 512.0
+        assert abs(st2.beta1_pow - 0.9 ** 3) < 1e-7
+        for arena in ("params", "f32"):
+            assert np.array_equal(out[arena], mem[arena])            # bit-identical: no partial update
+    img.init[1][1][n - 2] = 0.25
+    out, st3 = compare(ops, img, P.F32, state=dict(st, loss_scale=512.0), tol=1e-5, arenas=("params", "f32"))
+    assert st3.overflow == 0 and st3.step == 3 and st3.loss_scale == 512.0
 
 
 @pytest.mark.parametrize("n", [6, 70])                      # split-K Dense(32): a partial and several ragged sample groups

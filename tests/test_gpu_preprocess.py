@@ -118,3 +118,22 @@ def test_resize_u8_is_bit_exact_against_cv2():
     lib = importlib.import_module(PKG + "._lib")
     with pytest.raises(lib.B2UError):
         PP.resize(np.zeros((8, 8), np.uint8), (4, 4), 2)          # INTER_CUBIC: not part of the reference's path
+
+
+@pytest.mark.parametrize("h,w", [(630, 630), (512, 512), (1024, 1024), (160, 144), (700, 520), (768, 512)])
+def test_volume_slices_on_device_equals_the_reference_cv2_sequence(h, w):
+    """N3: rot90 / slice window on the host, INTER_AREA to 512 x 512 on float64 + per-slice min-max on the GPU: exactly the
+    arrays the reference's read_nii loop builds with cv2.resize and numpy (T1H:288-297, 335-337), NaN slices included"""
+    N = importlib.import_module(PKG + ".nifti")
+    rng = np.random.default_rng(h + w)
+    vol = rng.normal(-400.0, 350.0, (h, w, 10))
+    vol[:, :, 4] = 3.0                                                # a constant slice: 0/0 -> NaN in both
+    want = N.volume_slices(vol, 512, device=False)
+    got = N.volume_slices(vol, 512, device=True)
+    assert got.shape == want.shape == (6, 512, 512) and got.dtype == np.float64
+    # (a constant slice is 0/0 = NaN where the resize reproduces the constant exactly -- copy / integer scales --
+    # and finite noise where the area weights do not sum to exactly one: either way both sides must agree)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    if (h, w) in ((512, 512), (1024, 1024)):
+        assert np.isnan(want[2]).all()
+    assert np.array_equal(np.nan_to_num(got, nan=-1.0), np.nan_to_num(want, nan=-1.0))

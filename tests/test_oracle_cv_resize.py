@@ -44,3 +44,13 @@ def test_inter_linear_rectangular_is_bit_exact():
     src = _img(rng, 180, 333)
     want = cv2.resize(src, dsize=(224, 100), interpolation=cv2.INTER_LINEAR)
     assert np.array_equal(R.resize_linear_u8(src, 224, 100), want)
+
+
+@pytest.mark.parametrize("sh,sw", [(630, 630), (512, 512), (1024, 1024), (1536, 1024), (700, 520), (160, 144), (300, 600), (513, 512)])
+def test_inter_area_float64_to_512_is_bit_exact(sh, sw):
+    """the NIfTI ingest resizes raw float64 slices to 512 x 512 with INTER_AREA (T1H:335)"""
+    rng = np.random.default_rng(sh + sw)
+    src = rng.normal(-300.0, 400.0, (sh, sw))
+    want = cv2.resize(src, dsize=(64 if sh > 1000 else 512, 64 if sh > 1000 else 512), interpolation=cv2.INTER_AREA)
+    got = R.resize_area_f64(src, want.shape[1], want.shape[0])
+    assert got.dtype == np.float64 and np.array_equal(got, want), float(np.abs(got - want).max())
