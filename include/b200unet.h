@@ -172,6 +172,10 @@ int b2u_adam(float* params, const float* grads, float* m, float* v, long long n,
 /* dst[b, :] = (T) src[idx[b], :]  (src fp32, device-resident dataset; idx int32 device) */
 int b2u_gather_batch(int dt, const float* src, const int* idx, void* dst, long long per_sample, int nb,
                      void* stream);
+/* the same with the channel count zero-padded from c to cpad: inference plans feed a first conv of 2..15 input channels
+ * (T2:748 on 224 x 224 x 3 slices) to the tensor-core kernel through a 16-channel input tensor */
+int b2u_gather_batch_pad(int dt, const float* src, const int* idx, void* dst, long long pix_per_sample, int c, int cpad,
+                         int nb, void* stream);
 
 /* ---- sm.metrics threshold sweep (T1H:1206-1211) ------------------------------------------------ */
 /* for each threshold k: tp[k] += sum(t * (p > thr[k])), sum_pr[k] += sum(p > thr[k]); sum_gt += sum(t) */

@@ -36,7 +36,7 @@ SYMBOLS = [
     "b2u_convt2x2_wgrad", "b2u_bn_stats", "b2u_bn_finalize", "b2u_bn_apply", "b2u_bn_bwd_reduce",
     "b2u_bn_bwd_apply", "b2u_maxpool_fwd", "b2u_maxpool_bwd", "b2u_dropout_fwd", "b2u_dropout_bwd",
     "b2u_copy_slice", "b2u_head_fwd", "b2u_bce_dice_sums", "b2u_bce_dice_finalize", "b2u_head_bwd",
-    "b2u_dense_fwd", "b2u_dense_bwd", "b2u_bce_fwd", "b2u_bce_sigmoid_bwd", "b2u_adam", "b2u_gather_batch",
+    "b2u_dense_fwd", "b2u_dense_bwd", "b2u_bce_fwd", "b2u_bce_sigmoid_bwd", "b2u_adam", "b2u_gather_batch", "b2u_gather_batch_pad",
     "b2u_threshold_counts", "b2u_clahe_u8", "b2u_crop_resize", "b2u_resize_u8", "b2u_resize_area_f64", "b2u_run_ops", "b2u_run_ops_timed", "b2u_graph_create",
     "b2u_graph_launch", "b2u_graph_destroy", "b2u_launch_count", "b2u_comm_unique_id", "b2u_comm_create",
     "b2u_comm_destroy", "b2u_allreduce", "b2u_pack_weights", "b2u_bn_bwd_sums_from_wgrad", "b2u_bn_apply_pool",
@@ -65,6 +65,7 @@ def lib():
     l.b2u_graph_launch.argtypes = [vp, vp]
     l.b2u_graph_destroy.argtypes = [vp]
     l.b2u_gather_batch.argtypes = [i32, vp, vp, vp, i64, i32, vp]
+    l.b2u_gather_batch_pad.argtypes = [i32, vp, vp, vp, i64, i32, i32, i32, vp]
     l.b2u_threshold_counts.argtypes = [vp, vp, i64, vp, i32, vp, vp, vp, vp]
     l.b2u_comm_unique_id.argtypes = [vp]
     l.b2u_comm_create.argtypes = [vp, i32, i32, C.POINTER(vp)]

@@ -1,6 +1,7 @@
 #!/bin/bash
 # Builds libb200unet.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
 set -e
+set -o pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=default --expt-relaxed-constexpr"

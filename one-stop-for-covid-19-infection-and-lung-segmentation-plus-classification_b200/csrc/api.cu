@@ -140,8 +140,11 @@ static bool use_dwmerge(int K, int J, int h, int wd, int training) {
 // other paths, by one extra pass over y
 static int conv3x3_fwd_wp(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, int act, void* y,
                           int ldy, int cout, double* stats, int n, int h, int wd, void* ws, size_t ws_bytes,
-                          const void* wp, void* relu_bits, void* stream, int training = 0) {
+                          const void* wp, void* relu_bits, void* stream, int training = 0, int k_src = 0) {
   int rc;
+  if (k_src != 0)       // zero-padded input tensor: `w` has only k_src input channels, only the prepacked copy matches
+    B2U_REQUIRE(wp != nullptr && dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy),
+                "conv3x3_fwd: a channel-padded input needs the tensor path and prepacked weights");
   if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy)) {
     if (use_dwmerge(cin, cout, h, wd, training))
       return b2u_tc_conv3x3_dwmerge(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, nullptr, 0, 0, 0, n, h, wd,
@@ -274,7 +277,7 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
     case B2U_OP_CONV3X3_FWD:         // p[5] (optional): packed weights
       return conv3x3_fwd_wp(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], I(2), p[3], I(3), I(4),
                             (double*)p[4], I(5), I(6), I(7), ws, wsb, p[5], p[6], s,      // p[6] (optional): 1-bit ReLU mask out
-                            I(8));                                                       // i[8]: op of a training-mode plan
+                            I(8), I(9));                          // i[8]: op of a training-mode plan, i[9]: real Cin if padded
     case B2U_OP_CONV3X3_DGRAD:       // p[4] (optional): colsum
       return conv3x3_dgrad_cs(dt, p[0], I(0), I(1), (const float*)p[1], p[2], I(2), I(3), p[3], I(4), I(5), I(6),
                               (float*)p[4], I(7), I(8), I(9), ws, wsb, p[5], s);

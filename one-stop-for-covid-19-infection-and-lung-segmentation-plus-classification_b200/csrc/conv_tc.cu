@@ -395,24 +395,25 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const long long* __restri
     const float* w = params + e[0];
     __half* dst = wpack + e[1];
     const int mode = (int)e[3], J = (int)e[5], K = (int)e[6];
+    const int Ks = e[7] > 0 ? (int)e[7] : K;                        // source K (< K: the packed copy is zero-padded in K)
     const int tj = (J + 31) >> 5, tk = (K + 31) >> 5;
     const int lu = (int)(u - e[2]);
     const int t = lu / (tj * tk), r = lu % (tj * tk);
     const int j0 = (r / tk) * 32, k0 = (r % tk) * 32;
     const bool transpose = mode == 0 || mode == 3;                  // source tap matrix is [K][J] (else [J][K])
-    const float* src = w + (long long)(mode == 1 ? 8 - t : t) * J * K;
+    const float* src = w + (long long)(mode == 1 ? 8 - t : t) * J * Ks;
     __syncthreads();                                                // previous tile's readers are done
     if (transpose) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {                                 // rows = k, columns = j (coalesced in j)
         const int k = k0 + ty + 8 * i, j = j0 + tx;
-        tile[ty + 8 * i][tx] = (k < K && j < J) ? src[(long long)k * J + j] : 0.f;
+        tile[ty + 8 * i][tx] = (k < Ks && j < J) ? src[(long long)k * J + j] : 0.f;
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {                                 // rows = j, columns = k (coalesced in k)
         const int j = j0 + ty + 8 * i, k = k0 + tx;
-        tile[tx][ty + 8 * i] = (j < J && k < K) ? src[(long long)j * K + k] : 0.f;
+        tile[tx][ty + 8 * i] = (j < J && k < Ks) ? src[(long long)j * Ks + k] : 0.f;
       }
     }
     __syncthreads();

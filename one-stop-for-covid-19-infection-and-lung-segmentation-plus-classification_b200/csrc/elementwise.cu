@@ -695,28 +695,34 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(
   const float two_i1 = (float)(2.0 * I + 1.0);
   const float scale = st->loss_scale;
   const float half_inv_n = 0.5f / (float)count;
-  // two pixels per trip (both inside the block's contiguous span): all loads are issued before the arithmetic
+  // two pixels per trip: all loads are issued before the arithmetic (four pixels per trip measured slower: 119 registers,
+  // two blocks per SM: 0.099 ms against 0.092 ms).  ncu, round 2: memory-latency bound (5.5 long-scoreboard stalls per
+  // issue, 32 % of the DRAM rate), 40 of 183 instructions per pixel were two IEEE divisions -- which cancel:
+  //   d(0.5 mean BCE)/dz = 0.5/N (p - t)  inside the clip range   [(-t/p + (1-t)/(1-p)) p (1-p) = p - t]
+  //   d(0.5 (1 - dice))/dz = -0.5 (2 t (S+1) - (2I+1)) / (S+1)^2 * p (1 - p)
+  constexpr int kPx = 2;
   const int cg = C >> 3;
   const int lanes = kThreads / cg;
   const int g = threadIdx.x % cg, lane_ = threadIdx.x / cg;
   if (lane_ < lanes) {
-    for (long long p0 = (long long)blockIdx.x * lanes * 2 + lane_; p0 < npix; p0 += (long long)gridDim.x * lanes * 2) {
-      const long long p1 = p0 + lanes;
-      const bool two = p1 < npix;
-      float v[2][8], pr[2], tt[2];
-      pr[0] = prob[p0]; tt[0] = tgt[p0];
-      load8<T>(x + p0 * ldx + g * 8, v[0]);
-      pr[1] = two ? prob[p1] : 0.5f; tt[1] = two ? tgt[p1] : 0.f;
-      if (two) load8<T>(x + p1 * ldx + g * 8, v[1]);
+    for (long long p0 = (long long)blockIdx.x * lanes * kPx + lane_; p0 < npix; p0 += (long long)gridDim.x * lanes * kPx) {
+      float v[kPx][8], pr[kPx], tt[kPx];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (u == 1 && !two) break;
+      for (int u = 0; u < kPx; ++u) {
+        const long long pu = p0 + (long long)u * lanes;
+        const bool on = pu < npix;
+        pr[u] = on ? prob[pu] : 0.5f;
+        tt[u] = on ? tgt[pu] : 0.f;
+        if (on) load8<T>(x + pu * ldx + g * 8, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kPx; ++u) {
+        const long long pu = p0 + (long long)u * lanes;
+        if (pu >= npix) break;
         const float prv = pr[u], t = tt[u];
-        float gq = 0.f;
-        if (prv >= 1e-7f && prv <= 1.f - 1e-7f) gq = half_inv_n * (-t / prv + (1.f - t) / (1.f - prv));
-        // d(1-dice)/dp = -(2 t (S+1) - (2I+1)) / (S+1)^2
-        gq -= 0.5f * (2.f * t - two_i1 * inv_s1) * inv_s1;
-        const float dl = gq * prv * (1.f - prv) * scale;
+        float dl = (prv >= 1e-7f && prv <= 1.f - 1e-7f) ? half_inv_n * (prv - t) : 0.f;
+        dl -= 0.5f * (2.f * t - two_i1 * inv_s1) * inv_s1 * (prv * (1.f - prv));
+        dl *= scale;
         if (g == 0) accb += dl;
         float o[8];
 #pragma unroll
@@ -725,7 +731,7 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(
           o[k] = dl * wr[k] * act_bwd_from_y(v[u][k], x_act);
           cs[k] += o[k];
         }
-        store8<T>(dx + (u ? p1 : p0) * lddx + g * 8, o);
+        store8<T>(dx + pu * lddx + g * 8, o);
       }
     }
   }
@@ -842,6 +848,31 @@ __global__ void __launch_bounds__(kThreads) gather_batch_kernel(const float* __r
     long long e = i - b * per_sample;
     long long s = idx ? (long long)idx[b] : b;
     stf<T>(dst + i, src[s * per_sample + e]);
+  }
+}
+
+// the same gather with the channel count padded from c to cpad (zeros): an inference plan whose first conv has
+// 2..15 input channels (Task-2's 224 x 224 x 3 slices) pads them to 16 so that the tcgen05 kernel takes the layer
+template <typename T>
+__global__ void __launch_bounds__(kThreads) gather_batch_pad_kernel(const float* __restrict__ src,
+                                                                    const int* __restrict__ idx, T* __restrict__ dst,
+                                                                    long long pix_per_sample, int c, int cpad, int nb) {
+  B2U_PDL_PROLOGUE();
+  // thread = pixel: c contiguous floats in, cpad / 8 sixteen-byte (fp16) stores out (cpad % 8 == 0, c <= 8 handled in
+  // the first vector, the rest of the padding is zeros)
+  const long long total = (long long)nb * pix_per_sample;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const long long b = pix / pix_per_sample, e = pix - b * pix_per_sample;
+    const long long s = idx ? (long long)idx[b] : b;
+    const float* sp = src + (s * pix_per_sample + e) * c;
+    T* dp = dst + pix * cpad;
+    for (int v0 = 0; v0 < cpad; v0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (v0 + k < c) ? sp[v0 + k] : 0.f;
+      store8<T>(dp + v0, v);
+    }
   }
 }
 
@@ -1310,6 +1341,15 @@ extern "C" int b2u_gather_batch(int dt, const float* src, const int* idx, void* 
   B2U_REQUIRE(nb > 0 && per_sample > 0, "gather_batch: empty batch");
   int grid = stream_grid((long long)nb * per_sample);
   DISPATCH_T(dt, B2U_LAUNCH(gather_batch_kernel<T>, grid, kThreads, 0, stream, src, idx, (T*)dst, per_sample, nb));
+  return B2U_OK;
+}
+
+extern "C" int b2u_gather_batch_pad(int dt, const float* src, const int* idx, void* dst, long long pix_per_sample, int c,
+                                    int cpad, int nb, void* stream) {
+  B2U_REQUIRE(nb > 0 && pix_per_sample > 0 && c > 0 && cpad >= c && cpad % 8 == 0 && aligned16(dst), "gather_batch_pad: args");
+  int grid = stream_grid((long long)nb * pix_per_sample);
+  DISPATCH_T(dt, B2U_LAUNCH(gather_batch_pad_kernel<T>, grid, kThreads, 0, stream, src, idx, (T*)dst, pix_per_sample, c,
+                            cpad, nb));
   return B2U_OK;
 }
 

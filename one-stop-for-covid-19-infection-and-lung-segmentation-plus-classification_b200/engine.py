@@ -309,9 +309,14 @@ class Engine:
     def _load_inputs(self, b, x_src, idx, n, t_src=None, sw_src=None):
         pl = b.plan
         xv = pl.x_view
-        per = xv.h * xv.w * xv.c
         assert x_src.dtype == torch.float32 and x_src.is_contiguous()
-        self._gather(self.dt, x_src, idx, self._resolve(xv.ref), per, n)
+        if pl.x_pad:                     # channels zero-padded for the tensor-core first conv (plan.py)
+            _lib.check(self.lib.b2u_gather_batch_pad(self.dt, C.c_void_p(x_src.data_ptr()),
+                                                     C.c_void_p(idx.data_ptr()) if idx is not None else None,
+                                                     C.c_void_p(self._resolve(xv.ref)), xv.h * xv.w, pl.x_cin, pl.x_pad, n,
+                                                     C.c_void_p(self.stream.cuda_stream)), "gather_batch_pad")
+        else:
+            self._gather(self.dt, x_src, idx, self._resolve(xv.ref), xv.h * xv.w * xv.c, n)
         if t_src is not None:
             per_t = int(math.prod(pl.prob_shape[1:]))
             assert t_src.dtype == torch.float32 and t_src.is_contiguous()

@@ -104,7 +104,12 @@ class Emulator:
     def op_conv3x3_fwd(self, o):
         ldx, cin, act, ldy, cout, n, h, w = o.i[:8]
         x = self.view(o.p[0], ldx, cin, n * h * w, o.dt).astype(np.float32).reshape(n, h, w, cin)
-        wt = self._kernel(o.p[1], 9 * cin * cout, cin, cout, o.dt).reshape(3, 3, cin, cout)
+        k_src = o.i[9] if len(o.i) > 9 else 0
+        if k_src:                                        # zero-padded input: the kernel has k_src real input channels
+            wt = np.zeros((3, 3, cin, cout), np.float32)
+            wt[:, :, :k_src] = self._kernel(o.p[1], 9 * k_src * cout, cin, cout, o.dt).reshape(3, 3, k_src, cout)
+        else:
+            wt = self._kernel(o.p[1], 9 * cin * cout, cin, cout, o.dt).reshape(3, 3, cin, cout)
         b = self.f32(o.p[2], cout)
         y = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(wt.copy()).permute(3, 2, 0, 1),
                      torch.from_numpy(b.copy()), padding=1).permute(0, 2, 3, 1).numpy()

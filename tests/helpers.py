@@ -60,7 +60,10 @@ def load_emulator(em, plan, params, x, t):
     em.f32(P.Ref("params", 0), fp.size)[:] = fp
     em.f32(P.Ref("state", 0), fs.size)[:] = fs
     xv = plan.x_view
-    em.view(xv.ref, xv.ld, xv.c, x.shape[0] * xv.h * xv.w, xv.dt)[:] = x.reshape(-1, xv.c).astype(E.NPDT[xv.dt])
+    xin = x.reshape(-1, x.shape[-1])
+    if getattr(plan, "x_pad", 0):                       # channel-padded input tensor (inference plans, plan.py)
+        xin = np.concatenate([xin, np.zeros((len(xin), plan.x_pad - xin.shape[1]), xin.dtype)], axis=1)
+    em.view(xv.ref, xv.ld, xv.c, x.shape[0] * xv.h * xv.w, xv.dt)[:] = xin.astype(E.NPDT[xv.dt])
     em.f32(plan.target, t.size)[:] = t.reshape(-1)
     em.f32(plan.sample_w, x.shape[0])[:] = 1.0
     return fp, fs

@@ -13,7 +13,10 @@ def _load(em, plan, params, x, t):
     em.f32(P.Ref("params", 0), fp.size)[:] = fp
     em.f32(P.Ref("state", 0), fs.size)[:] = fs
     xv = plan.x_view
-    em.view(xv.ref, xv.ld, xv.c, x.shape[0] * xv.h * xv.w, xv.dt)[:] = x.reshape(-1, xv.c).astype(E.NPDT[xv.dt])
+    xin = x.reshape(-1, x.shape[-1])
+    if getattr(plan, "x_pad", 0):                       # channel-padded input tensor (inference plans, plan.py)
+        xin = np.concatenate([xin, np.zeros((len(xin), plan.x_pad - xin.shape[1]), xin.dtype)], axis=1)
+    em.view(xv.ref, xv.ld, xv.c, x.shape[0] * xv.h * xv.w, xv.dt)[:] = xin.astype(E.NPDT[xv.dt])
     em.f32(plan.target, t.size)[:] = t.reshape(-1)
     em.f32(plan.sample_w, x.shape[0])[:] = 1.0
     return fp, fs
@@ -169,3 +172,26 @@ def test_gradient_buckets_cover_the_buffer_and_follow_their_last_writer(gname, h
     assert plan.opt[0].kind == P.OP_ADAM and plan.opt[0].dt & P.OPF_JOIN
     one = P.Plan(G.GRAPHS[gname](hw, 1), 4, dt=P.F16, training=True, world=4, loss=loss, grad_bucket_bytes=0)
     assert [o.kind for o in one.opt][:2] == [P.OP_ALLREDUCE_F32, P.OP_ADAM] and not any(o.kind == P.OP_ALLREDUCE_F32 for o in one.bwd)
+
+
+def test_inference_plan_pads_a_three_channel_input_for_the_tensor_core_first_conv():
+    """Task-2 slices are 224 x 224 x 3 (BASELINE configs[4]): the fp16 inference plan stores the input zero-padded to 16
+    channels and runs conv2d_1 as a K = 16 tensor-core conv with a zero-padded packed kernel; the emulated forward equals
+    the oracle's, training plans and exact (fp32) plans keep the 3-channel tensor"""
+    hw, n, cin = 32, 3, 3
+    g = G.classifier(hw, cin)
+    params = perturbed_params("classifier", hw, cin=cin)
+    rng = np.random.default_rng(0)
+    x = rng.random((n, hw, hw, cin)).astype(np.float32)
+    plan = P.Plan(g, n, dt=P.F16, training=False, loss="bce")
+    assert plan.x_pad == 16 and plan.x_cin == 3 and plan.x_view.c == 16
+    op = plan.fwd[0]
+    assert op.kind == P.OP_CONV3X3_FWD and op.i[1] == 16 and op.i[9] == 3 and op.p[5] is not None
+    assert plan.pack_table()[0].tolist()[3:] == [0, 9, 16, 16, 3]
+    em = E.Emulator(plan.arena_sizes())
+    _load(em, plan, params, x, np.zeros((n, 1), np.float32))
+    em.run(plan.forward_ops())
+    want, _ = K.forward("classifier", params, x, training=False, dtype=torch.float32)
+    assert np.abs(em.f32(plan.prob, n).reshape(n, 1) - want).max() < 2e-3          # fp16 storage
+    assert P.Plan(g, n, dt=P.F16, training=True, loss="bce").x_pad == 0
+    assert P.Plan(g, n, dt=P.F32, training=False, loss="bce").x_pad == 0
