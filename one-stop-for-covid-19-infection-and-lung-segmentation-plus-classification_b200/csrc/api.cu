@@ -57,6 +57,11 @@ extern "C" int b2u_set_option(const char* name, int value) {
     g_b2u_tc_dwmerge = value;
     return old;
   }
+  if (strcmp(name, "tc_rowstrip") == 0) {
+    int old = g_b2u_tc_rowstrip;
+    g_b2u_tc_rowstrip = value;
+    return old;
+  }
   if (strcmp(name, "tc_dw_packed") == 0) {
     int old = g_b2u_tc_dw_packed;
     g_b2u_tc_dw_packed = value ? 1 : 0;
@@ -136,6 +141,17 @@ static bool use_dwmerge(int K, int J, int h, int wd, int training) {
   return g_b2u_tc_dwmerge == 3 && training && (long long)h * wd >= 128 * 128;
 }
 
+// Row-strip kernel (conv_tc3r.cu, Cout = 16 / 32).  Measured on B200 (tools/one_op.py, profiles/NOTES_r2.md): a tcgen05.mma
+// of M = 128 costs about 25 + 1.2 N cycles here whatever K slab it reads, so merging three taps into N = 96 saves only the
+// fixed part (150 clk against 3 x 62) while the kernel gives up the two-CTA interleaving of the halo kernel: slower at
+// K = 32 / 64 (0.093 against 0.081 ms for 32 -> 32 at 512^2), faster once the MMA phase dominates (128 -> 32 at 512^2:
+// 0.181 against 0.241 ms; U-Net++'s level-1 nodes with 96 / 128 input channels).
+static bool use_rowstrip(int K, int J, int h, int wd) {
+  if (g_b2u_tc_rowstrip == 0 || !b2u_tc_conv3x3_rowstrip_ok(K, J, wd)) return false;
+  if (g_b2u_tc_rowstrip == 1) return true;
+  return K >= 96 && wd >= 128 && (long long)h * wd >= 128 * 128;
+}
+
 // `relu_bits` (optional, op lists only): packed 1-bit mask of y > 0, written by the halo kernel's epilogue or, on the
 // other paths, by one extra pass over y
 static int conv3x3_fwd_wp(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, int act, void* y,
@@ -146,6 +162,9 @@ static int conv3x3_fwd_wp(int dt, const void* x, int ldx, int cin, const float* 
     B2U_REQUIRE(wp != nullptr && dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy),
                 "conv3x3_fwd: a channel-padded input needs the tensor path and prepacked weights");
   if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy)) {
+    if (use_rowstrip(cin, cout, h, wd))
+      return b2u_tc_conv3x3_rowstrip(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, nullptr, 0, 0, 0, n, h, wd, ws,
+                                     ws_bytes, wp, stream, relu_bits);
     if (use_dwmerge(cin, cout, h, wd, training))
       return b2u_tc_conv3x3_dwmerge(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, nullptr, 0, 0, 0, n, h, wd,
                                     ws, ws_bytes, wp, stream, relu_bits, training && g_b2u_tc_dw_packed);
@@ -178,6 +197,9 @@ static int conv3x3_dgrad_cs(int dt, const void* dy, int lddy, int cout, const fl
                             int wd, void* ws, size_t ws_bytes, const void* wp, void* stream) {
   const bool tc = dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cout, cin, lddy, lddx);
   const bool bits = mask != nullptr && mask_act == B2U_ACT_RELU_BITS;
+  if (tc && !(bits && accumulate) && use_rowstrip(cout, cin, h, wd))
+    return b2u_tc_conv3x3_rowstrip(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, colsum, mask, ldmask,
+                                   mask_act, accumulate, n, h, wd, ws, ws_bytes, wp, stream, nullptr);
   if (tc && !(bits && accumulate) && use_dwmerge(cout, cin, h, wd, 1))
     return b2u_tc_conv3x3_dwmerge(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, colsum, mask, ldmask,
                                   mask_act, accumulate, n, h, wd, ws, ws_bytes, wp, stream, nullptr, g_b2u_tc_dw_packed);

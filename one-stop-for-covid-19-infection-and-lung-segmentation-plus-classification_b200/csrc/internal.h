@@ -72,3 +72,11 @@ int b2u_tc_conv3x3_dwmerge(const void* x, int ldx, int K, const float* w, int dg
 extern int g_b2u_tc_dw_packed;
 int b2u_dense_fwd_ws(int dt, const void* x, int k, const float* w, const float* bias, int act, void* y, int m, int n,
                      void* ws, size_t ws_bytes, void* stream);
+// thinnest layers (Cout = 16 / 32): row strips, dh taps merged in N, shuffle-free epilogue (conv_tc3r.cu);
+// b2u_set_option("tc_rowstrip", 0|1|2)
+extern int g_b2u_tc_rowstrip;
+int b2u_tc_conv3x3_rowstrip_ok(int K, int J, int wd);
+int b2u_tc_conv3x3_rowstrip(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
+                            int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
+                            int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream,
+                            void* relu_bits_out);

@@ -284,18 +284,21 @@ def test_bn_bwd_sums_from_wgrad(c, cout):
 # ---- 1-bit ReLU masks (planner option relu_bits, B2U_ACT_RELU_BITS)
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 32, 32, 32), (1, 32, 40, 32, 64), (1, 16, 16, 64, 64), (2, 24, 40, 128, 128),
                                             (1, 16, 16, 256, 512), (1, 56, 56, 16, 16), (1, 16, 16, 32, 80)])
-@pytest.mark.parametrize("dwmerge", [0, 1])
+@pytest.mark.parametrize("dwmerge", [0, 1, "rowstrip"])
 def test_tc_conv3x3_relu_bits_roundtrip(n, h, w, cin, cout, dwmerge):
     """forward writes the packed mask of y > 0 (epilogue variant kF_BITS_OUT), the data gradient of the next conv reads
     it (kF_BITS_IN) with and without column sums.  A mask bit flips with the sign of a near-zero pre-activation, so the
     inputs are small integers and the weights multiples of 1/8: every partial sum is exact in fp32 in any order and
     the GPU must reproduce the emulator's bits, outputs and gradients EXACTLY (tolerance 0 up to fp16 storage)."""
     lib = importlib.import_module(PKG + "._lib").lib()
-    old = lib.b2u_set_option(b"tc_dwmerge", dwmerge)       # 1: thin layers through conv_tc3w.cu (same bits, same sums)
+    # 1: thin layers through conv_tc3w.cu, "rowstrip": the Cout = 16 / 32 ones through conv_tc3r.cu (same bits, same sums)
+    old = lib.b2u_set_option(b"tc_dwmerge", 1 if dwmerge == 1 else 0)
+    old_r = lib.b2u_set_option(b"tc_rowstrip", 1 if dwmerge == "rowstrip" else 0)
     try:
         _relu_bits_roundtrip(n, h, w, cin, cout)
     finally:
         lib.b2u_set_option(b"tc_dwmerge", old)
+        lib.b2u_set_option(b"tc_rowstrip", old_r)
 
 
 def _relu_bits_roundtrip(n, h, w, cin, cout):
@@ -347,3 +350,36 @@ def test_tc_conv3x3_dwmerge_fwd_and_dgrad(n, h, w, cin, cout):
             compare(ops, img, dt, tol=4e-3)
     finally:
         lib.b2u_set_option(b"tc_dwmerge", old)
+
+
+# ---- row-strip kernel for Cout = 16 / 32 (conv_tc3r.cu, b2u_set_option("tc_rowstrip", 1)) ----------------------------
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 20, 300, 32, 32), (1, 64, 128, 64, 32), (1, 9, 140, 16, 16), (2, 40, 96, 32, 16),
+                                            (1, 33, 257, 128, 32), (3, 5, 32, 48, 32), (1, 1, 130, 32, 32), (8, 64, 64, 32, 32)])
+def test_tc_conv3x3_rowstrip_fwd_and_dgrad(n, h, w, cin, cout):
+    """row strips of 128 pixels (ragged last strip, images narrower than a strip, one-row images, CTA ranges that cross
+    strip and image boundaries), every epilogue variant: statistics, 1-bit / fp16 masks, accumulate, column sums"""
+    lib = importlib.import_module(PKG + "._lib").lib()
+    old = lib.b2u_set_option(b"tc_rowstrip", 1)
+    try:
+        img = Img(93)
+        x = img.view(n, h, w, cin, dt, ld=2 * cin, c0=cin, fill="uniform")
+        y = img.view(n, h, w, cout, dt, ld=cout + 16, c0=8, fill=None)
+        wt = img.farr(img.par, 9 * cin * cout, scale=(2.0 / (9 * cin)) ** 0.5)
+        b = img.farr(img.par, cout, scale=0.1)
+        stats = img.zero.alloc(2 * cout * 8)
+        for act, st in ((1, stats), (2, None)):
+            ops = [P.Op(P.OP_CONV3X3_FWD, dt, [x.ref, wt, b, y.ref, st], [x.ld, cin, act, y.ld, cout, n, h, w])]
+            compare(ops, img, dt, tol=3e-3)
+        # data gradient INTO a thin tensor: dy has `cin` channels here, dx `cout` (= 16 / 32)
+        img = Img(94)
+        dy = img.view(n, h, w, cin, dt, ld=cin + 8, scale=0.5)
+        dx = img.view(n, h, w, cout, dt, ld=2 * cout, c0=0, scale=0.3)
+        mask = img.view(n, h, w, cout, dt)
+        wt = img.farr(img.par, 9 * cout * cin, scale=(2.0 / (9 * cin)) ** 0.5)
+        db = img.farr(img.gr, cout, scale=0.01)
+        for acc, mact, cs in ((0, 1, db), (1, 2, None), (0, 0, db), (0, 0, None)):
+            ops = [P.Op(P.OP_CONV3X3_DGRAD, dt, [dy.ref, wt, dx.ref, mask.ref if mact else None, cs],
+                        [dy.ld, cin, dx.ld, cout, mask.ld, mact, acc, n, h, w])]
+            compare(ops, img, dt, tol=4e-3)
+    finally:
+        lib.b2u_set_option(b"tc_rowstrip", old)

@@ -356,7 +356,7 @@ def test_train_on_batch_pipelined_matches_blocking():
     assert np.allclose(seqs[0][0], seqs[0][3], rtol=1e-4) and not np.allclose(seqs[0][0], seqs[0][1], rtol=1e-3)
 
 
-@pytest.mark.parametrize("option,value", [("tc_dwmerge", 1), ("tc_dwmerge", 0), ("tc_halo", 0)])
+@pytest.mark.parametrize("option,value", [("tc_dwmerge", 1), ("tc_dwmerge", 0), ("tc_halo", 0), ("tc_rowstrip", 1), ("tc_rowstrip", 0)])
 def test_train_step_kernel_selection_options(option, value):
     """b2u_set_option kernel-selection switches (dw-merged thin-layer kernel for every eligible layer / for none,
     per-tap loads instead of halo tiles) compute the same fp16 training step as the default selection: loss, Dice,

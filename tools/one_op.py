@@ -20,6 +20,7 @@ n, h, w, K, J = [int(v) for v in sys.argv[2:7]]
 flags = sys.argv[7:]
 lib = LIB.lib()
 lib.b2u_set_option(b"tc_dwmerge", 1 if "dwmerge" in flags else 0)
+lib.b2u_set_option(b"tc_rowstrip", 1 if "rowstrip" in flags else 0)
 npix = n * h * w
 x = (torch.rand(npix, K, device="cuda") - 0.3).half()
 y = torch.empty(npix, J, device="cuda", dtype=torch.float16)
@@ -66,6 +67,22 @@ ms = e0.elapsed_time(e1) / 10
 by = npix * (K + J) * 2 + (npix * J // 8 if "bits" in flags else 0)
 print("%s: %.4f ms per call (packs weights per call), %.0f GB/s algorithmic, %.1f clk/px/SM at 1.9 GHz"
       % (" ".join(sys.argv[1:]), ms, by / ms / 1e6, ms * 1e-3 * 1.9e9 * 148 / npix))
+if "notimeline" in flags:
+    sys.exit(0)
+if "rowstrip" in flags:
+    lib.b2u_set_option(b"tc_debug", 1)
+    run()
+    stream.synchronize()
+    buf = (C.c_longlong * 512)()
+    lib.b2u_debug_read.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+    assert lib.b2u_debug_read(buf, 512) == 0
+    a = np.array(buf[:], dtype=np.int64).reshape(64, 8)
+    t0 = a[0, 0]
+    print("row: tma_issue | mma_start mma_acc_empty mma_a_full mma_commit | epi_start(even rows) epi_landed epi_prefetched")
+    for k in range(8, 28):
+        print(k, [int(v - t0) if v else None for v in a[k]])
+    lib.b2u_set_option(b"tc_debug", 0)
+    sys.exit(0)
 lib.b2u_set_option(b"tc_debug", 1)
 run()
 stream.synchronize()
