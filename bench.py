@@ -597,7 +597,7 @@ def run_engine(args):
             "roofline": roof, "cpu_baseline": cpu, "op_breakdown_ms": breakdown,
         }
         _restore_stdout()
-    print(json.dumps(line))
+        print(json.dumps(line))
     if world > 1:
         # leave together and without running NCCL / process-group destructors (a rank that tears its communicator
         # down while a peer is still inside one would hang the launcher until its timeout)

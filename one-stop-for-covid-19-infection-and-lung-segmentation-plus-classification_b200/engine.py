@@ -180,6 +180,31 @@ class Engine:
     def lr(self, v):
         self._set_fields(lr=float(np.float32(v)))
 
+    def guard_small_gamma(self, threshold=1e-2):
+        """The default BatchNorm-backward fusions recover sum(dy * xhat) from the stored BN OUTPUT as (y - beta) / gamma
+        (plan.py: statistics from the max-pool backward / from <W, dW>): exact for |gamma| of order one, but the
+        rounding of y is amplified by 1 / gamma and a channel with gamma == 0 loses its d(gamma) altogether.
+        Keras initialises gamma = 1 and training rarely drives it to zero; when any |gamma| falls below `threshold` the
+        engine switches -- once, with a warning -- to the unfused reductions over dy and the BN input, which do not
+        divide by gamma.  Called by Model.fit after every epoch and by set_weights.  Returns True if it switched."""
+        if not self.plan_options.get("fuse_bn_bwd", True) and not self.plan_options.get("fuse_bn_bwd_wgrad", True):
+            return False
+        self.stream.synchronize()
+        p = self.params.cpu().numpy()
+        lo = min((float(np.abs(p[off:off + int(np.prod(shape))]).min()) for name, (arena, off, shape) in self.layout.offsets.items()
+                  if name.endswith("/gamma")), default=1.0)
+        if lo >= threshold:
+            return False
+        import warnings
+        warnings.warn("b200unet: min |BatchNorm gamma| = %.3g < %g: switching the BatchNorm backward statistics to the "
+                      "unfused reductions (no division by gamma)" % (lo, threshold))
+        self.plan_options.update(fuse_bn_bwd=False, fuse_bn_bwd_wgrad=False)
+        for b in self._bound.values():
+            for gph in b.graphs.values():
+                self.lib.b2u_graph_destroy(gph)
+        self._bound.clear()
+        return True
+
     def overflowed(self):
         """True once a step was skipped because its gradient was not finite (the device then halved the loss scale)"""
         return bool(self._pull_state().overflow)
@@ -199,6 +224,7 @@ class Engine:
             self.params.copy_(torch.from_numpy(fp))
             self.state[:fs.size].copy_(torch.from_numpy(fs))
         self.stream.synchronize()
+        self.guard_small_gamma()
 
     def get_weights(self):
         self.stream.synchronize()

@@ -529,6 +529,7 @@ class Model:
                     lossbuf[bi].copy_(eng.loss_dev(b))
                     lo += n
             eng.stream.synchronize()
+            eng.guard_small_gamma()
             if eng.overflowed():
                 print("warning: steps with non-finite gradients were skipped this epoch (loss scale now %g)" % eng.loss_scale)
                 eng._set_fields(overflow=0)

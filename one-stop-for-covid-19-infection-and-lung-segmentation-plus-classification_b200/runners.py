@@ -144,6 +144,36 @@ def runner_classification(cts=None, y_label=None, new_dim=224, epochs=25, batch_
     return out
 
 
+def cluster_experiment(model, cts, x_valid, y_valid, layer_name="conv2d_9", n_components=1000, batch_size=32, threshold=0.547):
+    """The reference's "easy / hard CT" clustering experiment (T1H:1386-1496): bottleneck activations of every slice
+    (`Model(inputs=model.input, outputs=model.get_layer(layer_name).output).predict`, flattened channel-major like the
+    reference's rollaxis + flatten), PCA, KMeans(2, random_state=0) fitted on `cts` and applied to the validation set,
+    then the validation metrics of each cluster (loss, F-score and IoU at the reference's threshold 0.547).
+    The network passes (activation tap, evaluation) run on the GPU; PCA / KMeans are the reference's own scikit-learn
+    calls on the host (its feature matrix is a few hundred MB: not part of the training / inference hot path)."""
+    from sklearn.cluster import KMeans
+    from sklearn.decomposition import PCA
+
+    def features(x):
+        out = model.intermediate(x, layer_name)                       # (N, h, w, C) on the host
+        return np.ascontiguousarray(np.transpose(out, (0, 3, 1, 2))).reshape(len(out), -1)      # rollaxis(img, 2).flatten()
+
+    data = features(cts)
+    pca = PCA(n_components=min(n_components, data.shape[0], data.shape[1]))
+    new_data = pca.fit_transform(data)
+    kmeans = KMeans(n_clusters=2, random_state=0, n_init=10).fit(new_data)
+    valid_labels = kmeans.predict(pca.transform(features(x_valid)))
+    model.compile(optimizer=M.Adam(lr=0.0005), loss=LS.bce_dice_loss,
+                  metrics=[LS.FScore(threshold=threshold), LS.IOUScore(threshold=threshold)])          # T1H:1475
+    out = dict(explained_variance=float(np.sum(pca.explained_variance_ratio_)), train_labels=kmeans.labels_,
+               valid_labels=valid_labels, score_all=model.evaluate(x_valid, y_valid, batch_size=batch_size))
+    for k in (0, 1):
+        sel = np.where(valid_labels == k)[0]
+        out["score_cluster_%d" % k] = model.evaluate(x_valid[sel], y_valid[sel], batch_size=batch_size) if len(sel) else None
+        out["count_cluster_%d" % k] = int(len(sel))
+    return out
+
+
 def load_cases(cases, new_dim=224):
     """File-driven front end of the runners (the reference reads its 20 Kaggle volumes in a loop, T1H:390-393):
     `cases` = iterable of (ct_path, lung_mask_path, infection_mask_path or None) NIfTI files -> (cts, lungs-free

@@ -86,6 +86,7 @@ def main():
                         dropout=False)
     eng.stream.synchronize()
     loss_sync = eng.loss_dev(b).cpu().numpy().copy()
+    g_sync = eng.get_grads()                                # the all-reduced gradient = the full-batch gradient
     w_sync = eng.get_weights()
     eng.close()
     same_everywhere(w_sync, "B/sync", tol=1e-6, moving=True)
@@ -96,12 +97,22 @@ def main():
                              dropout=False)
         one.stream.synchronize()
         loss_one = one.loss_dev(b1).cpu().numpy()
-        w_one = one.get_weights()
+        g_one, w_one = one.get_grads(), one.get_weights()
         one.close()
         assert np.allclose(loss_sync, loss_one, rtol=1e-5, atol=1e-6), (loss_sync, loss_one)
-        worst = max(float(np.abs(w_sync[k] - w_one[k]).max()) for k in w_one)
-        assert worst < 5e-5, "sync_stats step differs from the single-GPU full batch by %g" % worst
-        print("B: sync_stats vs single GPU full batch: max |dw| = %.2e, loss %s vs %s" % (worst, loss_sync, loss_one), flush=True)
+        # gradients (Adam's first step turns a sign flip of a noise-level gradient into a 2 * lr weight difference, so
+        # the weights are only checked at that scale) and BatchNorm moving statistics of the global batch
+        errs = sorted(((float(np.linalg.norm(g_sync[k].astype(np.float64) - g_one[k]) / (np.linalg.norm(g_one[k].astype(np.float64)) + 1e-12)), k)
+                       for k in g_one if not ("conv2d_transpose" in k and k.endswith("bias"))), reverse=True)
+        print("B: largest gradient differences (relative L2):", errs[:4], flush=True)
+        worst = errs[0][0]
+        # kernels agree to summation-order noise; the small cancelling sums (biases, BN affine gradients) additionally
+        # see the rare ReLU / max-pool flips described in test_side_stream_weight_gradients_match_single_stream
+        assert all(e < (2e-3 if g_one[k].ndim > 1 else 3e-2) for e, k in errs), errs[:4]
+        for k in w_one:
+            tol = 2e-5 if "moving_" in k else 2.5 * 5e-4
+            assert np.abs(w_sync[k] - w_one[k]).max() <= tol, (k, float(np.abs(w_sync[k] - w_one[k]).max()))
+        print("B: sync_stats vs single GPU full batch: worst gradient rel L2 = %.2e, loss %s vs %s" % (worst, loss_sync, loss_one), flush=True)
 
     # ---- C: Model.fit shards every epoch over the ranks -----------------------------------------------------------------
     xs, ts = S.make_slices(22, 32, seed=5)                       # 22 samples over 2 ranks, batch 4: 3 steps per rank and epoch

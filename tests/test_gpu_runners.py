@@ -193,3 +193,28 @@ def test_save_weights_h5_to_json_model_from_json_load_weights_round_trip(gname, 
     assert np.array_equal(b.predict(x), pa)
     a.engine.close()
     b.engine.close()
+
+
+def test_cluster_experiment_activation_tap_pca_kmeans_and_per_cluster_scores():
+    """N4 (T1H:1386-1496): bottleneck features through the device activation tap, PCA + KMeans(2) as the reference calls
+    them, per-cluster validation scores; the feature matrix equals the oracle's taps in the reference's channel-major order"""
+    hw = 32
+    x, t = S.make_slices(24, hw, seed=21)
+    xv, tv = S.make_slices(12, hw, seed=22)
+    params, _ = K.init_params("unet", (hw, hw, 1), seed=4)
+    model = M.Model(graph=G.unet(hw, 1), precision="float32")
+    model.set_weights_dict(params)
+    out = R.cluster_experiment(model, x, xv, tv, layer_name="conv2d_9", n_components=8, batch_size=8)
+    assert out["train_labels"].shape == (24,) and set(np.unique(out["train_labels"])) <= {0, 1}
+    assert out["valid_labels"].shape == (12,) and out["count_cluster_0"] + out["count_cluster_1"] == 12
+    assert 0.0 < out["explained_variance"] <= 1.0 + 1e-9 and len(out["score_all"]) == 3
+    for k in (0, 1):
+        if out["count_cluster_%d" % k]:
+            assert len(out["score_cluster_%d" % k]) == 3 and np.isfinite(out["score_cluster_%d" % k]).all()
+    # the weighted mean of the per-cluster losses is the loss of the whole set when every cluster is one batch or less
+    taps = {}
+    K.forward("unet", params, x[:3], training=False, dtype=torch.float32, taps=taps)
+    feat = np.transpose(model.intermediate(x[:3], "conv2d_9"), (0, 3, 1, 2)).reshape(3, -1)
+    want = np.transpose(taps["conv2d_9"], (0, 3, 1, 2)).reshape(3, -1)
+    assert np.abs(feat - want).max() < 1e-4 * max(1.0, float(np.abs(want).max()))
+    model.engine.close()

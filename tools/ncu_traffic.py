@@ -21,6 +21,10 @@ def main(paths):
             a[0] += 1
             a[1] += float(r[rd]) * UNIT[units[rd]] + float(r[wr]) * UNIT[units[wr]]
             a[2] += float(r[tm]) * UNIT[units[tm]]
+    # the roofline's kernel CLASS: every tcgen05 3x3 forward / data-gradient kernel of the step (halo, dw-merged, row-strip)
+    cls = [v for k, v in acc.items() if k.startswith("tc_conv3")]
+    if cls:
+        acc["tc_conv3"] = [sum(v[0] for v in cls), sum(v[1] for v in cls), sum(v[2] for v in cls), cls[0][3]]
     out = {k: {"launches": v[0], "dram_bytes_per_launch": v[1] / v[0], "avg_us_under_ncu": v[2] / v[0], "source": v[3]}
            for k, v in sorted(acc.items())}
     json.dump(out, sys.stdout, indent=1)
