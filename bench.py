@@ -212,7 +212,12 @@ def run_classifier(args):
     for kv in args.opt:
         k, v = kv.split("=")
         importlib.import_module(PKG + "._lib").lib().b2u_set_option(k.encode(), int(v))
-    model = M.Model(graph=G.classifier(size, cin), precision=args.precision, use_graph=not args.no_graph, seed=42)
+    plan_options = {}
+    for kv in args.plan:                      # e.g. --plan fuse_bn_infer=0,hoist_prep=0 (A/B of the inference fusions)
+        for one in kv.split(","):
+            plan_options[one.split("=")[0]] = int(one.split("=")[1])
+    model = M.Model(graph=G.classifier(size, cin), precision=args.precision, use_graph=not args.no_graph, seed=42,
+                    plan_options=plan_options)
     model.compile(loss='binary_crossentropy', optimizer=M.Adam(lr=0.0005), metrics=[])
     eng = model.engine
     nres = 4 * batch
@@ -275,7 +280,7 @@ def run_classifier(args):
     for rep in range(3):
         importlib.import_module(PKG + "._lib").check(lib.b2u_run_ops_timed(arr, cnt, C.c_void_p(eng.ws.data_ptr()), eng.ws.numel(), None,
                                                                           C.c_void_p(eng.stream.cuda_stream), msb), "run_ops_timed")
-    ops = bplan.plan.forward_ops()
+    ops = bplan.plan.forward_ops(prep=False)
     es = 2 if args.precision == "float16" else 4
     per_op = []
     for op, ms in zip(ops, msb):
@@ -323,6 +328,9 @@ def run_classifier(args):
             "config": {"workload": wl["name"], "global_batch": batch * world, "parallelism": "replicas%d" % world,
                        "l2": "4 resident batches of 38.5 MB (fp32 inputs) cycle through; activations of one batch (~1 GB) exceed the 126 MB L2",
                        "cuda_graph": not args.no_graph, "fwd_flop_per_slice": wl["flop"],
+                       "weight_only_ops": ("fp16 operand packing and BN scale/shift run when the weights change (once, in "
+                                           "warm-up), not per batch" if bplan.plan.hoist_prep else "inside every step"),
+                       "bn_folded_into_conv_epilogue": sorted(bplan.plan.folded_into_next),
                        "baseline_md_roofline_slices_per_s": 270000},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(xh[0].numel() * 4), "d2h_bytes_per_step": batch * 4,

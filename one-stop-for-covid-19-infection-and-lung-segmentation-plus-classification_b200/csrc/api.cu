@@ -47,6 +47,17 @@ extern "C" int b2u_set_option(const char* name, int value) {
     g_b2u_tc_halo = value;
     return old;
   }
+  if (strcmp(name, "l2_fetch") == 0) {
+    // DRAM -> L2 fetch granularity of the device (cudaLimitMaxL2FetchGranularity: 32 / 64 / 128 bytes).  Kernels that read
+    // one half of a 128-byte concat pixel (max-pool backward, transposed-conv gradients) pay for the other half at 128.
+    size_t old = 0;
+    cudaDeviceGetLimit(&old, cudaLimitMaxL2FetchGranularity);
+    if (value > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value) != cudaSuccess) {
+      cudaGetLastError();
+      return -1;
+    }
+    return (int)old;
+  }
   if (strcmp(name, "pdl") == 0) {
     int old = g_b2u_pdl;
     g_b2u_pdl = value ? 1 : 0;
@@ -156,11 +167,20 @@ static bool use_rowstrip(int K, int J, int h, int wd) {
 // other paths, by one extra pass over y
 static int conv3x3_fwd_wp(int dt, const void* x, int ldx, int cin, const float* w, const float* bias, int act, void* y,
                           int ldy, int cout, double* stats, int n, int h, int wd, void* ws, size_t ws_bytes,
-                          const void* wp, void* relu_bits, void* stream, int training = 0, int k_src = 0) {
+                          const void* wp, void* relu_bits, void* stream, int training = 0, int k_src = 0,
+                          const float* post_scale = nullptr, const float* post_shift = nullptr) {
   int rc;
   if (k_src != 0)       // zero-padded input tensor: `w` has only k_src input channels, only the prepacked copy matches
     B2U_REQUIRE(wp != nullptr && dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy),
                 "conv3x3_fwd: a channel-padded input needs the tensor path and prepacked weights");
+  if (post_scale != nullptr || post_shift != nullptr) {
+    // inference plans: the BatchNormalization that follows the activation, as a per-channel affine in the epilogue
+    B2U_REQUIRE(dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy) && stats == nullptr &&
+                relu_bits == nullptr && post_scale != nullptr && post_shift != nullptr,
+                "conv3x3_fwd: the post-activation affine needs the tensor path of a plain forward");
+    return b2u_tc_conv3x3_halo(x, ldx, cin, w, 0, bias, act, y, ldy, cout, nullptr, nullptr, nullptr, 0, 0, 0, n, h, wd, ws,
+                               ws_bytes, wp, stream, nullptr, post_scale, post_shift);
+  }
   if (dt == B2U_F16 && b2u_tensor_path_available() && b2u_tc_conv3x3_ok(cin, cout, ldx, ldy)) {
     if (use_rowstrip(cin, cout, h, wd))
       return b2u_tc_conv3x3_rowstrip(x, ldx, cin, w, 0, bias, act, y, ldy, cout, stats, nullptr, nullptr, 0, 0, 0, n, h, wd, ws,
@@ -203,10 +223,12 @@ static int conv3x3_dgrad_cs(int dt, const void* dy, int lddy, int cout, const fl
   if (tc && !(bits && accumulate) && use_dwmerge(cout, cin, h, wd, 1))
     return b2u_tc_conv3x3_dwmerge(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, colsum, mask, ldmask,
                                   mask_act, accumulate, n, h, wd, ws, ws_bytes, wp, stream, nullptr, g_b2u_tc_dw_packed);
-  if (tc && (!bits || g_b2u_tc_halo))
-    return (g_b2u_tc_halo ? b2u_tc_conv3x3_halo : b2u_tc_conv3x3)(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx,
-                                                                  cin, nullptr, colsum, mask, ldmask, mask_act,
-                                                                  accumulate, n, h, wd, ws, ws_bytes, wp, stream, nullptr);
+  if (tc && g_b2u_tc_halo)
+    return b2u_tc_conv3x3_halo(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, colsum, mask, ldmask, mask_act,
+                               accumulate, n, h, wd, ws, ws_bytes, wp, stream, nullptr);
+  if (tc && !bits)
+    return b2u_tc_conv3x3(dy, lddy, cout, w, 1, nullptr, B2U_ACT_NONE, dx, lddx, cin, nullptr, colsum, mask, ldmask, mask_act,
+                          accumulate, n, h, wd, ws, ws_bytes, wp, stream, nullptr);
   int rc;
   if (bits) {
     // 1-bit mask on a path whose kernel cannot read it: unmasked data gradient, then one masking pass
@@ -299,7 +321,8 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
     case B2U_OP_CONV3X3_FWD:         // p[5] (optional): packed weights
       return conv3x3_fwd_wp(dt, p[0], I(0), I(1), (const float*)p[1], (const float*)p[2], I(2), p[3], I(3), I(4),
                             (double*)p[4], I(5), I(6), I(7), ws, wsb, p[5], p[6], s,      // p[6] (optional): 1-bit ReLU mask out
-                            I(8), I(9));                          // i[8]: op of a training-mode plan, i[9]: real Cin if padded
+                            I(8), I(9),                           // i[8]: op of a training-mode plan, i[9]: real Cin if padded
+                            (const float*)p[7], (const float*)p[8]);      // optional: post-activation scale / shift
     case B2U_OP_CONV3X3_DGRAD:       // p[4] (optional): colsum
       return conv3x3_dgrad_cs(dt, p[0], I(0), I(1), (const float*)p[1], p[2], I(2), I(3), p[3], I(4), I(5), I(6),
                               (float*)p[4], I(7), I(8), I(9), ws, wsb, p[5], s);

@@ -48,6 +48,8 @@ struct C3Params {
   // (appended last: existing constant-bank offsets stay as they were)
   uint8_t* bits_out;      // kF_BITS_OUT: packed 1-bit ReLU mask of the values stored (bit pix*J + column)
   const uint8_t* bits_in; // kF_BITS_IN : packed 1-bit ReLU mask applied to the values written (data gradient)
+  const float* post_scale;  // kF_POST: y = post_scale[c] * act(conv + bias) + post_shift[c] -- the inference-mode
+  const float* post_shift;  // BatchNormalization that follows the activation (T2:749-750), folded into the epilogue
 };
 
 struct C3Maps {
@@ -77,6 +79,8 @@ __device__ __forceinline__ float transpose_reduce16_(float v[16], int lane) {
 // statistics and/or column sums.
 constexpr int kF_MASKACC = 1, kF_SUMS = 2;
 constexpr int kF_BITS_OUT = 4, kF_BITS_IN = 8;
+constexpr int kF_POST = 16;      // per-channel affine after the activation (never together with statistics: the two
+                                 // share the s_stats area of shared memory)
 template <int kFlags>
 __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_constant__ C3Maps maps,
                                                                  const __grid_constant__ C3Params prm) {
@@ -123,7 +127,14 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
   if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
   B2U_PDL_WAIT();                    // everything below may read what the preceding kernel wrote
   for (int i = threadIdx.x; i < prm.J; i += blockDim.x) s_bias[i] = prm.bias ? prm.bias[i] : 0.f;
-  for (int i = threadIdx.x; i < 2 * prm.J; i += blockDim.x) s_stats[i] = 0.f;
+  if constexpr ((kFlags & kF_POST) != 0) {
+    for (int i = threadIdx.x; i < prm.J; i += blockDim.x) {
+      s_stats[i] = prm.post_scale[i];
+      s_stats[prm.J + i] = prm.post_shift[i];
+    }
+  } else {
+    for (int i = threadIdx.x; i < 2 * prm.J; i += blockDim.x) s_stats[i] = 0.f;
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -334,6 +345,16 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
           }
+          if constexpr ((kFlags & kF_POST) != 0) {
+            const float4* sp = reinterpret_cast<const float4*>(s_stats + jt * JT + c0);
+            const float4* tp = reinterpret_cast<const float4*>(s_stats + prm.J + jt * JT + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 s4 = sp[q], t4 = tp[q];
+              v[4 * q + 0] = fmaf(v[4 * q + 0], s4.x, t4.x); v[4 * q + 1] = fmaf(v[4 * q + 1], s4.y, t4.y);
+              v[4 * q + 2] = fmaf(v[4 * q + 2], s4.z, t4.z); v[4 * q + 3] = fmaf(v[4 * q + 3], s4.w, t4.w);
+            }
+          }
           if constexpr ((kFlags & kF_BITS_IN) != 0) {
             if (valid) {
               const uint32_t w32 = cc < 32 ? mk[0].x : (cc < 64 ? mk[0].y : (cc < 96 ? mk[0].z : mk[0].w));
@@ -512,7 +533,7 @@ int g_b2u_tc_halo = 1;       // 0: per-tap loads (conv_tc.cu), 1: halo box, 2: h
 int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                         int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
                         int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream,
-                        void* relu_bits_out) {
+                        void* relu_bits_out, const float* post_scale, const float* post_shift) {
   int rc = get_enc3();
   if (rc != B2U_OK) return rc;
   C3Params p{};
@@ -527,6 +548,8 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   p.colsum = colsum;
   p.dbg = g_b2u_dbg;
   p.bits_out = (uint8_t*)relu_bits_out;
+  p.post_scale = post_scale; p.post_shift = post_shift;
+  B2U_REQUIRE((post_scale == nullptr) == (post_shift == nullptr), "tc_conv3: post-activation scale and shift come together");
   if (mask != nullptr && mask_act == B2U_ACT_RELU_BITS) {          // packed 1-bit mask instead of the activation tensor
     p.bits_in = (const uint8_t*)mask;
     p.mask = nullptr;
@@ -613,6 +636,7 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
     B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr3 = true;
   }
   long long tiles = (long long)n * b2u_cdiv(h, kTH) * b2u_cdiv(wd, kTW) * (J / p.JT);
@@ -623,7 +647,8 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   if (two_per_sm && tiles >= 2 * per_sm * B2U_NUM_SMS) ctas = per_sm * B2U_NUM_SMS;
   int grid = (int)(tiles < ctas ? tiles : ctas);
   const int flags = ((mask != nullptr || accumulate) ? kF_MASKACC : 0) | ((stats != nullptr || colsum != nullptr) ? kF_SUMS : 0) |
-                    (p.bits_out != nullptr ? kF_BITS_OUT : 0) | (p.bits_in != nullptr ? kF_BITS_IN : 0);
+                    (p.bits_out != nullptr ? kF_BITS_OUT : 0) | (p.bits_in != nullptr ? kF_BITS_IN : 0) |
+                    (post_scale != nullptr ? kF_POST : 0);
   const int nthr = 64 + 32 * p.epi_warps;
   switch (flags) {
     case 0: B2U_LAUNCH(tc_conv3_kernel<0>, grid, nthr, smem, stream, maps, p); break;
@@ -634,8 +659,9 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
     case 6: B2U_LAUNCH(tc_conv3_kernel<6>, grid, nthr, smem, stream, maps, p); break;      // ... + statistics
     case 8: B2U_LAUNCH(tc_conv3_kernel<8>, grid, nthr, smem, stream, maps, p); break;      // data gradient, 1-bit mask
     case 10: B2U_LAUNCH(tc_conv3_kernel<10>, grid, nthr, smem, stream, maps, p); break;    // ... + column sums
+    case 16: B2U_LAUNCH(tc_conv3_kernel<16>, grid, nthr, smem, stream, maps, p); break;    // inference forward + BN affine
     default:
-      b2u_set_error("tc_conv3: unsupported feature combination %d (1-bit masks do not combine with accumulate / fp16 masks)", flags);
+      b2u_set_error("tc_conv3: unsupported feature combination %d (1-bit masks do not combine with accumulate / fp16 masks, the post-activation affine only with a plain forward)", flags);
       return B2U_ERR_ARG;
   }
   return B2U_OK;

@@ -34,7 +34,7 @@ extern long long* g_b2u_dbg;
 int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                         int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
                         int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream,
-                        void* relu_bits_out);
+                        void* relu_bits_out, const float* post_scale = nullptr, const float* post_shift = nullptr);
 int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
                    int ldy, int J, double* stats, float* colsum, const void* mask, int ldmask, int mask_act,
                    int accumulate, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp, void* stream,

@@ -117,7 +117,8 @@ class Engine:
                                          beta1_pow=0.9, beta2_pow=0.999, loss_scale=1.0,
                                          grad_div=1.0 if self.sync_stats else float(self.world), overflow=0, skip_step=0)
         self._arenas = {}        # name -> torch uint8 tensor (grown on demand, shared between plans)
-        self._bound = {}         # (n, training, dropout, loss) -> _Bound
+        self._bound = {}         # (n, training, dropout, loss, tap) -> _Bound
+        self._prep_owner = None  # the inference plan whose weight-only ops (plan.prep_ops) are current in the arenas
         self._push_state()
         self.set_weights(init_weights(graph, seed))
         if self.comm is not None:
@@ -224,6 +225,7 @@ class Engine:
             self.params.copy_(torch.from_numpy(fp))
             self.state[:fs.size].copy_(torch.from_numpy(fs))
         self.stream.synchronize()
+        self._prep_owner = None
         self.guard_small_gamma()
 
     def get_weights(self):
@@ -245,6 +247,7 @@ class Engine:
                 dist.broadcast(h, src=0)
                 t.copy_(h)
         torch.cuda.synchronize(self.device)
+        self._prep_owner = None
 
     # ---------------------------------------------------------------------------------------
     # plans
@@ -261,15 +264,21 @@ class Engine:
             with torch.cuda.stream(self.stream):
                 t = torch.zeros(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
             self._arenas[name] = t
+            self._prep_owner = None
         return t
 
-    def _get_bound(self, n, training, dropout=True, loss=None):
-        key = (int(n), bool(training), bool(dropout), loss or self.loss)
+    def _get_bound(self, n, training, dropout=True, loss=None, tap=False):
+        """tap=True: a plan whose every layer output is materialised as the reference's layer would produce it
+        (`layer_output`); the default inference plan folds BatchNormalization into the producing conv."""
+        key = (int(n), bool(training), bool(dropout), loss or self.loss, bool(tap))
         b = self._bound.get(key)
         if b is None:
+            opts = dict(self.plan_options)
+            if tap:
+                opts["fuse_bn_infer"] = False
             pl = P.Plan(self.graph, n, dt=self.dt, training=training, dropout=dropout, loss=loss or self.loss,
                         world=self.world, sync_stats=self.sync_stats, layout=self.layout, rank=self.rank,
-                        **self.plan_options)
+                        **opts)
             b = _Bound(pl)
             self._bound[key] = b
         sizes = b.plan.arena_sizes()
@@ -304,16 +313,24 @@ class Engine:
     def _ops(self, b, name):
         if name not in b.ops:
             pl = b.plan
-            lst = {"train": pl.train_ops, "forward": pl.forward_ops,
-                   "forward_loss": lambda: pl.forward_ops(with_loss=True)}[name]()
+            lst = {"train": pl.train_ops, "forward": lambda: pl.forward_ops(prep=False),
+                   "forward_loss": lambda: pl.forward_ops(with_loss=True, prep=False), "prep": pl.prep_ops}[name]()
             resolve = lambda ref: (b.wtab.data_ptr() + ref.off) if ref.arena == "wtab" else self._resolve(ref)
             b.ops[name] = (_lib.make_ops(lst, resolve), len(lst))
         return b.ops[name]
 
     def _run(self, b, name):
-        arr, n = self._ops(b, name)
         comm = self.comm.handle if self.comm is not None else None
         s = C.c_void_p(self.stream.cuda_stream)
+        # inference plans keep their weight-only ops (operand packing, BN scale / shift) out of the per-batch list: they
+        # run here, eagerly, when the weights have changed or another plan has used the shared arenas since
+        if name != "train" and b.plan.hoist_prep and self._prep_owner is not b:
+            parr, pn = self._ops(b, "prep")
+            if pn:
+                _lib.check(self.lib.b2u_run_ops(parr, pn, C.c_void_p(self.ws.data_ptr()), self.ws.numel(), comm, s),
+                           "run_ops(prep)")
+        self._prep_owner = b if name != "train" else None
+        arr, n = self._ops(b, name)
         if self.use_graph:
             g = b.graphs.get(name)
             if g is None:
@@ -375,9 +392,9 @@ class Engine:
         self._run(b, "train")
         return b
 
-    def forward_batch(self, x_src, idx, n, t_src=None, sw_src=None, training=False):
+    def forward_batch(self, x_src, idx, n, t_src=None, sw_src=None, training=False, tap=False):
         """inference-mode forward (BN moving statistics, no dropout); with t_src also the loss."""
-        b = self._get_bound(n, training, False)
+        b = self._get_bound(n, training, False, tap=tap)
         self._load_inputs(b, x_src, idx, n, t_src, sw_src)
         self._run(b, "forward_loss" if t_src is not None else "forward")
         return b
@@ -404,6 +421,9 @@ class Engine:
     def layer_output(self, b, name):
         """host copy of an intermediate activation (Model(inputs, get_layer(name).output), T1H:1386)."""
         v = b.plan.layer_out[name]
+        if name in b.plan.folded_into_next:
+            raise ValueError("layer %r is fused with the BatchNormalization behind it in this plan: run forward_batch(..., "
+                             "tap=True) to read its own output" % name)
         self.stream.synchronize()
         a = self._arenas[v.ref.arena]
         es = P.ELEM[v.dt]
@@ -427,6 +447,7 @@ class Engine:
         [(plan.Op, milliseconds)].  Inputs must already be in place (call train_batch once before)."""
         b = self._get_bound(n, True, dropout)
         arr, cnt = self._ops(b, "train")
+        self._prep_owner = None
         ms = (C.c_float * cnt)()
         comm = self.comm.handle if self.comm is not None else None
         _lib.check(self.lib.b2u_run_ops_timed(arr, cnt, C.c_void_p(self.ws.data_ptr()), self.ws.numel(), comm,

@@ -166,6 +166,7 @@ class Model:
         self.metrics = []
         self.metrics_names = ["loss"]
         self.stop_training = False
+        self.pipeline_predict = True     # predict(): overlap the host->device copy of a host input with the forward passes
         self._shuffle_rng = np.random.RandomState(1234)
 
     # ---- structure --------------------------------------------------------------------------
@@ -401,14 +402,41 @@ class Model:
         return out if len(out) > 1 else out[0]
 
     def predict(self, x, batch_size=32, verbose=0, **kw):
+        """keras Model.predict (T1H:1113, T2:726).  A HOST input is copied in chunks on a separate copy stream while the
+        forward of the previous chunk runs (inference is per-sample independent, so the chunk size only changes speed:
+        `batch_size`, or a quarter of the input when the whole input is less than four batches); the probabilities come
+        back in one device->host copy at the end."""
         eng = self.engine
         x = self._check_x(x)
         n_tot = len(x)
-        xd = self._to_dev(x)
+        on_dev = isinstance(x, torch.Tensor) and x.is_cuda
+        chunk = int(batch_size)
+        if not on_dev and self.pipeline_predict and n_tot < 4 * chunk:
+            chunk = max(1, min(chunk, -(-n_tot // 4)))
         with torch.cuda.stream(eng.stream):
             out = torch.empty((n_tot,) + tuple(self.graph.output.shape), dtype=torch.float32, device=eng.device)
-            for lo in range(0, n_tot, batch_size):
-                n = min(batch_size, n_tot - lo)
+        if on_dev or not self.pipeline_predict or n_tot <= chunk:
+            xd, xt, cs = self._to_dev(x), None, None
+        else:
+            xt = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+            cs = getattr(self, "_predict_copy_stream", None)
+            if cs is None:
+                cs = self._predict_copy_stream = torch.cuda.Stream(eng.device)
+            with torch.cuda.stream(eng.stream):
+                xd = torch.empty(tuple(xt.shape), dtype=torch.float32, device=eng.device)
+            cs.wait_stream(eng.stream)                      # the buffer exists (and its previous user is done) before copying
+            xd.record_stream(cs)
+        for lo in range(0, n_tot, chunk):
+            n = min(chunk, n_tot - lo)
+            if cs is not None:
+                # copy, then enqueue the forward: with pageable memory the copy blocks the host while the device still
+                # runs the previous chunk; with pinned memory everything is queued at once and the two streams overlap
+                with torch.cuda.stream(cs):
+                    xd[lo:lo + n].copy_(xt[lo:lo + n], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                eng.stream.wait_event(ev)
+            with torch.cuda.stream(eng.stream):
                 b = eng.forward_batch(xd[lo:lo + n], None, n)
                 out[lo:lo + n].copy_(eng.probs(b))
         eng.stream.synchronize()
@@ -425,7 +453,7 @@ class Model:
         xd = self._to_dev(x)
         for lo in range(0, len(x), 32):
             n = min(32, len(x) - lo)
-            b = eng.forward_batch(xd[lo:lo + n], None, n)
+            b = eng.forward_batch(xd[lo:lo + n], None, n, tap=True)
             outs.append(eng.layer_output(b, layer_name))
         return np.concatenate(outs, 0)
 

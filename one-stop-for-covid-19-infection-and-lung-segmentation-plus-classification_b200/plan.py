@@ -130,7 +130,8 @@ class Plan:
 
     def __init__(self, graph, n, dt=F32, training=True, dropout=True, loss="bce_dice", world=1,
                  sync_stats=False, layout=None, rank=0, fuse_bn_bwd=True, fuse_bn_stats=True, fuse_bias_grad=True,
-                 prepack=True, fuse_bn_bwd_wgrad=True, fuse_bn_pool=True, relu_bits=None, grad_bucket_bytes=6 << 20):
+                 prepack=True, fuse_bn_bwd_wgrad=True, fuse_bn_pool=True, relu_bits=None, grad_bucket_bytes=6 << 20,
+                 fuse_bn_infer=True, hoist_prep=True):
         self.graph, self.n, self.dt, self.training = graph, int(n), dt, training
         self.dropout = dropout and training
         self.loss, self.world, self.sync_stats = loss, int(world), bool(sync_stats) and world > 1
@@ -140,6 +141,14 @@ class Plan:
         self.fuse_bias_grad = bool(fuse_bias_grad)
         self.fuse_bn_bwd_wgrad = bool(fuse_bn_bwd_wgrad)
         self.fuse_bn_pool = bool(fuse_bn_pool)
+        # inference plans (fp16 storage): Conv2D(relu) -> BatchNormalization (T2:749-750, 757-758, 766-767) runs as ONE kernel,
+        # the BN of the moving statistics being a per-channel affine after the activation in the conv epilogue; and the
+        # ops that depend on the weights only (operand packing, scale / shift of every BN) leave the per-batch op list:
+        # `prep_ops()` runs when the weights have changed (engine.py), `forward_ops(prep=False)` per batch.
+        # Classifier 224 x 224 x 3, batch 64 on B200: 0.446 -> see profiles/NOTES_r2.md.
+        self.fuse_bn_infer = bool(fuse_bn_infer) and not training and dt == F16
+        self.hoist_prep = bool(hoist_prep) and not training
+        self.prep = []                   # inference plans: weight-only ops (BN finalize from the moving statistics)
         # data parallel: the flat gradient buffer is exchanged in buckets of about this many bytes, each all-reduced as soon
         # as the last backward op that writes into it has been issued (0 = one all-reduce after the whole backward)
         self.grad_bucket_bytes = int(grad_bucket_bytes)
@@ -162,6 +171,7 @@ class Plan:
         self.views, self.gviews = {}, {}         # id(SymTensor) -> View
         self.layer_out = OrderedDict()           # layer name -> View (model.get_layer(name).output)
         self.n_dropout_ops = 0
+        self.folded_into_next = set()            # conv layers whose stored output is already the following BN's
         self._lower()
 
     # ---------------------------------------------------------------------------------------
@@ -206,6 +216,16 @@ class Plan:
 
     def _w(self, layer, short, arena=None):
         return self.layout.ref("%s/%s" % (layer.name, short), arena)
+
+    def _bn_finalize(self, l, aux, c, count):
+        """inference-mode BatchNormalization: scale / shift from the moving statistics -- a weight-only op"""
+        for nm in ("scale", "shift", "mean", "invstd"):
+            aux[nm] = self.f32.alloc(c * 4)
+        aux["count"] = count
+        op = Op(OP_BN_FINALIZE, 0,
+                [None, self._w(l, "gamma"), self._w(l, "beta"), self._w(l, "moving_mean"), self._w(l, "moving_variance"),
+                 aux["scale"], aux["shift"], aux["mean"], aux["invstd"]], [count, 0, c], [l.momentum, l.epsilon], tag=l.name)
+        (self.prep if self.hoist_prep else self.fwd).append(op)
 
     @staticmethod
     def _act_of(t):
@@ -323,8 +343,22 @@ class Plan:
                         tuple(cons[0].kernel_size) == (3, 3) and yv.c % 16 == 0):
                     bits = self._bits[id(t)] = self.act.alloc(self._npix(yv) * yv.c // 8)
                 k_src = x.shape[-1] if (x.producer.kind == "input" and self.x_pad) else 0
+                post = [None, None]
+                bn_ld = (concat_buf[id(home[id(cons[0].output)][0])].ld
+                         if len(cons) == 1 and id(cons[0].output) in home else yv.c)
+                if (self.fuse_bn_infer and self.prepack and len(cons) == 1 and cons[0].kind == "batch_normalization" and
+                        xv.c % 16 == 0 and yv.c % 16 == 0 and yv.c <= 1024 and xv.ld % 8 == 0 and bn_ld % 8 == 0):
+                    # the BN's output takes the conv's place: the conv writes normalised values, the BN layer emits nothing
+                    bn = cons[0]
+                    aux = bn_aux.setdefault(id(bn), {})
+                    self._bn_finalize(bn, aux, yv.c, self._npix(yv))
+                    aux["folded"] = True
+                    place(bn.output, dt)
+                    yv = self.views[id(t)] = self.views[id(bn.output)]
+                    post = [aux["scale"], aux["shift"]]
+                    self.folded_into_next.add(l.name)
                 self.fwd.append(Op(OP_CONV3X3_FWD, dt, [xv.ref, self._w(l, "kernel"), self._w(l, "bias"), yv.ref, stats,
-                                                        self._packed(l, 0, 9, yv.c, xv.c, k_src), bits],
+                                                        self._packed(l, 0, 9, yv.c, xv.c, k_src), bits] + post,
                                    [xv.ld, xv.c, ACT[l.activation], yv.ld, yv.c, n, xv.h, xv.w, 1 if self.training else 0,
                                     k_src], tag=l.name))
                 # i[8]: training-mode op (kernel selection may trade a rounding for speed); i[9]: the kernel's real input
@@ -345,13 +379,22 @@ class Plan:
                                    [xv.ld, xv.c, yv.ld, yv.c, n, xv.h, xv.w, 0], tag=l.name))
                 prod_op[id(t)] = self.fwd[-1]
             elif l.kind == "batch_normalization":
+                aux = bn_aux.setdefault(id(l), {})
+                if aux.get("folded"):                          # inference: applied by the producing conv's epilogue
+                    self.layer_out[l.name] = self.views[id(t)]
+                    continue
                 place(t, xv.dt)
                 yv = self.views[id(t)]
                 c = xv.c
-                aux = bn_aux.setdefault(id(l), {})
+                count = self._npix(xv)
+                if not self.training:
+                    self._bn_finalize(l, aux, c, count)
+                    self.fwd.append(Op(OP_BN_APPLY, xv.dt, [xv.ref, yv.ref, aux["scale"], aux["shift"], None],
+                                       [xv.ld, yv.ld, c, self._npix(xv), 0], tag=l.name))
+                    self.layer_out[l.name] = yv
+                    continue
                 for nm in ("scale", "shift", "mean", "invstd"):
                     aux[nm] = self.f32.alloc(c * 4)
-                count = self._npix(xv)
                 if self.training:
                     if "sums" not in aux:
                         aux["sums"] = self.zero.alloc(2 * c * 8)
@@ -699,13 +742,25 @@ class Plan:
             out.extend(inserts.get(k, []))
         self.bwd = out
 
-    def prologue(self):
+    def _pack_op(self):
+        if not self.pack_entries:
+            return []
+        total = sum(self._pack_tiles(t, j, k) for _, _, _, t, j, k, _ks in self.pack_entries)
+        return [Op(OP_PACK_WEIGHTS, 0, [Ref("wtab", 0), Ref("params", 0), Ref("wpack", 0)],
+                   [len(self.pack_entries), total], tag="pack-weights")]
+
+    def prep_ops(self):
+        """inference plans: the ops that depend on the weights only (fp16 operand copies, BN scale / shift from the moving
+        statistics); they must run again whenever the weights -- or another plan sharing the arenas -- have changed."""
+        return (self._pack_op() + self.prep) if self.hoist_prep else []
+
+    def prologue(self, prep=True):
         """ops that must run before every step: clear the statistics arena (and gradients)."""
         ops = []
-        if self.pack_entries:
-            total = sum(self._pack_tiles(t, j, k) for _, _, _, t, j, k, _ks in self.pack_entries)
-            ops.append(Op(OP_PACK_WEIGHTS, 0, [Ref("wtab", 0), Ref("params", 0), Ref("wpack", 0)],
-                          [len(self.pack_entries), total], tag="pack-weights"))
+        if self.hoist_prep:
+            ops += self.prep_ops() if prep else []
+        else:
+            ops += self._pack_op()
         if self.zero.size:
             ops.append(Op(OP_MEMSET, 0, [Ref("zero", 0)], [self.zero.size], tag="zero-sums"))
         if self.training:
@@ -715,8 +770,9 @@ class Plan:
     def train_ops(self):
         return self.prologue() + self.fwd + self.loss_ops + self.bwd + self.opt
 
-    def forward_ops(self, with_loss=False):
-        return self.prologue() + self.fwd + (self.loss_ops if with_loss else [])
+    def forward_ops(self, with_loss=False, prep=True):
+        """prep=False: without the weight-only ops of an inference plan (the caller has run `prep_ops()`)"""
+        return self.prologue(prep) + self.fwd + (self.loss_ops if with_loss else [])
 
     def arena_sizes(self):
         return {"act": self.act.size, "f32": self.f32.size, "zero": max(self.zero.size, 8),

@@ -114,6 +114,8 @@ class Emulator:
         y = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(wt.copy()).permute(3, 2, 0, 1),
                      torch.from_numpy(b.copy()), padding=1).permute(0, 2, 3, 1).numpy()
         y = self._act(self._jit(y), act).reshape(-1, cout)
+        if len(o.p) > 8 and o.p[7] is not None:          # inference plans: the following BatchNormalization as an affine
+            y = y * self.f32(o.p[7], cout)[None, :] + self.f32(o.p[8], cout)[None, :]
         yv = self.view(o.p[3], ldy, cout, n * h * w, o.dt)
         yv[:] = y.astype(yv.dtype)
         if o.p[4] is not None:

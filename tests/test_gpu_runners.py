@@ -218,3 +218,51 @@ def test_cluster_experiment_activation_tap_pca_kmeans_and_per_cluster_scores():
     want = np.transpose(taps["conv2d_9"], (0, 3, 1, 2)).reshape(3, -1)
     assert np.abs(feat - want).max() < 1e-4 * max(1.0, float(np.abs(want).max()))
     model.engine.close()
+
+
+def test_fp16_inference_plan_tracks_weight_changes_and_taps_layer_outputs():
+    """fp16 inference plans fold Conv2D -> BatchNormalization into one kernel and run their weight-only ops (operand packing,
+    BN scale / shift) only when needed: predictions must follow set_weights, a training step in between, another batch
+    size sharing the arenas, and `intermediate` (a tap plan) must still return each layer's OWN output (T1H:1386-1405)."""
+    hw, n = 32, 6
+    x, t = S.make_slices(n, hw, seed=12)
+    pa, _ = K.init_params("unet", (hw, hw, 1), seed=4)
+    pb, _ = K.init_params("unet", (hw, hw, 1), seed=9)
+    rng = np.random.default_rng(0)
+    for p in (pa, pb):                       # non-trivial moving statistics and affine parameters
+        for k in p:
+            if k.endswith("moving_variance") or k.endswith("gamma"):
+                p[k] = (0.5 + rng.random(p[k].shape)).astype(np.float32)
+            elif k.endswith("moving_mean") or k.endswith("beta"):
+                p[k] = (0.2 * rng.standard_normal(p[k].shape)).astype(np.float32)
+    model = M.Model(graph=G.unet(hw, 1), precision="float16")
+    model.compile(optimizer=M.Adam(lr=0.0005), loss=LS.bce_dice_loss, metrics=[LS.dice_coeff])
+    want = {}
+    for name, p in (("a", pa), ("b", pb)):
+        want[name], _ = K.forward("unet", p, x, training=False, dtype=torch.float32)
+    model.set_weights_dict(pa)
+    assert np.abs(model.predict(x, batch_size=n) - want["a"]).max() < 2e-3
+    assert np.abs(model.predict(x, batch_size=n) - want["a"]).max() < 2e-3            # second call: prep ops skipped
+    assert np.abs(model.predict(x[:4], batch_size=4) - want["a"][:4]).max() < 2e-3    # another plan, same arenas
+    assert np.abs(model.predict(x, batch_size=n) - want["a"]).max() < 2e-3
+    model.set_weights_dict(pb)
+    assert np.abs(model.predict(x, batch_size=n) - want["b"]).max() < 2e-3
+    # a training step changes the weights (and overwrites the shared arenas): the next predict must see them
+    before = model.predict(x, batch_size=n)
+    for _ in range(3):
+        model.train_on_batch(x, t)
+    after_w = model.get_weights_dict()
+    want_after, _ = K.forward("unet", after_w, x, training=False, dtype=torch.float32)
+    got_after = model.predict(x, batch_size=n)
+    assert np.abs(got_after - want_after).max() < 2e-3 and np.abs(got_after - before).max() > 1e-4
+    # taps: conv2d_2's own (pre-BN) output, the BN output, both against the oracle at fp16 accuracy
+    taps = {}
+    K.forward("unet", after_w, x, training=False, dtype=torch.float32, taps=taps)
+    for name in ("conv2d_2", "batch_normalization_1", "conv2d_10"):
+        got = model.intermediate(x, name)
+        assert np.abs(got - taps[name]).max() < 4e-3 * max(1.0, float(np.abs(taps[name]).max())), name
+    b = model.engine.forward_batch(model._to_dev(x), None, n)
+    with pytest.raises(ValueError, match="fused with the BatchNormalization"):
+        model.engine.layer_output(b, "conv2d_2")
+    assert np.abs(model.predict(x, batch_size=n) - want_after).max() < 2e-3           # after the tap plan used the arenas
+    model.engine.close()

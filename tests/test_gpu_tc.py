@@ -41,6 +41,26 @@ def test_tc_conv3x3_fwd(n, h, w, cin, cout):
         compare(ops, img, dt, tol=3e-3)
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 32, 16, 16), (1, 28, 28, 32, 32), (3, 14, 14, 64, 64), (1, 24, 40, 128, 256),
+                                            (1, 16, 16, 512, 512), (2, 56, 56, 16, 32)])
+def test_tc_conv3x3_fwd_with_post_activation_affine(n, h, w, cin, cout):
+    """inference plans: Conv2D(relu | elu) -> BatchNormalization as one kernel, y = scale * act(conv + b) + shift (p[7], p[8]),
+    here with the preceding BN finalize op producing scale / shift from moving statistics, strided input and output"""
+    img = Img(121)
+    x = img.view(n, h, w, cin, dt, ld=2 * cin, c0=cin, fill="uniform")
+    y = img.view(n, h, w, cout, dt, ld=cout + 16, c0=8, fill=None)
+    wt = img.farr(img.par, 9 * cin * cout, scale=(2.0 / (9 * cin)) ** 0.5)
+    b = img.farr(img.par, cout, scale=0.1)
+    gamma, beta = img.farr(img.par, cout, fill="pos"), img.farr(img.par, cout, scale=0.2)
+    mm, mv = img.farr(img.par, cout, scale=0.2), img.farr(img.par, cout, fill="pos")
+    sc, sh, mean, inv = (img.f32.alloc(cout * 4) for _ in range(4))
+    for act in (1, 2):
+        ops = [P.Op(P.OP_BN_FINALIZE, 0, [None, gamma, beta, mm, mv, sc, sh, mean, inv], [n * h * w, 0, cout], [0.99, 1e-3]),
+               P.Op(P.OP_CONV3X3_FWD, dt, [x.ref, wt, b, y.ref, None, None, None, sc, sh],
+                    [x.ld, cin, act, y.ld, cout, n, h, w, 0, 0])]
+        compare(ops, img, dt, tol=3e-3)
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout", TC_CONV)
 def test_tc_conv3x3_dgrad(n, h, w, cin, cout):
     img = Img(22)

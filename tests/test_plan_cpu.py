@@ -195,3 +195,49 @@ def test_inference_plan_pads_a_three_channel_input_for_the_tensor_core_first_con
     assert np.abs(em.f32(plan.prob, n).reshape(n, 1) - want).max() < 2e-3          # fp16 storage
     assert P.Plan(g, n, dt=P.F16, training=True, loss="bce").x_pad == 0
     assert P.Plan(g, n, dt=P.F32, training=False, loss="bce").x_pad == 0
+
+
+def test_inference_plan_folds_batchnorm_into_the_conv_epilogue_and_hoists_weight_only_ops():
+    """fp16 inference plans (T2:747-778 classifier; U-Net encoder): Conv2D(relu) -> BatchNormalization is one conv op with a
+    post-activation affine, BN finalize and operand packing live in `prep_ops()` (run when the weights change, not per
+    batch), the per-batch list holds no BN op for the folded layers; same probabilities as the unfused plan and the
+    oracle; training plans and exact plans are untouched; `tap` plans (fuse_bn_infer=False) keep every layer output."""
+    hw, n, cin = 32, 3, 3
+    g = G.classifier(hw, cin)
+    params = perturbed_params("classifier", hw, cin=cin)
+    x = np.random.default_rng(1).random((n, hw, hw, cin)).astype(np.float32)
+    want, _ = K.forward("classifier", params, x, training=False, dtype=torch.float32)
+    plan = P.Plan(g, n, dt=P.F16, training=False, loss="bce")
+    convs = [o for o in plan.fwd if o.kind == P.OP_CONV3X3_FWD]
+    assert len(convs) == 6 and all(o.p[7] is not None and o.p[8] is not None for o in convs)
+    assert plan.folded_into_next == {"conv2d_%d" % k for k in range(1, 7)}
+    per_batch = plan.forward_ops(prep=False)
+    assert not any(o.kind in (P.OP_BN_FINALIZE, P.OP_BN_APPLY, P.OP_BN_APPLY_POOL, P.OP_PACK_WEIGHTS) for o in per_batch)
+    assert sum(1 for o in per_batch if o.kind == P.OP_MAXPOOL_FWD) == 3
+    prep = plan.prep_ops()
+    assert prep[0].kind == P.OP_PACK_WEIGHTS and [o.kind for o in prep[1:]] == [P.OP_BN_FINALIZE] * 6
+    assert [repr(o) for o in plan.forward_ops()] == [repr(o) for o in prep + per_batch]
+    outs = {}
+    for name, pl in (("folded", plan), ("tap", P.Plan(g, n, dt=P.F16, training=False, loss="bce", fuse_bn_infer=False)),
+                     ("inline", P.Plan(g, n, dt=P.F16, training=False, loss="bce", hoist_prep=False))):
+        em = E.Emulator(pl.arena_sizes())
+        _load(em, pl, params, x, np.zeros((n, 1), np.float32))
+        em.run(pl.forward_ops())
+        outs[name] = em.f32(pl.prob, n).reshape(n, 1).copy()
+        assert np.abs(outs[name] - want).max() < 2e-3, name
+    assert np.array_equal(outs["folded"], outs["inline"])
+    tap = P.Plan(g, n, dt=P.F16, training=False, loss="bce", fuse_bn_infer=False)
+    assert not tap.folded_into_next and sum(1 for o in tap.fwd if o.kind in (P.OP_BN_APPLY, P.OP_BN_APPLY_POOL)) == 6
+    assert not P.Plan(g, n, dt=P.F32, training=False, loss="bce").folded_into_next
+    tr = P.Plan(g, n, dt=P.F16, training=True, loss="bce")
+    assert not tr.folded_into_next and tr.prep_ops() == [] and tr.train_ops()[0].kind == P.OP_PACK_WEIGHTS
+    # U-Net: only the encoder's conv -> BN pairs fold (the decoder BNs normalise a concat buffer)
+    un = P.Plan(G.unet(32, 1), 2, dt=P.F16, training=False)
+    assert un.folded_into_next == {"conv2d_2", "conv2d_4", "conv2d_6", "conv2d_8"}
+    xs = np.random.default_rng(2).random((2, 32, 32, 1)).astype(np.float32)
+    pu = perturbed_params("unet", 32)
+    wantu, _ = K.forward("unet", pu, xs, training=False, dtype=torch.float32)
+    em = E.Emulator(un.arena_sizes())
+    _load(em, un, pu, xs, np.zeros((2, 32 * 32), np.float32))
+    em.run(un.forward_ops())
+    assert np.abs(em.f32(un.prob, 2 * 32 * 32).reshape(wantu.shape) - wantu).max() < 2e-3
