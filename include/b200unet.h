@@ -258,7 +258,7 @@ enum {
 typedef struct b2u_op {
   int32_t kind;
   int32_t dt;
-  void* p[12];
+  void* p[14];
   int64_t i[12];
   float f[4];
 } b2u_op;

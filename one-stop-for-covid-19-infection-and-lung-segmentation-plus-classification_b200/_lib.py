@@ -23,7 +23,7 @@ class StepState(C.Structure):
 
 class Op(C.Structure):
     """mirror of b2u_op"""
-    _fields_ = [("kind", C.c_int32), ("dt", C.c_int32), ("p", C.c_void_p * 12), ("i", C.c_int64 * 12),
+    _fields_ = [("kind", C.c_int32), ("dt", C.c_int32), ("p", C.c_void_p * 14), ("i", C.c_int64 * 12),
                 ("f", C.c_float * 4)]
 
 

@@ -171,7 +171,10 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
                                                             int ldy, int C, long long npix,
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift,
-                                                            double* __restrict__ out_stats, int out_sq_off) {
+                                                            double* __restrict__ out_stats, int out_sq_off,
+                                                            const T* __restrict__ x2, int ldx2, int split) {
+  // (x2, ldx2, split): channels [split, C) are read from a second tensor -- a two-input concatenate whose halves live in
+  // dense tensors of their own instead of one interleaved buffer (plan.py "split concat"); split = C: one source
   B2U_PDL_PROLOGUE();
   extern __shared__ float sst[];          // [2*C] block partials of the optional output statistics
   float o1[8], o2[8];
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
   }
   PIXEL_LANE_LOOP(C, npix) {
     float v[8];
-    load8<T>(x + p * ldx + g * 8, v);
+    load8<T>(g * 8 < split ? x + p * ldx + g * 8 : x2 + p * ldx2 + (g * 8 - split), v);
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
     store8<T>(y + p * ldy + g * 8, v);
@@ -218,8 +221,11 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
     const T* __restrict__ dy, int lddy, const T* __restrict__ x, int ldx, T* __restrict__ dx, int lddx, int C,
     long long npix, long long count, const float* __restrict__ gamma, const float* __restrict__ mean,
     const float* __restrict__ invstd, const double* __restrict__ sums, float* __restrict__ dgamma,
-    float* __restrict__ dbeta, const T* __restrict__ mask, int ldmask, int mask_act, float* __restrict__ colsum) {
+    float* __restrict__ dbeta, const T* __restrict__ mask, int ldmask, int mask_act, float* __restrict__ colsum,
+    const T* __restrict__ x2, int ldx2, T* __restrict__ dx2, int lddx2, int split) {
   B2U_PDL_PROLOGUE();
+  // (x2, dx2, split): channels [split, C) of the BN input / its gradient live in a second tensor (split concat, see
+  // bn_apply_kernel); split = C: one tensor
   // colsum (optional): per-channel sums of the dx values written = bias gradient of the conv that feeds this BN
   extern __shared__ float scs[];          // [C] block partials of colsum
   float cs[kColsum ? 8 : 1];
@@ -254,8 +260,9 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
   }
   PIXEL_LANE_LOOP(C, npix) {
     float d[8], xv[8], o[8];
+    const bool first = g * 8 < split;
     load8<T>(dy + p * lddy + g * 8, d);
-    load8<T>(x + p * ldx + g * 8, xv);
+    load8<T>(first ? x + p * ldx + g * 8 : x2 + p * ldx2 + (g * 8 - split), xv);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = fmaf(ca[k], d[k], fmaf(cb[k], xv[k], cc[k]));
     if (mask != nullptr) {
@@ -264,7 +271,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] *= act_bwd_from_y(mv[k], mask_act);
     }
-    store8<T>(dx + p * lddx + g * 8, o);
+    store8<T>(first ? dx + p * lddx + g * 8 : dx2 + p * lddx2 + (g * 8 - split), o);
     if (kColsum) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) cs[kColsum ? k : 0] += o[k];
@@ -1131,13 +1138,23 @@ extern "C" int b2u_bn_finalize(const double* sums, long long count, const float*
 extern "C" int b2u_bn_apply(int dt, const void* x, int ldx, void* y, int ldy, int c, long long npix,
                             const float* scale, const float* shift, double* out_stats, int out_sq_off,
                             void* stream) {
+  return b2u_bn_apply_split(dt, x, ldx, nullptr, 0, c, y, ldy, c, npix, scale, shift, out_stats, out_sq_off, stream);
+}
+
+// channels [0, split) from x, [split, c) from x2 (op lists only: a two-input concatenate kept as two dense tensors)
+int b2u_bn_apply_split(int dt, const void* x, int ldx, const void* x2, int ldx2, int split, void* y, int ldy, int c,
+                       long long npix, const float* scale, const float* shift, double* out_stats, int out_sq_off,
+                       void* stream) {
   REQ_VEC8(c);
   B2U_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "bn_apply: alignment");
   B2U_REQUIRE(c <= 2048, "bn_apply: c <= 2048");
+  if (x2 == nullptr) split = c;
+  B2U_REQUIRE(split == c || (split > 0 && split < c && split % 8 == 0 && ldx2 % 8 == 0 && aligned16(x2)),
+              "bn_apply: bad second source (split=%d of %d)", split, c);
   int grid = lane_grid(npix, c, out_stats != nullptr ? 4 : 8);
   size_t smem = out_stats != nullptr ? 2 * (size_t)c * sizeof(float) : 0;
   DISPATCH_T(dt, B2U_LAUNCH(bn_apply_kernel<T>, grid, kThreads, smem, stream, (const T*)x, ldx, (T*)y, ldy, c, npix,
-                            scale, shift, out_stats, out_sq_off));
+                            scale, shift, out_stats, out_sq_off, (const T*)x2, ldx2, split));
   return B2U_OK;
 }
 
@@ -1182,13 +1199,19 @@ extern "C" int b2u_bn_bwd_sums_from_wgrad(const float* w, const float* dw, const
 
 extern "C" int b2u_bn_bwd_reduce(int dt, const void* dy, int lddy, const void* x, int ldx, int c, long long npix,
                                  const float* save_mean, const float* save_invstd, double* sums, void* stream) {
+  return b2u_bn_bwd_reduce_off(dt, dy, lddy, x, ldx, c, npix, save_mean, save_invstd, sums, c, stream);
+}
+
+// the same into a (possibly wider) sums buffer: sums[i], sums[sq_off + i] (one half of a split concatenate)
+int b2u_bn_bwd_reduce_off(int dt, const void* dy, int lddy, const void* x, int ldx, int c, long long npix,
+                          const float* save_mean, const float* save_invstd, double* sums, int sq_off, void* stream) {
   REQ_VEC8(c);
   B2U_REQUIRE(c <= 2048 && ldx % 8 == 0 && lddy % 8 == 0 && aligned16(x) && aligned16(dy), "bn_bwd_reduce: alignment");
   int lanes = kThreads / (c / 8);
   int grid = stream_grid((npix + 1) / 2, lanes, 4);
   size_t smem = 2 * (size_t)c * sizeof(float);
   DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, true>), grid, kThreads, smem, stream, (const T*)dy, lddy,
-                            (const T*)x, ldx, c, npix, save_mean, save_invstd, sums, c));
+                            (const T*)x, ldx, c, npix, save_mean, save_invstd, sums, sq_off));
   return B2U_OK;
 }
 
@@ -1203,20 +1226,27 @@ extern "C" int b2u_bn_bwd_apply(int dt, const void* dy, int lddy, const void* x,
 int b2u_bn_bwd_apply_cs(int dt, const void* dy, int lddy, const void* x, int ldx, void* dx, int lddx, int c,
                         long long npix, long long count, const float* gamma, const float* save_mean,
                         const float* save_invstd, const double* sums, float* dgamma, float* dbeta, const void* mask,
-                        int ldmask, int mask_act, float* colsum, void* stream) {
+                        int ldmask, int mask_act, float* colsum, void* stream, const void* x2, int ldx2, void* dx2,
+                        int lddx2, int split) {
   REQ_VEC8(c);
   B2U_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && (mask == nullptr || ldmask % 8 == 0),
               "bn_bwd_apply: alignment");
   B2U_REQUIRE(c <= 2048, "bn_bwd_apply: c <= 2048");
+  if (x2 == nullptr) split = c;
+  B2U_REQUIRE(split == c || (split > 0 && split < c && split % 8 == 0 && ldx2 % 8 == 0 && lddx2 % 8 == 0 && dx2 != nullptr &&
+                             aligned16(x2) && aligned16(dx2)),
+              "bn_bwd_apply: bad second tensor (split=%d of %d)", split, c);
   int grid = lane_grid(npix, c);
   if (colsum != nullptr) {
     DISPATCH_T(dt, B2U_LAUNCH((bn_bwd_apply_kernel<T, true>), grid, kThreads, c * sizeof(float), stream, (const T*)dy,
                               lddy, (const T*)x, ldx, (T*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums,
-                              dgamma, dbeta, (const T*)mask, ldmask, mask_act, colsum));
+                              dgamma, dbeta, (const T*)mask, ldmask, mask_act, colsum, (const T*)x2, ldx2, (T*)dx2, lddx2,
+                              split));
   } else {
     DISPATCH_T(dt, B2U_LAUNCH((bn_bwd_apply_kernel<T, false>), grid, kThreads, 0, stream, (const T*)dy,
                               lddy, (const T*)x, ldx, (T*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums,
-                              dgamma, dbeta, (const T*)mask, ldmask, mask_act, colsum));
+                              dgamma, dbeta, (const T*)mask, ldmask, mask_act, colsum, (const T*)x2, ldx2, (T*)dx2, lddx2,
+                              split));
   }
   return B2U_OK;
 }

@@ -425,13 +425,19 @@ class Engine:
             raise ValueError("layer %r is fused with the BatchNormalization behind it in this plan: run forward_batch(..., "
                              "tap=True) to read its own output" % name)
         self.stream.synchronize()
-        a = self._arenas[v.ref.arena]
-        es = P.ELEM[v.dt]
-        npix = b.plan.n * v.h * v.w
-        tdt = torch.float16 if v.dt == P.F16 else torch.float32
-        raw = a[v.ref.off:v.ref.off + ((npix - 1) * v.ld + v.c) * es].view(tdt)
-        out = torch.as_strided(raw, (npix, v.c), (v.ld, 1)).float().cpu().numpy()
-        return out.reshape(b.plan.n, v.h, v.w, v.c)
+
+        def read(v):
+            a = self._arenas[v.ref.arena]
+            es = P.ELEM[v.dt]
+            npix = b.plan.n * v.h * v.w
+            tdt = torch.float16 if v.dt == P.F16 else torch.float32
+            raw = a[v.ref.off:v.ref.off + ((npix - 1) * v.ld + v.c) * es].view(tdt)
+            out = torch.as_strided(raw, (npix, v.c), (v.ld, 1)).float().cpu().numpy()
+            return out.reshape(b.plan.n, v.h, v.w, v.c)
+
+        if isinstance(v, P.SplitView):          # a concatenate kept as two dense tensors
+            return np.concatenate([read(pv) for pv in v.parts], axis=-1)
+        return read(v)
 
     def threshold_counts(self, b, thresholds_dev, tp, spr, sgt):
         pl = b.plan

@@ -57,13 +57,27 @@ class View:
         return View(self.ref + c0 * ELEM[self.dt], self.ld, c, self.h, self.w, self.dt)
 
 
+class SplitView:
+    """A two-input concatenate kept as two dense tensors (`parts`): what reads it -- the BatchNormalization behind it --
+    takes both sources, so no kernel ever touches one half of an interleaved 2c-channel pixel."""
+    __slots__ = ("parts",)
+
+    def __init__(self, a, b):
+        self.parts = (a, b)
+
+    c = property(lambda self: self.parts[0].c + self.parts[1].c)
+    h = property(lambda self: self.parts[0].h)
+    w = property(lambda self: self.parts[0].w)
+    dt = property(lambda self: self.parts[0].dt)
+
+
 class Op:
     __slots__ = ("kind", "dt", "p", "i", "f", "tag")
 
     def __init__(self, kind, dt, p=(), i=(), f=(), tag=""):
         self.kind, self.dt, self.p, self.i, self.f, self.tag = kind, dt, list(p), [int(v) for v in i], \
             [float(v) for v in f], tag
-        assert len(self.p) <= 12 and len(self.i) <= 12 and len(self.f) <= 4
+        assert len(self.p) <= 14 and len(self.i) <= 12 and len(self.f) <= 4
 
     def __repr__(self):
         return "%s[%s] p=%s i=%s f=%s" % (OP_NAMES[self.kind], self.tag, self.p, self.i, self.f)
@@ -131,7 +145,7 @@ class Plan:
     def __init__(self, graph, n, dt=F32, training=True, dropout=True, loss="bce_dice", world=1,
                  sync_stats=False, layout=None, rank=0, fuse_bn_bwd=True, fuse_bn_stats=True, fuse_bias_grad=True,
                  prepack=True, fuse_bn_bwd_wgrad=True, fuse_bn_pool=True, relu_bits=None, grad_bucket_bytes=6 << 20,
-                 fuse_bn_infer=True, hoist_prep=True):
+                 fuse_bn_infer=True, hoist_prep=True, split_concat=True):
         self.graph, self.n, self.dt, self.training = graph, int(n), dt, training
         self.dropout = dropout and training
         self.loss, self.world, self.sync_stats = loss, int(world), bool(sync_stats) and world > 1
@@ -146,6 +160,14 @@ class Plan:
         # ops that depend on the weights only (operand packing, scale / shift of every BN) leave the per-batch op list:
         # `prep_ops()` runs when the weights have changed (engine.py), `forward_ops(prep=False)` per batch.
         # Classifier 224 x 224 x 3, batch 64 on B200: 0.446 -> see profiles/NOTES_r2.md.
+        # concatenate([up-sampled, skip]) -> BatchNormalization -> Conv2D (every U-Net decoder level, T1H:887-889): the two
+        # inputs stay dense tensors of their own and the BN kernels read / write both.  In one interleaved buffer each input
+        # is one 64-byte half of a 128-byte pixel, and every kernel that touches only one input (max-pool backward, the
+        # transposed conv's three passes, the encoder BN backward) fetches twice its bytes from DRAM (measured on B200 at
+        # 512^2 x 32 channels, tools/half_line_probe.py: max-pool backward 0.125 -> 0.101 ms, transposed-conv weight
+        # gradient 0.103 -> 0.072 ms, data gradient 0.069 -> 0.054 ms, BN backward 0.083 -> 0.066 ms; in the step:
+        # max-pool backward 0.125 -> 0.092, transposed-conv weight gradient 0.064 -> 0.049, step -0.05 ms).
+        self.split_concat = int(split_concat)        # 0: never, 1: inputs narrower than a 128-byte line, 2: every eligible concat
         self.fuse_bn_infer = bool(fuse_bn_infer) and not training and dt == F16
         self.hoist_prep = bool(hoist_prep) and not training
         self.prep = []                   # inference plans: weight-only ops (BN finalize from the moving statistics)
@@ -217,6 +239,37 @@ class Plan:
     def _w(self, layer, short, arena=None):
         return self.layout.ref("%s/%s" % (layer.name, short), arena)
 
+    def _bn_apply_op(self, xv, yv, aux, c, tag):
+        if isinstance(xv, SplitView):
+            a, b = xv.parts
+            return Op(OP_BN_APPLY, xv.dt, [a.ref, yv.ref, aux["scale"], aux["shift"], None, b.ref],
+                      [a.ld, yv.ld, c, self._npix(xv), 0, a.c, b.ld], tag=tag)
+        return Op(OP_BN_APPLY, xv.dt, [xv.ref, yv.ref, aux["scale"], aux["shift"], None], [xv.ld, yv.ld, c, self._npix(xv), 0],
+                  tag=tag)
+
+    def _splittable(self, l):
+        """concatenate of two tensors that only a BatchNormalization reads, that BN read by one 3x3 conv (its backward
+        statistics then come from that conv's weight gradient): see `split_concat` in __init__"""
+        if not self.split_concat or len(l.inputs) != 2:
+            return False
+        t = l.output
+        if len(t.consumers) != 1 or t.consumers[0].kind != "batch_normalization" or t is self.graph.output:
+            return False
+        bn = t.consumers[0]
+        cons = bn.output.consumers
+        if len(cons) != 1 or cons[0].kind != "conv2d" or tuple(cons[0].kernel_size) != (3, 3) or bn.output is self.graph.output:
+            return False
+        # only where an input is narrower than a 128-byte line (fp16: fewer than 64 channels -- the 512^2 level of the U-Net);
+        # wider inputs already fill whole lines in the interleaved buffer and the two-source BN kernels gain nothing
+        if all(ti.channels * ELEM[self.dt] >= 128 for ti in l.inputs) and self.split_concat != 2:
+            return False
+        for ti in l.inputs:
+            if ti.producer.kind not in ("conv2d_transpose", "batch_normalization") or ti.channels % 8:
+                return False
+            if sum(1 for cn in ti.consumers if cn.kind == "concatenate") != 1:
+                return False
+        return True
+
     def _bn_finalize(self, l, aux, c, count):
         """inference-mode BatchNormalization: scale / shift from the moving statistics -- a weight-only op"""
         for nm in ("scale", "shift", "mean", "invstd"):
@@ -269,8 +322,13 @@ class Plan:
         layers = g.layers
         # ---- placement: a tensor consumed by concatenate lives inside its LAST concat's buffer ----
         home = {}        # id(tensor) -> (concat layer, channel offset)
+        split = set()    # id(concat layer) kept as two dense tensors (SplitView)
         for l in layers:
-            if l.kind == "concatenate":
+            if l.kind == "concatenate" and self._splittable(l):
+                split.add(id(l))
+        self.split_concats = sorted(l.name for l in layers if id(l) in split)
+        for l in layers:
+            if l.kind == "concatenate" and id(l) not in split:
                 off = 0
                 for t in l.inputs:
                     if t.producer.kind in ("concatenate", "flatten", "input"):
@@ -279,7 +337,7 @@ class Plan:
                     off += t.channels
         concat_buf, concat_gbuf = {}, {}
         for l in layers:
-            if l.kind == "concatenate":
+            if l.kind == "concatenate" and id(l) not in split:
                 concat_buf[id(l)] = self._alloc_view(l.output.shape, dt)
                 if self.training:
                     concat_gbuf[id(l)] = self._alloc_view(l.output.shape, dt)
@@ -389,8 +447,7 @@ class Plan:
                 count = self._npix(xv)
                 if not self.training:
                     self._bn_finalize(l, aux, c, count)
-                    self.fwd.append(Op(OP_BN_APPLY, xv.dt, [xv.ref, yv.ref, aux["scale"], aux["shift"], None],
-                                       [xv.ld, yv.ld, c, self._npix(xv), 0], tag=l.name))
+                    self.fwd.append(self._bn_apply_op(xv, yv, aux, c, l.name))
                     self.layer_out[l.name] = yv
                     continue
                 for nm in ("scale", "shift", "mean", "invstd"):
@@ -400,8 +457,8 @@ class Plan:
                         aux["sums"] = self.zero.alloc(2 * c * 8)
                         src = x.producer
                         fusable = (self.fuse_bn_stats and src.kind == "concatenate" and
-                                   all(home[id(ti)][0] is src and id(ti) in prod_op and prod_op[id(ti)].p[4] is None
-                                       for ti in src.inputs))
+                                   all((id(src) in split or home[id(ti)][0] is src) and id(ti) in prod_op and
+                                       prod_op[id(ti)].p[4] is None for ti in src.inputs))
                         if fusable:
                             # BN over a concat buffer: every producer (transposed conv epilogue, encoder BN apply)
                             # accumulates the statistics of the channel slice it writes -- no pass over the buffer
@@ -411,6 +468,12 @@ class Plan:
                                 po.p[4] = aux["sums"] + off * 8
                                 po.i[7 if po.kind == OP_CONVT_FWD else 4] = c
                                 off += ti.channels
+                        elif isinstance(xv, SplitView):            # one statistics pass per dense half
+                            off = 0
+                            for pv in xv.parts:
+                                self.fwd.append(Op(OP_BN_STATS, pv.dt, [pv.ref, aux["sums"] + off * 8], [pv.ld, pv.c, count, c],
+                                                   tag=l.name))
+                                off += pv.c
                         else:
                             self.fwd.append(Op(OP_BN_STATS, xv.dt, [xv.ref, aux["sums"]], [xv.ld, c, count], tag=l.name))
                     if self.sync_stats:
@@ -421,8 +484,7 @@ class Plan:
                                    [aux.get("sums"), self._w(l, "gamma"), self._w(l, "beta"), self._w(l, "moving_mean"),
                                     self._w(l, "moving_variance"), aux["scale"], aux["shift"], aux["mean"], aux["invstd"]],
                                    [count, 1 if self.training else 0, c], [l.momentum, l.epsilon], tag=l.name))
-                self.fwd.append(Op(OP_BN_APPLY, xv.dt, [xv.ref, yv.ref, aux["scale"], aux["shift"], None],
-                                   [xv.ld, yv.ld, c, self._npix(xv), 0], tag=l.name))
+                self.fwd.append(self._bn_apply_op(xv, yv, aux, c, l.name))
                 if self.training:
                     prod_op[id(t)] = self.fwd[-1]
             elif l.kind == "max_pooling2d":
@@ -461,6 +523,10 @@ class Plan:
                     yv = self.views[id(t)]
                     self.fwd.append(Op(OP_DROPOUT_FWD, xv.dt, [xv.ref, yv.ref, self.step_ref],
                                        [xv.ld, yv.ld, xv.c, self._npix(xv), drop_index[id(l)]], [l.rate], tag=l.name))
+            elif l.kind == "concatenate" and id(l) in split:
+                self.views[id(t)] = SplitView(*(self.views[id(ti)] for ti in l.inputs))
+                if self.training:
+                    self.gviews[id(t)] = SplitView(*(self.gviews[id(ti)] for ti in l.inputs))
             elif l.kind == "concatenate":
                 buf = concat_buf[id(l)]
                 self.views[id(t)] = buf
@@ -610,6 +676,17 @@ class Plan:
                                                                  bsums], [c, cout, 9], tag=l.name))
                     if self.sync_stats:
                         self.bwd.append(Op(OP_ALLREDUCE_F64, 0, [bsums], [2 * c], tag=l.name))
+                elif isinstance(xv, SplitView):           # one reduction pass per dense half, into the shared sums
+                    bsums = self.zero.alloc(2 * c * 8)
+                    off = 0
+                    for pv in xv.parts:
+                        gs = View(gy.ref + off * ELEM[gy.dt], gy.ld, pv.c, gy.h, gy.w, gy.dt)
+                        self.bwd.append(Op(OP_BN_BWD_REDUCE, pv.dt, [gs.ref, pv.ref, aux["mean"] + off * 4, aux["invstd"] + off * 4,
+                                                                     bsums + off * 8], [gs.ld, pv.ld, pv.c, self._npix(pv), c],
+                                           tag=l.name))
+                        off += pv.c
+                    if self.sync_stats:
+                        self.bwd.append(Op(OP_ALLREDUCE_F64, 0, [bsums], [2 * c], tag=l.name))
                 else:
                     bsums = self.zero.alloc(2 * c * 8)
                     self.bwd.append(Op(OP_BN_BWD_REDUCE, xv.dt, [gy.ref, xv.ref, aux["mean"], aux["invstd"], bsums],
@@ -619,6 +696,17 @@ class Plan:
                 # npix is the LOCAL pixel count; the divisor (count) is the global one under sync_stats,
                 # where the all-reduced sums must enter dgamma/dbeta on one rank only (grads are summed)
                 own = (not self.sync_stats) or self.rank == 0
+                if isinstance(xv, SplitView):               # two dense (input, gradient) pairs: p[11], p[12], i[8..10]
+                    (xa, xb), (ga, gb) = xv.parts, gx.parts
+                    assert mv is None
+                    self.bwd.append(Op(OP_BN_BWD_APPLY, xv.dt,
+                                       [gy.ref, xa.ref, ga.ref, self._w(l, "gamma"), aux["mean"], aux["invstd"], bsums,
+                                        grads(l, "gamma") if own else None, grads(l, "beta") if own else None, None, None,
+                                        xb.ref, gb.ref],
+                                       [gy.ld, xa.ld, ga.ld, c, self._npix(xv), 0, 0, aux["count"], xa.c, xb.ld, gb.ld],
+                                       tag=l.name))
+                    written.add(id(x))
+                    continue
                 self.bwd.append(Op(OP_BN_BWD_APPLY, xv.dt,
                                    [gy.ref, xv.ref, gx.ref, self._w(l, "gamma"), aux["mean"], aux["invstd"], bsums,
                                     grads(l, "gamma") if own else None, grads(l, "beta") if own else None,
@@ -659,6 +747,11 @@ class Plan:
                                    [gy.ld, gx.ld, xv.c, self._npix(xv), drop_index[id(l)], mv.ld if mv else 0, ma],
                                    [l.rate], tag=l.name))
                 written.add(id(x))
+            elif l.kind == "concatenate" and id(l) in split:
+                for ti in l.inputs:                             # the BN backward wrote both gradient tensors in place
+                    if id(ti) in written:
+                        raise RuntimeError("split concat must be the last consumer of %r" % ti)
+                    written.add(id(ti))
             elif l.kind == "concatenate":
                 off = 0
                 for ti in l.inputs:

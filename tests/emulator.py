@@ -207,10 +207,11 @@ class Emulator:
 
     def op_bn_stats(self, o):
         ldx, c, npix = o.i[:3]
+        sq = o.i[3] if len(o.i) > 3 and o.i[3] else c        # offset of the squares (one half of a split concatenate)
         x = self.view(o.p[0], ldx, c, npix, o.dt).astype(np.float64)
-        s = self.f64(o.p[1], 2 * c)
+        s = self.f64(o.p[1], sq + c)
         s[:c] += x.sum(0)
-        s[c:] += (x * x).sum(0)
+        s[sq:sq + c] += (x * x).sum(0)
 
     def op_bn_finalize(self, o):
         count, training, c = o.i[:3]
@@ -236,7 +237,12 @@ class Emulator:
 
     def op_bn_apply(self, o):
         ldx, ldy, c, npix = o.i[:4]
-        x = self.view(o.p[0], ldx, c, npix, o.dt).astype(np.float32)
+        if len(o.p) > 5 and o.p[5] is not None and o.kind == P.OP_BN_APPLY:      # split concatenate: second source tensor
+            split, ldx2 = o.i[5], o.i[6]
+            x = np.concatenate([self.view(o.p[0], ldx, split, npix, o.dt).astype(np.float32),
+                                self.view(o.p[5], ldx2, c - split, npix, o.dt).astype(np.float32)], axis=1)
+        else:
+            x = self.view(o.p[0], ldx, c, npix, o.dt).astype(np.float32)
         y = self.view(o.p[1], ldy, c, npix, o.dt)
         y[:] = (x * self.f32(o.p[2], c) + self.f32(o.p[3], c)).astype(y.dtype)
         if len(o.p) > 4 and o.p[4] is not None:
@@ -266,22 +272,35 @@ class Emulator:
         dy = self.view(o.p[0], lddy, c, npix, o.dt).astype(np.float32)
         x = self.view(o.p[1], ldx, c, npix, o.dt).astype(np.float32)
         xh = (x - self.f32(o.p[2], c)) * self.f32(o.p[3], c)
-        s = self.f64(o.p[4], 2 * c)
+        sq = o.i[4] if len(o.i) > 4 and o.i[4] else c        # offset of the second sums (one half of a split concatenate)
+        s = self.f64(o.p[4], sq + c)
         s[:c] += dy.astype(np.float64).sum(0)
-        s[c:] += (dy * xh).astype(np.float64).sum(0)
+        s[sq:sq + c] += (dy * xh).astype(np.float64).sum(0)
 
     def op_bn_bwd_apply(self, o):
         lddy, ldx, lddx, c, npix, ldm, mact, count = o.i[:8]
         dy = self.view(o.p[0], lddy, c, npix, o.dt).astype(np.float32)
-        x = self.view(o.p[1], ldx, c, npix, o.dt).astype(np.float32)
+        two = len(o.p) > 12 and o.p[11] is not None                             # split concatenate: second (x, dx) pair
+        if two:
+            split, ldx2, lddx2 = o.i[8], o.i[9], o.i[10]
+            x = np.concatenate([self.view(o.p[1], ldx, split, npix, o.dt).astype(np.float32),
+                                self.view(o.p[11], ldx2, c - split, npix, o.dt).astype(np.float32)], axis=1)
+        else:
+            x = self.view(o.p[1], ldx, c, npix, o.dt).astype(np.float32)
         g, mean, inv = self.f32(o.p[3], c), self.f32(o.p[4], c), self.f32(o.p[5], c)
         s = self.f64(o.p[6], 2 * c)
         xh = (x - mean) * inv
         dx = g * inv * (dy - (s[:c] / count).astype(np.float32) - xh * (s[c:] / count).astype(np.float32))
         if o.p[9] is not None:
             dx = dx * self._dact(self.view(o.p[9], ldm, c, npix, o.dt), mact)
-        dv = self.view(o.p[2], lddx, c, npix, o.dt)
-        dv[:] = dx.astype(dv.dtype)
+        if two:
+            da, db_ = self.view(o.p[2], lddx, split, npix, o.dt), self.view(o.p[12], lddx2, c - split, npix, o.dt)
+            da[:] = dx[:, :split].astype(da.dtype)
+            db_[:] = dx[:, split:].astype(db_.dtype)
+            dv = np.concatenate([da, db_], axis=1)
+        else:
+            dv = self.view(o.p[2], lddx, c, npix, o.dt)
+            dv[:] = dx.astype(dv.dtype)
         self._colsum(o, 10, dv, c)
         if o.p[7] is not None:
             self.f32(o.p[7], c)[:] += s[c:].astype(np.float32)

@@ -189,6 +189,36 @@ def test_batchnorm_all_passes(dt, c, npix_shape):
 
 
 @pytest.mark.parametrize("dt", [P.F32, P.F16])
+@pytest.mark.parametrize("ca,cb,npix_shape", [(32, 32, (2, 16, 16)), (64, 32, (1, 10, 6)), (8, 24, (3, 8, 8)), (256, 256, (1, 4, 4))])
+def test_batchnorm_over_a_split_concatenate(dt, ca, cb, npix_shape):
+    """BN apply / backward apply whose input (and input gradient) is a two-input concatenate kept as two dense tensors
+    (plan.py split_concat): channels [0, ca) from / to the first tensor, the rest from / to the second"""
+    n, h, w = npix_shape
+    npix, c = n * h * w, ca + cb
+    img = Img(41)
+    xa = img.view(n, h, w, ca, dt, fill="uniform")
+    xb = img.view(n, h, w, cb, dt, ld=cb + 8, fill="uniform")
+    y = img.view(n, h, w, c, dt, fill=None)
+    dy = img.view(n, h, w, c, dt, scale=0.5)
+    da, db_ = img.view(n, h, w, ca, dt, ld=ca + 16, c0=8, fill=None), img.view(n, h, w, cb, dt, fill=None)
+    gamma, beta = img.farr(img.par, c, fill="pos"), img.farr(img.par, c, scale=0.1)
+    mm, mv = img.farr(img.par, c, scale=0.1), img.farr(img.par, c, fill="pos")
+    scale, shift, mean, inv = (img.f32.alloc(c * 4) for _ in range(4))
+    dg, dbt = img.farr(img.gr, c, scale=0.01), img.farr(img.gr, c, scale=0.01)
+    s1, s2 = img.zero.alloc(2 * c * 8), img.zero.alloc(2 * c * 8)
+    ostats = img.zero.alloc(2 * c * 8)
+    ops = [P.Op(P.OP_BN_STATS, dt, [xa.ref, s1], [xa.ld, ca, npix, c]),            # sums of the two halves, squares at offset c
+           P.Op(P.OP_BN_STATS, dt, [xb.ref, s1 + ca * 8], [xb.ld, cb, npix, c]),
+           P.Op(P.OP_BN_FINALIZE, 0, [s1, gamma, beta, mm, mv, scale, shift, mean, inv], [npix, 1, c], [0.99, 1e-3]),
+           P.Op(P.OP_BN_APPLY, dt, [xa.ref, y.ref, scale, shift, ostats, xb.ref], [xa.ld, y.ld, c, npix, c, ca, xb.ld]),
+           P.Op(P.OP_BN_BWD_APPLY, dt, [dy.ref, xa.ref, da.ref, gamma, mean, inv, s2, dg, dbt, None, None, xb.ref, db_.ref],
+                [dy.ld, xa.ld, da.ld, c, npix, 0, 0, npix, ca, xb.ld, db_.ld])]
+    # backward sums: any fixed numbers do (the kernels only consume them)
+    img.init.append((s2, np.linspace(-3.0, 3.0, 2 * c).astype(np.float64)))
+    compare(ops, img, dt, tol=3e-3 if dt == P.F16 else 3e-5)
+
+
+@pytest.mark.parametrize("dt", [P.F32, P.F16])
 @pytest.mark.parametrize("p", [0.0, 0.25])
 def test_maxpool_dropout_fwd_bwd(dt, p):
     n, h, w, c = 2, 12, 20, 32

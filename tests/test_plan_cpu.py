@@ -80,8 +80,10 @@ def test_unet_concat_is_zero_copy_and_fused():
     # BN backward statistics: encoder ones ride on the max-pool backward, decoder ones follow from the weight
     # gradient of the conv that reads the BN output (adjoint identity) -- no reduction pass is left
     assert kinds.count(P.OP_BN_BWD_REDUCE) == 0 and kinds.count(P.OP_BN_BWD_SUMS_WGRAD) == 4
-    legacy = [o.kind for o in P.Plan(G.unet(32, 1), 2, dt=P.F16, training=True, fuse_bn_bwd_wgrad=False).train_ops()]
+    legacy = [o.kind for o in P.Plan(G.unet(32, 1), 2, dt=P.F16, training=True, fuse_bn_bwd_wgrad=False, split_concat=False).train_ops()]
     assert legacy.count(P.OP_BN_BWD_REDUCE) == 4
+    halves = [o.kind for o in P.Plan(G.unet(32, 1), 2, dt=P.F16, training=True, fuse_bn_bwd_wgrad=False, split_concat=2).train_ops()]
+    assert halves.count(P.OP_BN_BWD_REDUCE) == 8          # split concats: one reduction per dense half
     assert kinds.count(P.OP_CONV3X3_FWD) == 18 and kinds.count(P.OP_CONVT_FWD) == 4
 
 
@@ -241,3 +243,47 @@ def test_inference_plan_folds_batchnorm_into_the_conv_epilogue_and_hoists_weight
     _load(em, un, pu, xs, np.zeros((2, 32 * 32), np.float32))
     em.run(un.forward_ops())
     assert np.abs(em.f32(un.prob, 2 * 32 * 32).reshape(wantu.shape) - wantu).max() < 2e-3
+
+
+def test_unet_decoder_concats_stay_two_dense_tensors():
+    """concatenate([Conv2DTranspose, skip]) -> BatchNormalization -> Conv2D (T1H:887-889 and the three levels below): the
+    planner keeps the two inputs as dense tensors (no interleaved 2c-channel buffer) and the BN ops carry both sources /
+    both gradient destinations; U-Net++ (concats read by convs, up to five inputs) keeps its buffers; the emulated step
+    equals the one planned with split_concat=False bit for bit (same arithmetic, different addresses)."""
+    hw, n = 32, 2
+    g = G.unet(hw, 1)
+    # default: only where an input is narrower than a 128-byte line (32 fp16 channels: the full-resolution level)
+    assert P.Plan(g, n, dt=P.F16, training=True).split_concats == ["concatenate_4"]
+    assert P.Plan(g, n, dt=P.F16, training=False).split_concats == ["concatenate_4"]
+    assert not P.Plan(g, n, dt=P.F32, training=True).split_concats
+    plan = P.Plan(g, n, dt=P.F16, training=True, split_concat=2)          # every eligible concat
+    assert plan.split_concats == ["concatenate_%d" % k for k in range(1, 5)]
+    assert not P.Plan(G.unetpp(hw, 1), n, dt=P.F16, training=True, split_concat=2).split_concats
+    two_src = [o for o in plan.fwd if o.kind == P.OP_BN_APPLY and len(o.p) > 5 and o.p[5] is not None]
+    two_dst = [o for o in plan.bwd if o.kind == P.OP_BN_BWD_APPLY and len(o.p) > 12 and o.p[12] is not None]
+    assert len(two_src) == 4 and len(two_dst) == 4 and all(o.i[5] * 2 == o.i[2] for o in two_src)
+    # every tensor that was half of a concat pixel is dense now: transposed-conv outputs and skip tensors have ld == c
+    for o in plan.fwd:
+        if o.kind == P.OP_CONVT_FWD:
+            assert o.i[2] == o.i[3]
+        if o.kind == P.OP_BN_APPLY_POOL:
+            assert o.i[1] == o.i[2]
+    params = perturbed_params("unet", hw)
+    x, t = synth_batch(n, hw, seg=True)
+    # ... also with the BN fusions off (one statistics / reduction pass per dense half instead of producer epilogues)
+    for opts in ({}, dict(fuse_bn_stats=False, fuse_bn_bwd_wgrad=False, fuse_bn_bwd=False)):
+        res = []
+        for split in (2, 0):
+            pl = P.Plan(g, n, dt=P.F16, training=True, split_concat=split, **opts)
+            assert bool(pl.split_concats) == bool(split)
+            em = E.Emulator(pl.arena_sizes())
+            em.fp16_weights = True
+            _load(em, pl, params, x, t.reshape(n, -1))
+            em.run(pl.train_ops())
+            res.append((em.f32(pl.loss_out, 2).copy(), em.mem["grads"].copy(), em.mem["params"].copy()))
+        if opts:
+            assert sum(1 for o in pl.fwd if o.kind == P.OP_BN_STATS) > 0
+        assert np.array_equal(res[0][0], res[1][0]), opts
+        tol = 0 if not opts else 1e-6          # two half reductions add their double sums in another order than one pass
+        ga, gb = (np.frombuffer(r[1], np.float32, len(r[1]) // 4) for r in res)
+        assert np.abs(ga - gb).max() <= tol * max(1.0, np.abs(gb).max()), opts

@@ -34,7 +34,7 @@ def main():
     S = importlib.import_module(PKG + ".synthetic")
     graph, size, batch = WL[args.workload]
     torch.cuda.set_device(0)
-    plan_options = {k: bool(int(v)) for k, v in (kv.split("=") for kv in args.plan.split(",") if kv)}
+    plan_options = {k: int(v) for k, v in (kv.split("=") for kv in args.plan.split(",") if kv)}
     eng = E.Engine(G.GRAPHS[graph](size, 1), precision="float16", use_graph=False, dropout_seed=7,
                    plan_options=plan_options)
     x, t = S.make_slices(batch, size, seed=1234)
