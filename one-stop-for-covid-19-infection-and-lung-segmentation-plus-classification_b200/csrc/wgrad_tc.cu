@@ -205,6 +205,11 @@ struct WhParams {
   int nacc_per_dh;             // 1 (slab <= 32: dw 0..2 in one MMA) or 2 (slab = 64: [dw0,dw1] and [dw2,-])
   int nsplit, stages;
   float* dw;
+  // dh-merged variant: the three tap ROWS sit side by side in N (N = 3 * Cout): the dy tile is loaded with a one-row
+  // halo above and below (18 x 8) and N chunk c of the B descriptor starts c tile rows further down (LBO = one tile row),
+  // i.e. it pairs the x pixel q with dy[q - (dh, 0)], dh = 1 - c; the x patch then needs its dw halo only (16 x 10).
+  // One MMA instead of three per K step: 32 + N/4 cycles each (tools/mma_probe.cu) -> 56 instead of 3 * 40 at Cout = 32.
+  int dhm;
 };
 struct WhMaps { CUtensorMap a, b; };
 
@@ -215,9 +220,10 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int cin = prm.cs, JT = prm.JT, KSB = prm.KSB, stages = prm.stages;   // `cin` = slab width from here on
   const uint32_t rowa = cin * 2, rowb = KSB * 2;
-  const uint32_t a_bytes = 180u * rowa, a_stride = (a_bytes + 1023) & ~1023u;
-  const int nb = JT / KSB;
-  const uint32_t b_tile = 128u * rowb, b_bytes = b_tile * nb;
+  const int dhm = prm.dhm;
+  const uint32_t a_bytes = (dhm ? 160u : 180u) * rowa, a_stride = (a_bytes + 1023) & ~1023u;
+  const int nb = JT / KSB;                                      // (dhm: KSB == JT, one chunk per tap row)
+  const uint32_t b_tile = (dhm ? 144u : 128u) * rowb, b_bytes = b_tile * nb;
   const uint32_t stage_stride = a_stride + b_bytes;
   uint8_t* tail = smem + stages * stage_stride;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
@@ -233,9 +239,10 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
   const int nj = prm.cout / JT;
   const int njs = nj * prm.nslab;                             // task = (split, slab, jt), jt fastest
   const int ntasks = prm.nsplit * njs;
-  const int nacc = 3 * prm.nacc_per_dh;
+  const int nacc = dhm ? prm.nacc_per_dh : 3 * prm.nacc_per_dh;
+  const int NW = dhm ? 3 * JT : JT;                             // accumulator width = MMA N
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(nacc * JT)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(nacc * NW)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
@@ -261,22 +268,24 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_stride;
           tc::mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-          tc::tma_load_4d(sa, &maps.a, &full_bar[stage], slab * cin, tw * 8 - 1, th * 16 - 1, n);
+          tc::tma_load_4d(sa, &maps.a, &full_bar[stage], slab * cin, tw * 8 - 1, th * 16 - (dhm ? 0 : 1), n);
           for (int s = 0; s < nb; ++s)
-            tc::tma_load_4d(sa + a_stride + s * b_tile, &maps.b, &full_bar[stage], jt * JT + s * KSB, tw * 8, th * 16, n);
+            tc::tma_load_4d(sa + a_stride + s * b_tile, &maps.b, &full_bar[stage], jt * JT + s * KSB, tw * 8,
+                            th * 16 - (dhm ? 1 : 0), n);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     {   // whole warp, uniform control flow; one elected lane issues
-      const uint32_t idesc = tc::idesc_f16(128, JT, 1, 1);
+      const uint32_t idesc = tc::idesc_f16(128, NW, 1, 1);
       const uint64_t la = cin == 64 ? tc::SWZ_128B : (cin == 32 ? tc::SWZ_64B : tc::SWZ_32B);
       const uint64_t lb = KSB == 64 ? tc::SWZ_128B : (KSB == 32 ? tc::SWZ_64B : tc::SWZ_32B);
       // A: chunks one pixel row apart (LBO = rowa), 8-row K groups 10 halo rows apart (SBO = 10 * rowa)
       const uint32_t a_hi = (uint32_t)(tc::smem_desc(0, rowa, 10 * rowa, la) >> 32);
       const uint32_t b_hi = (uint32_t)(tc::smem_desc(0, b_tile, 8 * rowb, lb) >> 32);
-      const uint32_t a_lbo = ((rowa >> 4) & 0x3FFF) << 16, b_lbo = ((b_tile >> 4) & 0x3FFF) << 16;
+      // B chunk stride: the next KSB-wide tile (JT > KSB), or -- dh-merged -- the next dy tile row (8 pixels)
+      const uint32_t a_lbo = ((rowa >> 4) & 0x3FFF) << 16, b_lbo = ((((dhm ? 8u * rowb : b_tile)) >> 4) & 0x3FFF) << 16;
       const uint32_t smem_lo = (tc::smem_u32(smem) & 0x3FFFF) >> 4;
       const uint32_t stage16 = stage_stride >> 4, a_stride16 = a_stride >> 4;
       const uint32_t rowa16 = rowa >> 4, kb16 = (16 * rowb) >> 4;
@@ -292,6 +301,17 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
           tc::fence_after_sync();
           const uint32_t a0 = smem_lo + (uint32_t)stage * stage16;
           const uint32_t b0 = (a0 + a_stride16) | b_lbo;
+          if (dhm) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b0 + kk * kb16);
+              const uint32_t ar = (a0 + (uint32_t)(2 * kk * 10) * rowa16) | a_lbo;
+              const uint32_t accf = (kk != 0) ? 1u : (first ? 0u : 1u);
+              tc::mma_f16_ss_elect(tmem_base, ((uint64_t)a_hi << 32) | (uint64_t)ar, bd, idesc, accf);
+              if (prm.nacc_per_dh == 2)
+                tc::mma_f16_ss_elect(tmem_base + NW, ((uint64_t)a_hi << 32) | (uint64_t)(ar + 2 * rowa16), bd, idesc, accf);
+            }
+          } else {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b0 + kk * kb16);
@@ -306,6 +326,7 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
                 tc::mma_f16_ss_elect(tmem_base + (dh * 2 + 1) * JT, ad2, bd, idesc, (kk != 0) ? 1u : (first ? 0u : 1u));
               }
             }
+          }
           }
           first = 0;
           tc::mma_commit_elect(&empty_bar[stage]);
@@ -325,13 +346,15 @@ __global__ void __launch_bounds__(kThreadsW, 2) tc_wgrad_halo_kernel(const __gri
       tc::mbar_wait(tfull_bar, tphase);
       tc::fence_after_sync();
       for (int a = 0; a < nacc; ++a) {
-        const int dh = a / prm.nacc_per_dh;
         const int dwp = chunk + (prm.nacc_per_dh == 2 ? 2 * (a % 2) : 0);
         const bool live = dwp < 3;
-        float* out = prm.dw + ((long long)((dh * 3 + (live ? dwp : 0)) * prm.cin + slab * cin + ci)) * prm.cout + jt * JT;
-        for (int c0 = 0; c0 < JT; c0 += 16) {
+        for (int cw = 0; cw < NW; cw += 16) {
+          // dh-merged: N chunk cw / JT holds tap row 2 - chunk (see WhParams::dhm)
+          const int dh = dhm ? 2 - cw / JT : a / prm.nacc_per_dh;
+          const int c0 = dhm ? cw % JT : cw;
+          float* out = prm.dw + ((long long)((dh * 3 + (live ? dwp : 0)) * prm.cin + slab * cin + ci)) * prm.cout + jt * JT;
           float v[16];
-          tc::tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + a * JT + c0, v);
+          tc::tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + a * NW + cw, v);
           if (live) {
 // 16-byte vector reductions (red.global.add.v4.f32): 4 L2 atomic operations instead of 16
 #pragma unroll
@@ -441,6 +464,7 @@ int b2u_tc_convt_wgrad_ok(int cin, int cout, int ldx, int lddy) {
 }
 
 // dw[t][ci][co] += sum_p x[p + off_t][ci] * dy[p][co];  db[co] += sum_p dy[p][co]
+int g_b2u_wgrad_dhm = 1;    // 1: dh-merged tiles for Cout = 32 / 64 (see WhParams::dhm)
 int g_b2u_wgrad_halo = 2;   // 0: per-tap tiles only, 1: halo for Cin <= 64, 2: + 32-channel slabs for wide layers, 3: 64-channel slabs
 bool g_attr_h = false;
 
@@ -464,22 +488,29 @@ static int pick_nsplit(int base, int ctas, int nblocks) {
 }
 
 static int wgrad_halo(const void* x, int ldx, int cin, int cs, const void* dy, int lddy, int cout, float* dw, int n, int h,
-                      int wd, void* stream) {
+                      int wd, void* stream, int dhm = 0) {
   WhParams p{};
   p.N = n; p.H = h; p.W = wd; p.cin = cin; p.cout = cout; p.dw = dw;
   p.cs = cs; p.nslab = cin / cs;
   p.nacc_per_dh = cs == 64 ? 2 : 1;
-  const int nacc = 3 * p.nacc_per_dh;
+  p.dhm = dhm;
+  const int nacc = dhm ? p.nacc_per_dh : 3 * p.nacc_per_dh;
   int jt = cout <= 128 ? cout : 128;
-  while (nacc * jt > 512 || cout % jt) jt -= 16;
+  if (dhm) {
+    B2U_REQUIRE((cout == 32 || cout == 64) && nacc * 3 * cout <= 256, "tc_wgrad_halo: dh-merged tiles need Cout 32 / 64 (cout=%d cs=%d)",
+                cout, cs);
+  } else {
+    while (nacc * jt > 512 || cout % jt) jt -= 16;
+  }
   B2U_REQUIRE(jt >= 16, "tc_wgrad_halo: no N tile for cout=%d", cout);
   p.JT = jt;
   p.KSB = ks_for(jt);
-  const size_t a_stride = ((size_t)180 * cs * 2 + 1023) & ~(size_t)1023, b_bytes = (size_t)jt * 256;
+  const size_t a_stride = ((size_t)(dhm ? 160 : 180) * cs * 2 + 1023) & ~(size_t)1023;
+  const size_t b_bytes = dhm ? (size_t)144 * jt * 2 : (size_t)jt * 256;
   const size_t tailb = 256;
   // two CTAs per SM (two MMA issuers) when both fit TMEM (512 columns per SM) -- else one CTA with a deep ring
   int cols = 32;
-  while (cols < nacc * jt) cols <<= 1;
+  while (cols < nacc * (dhm ? 3 * jt : jt)) cols <<= 1;
   const int per_sm = cols <= 256 ? 2 : 1;
   const size_t cap = per_sm == 2 ? 108 * 1024 : 216 * 1024;
   int st = (int)((cap - 1024 - tailb) / (a_stride + b_bytes));
@@ -503,7 +534,7 @@ static int wgrad_halo(const void* x, int ldx, int cin, int cs, const void* dy, i
   {
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)wd * ldx * 2, (cuuint64_t)h * wd * ldx * 2};
-    cuuint32_t box[4] = {(cuuint32_t)cs, 10, 18, 1};
+    cuuint32_t box[4] = {(cuuint32_t)cs, 10, (cuuint32_t)(dhm ? 16 : 18), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUtensorMapSwizzle sw = cs == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cs == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult r = g_enc(&maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
@@ -511,7 +542,7 @@ static int wgrad_halo(const void* x, int ldx, int cin, int cs, const void* dy, i
     if (r != CUDA_SUCCESS) { b2u_set_error("tc_wgrad_halo: x tensor map failed (%d)", (int)r); return B2U_ERR_CUDA; }
     cuuint64_t bd[4] = {(cuuint64_t)cout, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t bs[3] = {(cuuint64_t)lddy * 2, (cuuint64_t)wd * lddy * 2, (cuuint64_t)h * wd * lddy * 2};
-    cuuint32_t bb[4] = {(cuuint32_t)p.KSB, 8, 16, 1};
+    cuuint32_t bb[4] = {(cuuint32_t)p.KSB, 8, (cuuint32_t)(dhm ? 18 : 16), 1};
     CUtensorMapSwizzle swb = p.KSB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.KSB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     r = g_enc(&maps.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(dy), bd, bs, bb, es,
               CU_TENSOR_MAP_INTERLEAVE_NONE, swb, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -538,8 +569,15 @@ int b2u_tc_conv3x3_wgrad(const void* x, int ldx, int cin, const void* dy, int ld
   int cs = 0;
   if (g_b2u_wgrad_halo && (cin == 16 || cin == 32 || cin == 64)) cs = (g_b2u_wgrad_halo == 4 && cin == 64) ? 32 : cin;
   else if (g_b2u_wgrad_halo >= 2 && cin > 64 && cin % 32 == 0) cs = (g_b2u_wgrad_halo == 3 && cin % 64 == 0) ? 64 : 32;
+  // thin outputs (Cout = 32 / 64): the three tap rows merged in N (WhParams::dhm); its accumulators (3 * Cout columns per
+  // 128 rows) must leave room for two CTAs per SM, so 64-channel slabs only with Cout = 32
+  int dhm = 0;
+  if (g_b2u_wgrad_dhm && g_b2u_wgrad_halo && (cout == 32 || cout == 64) && cin % 32 == 0) {
+    dhm = 1;
+    cs = (cin == 64 && cout == 32) ? 64 : 32;
+  }
   if (cs != 0 && cout % 16 == 0) {
-    rc = wgrad_halo(x, ldx, cin, cs, dy, lddy, cout, dw, n, h, wd, stream);
+    rc = wgrad_halo(x, ldx, cin, cs, dy, lddy, cout, dw, n, h, wd, stream, dhm);
     if (rc != B2U_OK) return rc;
     if (db != nullptr) return b2u_channel_sum_f16(dy, lddy, cout, (long long)n * h * wd, db, stream);
     return B2U_OK;

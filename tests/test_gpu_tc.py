@@ -155,6 +155,29 @@ def test_tc_convt_wgrad(n, h, w, cin, cout):
     compare(ops, img, dt, tol=3e-3)
 
 
+@pytest.mark.parametrize("dhm", [1, 0])
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 32, 32), (1, 32, 32, 64, 32), (1, 32, 32, 64, 64), (1, 20, 12, 32, 64),
+                                            (3, 21, 13, 32, 32), (1, 40, 72, 64, 32), (1, 32, 32, 128, 64), (1, 16, 24, 96, 32),
+                                            (2, 17, 9, 160, 64), (4, 128, 128, 32, 32), (2, 64, 64, 64, 64)])
+def test_tc_conv3x3_wgrad_thin_outputs_dh_merged(n, h, w, cin, cout, dhm):
+    """Cout = 32 / 64: the three tap rows merged in N (one MMA per K step against a dy tile with a row halo, wgrad_tc.cu
+    WhParams::dhm) against the per-row accumulators; ragged tiles (TMA zero fill is the padding), several images, 32- and
+    64-channel slabs, concat-slice strides; integer data so that both variants and the emulator agree to fp32 summation
+    order (tolerance 1e-5 instead of the fp16-product tolerance)."""
+    lib = importlib.import_module(PKG + "._lib").lib()
+    old = lib.b2u_set_option(b"wgrad_dhm", dhm)
+    try:
+        img = Img(131)
+        x = img.view(n, h, w, cin, dt, ld=2 * cin, c0=cin, fill="int")
+        dy = img.view(n, h, w, cout, dt, ld=cout + 8, fill="int", scale=0.25)
+        dw = img.farr(img.gr, 9 * cin * cout, scale=0.01)
+        db = img.farr(img.gr, cout, scale=0.01)
+        ops = [P.Op(P.OP_CONV3X3_WGRAD, dt, [x.ref, dy.ref, dw, db], [x.ld, cin, dy.ld, cout, n, h, w])]
+        compare(ops, img, dt, tol=1e-5)
+    finally:
+        lib.b2u_set_option(b"wgrad_dhm", old)
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout", [(1, 32, 32, 96, 32), (1, 16, 24, 192, 64), (2, 16, 16, 128, 32)])
 def test_tc_wgrad_unetpp_concat_widths(n, h, w, cin, cout):
     """U-Net++ level-1/2 'a' convs see 96- and 192-channel concat inputs (UPP:905, 919)"""

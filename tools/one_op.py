@@ -19,6 +19,9 @@ kind = sys.argv[1]
 n, h, w, K, J = [int(v) for v in sys.argv[2:7]]
 flags = sys.argv[7:]
 lib = LIB.lib()
+for f in flags:                                   # opt:name=value -> b2u_set_option(name, value)
+    if f.startswith("opt:"):
+        lib.b2u_set_option(f[4:].split("=")[0].encode(), int(f.split("=")[1]))
 lib.b2u_set_option(b"tc_dwmerge", 1 if "dwmerge" in flags else 0)
 lib.b2u_set_option(b"tc_rowstrip", 1 if "rowstrip" in flags else 0)
 npix = n * h * w
@@ -92,7 +95,12 @@ assert lib.b2u_debug_read(buf, 512) == 0
 a = np.array(buf[:], dtype=np.int64).reshape(64, 8)
 t0 = a[0, 0] if a[0, 0] else a[0, 2]
 d = lambda k, i, j: int(a[k, i] - a[k, j]) if a[k, i] and a[k, j] else None
-rows = range(6, 22)
+first = int(os.environ.get("TL_FIRST", "6"))        # steady state: TL_FIRST=36 (the first tiles run on an idle memory system)
+rows = range(first, first + 16)
+if os.environ.get("TL_DUMP"):
+    print("iter: prod_wait prod_issued | mma_tempty mma_afull mma_commit | epi_tfull epi_done  (cycles from start)")
+    for k in rows:
+        print(k, [int(v - t0) if v else None for v in a[k, :7]])
 per = np.median([a[k + 1, 2] - a[k, 2] for k in rows if a[k + 1, 2] and a[k, 2]])
 mma = np.median([d(k, 4, 3) for k in rows if d(k, 4, 3)])
 epi = np.median([d(k, 6, 5) for k in rows if d(k, 6, 5)])
