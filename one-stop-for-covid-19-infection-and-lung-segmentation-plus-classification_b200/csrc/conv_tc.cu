@@ -84,7 +84,11 @@ __device__ __forceinline__ float transpose_reduce16(float v[16], int lane) {
 // kRegStats: BatchNorm statistics accumulate in registers over ALL tiles of the persistent CTA (a thread owns
 // <= 32 fixed columns; requires gridDim.x % (J / JT) == 0 so that the CTA always sees the same N tile) and are
 // reduced across lanes once at the end, instead of two 31-shuffle transposes per 16 columns per tile.
-template <bool kRegStats>
+// kRegStats = number of columns a thread keeps statistics for (0: none / shared-memory path, 16, 32): with 576 threads the
+// kernel has 96 registers per thread, and 2 x 32 statistics registers beside the 16-column chunk spilled ~30 of them
+// (ncu: 11 % of the stall samples on LDL / STL, profiles/r2_convt_*_ncu_source_top.txt) -- the host picks N tiles that
+// leave 16 columns per thread wherever it can.
+template <int kRegStats>
 __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_constant__ TcMaps maps,
                                                                  const __grid_constant__ TcParams prm) {
   B2U_PDL_LAUNCH_DEPENDENTS();      // B2U_PDL_WAIT() follows the CTA-local setup (barriers, TMEM)
@@ -208,9 +212,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
     const int ccols = JT / nparts;
     const int cbeg = part * ccols;
     const bool has_cols = part < nparts;
-    float rs1[kRegStats ? 32 : 1], rs2[kRegStats ? 32 : 1];
+    float rs1[kRegStats ? kRegStats : 1], rs2[kRegStats ? kRegStats : 1];
 #pragma unroll
-    for (int i = 0; i < (kRegStats ? 32 : 1); ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
+    for (int i = 0; i < (kRegStats ? kRegStats : 1); ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -223,6 +227,21 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
       const int h = th * kTileH + row / kTileW, w = tw * kTileW + row % kTileW;
       const bool valid = h < prm.H && w < prm.W;
       const long long pix = ((long long)n * prm.H + h) * prm.W + w;
+      // activation-derivative mask of this thread's (<= 32) columns: loaded BEFORE the accumulator wait, so that its DRAM
+      // round trip overlaps the wait instead of following it chunk by chunk (ncu: 26 % of the stall samples sat on the
+      // first use of the mask in the transposed-conv data gradient)
+      // (the 32-column statistics variant has no registers to spare for it; the 16-column one holds 16 columns of mask)
+      constexpr int kMk = kRegStats == 16 ? 2 : 4;
+      const bool mask_early = kRegStats != 32 && prm.mask != nullptr && ccols <= 8 * kMk && has_cols && valid;
+      uint4 mk[kMk];
+      if (mask_early) {
+        const uint4* mp = reinterpret_cast<const uint4*>(prm.mask + pix * prm.ldmask + jt * JT + cbeg);
+        mk[0] = __ldg(mp);
+        mk[1] = __ldg(mp + 1);
+        if constexpr (kMk == 4) {
+          if (ccols > 16) { mk[2] = __ldg(mp + 2); mk[3] = __ldg(mp + 3); }
+        }
+      }
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::fence_after_sync();
       if (has_cols) {
@@ -254,7 +273,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
             dst = prm.y + pix * prm.ldy + j0;
           }
           if (valid) {
-            if (prm.mask != nullptr) {
+            if (mask_early) {
+              float m[8];
+              unpack8h(cc == 0 ? mk[0] : mk[kMk == 4 ? 2 : 0], m);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= act_bwd_from_y(m[i], prm.mask_act);
+              unpack8h(cc == 0 ? mk[1] : mk[kMk == 4 ? 3 : 1], m);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 + i] *= act_bwd_from_y(m[i], prm.mask_act);
+            } else if (prm.mask != nullptr) {
               float m[8];
               load8<__half>(prm.mask + pix * prm.ldmask + j0, m);
 #pragma unroll
@@ -277,12 +304,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
           }
           if (kRegStats) {                       // (launched only when statistics or column sums are wanted)
             if (valid) {
-              if (cc == 0) {
+              if (kRegStats < 32 || cc == 0) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { rs1[i] += v[i]; rs2[i] = fmaf(v[i], v[i], rs2[i]); }
               } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) { rs1[(kRegStats ? 16 : 0) + i] += v[i]; rs2[(kRegStats ? 16 : 0) + i] = fmaf(v[i], v[i], rs2[(kRegStats ? 16 : 0) + i]); }
+                for (int i = 0; i < 16; ++i) { rs1[(kRegStats == 32 ? 16 : 0) + i] += v[i]; rs2[(kRegStats == 32 ? 16 : 0) + i] = fmaf(v[i], v[i], rs2[(kRegStats == 32 ? 16 : 0) + i]); }
               }
             }
           } else if (prm.stats != nullptr || prm.colsum != nullptr) {
@@ -314,8 +341,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_conv_kernel(const __grid_con
         float q[16], sq[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          q[i] = cc == 0 ? rs1[i] : rs1[(kRegStats ? 16 : 0) + i];
-          sq[i] = cc == 0 ? rs2[i] : rs2[(kRegStats ? 16 : 0) + i];
+          q[i] = cc == 0 ? rs1[i] : rs1[(kRegStats == 32 ? 16 : 0) + i];
+          sq[i] = cc == 0 ? rs2[i] : rs2[(kRegStats == 32 ? 16 : 0) + i];
         }
         float s1 = transpose_reduce16(q, lane);
         float s2 = transpose_reduce16(sq, lane);
@@ -509,8 +536,9 @@ int launch_tc(const TcMaps& maps, TcParams& prm, void* stream) {
   size_t smem = smem_bytes_for(prm.KS, prm.JT, prm.J, prm.stages);
   B2U_REQUIRE(smem <= 227 * 1024, "tc_conv: shared memory %zu exceeds 227 KB", smem);
   if (!g_attr_set) {
-    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr_set = true;
   }
   const int nj = prm.J / prm.JT;
@@ -524,8 +552,9 @@ int launch_tc(const TcMaps& maps, TcParams& prm, void* stream) {
     const int g2 = grid / nj * nj;
     if (g2 >= 1) grid = g2; else reg_stats = false;
   }
-  if (reg_stats) { B2U_LAUNCH(tc_conv_kernel<true>, grid, kThreadsTc, smem, stream, maps, prm); }
-  else { B2U_LAUNCH(tc_conv_kernel<false>, grid, kThreadsTc, smem, stream, maps, prm); }
+  if (reg_stats && prm.JT / nparts <= 16) { B2U_LAUNCH(tc_conv_kernel<16>, grid, kThreadsTc, smem, stream, maps, prm); }
+  else if (reg_stats) { B2U_LAUNCH(tc_conv_kernel<32>, grid, kThreadsTc, smem, stream, maps, prm); }
+  else { B2U_LAUNCH(tc_conv_kernel<0>, grid, kThreadsTc, smem, stream, maps, prm); }
   return B2U_OK;
 }
 
@@ -588,6 +617,11 @@ int b2u_tc_conv3x3(const void* x, int ldx, int K, const float* w, int dgrad, con
   return launch_tc(maps, p, stream);
 }
 
+// N tile of the transposed-conv kernels when their epilogue keeps statistics / reads a mask: 64 (16 columns per thread, no
+// register spills) measured no faster than 128 on B200 (forward 0.093 vs 0.091 ms at 256^2 x 64 -> 32; data gradient of the
+// 128-channel level 0.054 vs 0.049): the spills were not what bounds these epilogues.  Default 128.
+int g_b2u_convt_jt = 128;
+
 int b2u_tc_convt_fwd(const void* x, int ldx, int cin, const float* w, const float* bias, void* y, int ldy, int cout,
                      double* stats, int stats_sq_off, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp,
                      void* stream) {
@@ -595,7 +629,9 @@ int b2u_tc_convt_fwd(const void* x, int ldx, int cin, const float* w, const floa
   if (rc != B2U_OK) return rc;
   TcParams p{};
   p.N = n; p.H = h; p.W = wd; p.K = cin; p.J = 4 * cout; p.KS = pick_ks(cin); p.JT = pick_jt(4 * cout);
-  if (stats != nullptr && p.J % 128 == 0) p.JT = 128;     // <= 32 columns per epilogue thread: statistics stay in registers
+  // statistics in registers: 64-column N tiles leave 16 columns per epilogue thread (no spills, see tc_conv_kernel);
+  // `convt_jt` = 128 restores round 1's 32 columns per thread
+  if (stats != nullptr && p.J % 128 == 0) p.JT = (g_b2u_convt_jt == 64 && p.J % 64 == 0) ? 64 : 128;
   if (p.JT > cout && p.JT % cout != 0) p.JT = cout;       // a 16-column chunk must not straddle two (a,b) groups
   p.ntaps = 1; p.tap_dh[0] = 0; p.tap_dw[0] = 0; p.tap_map[0] = 0;
   p.mode = 1; p.cout = cout; p.y = (__half*)y; p.ldy = ldy; p.bias = bias; p.act = B2U_ACT_NONE;
@@ -626,6 +662,7 @@ int b2u_tc_convt_dgrad(const void* dy, int lddy, int cout, const float* w, void*
   p.mask = (const __half*)mask; p.ldmask = ldmask; p.mask_act = mask_act; p.accumulate = accumulate;
   p.colsum = colsum;
   if (colsum != nullptr && cin % 128 == 0 && p.JT > 128) p.JT = 128;   // <= 32 columns per epilogue thread
+  if ((colsum != nullptr || mask != nullptr) && g_b2u_convt_jt == 64 && cin % 64 == 0 && p.JT > 64) p.JT = 64;   // 16 per thread
   if (wp == nullptr) {
     rc = pack(w, ws, ws_bytes, 3, 4, cin, cout, stream);
     if (rc != B2U_OK) return rc;

@@ -26,6 +26,7 @@ int b2u_tc_convt_wgrad_ok(int cin, int cout, int ldx, int lddy);
 extern int g_b2u_tc_halo;
 extern int g_b2u_wgrad_halo;
 extern int g_b2u_wgrad_dhm;
+extern int g_b2u_convt_jt;
 extern int g_b2u_tc_2sm_max_j;
 extern int g_b2u_tc_3sm;
 extern long long* g_b2u_dbg;
