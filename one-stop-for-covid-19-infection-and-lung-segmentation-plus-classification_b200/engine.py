@@ -249,6 +249,23 @@ class Engine:
         torch.cuda.synchronize(self.device)
         self._prep_owner = None
 
+    def average_moving_statistics(self):
+        """data parallel without sync_stats: mean over the ranks of the BatchNorm moving means / variances (the `state`
+        buffer); every rank then validates and checkpoints with the same statistics"""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        self.stream.synchronize()
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(self.state)
+            self.state /= self.world
+        else:
+            h = self.state.cpu()
+            dist.all_reduce(h)
+            self.state.copy_(h / self.world)
+        torch.cuda.synchronize(self.device)
+        self._prep_owner = None
+
     # ---------------------------------------------------------------------------------------
     # plans
     # ---------------------------------------------------------------------------------------

@@ -570,12 +570,20 @@ class Model:
                 for k in ("loss", "dice_coeff"):
                     if k in logs:
                         logs[k] = D.mean_over_ranks(logs[k], world)
+            if world > 1 and not eng.sync_stats:
+                # BatchNorm moving statistics follow each rank's own batches: average them once per epoch so that validation,
+                # checkpoints and every callback decision (best-only saves, early stopping) are the same on all ranks
+                eng.average_moving_statistics()
             if validation_data is not None:
                 xv, yv = validation_data[0], validation_data[1]
                 vals = self._run_eval(xv, yv, batch_size, self.metrics)
                 logs["val_loss"] = vals[0]
                 for nm, v in zip(metric_names, vals[1:]):
                     logs["val_" + nm] = v
+                if world > 1:                  # identical weights and statistics: the mean only removes last-bit noise
+                    for k in list(logs):
+                        if k.startswith("val_"):
+                            logs[k] = D.mean_over_ranks(logs[k], world)
             dt_ = time.time() - t0
             for cb in cbs:
                 cb.on_epoch_end(epoch, logs)

@@ -125,7 +125,7 @@ def main():
     m.compile(optimizer=M.Adam(lr=0.0005), loss=LS.bce_dice_loss, metrics=[LS.dice_coeff])
     h = m.fit(xs, ts, batch_size=4, epochs=2, validation_data=(xs[:6], ts[:6]), verbose=0,
               callbacks=[M.ModelCheckpoint(ck, monitor="val_dice_coeff", mode="max", save_best_only=True)])
-    same_everywhere(m.get_weights_dict(), "C/fit")
+    same_everywhere(m.get_weights_dict(), "C/fit", moving=True)     # fit averages the moving statistics once per epoch
     logs = torch.tensor([h.history["loss"][-1], h.history["val_loss"][-1]], dtype=torch.float64).cuda()
     ref = logs.clone()
     dist.broadcast(ref, src=0)
