@@ -349,22 +349,26 @@ static int run_one(const b2u_op& o, void* ws, size_t wsb, void* comm, void* s) {
       return b2u_convt2x2_wgrad(dt, p[0], I(0), I(1), p[1], I(2), I(3), (float*)p[2], (float*)p[3], I(4), I(5), I(6), ws,
                                 wsb, s);
     case B2U_OP_BN_STATS:            // i[3] (optional): offset of the squares in a wider sums buffer (default: c)
-      return b2u_bn_stats_off(dt, p[0], I(0), I(1), i[2], (double*)p[1], I(3) ? I(3) : I(1), s);
+      return b2u_bn_stats_off(dt, p[0], I(0), I(1), i[2], (double*)p[1], I(3) ? I(3) : I(1), s,
+                              f[0], I(4), (const b2u_step_state*)p[2], p[3]);   // f[0] = rate, i[4] = op index, p[2] = step
+                                                                                // state, p[3] = keep bits out: dropout(x)
     case B2U_OP_BN_FINALIZE:
       return b2u_bn_finalize((const double*)p[0], i[0], (const float*)p[1], (const float*)p[2], (float*)p[3],
                              (float*)p[4], f[0], f[1], I(1), (float*)p[5], (float*)p[6], (float*)p[7], (float*)p[8], I(2),
                              s);
     case B2U_OP_BN_APPLY:          // p[5], i[5] = split, i[6] = ld (optional): second source tensor of a split concatenate
       return b2u_bn_apply_split(dt, p[0], I(0), p[5], I(6), I(5), p[1], I(1), I(2), i[3], (const float*)p[2],
-                                (const float*)p[3], (double*)p[4], I(4), s);
+                                (const float*)p[3], (double*)p[4], I(4), s, f[0], p[6]);    // p[6]: keep bits of dropout(x)
     case B2U_OP_BN_BWD_REDUCE:
       return b2u_bn_bwd_reduce_off(dt, p[0], I(0), p[1], I(1), I(2), i[3], (const float*)p[2], (const float*)p[3],
-                                   (double*)p[4], I(4) ? I(4) : I(2), s);     // i[4] (optional): offset of the second sums
+                                   (double*)p[4], I(4) ? I(4) : I(2), s,      // i[4] (optional): offset of the second sums
+                                   f[0], p[5]);                              // p[5]: keep bits of dropout(x)
     case B2U_OP_BN_BWD_APPLY:        // p[10] (optional): colsum
       return b2u_bn_bwd_apply_cs(dt, p[0], I(0), p[1], I(1), p[2], I(2), I(3), i[4], i[7], (const float*)p[3],
                                  (const float*)p[4], (const float*)p[5], (const double*)p[6], (float*)p[7],
                                  (float*)p[8], p[9], I(5), I(6), (float*)p[10], s,
-                                 p[11], I(9), p[12], I(10), I(8));     // optional second (x, dx) pair, i[8] = split
+                                 p[11], I(9), p[12], I(10), I(8),      // optional second (x, dx) pair, i[8] = split
+                                 f[0], p[13]);                         // p[13]: keep bits of dropout(x)
     case B2U_OP_MAXPOOL_FWD:
       return b2u_maxpool_fwd(dt, p[0], I(0), p[1], I(1), I(2), I(3), I(4), I(5), f[0], I(6),
                              (const b2u_step_state*)p[2], s);

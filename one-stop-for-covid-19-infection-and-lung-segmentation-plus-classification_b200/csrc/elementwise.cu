@@ -37,15 +37,52 @@ __host__ int stream_grid(long long work_items, int per_block = kThreads, int wav
   return (int)b;
 }
 
+__device__ __forceinline__ void keep_factors(float p, uint64_t e0, const b2u_step_state* st, int op_id, float f[8]);
+// 8 channels kept PACKED (as loaded) in registers and unpacked on demand
+template <typename T> struct Pack8;
+template <> struct Pack8<__half> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __half* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float v[8]) const {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+};
+template <> struct Pack8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void get(float v[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+// dropout factors of 8 consecutive elements from their stored keep bits
+__device__ __forceinline__ void bits_factors(unsigned b, float sc, float f[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = ((b >> i) & 1u) ? sc : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------
 // BatchNorm statistics: sums[c] += sum x, sums[C + c] += sum x^2   (double accumulators)
+// kDrop: the BN input is dropout(x) of a Dropout layer that is NOT materialised (Conv2D -> Dropout -> BatchNormalization,
+// UPP:874-876 ...): the keep mask is regenerated from the Philox stream (element index pix * C + c of the dropout
+// layer's tensor, as dropout_kernel does) and x * keep / (1 - p) takes the place of x.
 // ------------------------------------------------------------------------------------------
-template <typename T, bool kBwd>
-__global__ void __launch_bounds__(kThreads, 4) bn_reduce_kernel(const T* __restrict__ a, int lda,
+template <typename T, bool kBwd, bool kDrop>
+__global__ void __launch_bounds__(kThreads, kDrop ? 2 : 4) bn_reduce_kernel(const T* __restrict__ a, int lda,
                                                              const T* __restrict__ x, int ldx, int C,
                                                              long long npix, const float* __restrict__ mean,
                                                              const float* __restrict__ invstd,
-                                                             double* __restrict__ sums, int sq_off) {
+                                                             double* __restrict__ sums, int sq_off,
+                                                             const b2u_step_state* __restrict__ st, float p_drop,
+                                                             int op_id, uint8_t* __restrict__ drop_bits) {
+  // drop_bits (bit pix * C + c, one byte per thread and pixel): the forward statistics pass runs Philox ONCE and stores the
+  // keep mask; every later pass over the same tensor (apply, backward reduce / apply) reads one byte per 8 elements
+  // instead of regenerating it (regenerating in all four passes cost what the removed Dropout passes had cost)
   B2U_PDL_PROLOGUE();
   // kBwd == false: a = x (stats of a).  kBwd == true: a = dy, x = bn input; sums of dy and dy*xhat.
   // block-level partial sums in fp32 (native shared-memory atomics; fp64 shared atomics are CAS loops and
@@ -75,6 +112,25 @@ __global__ void __launch_bounds__(kThreads, 4) bn_reduce_kernel(const T* __restr
       if (kBwd) {
         load8<T>(x + p * ldx + g * 8, xv[0]);
         if (two) load8<T>(x + p2 * ldx + g * 8, xv[1]);
+      }
+      if (kDrop) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u == 1 && !two) break;
+          float f[8];
+          const uint64_t e0 = (uint64_t)(u ? p2 : p) * C + g * 8;
+          if (kBwd) {
+            bits_factors(drop_bits[e0 >> 3], 1.f / (1.f - p_drop), f);
+          } else {
+            keep_factors(p_drop, e0, st, op_id, f);
+            unsigned b = 0u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b |= (f[i] != 0.f ? 1u : 0u) << i;
+            drop_bits[e0 >> 3] = (uint8_t)b;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { if (kBwd) xv[u][i] *= f[i]; else v[u][i] *= f[i]; }
+        }
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -172,7 +228,10 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift,
                                                             double* __restrict__ out_stats, int out_sq_off,
-                                                            const T* __restrict__ x2, int ldx2, int split) {
+                                                            const T* __restrict__ x2, int ldx2, int split,
+                                                            const uint8_t* __restrict__ drop_bits, float p_drop) {
+  // (drop_bits, p_drop): the input is dropout(x) of an unmaterialised Dropout layer, keep mask as stored by the statistics
+  // pass (see bn_reduce_kernel); p_drop = 0: none
   // (x2, ldx2, split): channels [split, C) are read from a second tensor -- a two-input concatenate whose halves live in
   // dense tensors of their own instead of one interleaved buffer (plan.py "split concat"); split = C: one source
   B2U_PDL_PROLOGUE();
@@ -193,6 +252,12 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
   PIXEL_LANE_LOOP(C, npix) {
     float v[8];
     load8<T>(g * 8 < split ? x + p * ldx + g * 8 : x2 + p * ldx2 + (g * 8 - split), v);
+    if (p_drop > 0.f) {
+      float f[8];
+      bits_factors(drop_bits[((uint64_t)p * C + g * 8) >> 3], 1.f / (1.f - p_drop), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= f[k];
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
     store8<T>(y + p * ldy + g * 8, v);
@@ -216,14 +281,20 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* __restrict_
   }
 }
 
-template <typename T, bool kColsum>
-__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
+// kTwo: two pixels per trip with every load issued before the first use.  Measured on B200 at 512^2 x 32 channels, batch 8
+// (tools/bn_bwd_probe.py): the plain variant is fastest with one pixel per trip and its higher occupancy (0.074 against
+// 0.085 ms), the variants with column sums / an activation mask / dropout bits with two (0.097 -> 0.093, 0.133 -> 0.101).
+template <typename T, bool kColsum, bool kTwo>
+__global__ void __launch_bounds__(kThreads, kTwo ? 2 : 4) bn_bwd_apply_kernel(
     const T* __restrict__ dy, int lddy, const T* __restrict__ x, int ldx, T* __restrict__ dx, int lddx, int C,
     long long npix, long long count, const float* __restrict__ gamma, const float* __restrict__ mean,
     const float* __restrict__ invstd, const double* __restrict__ sums, float* __restrict__ dgamma,
     float* __restrict__ dbeta, const T* __restrict__ mask, int ldmask, int mask_act, float* __restrict__ colsum,
-    const T* __restrict__ x2, int ldx2, T* __restrict__ dx2, int lddx2, int split) {
+    const T* __restrict__ x2, int ldx2, T* __restrict__ dx2, int lddx2, int split,
+    const uint8_t* __restrict__ drop_bits, float p_drop) {
   B2U_PDL_PROLOGUE();
+  // (drop_bits, p_drop): the BN input is dropout(x) of an unmaterialised Dropout layer: x * f enters the BN backward and the
+  // gradient written is the one of x itself (times f: the dropout backward), p_drop = 0: none
   // (x2, dx2, split): channels [split, C) of the BN input / its gradient live in a second tensor (split concat, see
   // bn_apply_kernel); split = C: one tensor
   // colsum (optional): per-channel sums of the dx values written = bias gradient of the conv that feeds this BN
@@ -258,23 +329,60 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(
       cc[k] = -a * s1 + a * is * mu * s2;
     }
   }
-  PIXEL_LANE_LOOP(C, npix) {
-    float d[8], xv[8], o[8];
-    const bool first = g * 8 < split;
-    load8<T>(dy + p * lddy + g * 8, d);
-    load8<T>(first ? x + p * ldx + g * 8 : x2 + p * ldx2 + (g * 8 - split), xv);
+  // the activation mask of a BN whose input is the activated conv output itself (mask == x) is taken from the registers
+  // that already hold x
+  const int cg = C >> 3;
+  const int lanes = kThreads / cg;
+  const int g = threadIdx.x % cg, lane_ = threadIdx.x / cg;
+  const bool first = g * 8 < split;
+  const bool mask_is_x = mask != nullptr && mask == x && ldmask == ldx && split == C;
+  const float dsc = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  if (lane_ < lanes) {
+    const long long stride = (long long)gridDim.x * lanes;
+    constexpr int kU = kTwo ? 2 : 1;
+    for (long long p0 = (long long)blockIdx.x * lanes + lane_; p0 < npix; p0 += kU * stride) {
+      const bool two = kTwo && p0 + stride < npix;
+      Pack8<T> pd[kU], px[kU], pm[kU];                    // packed as loaded: 12 registers in flight per pixel (fp16)
+      unsigned db[kU];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = fmaf(ca[k], d[k], fmaf(cb[k], xv[k], cc[k]));
-    if (mask != nullptr) {
-      float mv[8];
-      load8<T>(mask + p * ldmask + g * 8, mv);
+      for (int u = 0; u < kU; ++u) {
+        db[u] = 0xffu;
+        if (u == 0 || two) {
+          const long long p = p0 + u * stride;
+          pd[u].load(dy + p * lddy + g * 8);
+          px[u].load(first ? x + p * ldx + g * 8 : x2 + p * ldx2 + (g * 8 - split));
+          if (mask != nullptr && !mask_is_x) pm[u].load(mask + p * ldmask + g * 8);
+          if (p_drop > 0.f) db[u] = drop_bits[((uint64_t)p * C + g * 8) >> 3];
+        }
+      }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] *= act_bwd_from_y(mv[k], mask_act);
-    }
-    store8<T>(first ? dx + p * lddx + g * 8 : dx2 + p * lddx2 + (g * 8 - split), o);
-    if (kColsum) {
+      for (int u = 0; u < kU; ++u) {
+        if (u == 1 && !two) continue;
+        const long long p = p0 + u * stride;
+        float o[8], d[8], xv[8];
+        pd[u].get(d);
+        px[u].get(xv);
+        if (p_drop > 0.f) {
+          float f[8];
+          bits_factors(db[u], dsc, f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) cs[kColsum ? k : 0] += o[k];
+          for (int k = 0; k < 8; ++k) o[k] = f[k] * fmaf(ca[k], d[k], fmaf(cb[k], xv[k] * f[k], cc[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = fmaf(ca[k], d[k], fmaf(cb[k], xv[k], cc[k]));
+        }
+        if (mask != nullptr) {
+          float mv[8];
+          if (!mask_is_x) pm[u].get(mv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] *= act_bwd_from_y(mask_is_x ? xv[k] : mv[k], mask_act);
+        }
+        store8<T>(first ? dx + p * lddx + g * 8 : dx2 + p * lddx2 + (g * 8 - split), o);
+        if (kColsum) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) cs[kColsum ? k : 0] += o[k];
+        }
+      }
     }
   }
   if (kColsum) {
@@ -302,28 +410,6 @@ __device__ __forceinline__ void keep_factors(float p, uint64_t e0, const b2u_ste
   f[0] = a.x >= thr ? sc : 0.f; f[1] = a.y >= thr ? sc : 0.f; f[2] = a.z >= thr ? sc : 0.f; f[3] = a.w >= thr ? sc : 0.f;
   f[4] = b.x >= thr ? sc : 0.f; f[5] = b.y >= thr ? sc : 0.f; f[6] = b.z >= thr ? sc : 0.f; f[7] = b.w >= thr ? sc : 0.f;
 }
-
-// 8 channels kept PACKED (as loaded) in registers and unpacked on demand
-template <typename T> struct Pack8;
-template <> struct Pack8<__half> {
-  uint4 u;
-  __device__ __forceinline__ void load(const __half* p) { u = *reinterpret_cast<const uint4*>(p); }
-  __device__ __forceinline__ void get(float v[8]) const {
-    const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-  }
-};
-template <> struct Pack8<float> {
-  float4 a, b;
-  __device__ __forceinline__ void load(const float* p) {
-    a = *reinterpret_cast<const float4*>(p);
-    b = *reinterpret_cast<const float4*>(p + 4);
-  }
-  __device__ __forceinline__ void get(float v[8]) const {
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  }
-};
 
 template <typename T> __device__ __forceinline__ float round_to(float v);
 template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
@@ -1103,25 +1189,28 @@ extern "C" int b2u_state_advance(b2u_step_state* d_state, void* stream) {
 }
 
 extern "C" int b2u_bn_stats(int dt, const void* x, int ldx, int c, long long npix, double* sums, void* stream) {
-  REQ_VEC8(c);
-  B2U_REQUIRE(c <= 2048 && ldx % 8 == 0 && aligned16(x), "bn_stats: c<=2048, ld%%8==0, 16B-aligned base required");
-  int lanes = kThreads / (c / 8);
-  int grid = stream_grid((npix + 1) / 2, lanes, 4);
-  size_t smem = 2 * (size_t)c * sizeof(float);
-  DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, false>), grid, kThreads, smem, stream, (const T*)x, ldx,
-                            (const T*)nullptr, 0, c, npix, (const float*)nullptr, (const float*)nullptr, sums, c));
-  return B2U_OK;
+  return b2u_bn_stats_off(dt, x, ldx, c, npix, sums, c, stream, 0.f, 0, nullptr, nullptr);
 }
 
 // statistics of a tensor into a (possibly wider) BN sums buffer: sums[i], sums[sq_off + i]
-int b2u_bn_stats_off(int dt, const void* x, int ldx, int c, long long npix, double* sums, int sq_off, void* stream) {
+int b2u_bn_stats_off(int dt, const void* x, int ldx, int c, long long npix, double* sums, int sq_off, void* stream,
+                     float p_drop, int op_id, const b2u_step_state* d_state, void* drop_bits) {
   REQ_VEC8(c);
   B2U_REQUIRE(c <= 2048 && ldx % 8 == 0 && aligned16(x), "bn_stats: c<=2048, ld%%8==0, 16B-aligned base required");
   int lanes = kThreads / (c / 8);
   int grid = stream_grid((npix + 1) / 2, lanes, 4);
   size_t smem = 2 * (size_t)c * sizeof(float);
-  DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, false>), grid, kThreads, smem, stream, (const T*)x, ldx,
-                            (const T*)nullptr, 0, c, npix, (const float*)nullptr, (const float*)nullptr, sums, sq_off));
+  if (p_drop > 0.f) {
+    B2U_REQUIRE(d_state != nullptr && drop_bits != nullptr && p_drop < 1.f,
+                "bn_stats: dropout needs a step state, a keep-mask buffer and 0 <= p < 1");
+    DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, false, true>), grid, kThreads, smem, stream, (const T*)x, ldx,
+                              (const T*)nullptr, 0, c, npix, (const float*)nullptr, (const float*)nullptr, sums, sq_off,
+                              d_state, p_drop, op_id, (uint8_t*)drop_bits));
+  } else {
+    DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, false, false>), grid, kThreads, smem, stream, (const T*)x, ldx,
+                              (const T*)nullptr, 0, c, npix, (const float*)nullptr, (const float*)nullptr, sums, sq_off,
+                              (const b2u_step_state*)nullptr, 0.f, 0, (uint8_t*)nullptr));
+  }
   return B2U_OK;
 }
 
@@ -1138,23 +1227,27 @@ extern "C" int b2u_bn_finalize(const double* sums, long long count, const float*
 extern "C" int b2u_bn_apply(int dt, const void* x, int ldx, void* y, int ldy, int c, long long npix,
                             const float* scale, const float* shift, double* out_stats, int out_sq_off,
                             void* stream) {
-  return b2u_bn_apply_split(dt, x, ldx, nullptr, 0, c, y, ldy, c, npix, scale, shift, out_stats, out_sq_off, stream);
+  return b2u_bn_apply_split(dt, x, ldx, nullptr, 0, c, y, ldy, c, npix, scale, shift, out_stats, out_sq_off, stream, 0.f,
+                            nullptr);
 }
 
 // channels [0, split) from x, [split, c) from x2 (op lists only: a two-input concatenate kept as two dense tensors)
 int b2u_bn_apply_split(int dt, const void* x, int ldx, const void* x2, int ldx2, int split, void* y, int ldy, int c,
                        long long npix, const float* scale, const float* shift, double* out_stats, int out_sq_off,
-                       void* stream) {
+                       void* stream, float p_drop, const void* drop_bits) {
   REQ_VEC8(c);
   B2U_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "bn_apply: alignment");
   B2U_REQUIRE(c <= 2048, "bn_apply: c <= 2048");
   if (x2 == nullptr) split = c;
   B2U_REQUIRE(split == c || (split > 0 && split < c && split % 8 == 0 && ldx2 % 8 == 0 && aligned16(x2)),
               "bn_apply: bad second source (split=%d of %d)", split, c);
+  B2U_REQUIRE(p_drop == 0.f || (drop_bits != nullptr && p_drop > 0.f && p_drop < 1.f && split == c),
+              "bn_apply: dropout needs the keep mask, 0 <= p < 1 and a single source");
   int grid = lane_grid(npix, c, out_stats != nullptr ? 4 : 8);
   size_t smem = out_stats != nullptr ? 2 * (size_t)c * sizeof(float) : 0;
   DISPATCH_T(dt, B2U_LAUNCH(bn_apply_kernel<T>, grid, kThreads, smem, stream, (const T*)x, ldx, (T*)y, ldy, c, npix,
-                            scale, shift, out_stats, out_sq_off, (const T*)x2, ldx2, split));
+                            scale, shift, out_stats, out_sq_off, (const T*)x2, ldx2, split, (const uint8_t*)drop_bits,
+                            p_drop));
   return B2U_OK;
 }
 
@@ -1199,19 +1292,28 @@ extern "C" int b2u_bn_bwd_sums_from_wgrad(const float* w, const float* dw, const
 
 extern "C" int b2u_bn_bwd_reduce(int dt, const void* dy, int lddy, const void* x, int ldx, int c, long long npix,
                                  const float* save_mean, const float* save_invstd, double* sums, void* stream) {
-  return b2u_bn_bwd_reduce_off(dt, dy, lddy, x, ldx, c, npix, save_mean, save_invstd, sums, c, stream);
+  return b2u_bn_bwd_reduce_off(dt, dy, lddy, x, ldx, c, npix, save_mean, save_invstd, sums, c, stream, 0.f, nullptr);
 }
 
 // the same into a (possibly wider) sums buffer: sums[i], sums[sq_off + i] (one half of a split concatenate)
 int b2u_bn_bwd_reduce_off(int dt, const void* dy, int lddy, const void* x, int ldx, int c, long long npix,
-                          const float* save_mean, const float* save_invstd, double* sums, int sq_off, void* stream) {
+                          const float* save_mean, const float* save_invstd, double* sums, int sq_off, void* stream,
+                          float p_drop, const void* drop_bits) {
   REQ_VEC8(c);
   B2U_REQUIRE(c <= 2048 && ldx % 8 == 0 && lddy % 8 == 0 && aligned16(x) && aligned16(dy), "bn_bwd_reduce: alignment");
   int lanes = kThreads / (c / 8);
   int grid = stream_grid((npix + 1) / 2, lanes, 4);
   size_t smem = 2 * (size_t)c * sizeof(float);
-  DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, true>), grid, kThreads, smem, stream, (const T*)dy, lddy,
-                            (const T*)x, ldx, c, npix, save_mean, save_invstd, sums, sq_off));
+  if (p_drop > 0.f) {
+    B2U_REQUIRE(drop_bits != nullptr && p_drop < 1.f, "bn_bwd_reduce: dropout needs the keep mask and 0 <= p < 1");
+    DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, true, true>), grid, kThreads, smem, stream, (const T*)dy, lddy,
+                              (const T*)x, ldx, c, npix, save_mean, save_invstd, sums, sq_off,
+                              (const b2u_step_state*)nullptr, p_drop, 0, (uint8_t*)const_cast<void*>(drop_bits)));
+  } else {
+    DISPATCH_T(dt, B2U_LAUNCH((bn_reduce_kernel<T, true, false>), grid, kThreads, smem, stream, (const T*)dy, lddy,
+                              (const T*)x, ldx, c, npix, save_mean, save_invstd, sums, sq_off,
+                              (const b2u_step_state*)nullptr, 0.f, 0, (uint8_t*)nullptr));
+  }
   return B2U_OK;
 }
 
@@ -1227,7 +1329,7 @@ int b2u_bn_bwd_apply_cs(int dt, const void* dy, int lddy, const void* x, int ldx
                         long long npix, long long count, const float* gamma, const float* save_mean,
                         const float* save_invstd, const double* sums, float* dgamma, float* dbeta, const void* mask,
                         int ldmask, int mask_act, float* colsum, void* stream, const void* x2, int ldx2, void* dx2,
-                        int lddx2, int split) {
+                        int lddx2, int split, float p_drop, const void* drop_bits) {
   REQ_VEC8(c);
   B2U_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && (mask == nullptr || ldmask % 8 == 0),
               "bn_bwd_apply: alignment");
@@ -1236,17 +1338,24 @@ int b2u_bn_bwd_apply_cs(int dt, const void* dy, int lddy, const void* x, int ldx
   B2U_REQUIRE(split == c || (split > 0 && split < c && split % 8 == 0 && ldx2 % 8 == 0 && lddx2 % 8 == 0 && dx2 != nullptr &&
                              aligned16(x2) && aligned16(dx2)),
               "bn_bwd_apply: bad second tensor (split=%d of %d)", split, c);
+  B2U_REQUIRE(p_drop == 0.f || (drop_bits != nullptr && p_drop > 0.f && p_drop < 1.f && split == c),
+              "bn_bwd_apply: dropout needs the keep mask, 0 <= p < 1 and a single tensor");
   int grid = lane_grid(npix, c);
   if (colsum != nullptr) {
-    DISPATCH_T(dt, B2U_LAUNCH((bn_bwd_apply_kernel<T, true>), grid, kThreads, c * sizeof(float), stream, (const T*)dy,
+    DISPATCH_T(dt, B2U_LAUNCH((bn_bwd_apply_kernel<T, true, true>), grid, kThreads, c * sizeof(float), stream, (const T*)dy,
                               lddy, (const T*)x, ldx, (T*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums,
                               dgamma, dbeta, (const T*)mask, ldmask, mask_act, colsum, (const T*)x2, ldx2, (T*)dx2, lddx2,
-                              split));
+                              split, (const uint8_t*)drop_bits, p_drop));
+  } else if (p_drop > 0.f) {
+    DISPATCH_T(dt, B2U_LAUNCH((bn_bwd_apply_kernel<T, false, true>), grid, kThreads, 0, stream, (const T*)dy,
+                              lddy, (const T*)x, ldx, (T*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums,
+                              dgamma, dbeta, (const T*)mask, ldmask, mask_act, colsum, (const T*)x2, ldx2, (T*)dx2, lddx2,
+                              split, (const uint8_t*)drop_bits, p_drop));
   } else {
-    DISPATCH_T(dt, B2U_LAUNCH((bn_bwd_apply_kernel<T, false>), grid, kThreads, 0, stream, (const T*)dy,
+    DISPATCH_T(dt, B2U_LAUNCH((bn_bwd_apply_kernel<T, false, false>), grid, kThreads, 0, stream, (const T*)dy,
                               lddy, (const T*)x, ldx, (T*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums,
                               dgamma, dbeta, (const T*)mask, ldmask, mask_act, colsum, (const T*)x2, ldx2, (T*)dx2, lddx2,
-                              split));
+                              split, (const uint8_t*)drop_bits, p_drop));
   }
   return B2U_OK;
 }

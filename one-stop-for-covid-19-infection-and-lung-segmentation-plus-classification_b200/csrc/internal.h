@@ -49,19 +49,23 @@ int b2u_bn_bwd_apply_cs(int dt, const void* dy, int lddy, const void* x, int ldx
                         long long npix, long long count, const float* gamma, const float* save_mean,
                         const float* save_invstd, const double* sums, float* dgamma, float* dbeta, const void* mask,
                         int ldmask, int mask_act, float* colsum, void* stream, const void* x2 = nullptr, int ldx2 = 0,
-                        void* dx2 = nullptr, int lddx2 = 0, int split = 0);
+                        void* dx2 = nullptr, int lddx2 = 0, int split = 0, float p_drop = 0.f, const void* drop_bits = nullptr);
 // BatchNorm over a two-input concatenate whose inputs are two dense tensors (channels [0, split) from x, the rest from x2)
 int b2u_bn_apply_split(int dt, const void* x, int ldx, const void* x2, int ldx2, int split, void* y, int ldy, int c,
                        long long npix, const float* scale, const float* shift, double* out_stats, int out_sq_off,
-                       void* stream);
+                       void* stream, float p_drop = 0.f, const void* drop_bits = nullptr);
 int b2u_tc_conv3x3_wgrad(const void* x, int ldx, int cin, const void* dy, int lddy, int cout, float* dw, float* db,
                          int n, int h, int wd, void* ws, size_t ws_bytes, void* stream);
 int b2u_tc_convt_fwd(const void* x, int ldx, int cin, const float* w, const float* bias, void* y, int ldy, int cout,
                      double* stats, int stats_sq_off, int n, int h, int wd, void* ws, size_t ws_bytes, const void* wp,
                      void* stream);
-int b2u_bn_stats_off(int dt, const void* x, int ldx, int c, long long npix, double* sums, int sq_off, void* stream);
+// p_drop > 0: the tensor read as the BN input is dropout(x) of a Dropout layer that is not materialised; the statistics pass
+// generates the keep mask (Philox: op_id, d_state) and stores it as packed bits, the other passes read `drop_bits`
+int b2u_bn_stats_off(int dt, const void* x, int ldx, int c, long long npix, double* sums, int sq_off, void* stream,
+                     float p_drop = 0.f, int op_id = 0, const b2u_step_state* d_state = nullptr, void* drop_bits = nullptr);
 int b2u_bn_bwd_reduce_off(int dt, const void* dy, int lddy, const void* x, int ldx, int c, long long npix,
-                          const float* save_mean, const float* save_invstd, double* sums, int sq_off, void* stream);
+                          const float* save_mean, const float* save_invstd, double* sums, int sq_off, void* stream,
+                          float p_drop = 0.f, const void* drop_bits = nullptr);
 int b2u_tc_convt_dgrad(const void* dy, int lddy, int cout, const float* w, void* dx, int lddx, int cin,
                        const void* mask, int ldmask, int mask_act, int accumulate, float* colsum, int n, int h, int wd,
                        void* ws, size_t ws_bytes, const void* wp, void* stream);

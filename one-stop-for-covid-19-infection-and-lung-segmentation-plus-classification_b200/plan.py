@@ -145,7 +145,7 @@ class Plan:
     def __init__(self, graph, n, dt=F32, training=True, dropout=True, loss="bce_dice", world=1,
                  sync_stats=False, layout=None, rank=0, fuse_bn_bwd=True, fuse_bn_stats=True, fuse_bias_grad=True,
                  prepack=True, fuse_bn_bwd_wgrad=True, fuse_bn_pool=True, relu_bits=None, grad_bucket_bytes=6 << 20,
-                 fuse_bn_infer=True, hoist_prep=True, split_concat=True):
+                 fuse_bn_infer=True, hoist_prep=True, split_concat=True, fuse_dropout_bn=True):
         self.graph, self.n, self.dt, self.training = graph, int(n), dt, training
         self.dropout = dropout and training
         self.loss, self.world, self.sync_stats = loss, int(world), bool(sync_stats) and world > 1
@@ -167,6 +167,12 @@ class Plan:
         # 512^2 x 32 channels, tools/half_line_probe.py: max-pool backward 0.125 -> 0.101 ms, transposed-conv weight
         # gradient 0.103 -> 0.072 ms, data gradient 0.069 -> 0.054 ms, BN backward 0.083 -> 0.066 ms; in the step:
         # max-pool backward 0.125 -> 0.092, transposed-conv weight gradient 0.064 -> 0.049, step -0.05 ms).
+        # Conv2D -> Dropout -> BatchNormalization (the U-Net++ decoder blocks, UPP:874-876 ...): the Dropout output is never
+        # written; the BN statistics pass runs Philox once and stores the keep mask as packed bits, the apply / backward reduce /
+        # backward apply kernels read one byte per 8 elements and the conv output instead -- one full read + write pass less in
+        # each direction per block (regenerating the mask in all four passes cost what the removed passes had cost).
+        self.fuse_dropout_bn = bool(fuse_dropout_bn)
+        self._lazy_drop = {}             # id(dropout output tensor) -> (rate, dropout op index)
         self.split_concat = int(split_concat)        # 0: never, 1: inputs narrower than a 128-byte line, 2: every eligible concat
         self.fuse_bn_infer = bool(fuse_bn_infer) and not training and dt == F16
         self.hoist_prep = bool(hoist_prep) and not training
@@ -239,7 +245,10 @@ class Plan:
     def _w(self, layer, short, arena=None):
         return self.layout.ref("%s/%s" % (layer.name, short), arena)
 
-    def _bn_apply_op(self, xv, yv, aux, c, tag):
+    def _bn_apply_op(self, xv, yv, aux, c, tag, lazy=None):
+        if lazy is not None:                 # unmaterialised dropout on the input: p[6] = its keep bits, f[0] = rate
+            return Op(OP_BN_APPLY, xv.dt, [xv.ref, yv.ref, aux["scale"], aux["shift"], None, None, lazy[2]],
+                      [xv.ld, yv.ld, c, self._npix(xv), 0], [lazy[0]], tag=tag)
         if isinstance(xv, SplitView):
             a, b = xv.parts
             return Op(OP_BN_APPLY, xv.dt, [a.ref, yv.ref, aux["scale"], aux["shift"], None, b.ref],
@@ -474,6 +483,10 @@ class Plan:
                                 self.fwd.append(Op(OP_BN_STATS, pv.dt, [pv.ref, aux["sums"] + off * 8], [pv.ld, pv.c, count, c],
                                                    tag=l.name))
                                 off += pv.c
+                        elif id(x) in self._lazy_drop:             # statistics of dropout(x), the mask regenerated
+                            rate, op_id, bits = self._lazy_drop[id(x)]
+                            self.fwd.append(Op(OP_BN_STATS, xv.dt, [xv.ref, aux["sums"], self.step_ref, bits],
+                                               [xv.ld, c, count, 0, op_id], [rate], tag=l.name))
                         else:
                             self.fwd.append(Op(OP_BN_STATS, xv.dt, [xv.ref, aux["sums"]], [xv.ld, c, count], tag=l.name))
                     if self.sync_stats:
@@ -484,7 +497,7 @@ class Plan:
                                    [aux.get("sums"), self._w(l, "gamma"), self._w(l, "beta"), self._w(l, "moving_mean"),
                                     self._w(l, "moving_variance"), aux["scale"], aux["shift"], aux["mean"], aux["invstd"]],
                                    [count, 1 if self.training else 0, c], [l.momentum, l.epsilon], tag=l.name))
-                self.fwd.append(self._bn_apply_op(xv, yv, aux, c, l.name))
+                self.fwd.append(self._bn_apply_op(xv, yv, aux, c, l.name, self._lazy_drop.get(id(x))))
                 if self.training:
                     prod_op[id(t)] = self.fwd[-1]
             elif l.kind == "max_pooling2d":
@@ -518,6 +531,17 @@ class Plan:
                     self.views[id(t)] = xv                     # alias: identity (fused or inference)
                     if self.training:
                         self.gviews[id(t)] = self.gviews[id(x)]
+                elif (self.fuse_dropout_bn and self.training and id(t) not in home and len(t.consumers) == 1 and
+                      t.consumers[0].kind == "batch_normalization" and len(x.consumers) == 1 and
+                      not isinstance(xv, SplitView) and xv.c % 8 == 0 and
+                      not (len(t.consumers[0].output.consumers) == 1 and
+                           t.consumers[0].output.consumers[0].kind == "max_pooling2d")):
+                    # not materialised: the BatchNormalization behind it applies the mask on the fly (aliases like an
+                    # identity dropout; `_lazy_drop` tells the BN ops)
+                    self.views[id(t)] = xv
+                    self.gviews[id(t)] = self.gviews[id(x)]
+                    # (rate, dropout op index, packed keep mask: written by the BN statistics pass, read by the others)
+                    self._lazy_drop[id(t)] = (float(l.rate), drop_index[id(l)], self.act.alloc(self._npix(xv) * xv.c // 8))
                 else:
                     place(t, xv.dt)
                     yv = self.views[id(t)]
@@ -689,8 +713,10 @@ class Plan:
                         self.bwd.append(Op(OP_ALLREDUCE_F64, 0, [bsums], [2 * c], tag=l.name))
                 else:
                     bsums = self.zero.alloc(2 * c * 8)
-                    self.bwd.append(Op(OP_BN_BWD_REDUCE, xv.dt, [gy.ref, xv.ref, aux["mean"], aux["invstd"], bsums],
-                                       [gy.ld, xv.ld, c, self._npix(xv)], tag=l.name))
+                    lazy = self._lazy_drop.get(id(x))
+                    self.bwd.append(Op(OP_BN_BWD_REDUCE, xv.dt, [gy.ref, xv.ref, aux["mean"], aux["invstd"], bsums] +
+                                       ([lazy[2]] if lazy else []),
+                                       [gy.ld, xv.ld, c, self._npix(xv)], [lazy[0]] if lazy else [], tag=l.name))
                     if self.sync_stats:
                         self.bwd.append(Op(OP_ALLREDUCE_F64, 0, [bsums], [2 * c], tag=l.name))
                 # npix is the LOCAL pixel count; the divisor (count) is the global one under sync_stats,
@@ -707,11 +733,14 @@ class Plan:
                                        tag=l.name))
                     written.add(id(x))
                     continue
+                lazy = self._lazy_drop.get(id(x))     # unmaterialised dropout: p[13] = its keep bits, f[0] = rate
                 self.bwd.append(Op(OP_BN_BWD_APPLY, xv.dt,
                                    [gy.ref, xv.ref, gx.ref, self._w(l, "gamma"), aux["mean"], aux["invstd"], bsums,
                                     grads(l, "gamma") if own else None, grads(l, "beta") if own else None,
-                                    mv.ref if mv else None, self._bias_sink(x) if mv is not None else None],
+                                    mv.ref if mv else None, self._bias_sink(x) if mv is not None else None] +
+                                   ([None, None, lazy[2]] if lazy else []),
                                    [gy.ld, xv.ld, gx.ld, c, self._npix(xv), mv.ld if mv else 0, ma, aux["count"]],
+                                   [lazy[0]] if lazy else [],
                                    tag=l.name))
                 written.add(id(x))
             elif l.kind == "max_pooling2d":

@@ -85,6 +85,21 @@ class Emulator:
             return np.where(x > 0, x, np.expm1(np.minimum(x, 0)))
         return x
 
+    def _drop_factor(self, o, shape, bits_ref, op_id=None):
+        """unmaterialised Dropout in front of a BatchNormalization op (f[0] = rate): keep / (1 - p) per element, or None.
+        The statistics op (op_id given) draws the keep mask from the Philox stream and stores it as packed bits (bit index
+        = dense element index), every other op reads those bits."""
+        p = o.f[0] if len(o.f) > 0 else 0.0
+        if not p:
+            return None
+        n = int(np.prod(shape))
+        if op_id is not None:
+            keep = self._keep(n, p, op_id).reshape(-1)
+            self.arr(bits_ref, n // 8, np.uint8)[:] = np.packbits(keep.astype(np.uint8), bitorder="little")
+        else:
+            keep = np.unpackbits(self.arr(bits_ref, n // 8, np.uint8), bitorder="little")[:n].astype(np.float32)
+        return keep.reshape(shape).astype(np.float32) * np.float32(1.0 / (1.0 - np.float32(p)))
+
     def _keep(self, nelem, p, op_id):
         return philox.dropout_keep_mask(nelem, p, self.state["seed"], self.state["step"], op_id)
 
@@ -208,7 +223,11 @@ class Emulator:
     def op_bn_stats(self, o):
         ldx, c, npix = o.i[:3]
         sq = o.i[3] if len(o.i) > 3 and o.i[3] else c        # offset of the squares (one half of a split concatenate)
-        x = self.view(o.p[0], ldx, c, npix, o.dt).astype(np.float64)
+        x = self.view(o.p[0], ldx, c, npix, o.dt).astype(np.float32)
+        f = self._drop_factor(o, x.shape, o.p[3] if len(o.p) > 3 else None, o.i[4] if len(o.i) > 4 else 0)
+        if f is not None:
+            x = x * f
+        x = x.astype(np.float64)
         s = self.f64(o.p[1], sq + c)
         s[:c] += x.sum(0)
         s[sq:sq + c] += (x * x).sum(0)
@@ -243,6 +262,10 @@ class Emulator:
                                 self.view(o.p[5], ldx2, c - split, npix, o.dt).astype(np.float32)], axis=1)
         else:
             x = self.view(o.p[0], ldx, c, npix, o.dt).astype(np.float32)
+        if o.kind == P.OP_BN_APPLY:
+            f = self._drop_factor(o, x.shape, o.p[6] if len(o.p) > 6 else None)
+            if f is not None:
+                x = x * f
         y = self.view(o.p[1], ldy, c, npix, o.dt)
         y[:] = (x * self.f32(o.p[2], c) + self.f32(o.p[3], c)).astype(y.dtype)
         if len(o.p) > 4 and o.p[4] is not None:
@@ -271,6 +294,9 @@ class Emulator:
         lddy, ldx, c, npix = o.i[:4]
         dy = self.view(o.p[0], lddy, c, npix, o.dt).astype(np.float32)
         x = self.view(o.p[1], ldx, c, npix, o.dt).astype(np.float32)
+        f = self._drop_factor(o, x.shape, o.p[5] if len(o.p) > 5 else None)
+        if f is not None:
+            x = x * f
         xh = (x - self.f32(o.p[2], c)) * self.f32(o.p[3], c)
         sq = o.i[4] if len(o.i) > 4 and o.i[4] else c        # offset of the second sums (one half of a split concatenate)
         s = self.f64(o.p[4], sq + c)
@@ -289,8 +315,13 @@ class Emulator:
             x = self.view(o.p[1], ldx, c, npix, o.dt).astype(np.float32)
         g, mean, inv = self.f32(o.p[3], c), self.f32(o.p[4], c), self.f32(o.p[5], c)
         s = self.f64(o.p[6], 2 * c)
+        f = self._drop_factor(o, x.shape, o.p[13] if len(o.p) > 13 else None)
+        if f is not None:
+            x = x * f
         xh = (x - mean) * inv
         dx = g * inv * (dy - (s[:c] / count).astype(np.float32) - xh * (s[c:] / count).astype(np.float32))
+        if f is not None:
+            dx = dx * f                                    # the dropout backward
         if o.p[9] is not None:
             dx = dx * self._dact(self.view(o.p[9], ldm, c, npix, o.dt), mact)
         if two:

@@ -219,6 +219,46 @@ def test_batchnorm_over_a_split_concatenate(dt, ca, cb, npix_shape):
 
 
 @pytest.mark.parametrize("dt", [P.F32, P.F16])
+@pytest.mark.parametrize("c,npix_shape,rate", [(32, (2, 16, 16), 0.5), (64, (1, 10, 6), 0.2), (128, (3, 8, 8), 0.5), (8, (1, 7, 5), 0.1)])
+def test_batchnorm_over_an_unmaterialised_dropout(dt, c, npix_shape, rate):
+    """Conv2D -> Dropout -> BatchNormalization without the Dropout pass (plan.py fuse_dropout_bn): the statistics op draws the
+    keep mask (same Philox stream / element index as dropout_kernel) and stores it as packed bits, apply / backward reduction /
+    backward apply read the bits -- and the explicit Dropout op on the same stream gives the same masked values"""
+    n, h, w = npix_shape
+    npix = n * h * w
+    img = Img(51)
+    x = img.view(n, h, w, c, dt, ld=c + 8, fill="uniform")
+    xd = img.view(n, h, w, c, dt, fill=None)                  # explicit dropout output (reference path inside this test)
+    y, y2 = img.view(n, h, w, c, dt, fill=None), img.view(n, h, w, c, dt, fill=None)
+    dy = img.view(n, h, w, c, dt, scale=0.5)
+    dx = img.view(n, h, w, c, dt, ld=c + 16, c0=8, fill=None)
+    gamma, beta = img.farr(img.par, c, fill="pos"), img.farr(img.par, c, scale=0.1)
+    mm, mv = img.farr(img.par, c, scale=0.1), img.farr(img.par, c, fill="pos")
+    scale, shift, mean, inv = (img.f32.alloc(c * 4) for _ in range(4))
+    dg, dbt = img.farr(img.gr, c, scale=0.01), img.farr(img.gr, c, scale=0.01)
+    bias_g = img.farr(img.gr, c, scale=0.01)
+    s1, s2 = img.zero.alloc(2 * c * 8), img.zero.alloc(2 * c * 8)
+    step = P.Ref("step", 0)
+    op_id = 5
+    bits = img.act.alloc(npix * c // 8)                       # packed keep mask: written by the statistics op, read by the others
+    ops = [P.Op(P.OP_BN_STATS, dt, [x.ref, s1, step, bits], [x.ld, c, npix, 0, op_id], [rate]),
+           P.Op(P.OP_BN_FINALIZE, 0, [s1, gamma, beta, mm, mv, scale, shift, mean, inv], [npix, 1, c], [0.99, 1e-3]),
+           P.Op(P.OP_BN_APPLY, dt, [x.ref, y.ref, scale, shift, None, None, bits], [x.ld, y.ld, c, npix, 0], [rate]),
+           P.Op(P.OP_BN_BWD_REDUCE, dt, [dy.ref, x.ref, mean, inv, s2, bits], [dy.ld, x.ld, c, npix], [rate]),
+           P.Op(P.OP_BN_BWD_APPLY, dt, [dy.ref, x.ref, dx.ref, gamma, mean, inv, s2, dg, dbt, x.ref, bias_g, None, None, bits],
+                [dy.ld, x.ld, dx.ld, c, npix, x.ld, 2, npix], [rate]),
+           # the explicit pair on the same stream: dropout, then BN apply of its output
+           P.Op(P.OP_DROPOUT_FWD, dt, [x.ref, xd.ref, step], [x.ld, xd.ld, c, npix, op_id], [rate]),
+           P.Op(P.OP_BN_APPLY, dt, [xd.ref, y2.ref, scale, shift, None], [xd.ld, y2.ld, c, npix, 0])]
+    out, _ = compare(ops, img, dt, state=dict(seed=987654321, step=11), tol=3e-3 if dt == P.F16 else 3e-5)
+    # GPU: fused and explicit outputs agree (the explicit path rounds the dropout output to the storage type first)
+    es = P.ELEM[dt]
+    a = np.frombuffer(out["act"], dtype=NPDT[dt], count=npix * c, offset=y.ref.off).astype(np.float32)
+    b = np.frombuffer(out["act"], dtype=NPDT[dt], count=npix * c, offset=y2.ref.off).astype(np.float32)
+    assert np.abs(a - b).max() <= (4e-3 if dt == P.F16 else 1e-6) * max(1.0, np.abs(b).max())
+
+
+@pytest.mark.parametrize("dt", [P.F32, P.F16])
 @pytest.mark.parametrize("p", [0.0, 0.25])
 def test_maxpool_dropout_fwd_bwd(dt, p):
     n, h, w, c = 2, 12, 20, 32

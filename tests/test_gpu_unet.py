@@ -360,7 +360,7 @@ def test_train_on_batch_pipelined_matches_blocking():
                                    dict(fuse_bias_grad=False), dict(fuse_bn_pool=False), dict(fuse_bn_stats=False),
                                    dict(fuse_bn_bwd=False, fuse_bn_stats=False, fuse_bias_grad=False, fuse_bn_pool=False,
                                         fuse_bn_bwd_wgrad=False),
-                                   dict(split_concat=0), dict(split_concat=2),
+                                   dict(split_concat=0), dict(split_concat=2), dict(fuse_dropout_bn=False),
                                    dict(split_concat=2, fuse_bn_stats=False, fuse_bn_bwd_wgrad=False, fuse_bn_bwd=False)],
                          ids=lambda d: "+".join(sorted(d)))
 def test_every_planner_fusion_can_be_switched_off_on_the_gpu(flags):

@@ -287,3 +287,34 @@ def test_unet_decoder_concats_stay_two_dense_tensors():
         tol = 0 if not opts else 1e-6          # two half reductions add their double sums in another order than one pass
         ga, gb = (np.frombuffer(r[1], np.float32, len(r[1]) // 4) for r in res)
         assert np.abs(ga - gb).max() <= tol * max(1.0, np.abs(gb).max()), opts
+
+
+def test_unetpp_dropout_in_front_of_batchnorm_is_never_materialised():
+    """Conv2D -> Dropout -> BatchNormalization (UPP:874-876 and every decoder block): the BN ops regenerate the keep mask and
+    read the conv output; 12 of the 16 Dropout layers lose their forward and backward passes; the emulated step still
+    reproduces the oracle's autograd with the SAME dropout stream (and equals the unfused plan in exact mode)."""
+    hw, n = 16, 2
+    g = G.unetpp(hw, 1)
+    plan = P.Plan(g, n, dt=P.F32, training=True, dropout=True)
+    off = P.Plan(g, n, dt=P.F32, training=True, dropout=True, fuse_dropout_bn=False)
+    count = lambda pl, k: sum(1 for o in pl.train_ops() if o.kind == k)
+    assert (count(off, P.OP_DROPOUT_FWD), count(off, P.OP_DROPOUT_BWD)) == (16, 16)
+    assert (count(plan, P.OP_DROPOUT_FWD), count(plan, P.OP_DROPOUT_BWD)) == (4, 4) and len(plan._lazy_drop) == 12
+    assert sum(1 for o in plan.fwd if o.kind == P.OP_BN_STATS and o.f and o.f[0] > 0 and o.p[3] is not None) == 12
+    assert sum(1 for o in plan.fwd if o.kind == P.OP_BN_APPLY and o.f and o.f[0] > 0) == 12
+    assert sum(1 for o in plan.bwd if o.kind == P.OP_BN_BWD_APPLY and o.f and o.f[0] > 0) == 12
+    params = perturbed_params("unetpp", hw)
+    x, t = synth_batch(n, hw, seg=True)
+    r = K.loss_and_grads("unetpp", params, x, t, dtype=torch.float64, dropout=dict(seed=7, step=5), loss="bce_dice")
+    res = []
+    for pl in (plan, off):
+        em = E.Emulator(pl.arena_sizes())
+        em.state.update(seed=7, step=5)
+        _load(em, pl, params, x, t.reshape(n, -1))
+        em.run(pl.train_ops())
+        assert em.f32(pl.loss_out, 1)[0] == pytest.approx(r["loss"], rel=2e-5)
+        grads = pl.layout.unpack(em.f32(P.Ref("grads", 0), pl.layout.n_params), None)
+        worst, who = grad_errors(grads, r["grads"])
+        assert worst < 2e-3, (who, worst)
+        res.append(em.f32(P.Ref("grads", 0), pl.layout.n_params).copy())
+    assert np.abs(res[0] - res[1]).max() <= 2e-6 * max(1.0, np.abs(res[1]).max())
