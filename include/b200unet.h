@@ -251,6 +251,18 @@ enum {
  * gradient of a conv output: CONV3X3_DGRAD p[4], CONVT_DGRAD p[4], BN_BWD_APPLY p[10], HEAD_BWD p[9].  The kernel adds
  * the per-channel sums of the dx values it writes, which is that conv's bias gradient (Keras: the `bias` slot of
  * Conv2D, T1H:859); the matching *_WGRAD op is then given db = NULL and skips its own pass over the gradient. */
+/* Further optional op-list slots (all may be NULL / 0; they extend, never reorder, the function arguments):
+ *  CONV3X3_FWD   p[6] packed 1-bit ReLU mask out; p[7], p[8] per-channel scale / shift applied AFTER the activation (the
+ *                inference-mode BatchNormalization behind the conv, T2:749-750, folded into the epilogue); i[8] = 1: op of a
+ *                training plan; i[9]: real Cin when the input tensor is zero-padded to 16 channels.
+ *  BN_STATS      i[3] offset of the squares in a wider sums buffer; f[0], i[4], p[2] (step state), p[3]: the input is
+ *                dropout(x) of a Dropout layer that is not materialised (UPP:874-876) -- the kernel draws the keep mask
+ *                (rate f[0], dropout op index i[4]) and stores it as packed bits (bit pix * C + c) at p[3].
+ *  BN_APPLY      p[5], i[5] = split, i[6] = ld: channels [split, C) come from a second tensor (a two-input concatenate kept
+ *                as two dense tensors); f[0], p[6]: dropout(x) as above, keep bits READ from p[6].
+ *  BN_BWD_REDUCE i[4] offset of the second sums; f[0], p[5]: dropout(x), keep bits read from p[5].
+ *  BN_BWD_APPLY  p[11], i[9] = ld, p[12], i[10] = ld, i[8] = split: second (input, input-gradient) pair of a split
+ *                concatenate; f[0], p[13]: dropout(x), keep bits read from p[13] (the gradient written is the one of x). */
 /* executor flags, OR-ed into b2u_op.dt above the storage type (dt & 0xff): */
 #define B2U_OPF_SIDE 0x100 /* may run on the executor's side stream (forked / joined with events; weight gradients) */
 #define B2U_OPF_JOIN 0x200 /* reads what earlier B2U_OPF_SIDE ops wrote: wait for the side stream first            */
