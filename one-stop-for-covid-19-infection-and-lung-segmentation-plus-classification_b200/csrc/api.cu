@@ -105,6 +105,11 @@ extern "C" int b2u_set_option(const char* name, int value) {
     g_b2u_comm_overlap = value ? 1 : 0;
     return old;
   }
+  if (strcmp(name, "tc_bgroup") == 0) {
+    int old = g_b2u_tc_bgroup;
+    g_b2u_tc_bgroup = value;
+    return old;
+  }
   if (strcmp(name, "convt_jt") == 0) {
     int old = g_b2u_convt_jt;
     g_b2u_convt_jt = value;

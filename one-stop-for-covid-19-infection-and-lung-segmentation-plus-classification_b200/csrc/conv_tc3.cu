@@ -34,7 +34,11 @@ struct C3Params {
   int amode;              // 1: one halo box (18 x 10), 3: three boxes (18 x 8), one per dw
   int bo_mode;            // amode 1: 0 = descriptor base_offset 0, 1 = (start >> 7) & 7
   int bres;               // weights resident in smem
-  int SA, SB;             // ring depths
+  int SA, SB;             // ring depths (SB counts GROUPS of `bgroup` weight tiles)
+  int bgroup;             // streamed weights: tiles per ring slot (1, or 3 = the taps of one filter row).  A
+                          // tcgen05.commit makes the issuing thread's next MMA start >= ~465 cycles after the previous
+                          // batch's first (tools/mma_probe.cu): four N = 128 MMAs (256 cycles) per commit ran at 55 % of the
+                          // pipe rate, twelve (768 cycles) do not notice it.  N = 256 tiles (512 cycles per four) keep 1.
   int epi_warps;          // 4 or 8 (block = 64 + 32 * epi_warps threads)
   uint32_t a_sub;         // bytes of one A sub-tile (1024-aligned), a_stage = a_sub * (amode == 3 ? 3 : 1)
   __half* y; int ldy;
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
   // layout: [A ring][B ring or resident weights][barriers][tmem ptr][bias][stats]
   uint8_t* a_ring = smem;
   uint8_t* b_area = a_ring + (size_t)SA * a_stage;
-  const uint32_t b_bytes_total = prm.bres ? 9u * kslabs * b_tile : (uint32_t)SB * b_tile;
+  const uint32_t b_bytes_total = prm.bres ? 9u * kslabs * b_tile : (uint32_t)(SB * prm.bgroup) * b_tile;
   uint8_t* tail = b_area + b_bytes_total;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* a_empty = a_full + kMaxSA;
@@ -174,10 +178,12 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
           if (prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64) prm.dbg[(tile / gridDim.x) * 8 + 1] = clock64();
           if (++sa == SA) { sa = 0; pa ^= 1; }
           if (!prm.bres) {
-            for (int t = 0; t < 9; ++t) {
+            const int G = prm.bgroup;
+            for (int t = 0; t < 9; t += G) {
               tc::mbar_wait(&b_empty[sb], pb ^ 1);
-              tc::mbar_expect_tx(&b_full[sb], (uint32_t)JT * rowb);
-              tc::tma_load_3d(b_area + (size_t)sb * b_tile, &maps.b, &b_full[sb], ks * KS, jt * JT, t);
+              tc::mbar_expect_tx(&b_full[sb], (uint32_t)(G * JT) * rowb);
+              for (int gi = 0; gi < G; ++gi)
+                tc::tma_load_3d(b_area + (size_t)(sb * G + gi) * b_tile, &maps.b, &b_full[sb], ks * KS, jt * JT, t + gi);
               if (++sb == SB) { sb = 0; pb ^= 1; }
             }
           }
@@ -215,12 +221,15 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           uint32_t b_lo;
+          const bool g3 = prm.bgroup == 3;
           if (prm.bres) {
             b_lo = b_area_lo + (uint32_t)(t * kslabs + ks) * b_tile16;
           } else {
-            tc::mbar_wait(&b_full[sb], pb);
-            tc::fence_after_sync();
-            b_lo = b_area_lo + (uint32_t)sb * b_tile16;
+            if (!g3 || t % 3 == 0) {                     // first tile of a ring slot
+              tc::mbar_wait(&b_full[sb], pb);
+              tc::fence_after_sync();
+            }
+            b_lo = b_area_lo + (uint32_t)(g3 ? sb * 3 + t % 3 : sb) * b_tile16;
           }
           const uint32_t at = a_lo + tap_off[t];
 #pragma unroll
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
             const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2 * kk);
             tc::mma_f16_ss_elect(d_tmem, ad, bd, idesc, (t | kk) != 0 ? 1u : (ks != 0 ? 1u : 0u));
           }
-          if (!prm.bres) {
+          if (!prm.bres && (!g3 || t % 3 == 2)) {        // last tile of the slot: one commit releases all of it
             tc::mma_commit_elect(&b_empty[sb]);
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
@@ -528,6 +537,7 @@ CUtensorMapSwizzle swz3(int ks) {
 long long* g_b2u_dbg = nullptr;   // device timeline buffer (b2u_set_option("tc_debug", 1))
 int g_b2u_tc_2sm_max_j = 64;  // largest N tile that runs two CTAs per SM
 int g_b2u_tc_3sm = 0;         // 1: three CTAs per SM for the low-register variants of thin layers (untested)
+int g_b2u_tc_bgroup = 3;      // streamed weights: 3 = ring slots of one filter row for N <= 128 tiles, 1 = one tile per slot
 int g_b2u_tc_halo = 1;       // 0: per-tap loads (conv_tc.cu), 1: halo box, 2: halo box + base_offset, 3: three boxes
 
 int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad, const float* bias, int act, void* y,
@@ -565,6 +575,7 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   const size_t budget = 222 * 1024 - 1024 - tail;
   const size_t wres = 9 * (size_t)kslabs * b_tile;
   p.bres = (p.JT == J && wres + 2 * a_stage <= budget && wres <= 120 * 1024) ? 1 : 0;
+  p.bgroup = 1;
   if (p.bres) {
     p.SB = 1;
     p.SA = (int)((budget - wres) / a_stage);
@@ -572,10 +583,13 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
     // split the budget: at least 2 A stages, the rest to the weight ring (>= 3 tiles)
     p.SA = 2;
     long long room = (long long)budget - 2 * (long long)a_stage;
-    p.SB = (int)(room / (long long)b_tile);
+    // ring slots of three tiles (one filter row) when the MMAs of one tile are shorter than a commit's issue gap (N <= 128)
+    // and two such slots fit: see C3Params::bgroup
+    p.bgroup = (g_b2u_tc_bgroup == 3 && p.JT <= 128 && room >= 6 * (long long)b_tile) ? 3 : 1;
+    p.SB = (int)(room / ((long long)b_tile * p.bgroup));
     if (p.SB > kMaxSB) {
       p.SB = kMaxSB;
-      p.SA = (int)((budget - (size_t)p.SB * b_tile) / a_stage);
+      p.SA = (int)((budget - (size_t)p.SB * p.bgroup * b_tile) / a_stage);
     }
   }
   if (p.SA > kMaxSA) p.SA = kMaxSA;
@@ -596,7 +610,7 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
     }
   }
   p.epi_warps = two_per_sm ? 4 : 8;
-  const size_t smem = 1024 + (size_t)p.SA * a_stage + (p.bres ? wres : (size_t)p.SB * b_tile) + tail;
+  const size_t smem = 1024 + (size_t)p.SA * a_stage + (p.bres ? wres : (size_t)p.SB * p.bgroup * b_tile) + tail;
   B2U_REQUIRE(smem <= 227 * 1024, "tc_conv3: shared memory %zu exceeds 227 KB", smem);
 
   // packed fp16 weights: the caller's (b2u_pack_weights, once per step for the whole model) or packed here

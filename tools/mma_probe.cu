@@ -160,10 +160,10 @@ int main() {
     for (int wait_prev = 0; wait_prev < 2; ++wait_prev) {
       printf("---- batched issue, %s, %s: cycles per MMA (issue loop)\n", two ? "two CTAs per SM" : "one CTA per SM",
              wait_prev ? "wait for batch i-2 + fence before batch i" : "commit only");
-      for (int N : {32, 64, 96}) {
+      for (int N : {32, 64, 96, 128, 256}) {
         printf("N=%-3d", N);
-        for (int batch : {6, 18, 36, 72, 144}) {
-          const int nb = 1152 / batch;
+        for (int batch : {4, 6, 18, 36, 72, 144}) {
+          const int nb = 1152 / batch / (N >= 128 ? 2 : 1);
           long long h[2] = {0, 0};
           for (int it = 0; it < 2; ++it) {
             probe_batched<<<two ? 296 : 148, 64, 90 * 1024>>>(N, batch, nb, wait_prev, d);
