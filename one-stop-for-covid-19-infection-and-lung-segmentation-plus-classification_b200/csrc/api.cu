@@ -105,6 +105,16 @@ extern "C" int b2u_set_option(const char* name, int value) {
     g_b2u_comm_overlap = value ? 1 : 0;
     return old;
   }
+  if (strcmp(name, "tc_mcast") == 0) {
+    int old = g_b2u_tc_mcast;
+    g_b2u_tc_mcast = value;
+    return old;
+  }
+  if (strcmp(name, "tc_max_ctas") == 0) {
+    int old = g_b2u_tc_max_ctas;
+    g_b2u_tc_max_ctas = value;
+    return old;
+  }
   if (strcmp(name, "tc_bgroup") == 0) {
     int old = g_b2u_tc_bgroup;
     g_b2u_tc_bgroup = value;

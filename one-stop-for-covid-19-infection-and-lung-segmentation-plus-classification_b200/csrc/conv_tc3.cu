@@ -35,6 +35,10 @@ struct C3Params {
   int bo_mode;            // amode 1: 0 = descriptor base_offset 0, 1 = (start >> 7) & 7
   int bres;               // weights resident in smem
   int SA, SB;             // ring depths (SB counts GROUPS of `bgroup` weight tiles)
+  int mcast;              // streamed weights, launched as clusters of two CTAs: both CTAs work on the same N tile and the
+                          // same K order for two different pixel tiles, and every weight tile is loaded ONCE for the pair
+                          // (TMA multicast, the two CTAs alternate as the loader): half the L2 -> SM weight traffic that
+                          // bounds the wide layers (profiles/NOTES_r2.md)
   int bgroup;             // streamed weights: tiles per ring slot (1, or 3 = the taps of one filter row).  A
                           // tcgen05.commit makes the issuing thread's next MMA start >= ~465 cycles after the previous
                           // batch's first (tools/mma_probe.cu): four N = 128 MMAs (256 cycles) per commit ran at 55 % of the
@@ -118,12 +122,20 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
   const int tiles_w = (prm.W + kTW - 1) / kTW, tiles_h = (prm.H + kTH - 1) / kTH;
   const int nj = prm.J / JT;
   const int ntiles = prm.N * tiles_h * tiles_w * nj;          // host guarantees < 2^31
+  // tile walk: CTA b takes tiles b, b + grid, ... (N tile fastest); clusters of two (mcast) walk "super tiles" = one N tile
+  // x a PAIR of pixel tiles, CTA rank r taking pixel tile 2 * pair + r (the last pair of an odd count has a dummy tile: its
+  // loads are zero-filled by TMA and nothing is stored)
+  const uint32_t crank = prm.mcast ? tc::cluster_ctarank() : 0u;
+  const unsigned npt = (unsigned)(prm.N * tiles_h * tiles_w);
+  const unsigned t_first = prm.mcast ? (blockIdx.x >> 1) : blockIdx.x;
+  const unsigned t_step = prm.mcast ? (gridDim.x >> 1) : gridDim.x;
+  const unsigned t_end = prm.mcast ? ((npt + 1) / 2) * (unsigned)nj : (unsigned)ntiles;
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(2 * JT)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < SB; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < SB; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], prm.mcast ? 2 : 1); }
     tc::mbar_init(w_full, 1);
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], prm.epi_warps); }
     tc::fence_barrier_init();
@@ -142,6 +154,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  if (prm.mcast) tc::cluster_sync();          // the peer's barriers are initialised before anything is multicast to them
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
@@ -158,15 +171,16 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const uint32_t a_tx = (prm.amode == 3 ? 3u * 18 * 8 : 18u * 10) * rowb;
-      for (unsigned tile = blockIdx.x; tile < (unsigned)ntiles; tile += gridDim.x) {
+      unsigned slot_no = 0;                          // weight ring slots issued so far (mcast: parity = loading CTA)
+      for (unsigned tile = t_first; tile < t_end; tile += t_step) {
         const int jt = (int)(tile % (unsigned)nj);
-        const unsigned pt = tile / (unsigned)nj;
+        const unsigned pt = prm.mcast ? 2 * (tile / (unsigned)nj) + crank : tile / (unsigned)nj;
         const int tw = (int)(pt % (unsigned)tiles_w);
         const unsigned r = pt / (unsigned)tiles_w;
         const int th = (int)(r % (unsigned)tiles_h), n = (int)(r / (unsigned)tiles_h);
         for (int ks = 0; ks < kslabs; ++ks) {
           tc::mbar_wait(&a_empty[sa], pa ^ 1);
-          if (prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64) prm.dbg[(tile / gridDim.x) * 8 + 0] = clock64();
+          if (prm.dbg && blockIdx.x == 0 && tile / t_step < 64) prm.dbg[(tile / t_step) * 8 + 0] = clock64();
           uint8_t* dst = a_ring + (size_t)sa * a_stage;
           tc::mbar_expect_tx(&a_full[sa], a_tx);
           if (prm.amode == 3) {
@@ -175,15 +189,22 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
           } else {
             tc::tma_load_4d(dst, &maps.a, &a_full[sa], ks * KS, tw * kTW - 1, th * kTH - 1, n);
           }
-          if (prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64) prm.dbg[(tile / gridDim.x) * 8 + 1] = clock64();
+          if (prm.dbg && blockIdx.x == 0 && tile / t_step < 64) prm.dbg[(tile / t_step) * 8 + 1] = clock64();
           if (++sa == SA) { sa = 0; pa ^= 1; }
           if (!prm.bres) {
             const int G = prm.bgroup;
             for (int t = 0; t < 9; t += G) {
-              tc::mbar_wait(&b_empty[sb], pb ^ 1);
+              tc::mbar_wait(&b_empty[sb], pb ^ 1);        // (mcast: released by BOTH CTAs' MMA warps)
               tc::mbar_expect_tx(&b_full[sb], (uint32_t)(G * JT) * rowb);
-              for (int gi = 0; gi < G; ++gi)
-                tc::tma_load_3d(b_area + (size_t)(sb * G + gi) * b_tile, &maps.b, &b_full[sb], ks * KS, jt * JT, t + gi);
+              if (!prm.mcast) {
+                for (int gi = 0; gi < G; ++gi)
+                  tc::tma_load_3d(b_area + (size_t)(sb * G + gi) * b_tile, &maps.b, &b_full[sb], ks * KS, jt * JT, t + gi);
+              } else if ((slot_no & 1u) == crank) {       // this CTA's turn: one load fills the slot of both CTAs
+                for (int gi = 0; gi < G; ++gi)
+                  tc::tma_load_3d_mcast(b_area + (size_t)(sb * G + gi) * b_tile, &maps.b, &b_full[sb], ks * KS, jt * JT,
+                                        t + gi, (uint16_t)3);
+              }
+              ++slot_no;
               if (++sb == SB) { sb = 0; pb ^= 1; }
             }
           }
@@ -239,21 +260,22 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
             tc::mma_f16_ss_elect(d_tmem, ad, bd, idesc, (t | kk) != 0 ? 1u : (ks != 0 ? 1u : 0u));
           }
           if (!prm.bres && (!g3 || t % 3 == 2)) {        // last tile of the slot: one commit releases all of it
-            tc::mma_commit_elect(&b_empty[sb]);
+            if (prm.mcast) tc::mma_commit_mcast_elect(&b_empty[sb], (uint16_t)3);   // ... in both CTAs of the pair
+            else tc::mma_commit_elect(&b_empty[sb]);
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
         }
       };
-      for (unsigned tile = blockIdx.x; tile < (unsigned)ntiles; tile += gridDim.x) {
+      for (unsigned tile = t_first; tile < t_end; tile += t_step) {
         tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc::fence_after_sync();
-        const bool dbg_on = prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64;
-        if (dbg_on && lane == 0) prm.dbg[(tile / gridDim.x) * 8 + 2] = clock64();
+        const bool dbg_on = prm.dbg && blockIdx.x == 0 && tile / t_step < 64;
+        if (dbg_on && lane == 0) prm.dbg[(tile / t_step) * 8 + 2] = clock64();
         const uint32_t d_tmem = tmem_base + acc * JT;
         for (int ks = 0; ks < kslabs; ++ks) {
           tc::mbar_wait(&a_full[sa], pa);
           tc::fence_after_sync();
-          if (dbg_on && ks == 0 && lane == 0) prm.dbg[(tile / gridDim.x) * 8 + 3] = clock64();
+          if (dbg_on && ks == 0 && lane == 0) prm.dbg[(tile / t_step) * 8 + 3] = clock64();
           const uint32_t a_lo = a_ring_lo + (uint32_t)sa * a_stage16;
           if (KS == 64) issue_slab(std::integral_constant<int, 4>{}, d_tmem, a_lo, ks);
           else if (KS == 32) issue_slab(std::integral_constant<int, 2>{}, d_tmem, a_lo, ks);
@@ -262,7 +284,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
           if (++sa == SA) { sa = 0; pa ^= 1; }
         }
         tc::mma_commit_elect(&tfull[acc]);
-        if (dbg_on && lane == 0) prm.dbg[(tile / gridDim.x) * 8 + 4] = clock64();
+        if (dbg_on && lane == 0) prm.dbg[(tile / t_step) * 8 + 4] = clock64();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -292,14 +314,14 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
     for (int i = 0; i < kRS; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (unsigned tile = blockIdx.x; tile < (unsigned)ntiles; tile += gridDim.x) {
+    for (unsigned tile = t_first; tile < t_end; tile += t_step) {
       const int jt = (int)(tile % (unsigned)nj);
-      const unsigned pt = tile / (unsigned)nj;
+      const unsigned pt = prm.mcast ? 2 * (tile / (unsigned)nj) + crank : tile / (unsigned)nj;
       const int tw = (int)(pt % (unsigned)tiles_w);
       const unsigned r = pt / (unsigned)tiles_w;
       const int th = (int)(r % (unsigned)tiles_h), n = (int)(r / (unsigned)tiles_h);
       const int h = th * kTH + (row >> 3), w = tw * kTW + (row & 7);
-      const bool valid = h < prm.H && w < prm.W;
+      const bool valid = h < prm.H && w < prm.W && pt < npt;
       const long long pix = ((long long)n * prm.H + h) * prm.W + w;
       __half* yrow = prm.y + pix * prm.ldy + jt * JT;
       const __half* mrow = (kMaskAcc && prm.mask != nullptr) ? prm.mask + pix * prm.ldmask + jt * JT : nullptr;
@@ -332,8 +354,8 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
       }
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::fence_after_sync();
-      const bool dbg_e = prm.dbg && blockIdx.x == 0 && tile / gridDim.x < 64 && threadIdx.x == 64;
-      if (dbg_e) prm.dbg[(tile / gridDim.x) * 8 + 5] = clock64();
+      const bool dbg_e = prm.dbg && blockIdx.x == 0 && tile / t_step < 64 && threadIdx.x == 64;
+      if (dbg_e) prm.dbg[(tile / t_step) * 8 + 5] = clock64();
       if (has_cols) {
 #pragma unroll 2
         for (int cc = 0; cc < ccols; cc += 16) {
@@ -451,7 +473,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
           }
         }
       }
-      if (dbg_e) prm.dbg[(tile / gridDim.x) * 8 + 6] = clock64();
+      if (dbg_e) prm.dbg[(tile / t_step) * 8 + 6] = clock64();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty[acc]);
@@ -492,6 +514,7 @@ __global__ void __launch_bounds__(kThreads3, 1) tc_conv3_kernel(const __grid_con
       if (s != 0.f) atomicAdd(&prm.colsum[i], s);
     }
   }
+  if (prm.mcast) tc::cluster_sync();          // the peer may still be arriving on this CTA's barriers
   if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
 }
 
@@ -537,6 +560,8 @@ CUtensorMapSwizzle swz3(int ks) {
 long long* g_b2u_dbg = nullptr;   // device timeline buffer (b2u_set_option("tc_debug", 1))
 int g_b2u_tc_2sm_max_j = 64;  // largest N tile that runs two CTAs per SM
 int g_b2u_tc_3sm = 0;         // 1: three CTAs per SM for the low-register variants of thin layers (untested)
+int g_b2u_tc_mcast = 0;      // streamed weights: clusters of two CTAs sharing every weight tile by TMA multicast
+int g_b2u_tc_max_ctas = 0;   // probe only: cap on the number of CTAs (0 = one or two per SM)
 int g_b2u_tc_bgroup = 3;      // streamed weights: 3 = ring slots of one filter row for N <= 128 tiles, 1 = one tile per slot
 int g_b2u_tc_halo = 1;       // 0: per-tap loads (conv_tc.cu), 1: halo box, 2: halo box + base_offset, 3: three boxes
 
@@ -659,11 +684,38 @@ int b2u_tc_conv3x3_halo(const void* x, int ldx, int K, const float* w, int dgrad
   // per SM (two issuers) when shared memory and TMEM (2*JT columns each) allow it
   int ctas = B2U_NUM_SMS;
   if (two_per_sm && tiles >= 2 * per_sm * B2U_NUM_SMS) ctas = per_sm * B2U_NUM_SMS;
+  if (g_b2u_tc_max_ctas > 0 && ctas > g_b2u_tc_max_ctas) ctas = g_b2u_tc_max_ctas;   // probe: fewer CTAs than SMs
   int grid = (int)(tiles < ctas ? tiles : ctas);
+  // streamed weights: CTA pairs sharing every weight tile (C3Params::mcast) when there are at least two pixel tiles
+  const long long npt = (long long)n * b2u_cdiv(h, kTH) * b2u_cdiv(wd, kTW);
+  p.mcast = (g_b2u_tc_mcast && !p.bres && !two_per_sm && npt >= 2 && p.dbg == nullptr) ? 1 : 0;
+  if (p.mcast) {
+    const long long nsuper = ((npt + 1) / 2) * (J / p.JT);
+    long long clusters = ctas / 2;
+    if (clusters > nsuper) clusters = nsuper;
+    grid = (int)(2 * clusters);
+  }
   const int flags = ((mask != nullptr || accumulate) ? kF_MASKACC : 0) | ((stats != nullptr || colsum != nullptr) ? kF_SUMS : 0) |
                     (p.bits_out != nullptr ? kF_BITS_OUT : 0) | (p.bits_in != nullptr ? kF_BITS_IN : 0) |
                     (post_scale != nullptr ? kF_POST : 0);
   const int nthr = 64 + 32 * p.epi_warps;
+  if (p.mcast) {
+    switch (flags) {
+      case 0: B2U_LAUNCH_CLUSTER(tc_conv3_kernel<0>, grid, nthr, smem, stream, 2, maps, p); break;
+      case 1: B2U_LAUNCH_CLUSTER(tc_conv3_kernel<1>, grid, nthr, smem, stream, 2, maps, p); break;
+      case 2: B2U_LAUNCH_CLUSTER(tc_conv3_kernel<2>, grid, nthr, smem, stream, 2, maps, p); break;
+      case 3: B2U_LAUNCH_CLUSTER(tc_conv3_kernel<3>, grid, nthr, smem, stream, 2, maps, p); break;
+      case 4: B2U_LAUNCH_CLUSTER(tc_conv3_kernel<4>, grid, nthr, smem, stream, 2, maps, p); break;
+      case 6: B2U_LAUNCH_CLUSTER(tc_conv3_kernel<6>, grid, nthr, smem, stream, 2, maps, p); break;
+      case 8: B2U_LAUNCH_CLUSTER(tc_conv3_kernel<8>, grid, nthr, smem, stream, 2, maps, p); break;
+      case 10: B2U_LAUNCH_CLUSTER(tc_conv3_kernel<10>, grid, nthr, smem, stream, 2, maps, p); break;
+      case 16: B2U_LAUNCH_CLUSTER(tc_conv3_kernel<16>, grid, nthr, smem, stream, 2, maps, p); break;
+      default:
+        b2u_set_error("tc_conv3: unsupported feature combination %d", flags);
+        return B2U_ERR_ARG;
+    }
+    return B2U_OK;
+  }
   switch (flags) {
     case 0: B2U_LAUNCH(tc_conv3_kernel<0>, grid, nthr, smem, stream, maps, p); break;
     case 1: B2U_LAUNCH(tc_conv3_kernel<1>, grid, nthr, smem, stream, maps, p); break;

@@ -25,6 +25,8 @@ int b2u_tc_convt_ok(int cin, int cout, int ld_small, int ld_big);
 int b2u_tc_convt_wgrad_ok(int cin, int cout, int ldx, int lddy);
 extern int g_b2u_tc_halo;
 extern int g_b2u_tc_bgroup;
+extern int g_b2u_tc_max_ctas;
+extern int g_b2u_tc_mcast;
 extern int g_b2u_wgrad_halo;
 extern int g_b2u_wgrad_dhm;
 extern int g_b2u_convt_jt;

@@ -36,6 +36,37 @@ static inline cudaError_t b2u_launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// the same with thread-block clusters of `cluster_x` CTAs along x (grid.x must be a multiple of it)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t b2u_launch_cluster_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                                cudaStream_t stream, int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster_x;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_b2u_pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+#define B2U_LAUNCH_CLUSTER(kern, grid, block, smem, stream, cluster_x, ...)                          \
+  do {                                                                                               \
+    auto _kfn = kern;                                                                                \
+    cudaError_t _le = b2u_launch_cluster_ex(_kfn, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), \
+                                            (cluster_x), __VA_ARGS__);                               \
+    __atomic_fetch_add(&g_b2u_launches, 1ULL, __ATOMIC_RELAXED);                                     \
+    B2U_CHECK_CUDA(_le);                                                                             \
+    B2U_LAUNCH_CHECK();                                                                              \
+  } while (0)
+
 #define B2U_LAUNCH(kern, grid, block, smem, stream, ...)                                             \
   do {                                                                                               \
     auto _kfn = kern;                                                                                \

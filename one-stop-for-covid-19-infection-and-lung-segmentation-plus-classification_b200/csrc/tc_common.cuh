@@ -67,6 +67,28 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// multicast: the box lands at the same shared-memory offset of every CTA of the cluster whose bit is set in `cta_mask`, and
+// completes `bytes` on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_3d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                  uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "h"(cta_mask)
+      : "memory");
+}
+// ---- thread-block clusters --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {      // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- TMEM ----------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // whole warp, ncols pow2 >= 32
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
@@ -122,6 +144,14 @@ __device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
       "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}"
       ::"r"(smem_u32(bar))
+      : "memory");
+}
+// the same arrive, delivered to the mbarrier at this offset in every CTA of the cluster selected by `cta_mask`
+__device__ __forceinline__ void mma_commit_mcast_elect(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
       : "memory");
 }
 // arrives on the mbarrier once all previously issued MMAs of this thread have completed

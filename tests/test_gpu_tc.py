@@ -363,6 +363,33 @@ def _relu_bits_roundtrip(n, h, w, cin, cout):
         compare(ops, img, dt, tol=1e-6)
 
 
+# ---- streamed weights shared by CTA pairs (TMA multicast inside clusters of two, b2u_set_option("tc_mcast", 1)) -------------
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 32, 32, 256, 512), (1, 14, 14, 256, 512), (1, 16, 16, 512, 256), (2, 24, 40, 128, 128),
+                                            (3, 16, 8, 256, 256), (1, 16, 8, 256, 256), (4, 128, 128, 128, 128), (5, 40, 24, 192, 128)])
+def test_tc_conv3x3_streamed_weights_multicast_pairs(n, h, w, cin, cout):
+    """wide layers stream their filter bank through shared memory; with tc_mcast the kernel runs as clusters of two CTAs that
+    work on the same N tile for two pixel tiles and load every weight tile once for the pair.  Same results as the
+    single-CTA schedule: forward with BN statistics, data gradient with mask + column sums; odd pixel-tile counts (a dummy
+    tile in the last pair), a single pixel tile (falls back), several N tiles, ring slots of one and of three tiles"""
+    lib = importlib.import_module(PKG + "._lib").lib()
+    old = lib.b2u_set_option(b"tc_mcast", 1)
+    try:
+        img = Img(141)
+        x = img.view(n, h, w, cin, dt, fill="uniform")
+        y = img.view(n, h, w, cout, dt, ld=cout + 16, c0=8, fill=None)
+        wt = img.farr(img.par, 9 * cin * cout, scale=(2.0 / (9 * cin)) ** 0.5)
+        b = img.farr(img.par, cout, scale=0.1)
+        stats = img.zero.alloc(2 * cout * 8)
+        dy = img.view(n, h, w, cout, dt, scale=0.5)
+        dx = img.view(n, h, w, cin, dt, fill=None)
+        db = img.farr(img.gr, cin, scale=0.01)
+        ops = [P.Op(P.OP_CONV3X3_FWD, dt, [x.ref, wt, b, y.ref, stats], [x.ld, cin, 1, y.ld, cout, n, h, w]),
+               P.Op(P.OP_CONV3X3_DGRAD, dt, [dy.ref, wt, dx.ref, x.ref, db], [dy.ld, cout, dx.ld, cin, x.ld, 1, 0, n, h, w])]
+        compare(ops, img, dt, tol=4e-3)
+    finally:
+        lib.b2u_set_option(b"tc_mcast", old)
+
+
 # ---- dw-merged thin-layer kernel (conv_tc3w.cu, b2u_set_option("tc_dwmerge", 1))
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 32, 32, 32), (1, 24, 40, 64, 32), (1, 16, 30, 64, 64), (1, 56, 56, 16, 16),
                                             (1, 8, 14, 32, 48), (2, 64, 64, 32, 64), (4, 128, 128, 32, 32)])
