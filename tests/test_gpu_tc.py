@@ -366,13 +366,14 @@ def _relu_bits_roundtrip(n, h, w, cin, cout):
 # ---- streamed weights shared by CTA pairs (TMA multicast inside clusters of two, b2u_set_option("tc_mcast", 1)) -------------
 @pytest.mark.parametrize("n,h,w,cin,cout", [(1, 32, 32, 256, 512), (1, 14, 14, 256, 512), (1, 16, 16, 512, 256), (2, 24, 40, 128, 128),
                                             (3, 16, 8, 256, 256), (1, 16, 8, 256, 256), (4, 128, 128, 128, 128), (5, 40, 24, 192, 128)])
-def test_tc_conv3x3_streamed_weights_multicast_pairs(n, h, w, cin, cout):
+@pytest.mark.parametrize("cs", [2, 8])
+def test_tc_conv3x3_streamed_weights_multicast_pairs(n, h, w, cin, cout, cs):
     """wide layers stream their filter bank through shared memory; with tc_mcast the kernel runs as clusters of two CTAs that
     work on the same N tile for two pixel tiles and load every weight tile once for the pair.  Same results as the
     single-CTA schedule: forward with BN statistics, data gradient with mask + column sums; odd pixel-tile counts (a dummy
     tile in the last pair), a single pixel tile (falls back), several N tiles, ring slots of one and of three tiles"""
     lib = importlib.import_module(PKG + "._lib").lib()
-    old = lib.b2u_set_option(b"tc_mcast", 1)
+    old = lib.b2u_set_option(b"tc_mcast", cs)
     try:
         img = Img(141)
         x = img.view(n, h, w, cin, dt, fill="uniform")
