@@ -105,6 +105,11 @@ extern "C" int b2u_set_option(const char* name, int value) {
     g_b2u_comm_overlap = value ? 1 : 0;
     return old;
   }
+  if (strcmp(name, "bn_async") == 0) {
+    int old = g_b2u_bn_async;
+    g_b2u_bn_async = value;
+    return old;
+  }
   if (strcmp(name, "tc_mcast") == 0) {
     int old = g_b2u_tc_mcast;
     g_b2u_tc_mcast = value;

@@ -397,6 +397,158 @@ __global__ void __launch_bounds__(kThreads, kTwo ? 2 : 4) bn_bwd_apply_kernel(
   }
 }
 
+// The plain fp16 case (decoder BatchNorms: no mask, no column sums, one tensor) with the loads decoupled from the
+// registers: every thread keeps kAD (dy, x) pairs of 16-byte cp.async copies in flight into its own shared-memory slots
+// (4 blocks x 256 threads x kAD x 32 B = 128 KB of loads in flight per SM against 32 KB of the register version, which
+// ran at 5.4 TB/s); a thread only ever reads the slots it filled itself, so cp.async.wait_group is all the
+// synchronisation there is.
+constexpr int kAD = 4;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+// BN apply, same scheme (one 16-byte copy per pixel group in flight kAD deep); channels [split, C) from a second tensor
+__global__ void __launch_bounds__(kThreads, 4) bn_apply_async_kernel(const __half* __restrict__ x, int ldx,
+                                                                     __half* __restrict__ y, int ldy, int C, long long npix,
+                                                                     const float* __restrict__ scale,
+                                                                     const float* __restrict__ shift,
+                                                                     const __half* __restrict__ x2, int ldx2, int split) {
+  B2U_PDL_PROLOGUE();
+  extern __shared__ __align__(16) uint4 ring[];            // [kAD][kThreads]
+  const int cg = C >> 3;
+  const int lanes = kThreads / cg;
+  const int g = threadIdx.x % cg, lane_ = threadIdx.x / cg;
+  if (lane_ >= lanes) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sc[k] = scale[g * 8 + k]; sh[k] = shift[g * 8 + k]; }
+  const __half* src = g * 8 < split ? x + g * 8 : x2 + (g * 8 - split);
+  const long long lds = g * 8 < split ? ldx : ldx2;
+  const long long stride = (long long)gridDim.x * lanes;
+  uint4* my = ring + threadIdx.x;
+  long long pl = (long long)blockIdx.x * lanes + lane_;
+#pragma unroll
+  for (int d = 0; d < kAD; ++d) {
+    if (pl < npix) cp_async16(my + d * kThreads, src + pl * lds);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pl += stride;
+  }
+  int slot = 0;
+  for (long long p = (long long)blockIdx.x * lanes + lane_; p < npix; p += stride) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kAD - 1) : "memory");
+    const uint4 ux = my[slot * kThreads];
+    if (pl < npix) cp_async16(my + slot * kThreads, src + pl * lds);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pl += stride;
+    float v[8];
+    unpack8h(ux, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+    store8<__half>(y + p * ldy + g * 8, v);
+    if (++slot == kAD) slot = 0;
+  }
+}
+
+// kColsum / mask_act: the encoder BatchNorms -- column sums of the gradient written (bias gradient of the producing conv) and
+// its activation derivative taken from x itself (mask == x).
+template <bool kColsum>
+__global__ void __launch_bounds__(kThreads, kColsum ? 3 : 4) bn_bwd_apply_async_kernel(
+    const __half* __restrict__ dy, int lddy, const __half* __restrict__ x, int ldx, __half* __restrict__ dx, int lddx, int C,
+    long long npix, long long count, const float* __restrict__ gamma, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const double* __restrict__ sums, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, int mask_act, float* __restrict__ colsum, const __half* __restrict__ x2, int ldx2,
+    __half* __restrict__ dx2, int lddx2, int split) {
+  // (x2, dx2, split): channels [split, C) of the BN input / its gradient live in a second tensor (split concatenate)
+  B2U_PDL_PROLOGUE();
+  extern __shared__ __align__(16) uint4 ring[];            // [kAD][2][kThreads], then [C] floats of column-sum partials
+  float* scs = reinterpret_cast<float*>(ring + kAD * 2 * kThreads);
+  float cs[kColsum ? 8 : 1];
+#pragma unroll
+  for (int k = 0; k < (kColsum ? 8 : 1); ++k) cs[k] = 0.f;
+  if (kColsum) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) scs[i] = 0.f;
+    __syncthreads();
+  }
+  const float inv_n = 1.f / (float)count;
+  if (blockIdx.x == 0 && dgamma != nullptr) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dbeta[c] += (float)sums[c];
+      dgamma[c] += (float)sums[C + c];
+    }
+  }
+  float ca[8], cb[8], cc[8];
+  {
+    const int g0 = (threadIdx.x % (C >> 3)) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = g0 + k;
+      const float is = invstd[c], mu = mean[c];
+      const float s1 = (float)(sums[c] * (double)inv_n), s2 = (float)(sums[C + c] * (double)inv_n);
+      const float a = gamma[c] * is;
+      ca[k] = a;
+      cb[k] = -a * is * s2;
+      cc[k] = -a * s1 + a * is * mu * s2;
+    }
+  }
+  const int cg = C >> 3;
+  const int lanes = kThreads / cg;
+  const int g = threadIdx.x % cg, lane_ = threadIdx.x / cg;
+  if (lane_ < lanes) {
+  const long long stride = (long long)gridDim.x * lanes;
+  uint4* my = ring + threadIdx.x;
+  const bool first = g * 8 < split;
+  const __half* xs = first ? x + g * 8 : x2 + (g * 8 - split);       // this thread's channel group: source / destination
+  __half* ds = first ? dx + g * 8 : dx2 + (g * 8 - split);
+  const long long lxs = first ? ldx : ldx2, lds = first ? lddx : lddx2;
+  long long pl = (long long)blockIdx.x * lanes + lane_;     // next pixel to load
+#pragma unroll
+  for (int d = 0; d < kAD; ++d) {
+    if (pl < npix) {
+      cp_async16(my + (d * 2 + 0) * kThreads, dy + pl * lddy + g * 8);
+      cp_async16(my + (d * 2 + 1) * kThreads, xs + pl * lxs);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pl += stride;
+  }
+  int slot = 0;
+  for (long long p = (long long)blockIdx.x * lanes + lane_; p < npix; p += stride) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kAD - 1) : "memory");
+    const uint4 ud = my[(slot * 2 + 0) * kThreads], ux = my[(slot * 2 + 1) * kThreads];
+    if (pl < npix) {                                        // refill the slot just read
+      cp_async16(my + (slot * 2 + 0) * kThreads, dy + pl * lddy + g * 8);
+      cp_async16(my + (slot * 2 + 1) * kThreads, xs + pl * lxs);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pl += stride;
+    float d[8], xv[8], o[8];
+    unpack8h(ud, d);
+    unpack8h(ux, xv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(ca[k], d[k], fmaf(cb[k], xv[k], cc[k]));
+    if (mask_act != B2U_ACT_NONE) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] *= act_bwd_from_y(xv[k], mask_act);
+    }
+    store8<__half>(ds + p * lds, o);
+    if (kColsum) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[kColsum ? k : 0] += o[k];
+    }
+    if (++slot == kAD) slot = 0;
+  }
+  }
+  if (kColsum) {
+    if (lane_ < lanes) {
+      float c8[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c8[k] = cs[kColsum ? k : 0];
+      group_add8(scs, c8, cg, g);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&colsum[i], scs[i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // 2x2 max-pool (+ optional dropout on the pooled output)
 // ------------------------------------------------------------------------------------------
@@ -1183,6 +1335,8 @@ __global__ void bce_sigmoid_bwd_kernel(const float* __restrict__ prob, const flo
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+int g_b2u_bn_async = 1;     // 1: cp.async versions of the fp16 BatchNorm apply / backward apply kernels
+
 extern "C" int b2u_state_advance(b2u_step_state* d_state, void* stream) {
   B2U_LAUNCH(state_advance_kernel, 1, 1, 0, stream, d_state);
   return B2U_OK;
@@ -1245,6 +1399,11 @@ int b2u_bn_apply_split(int dt, const void* x, int ldx, const void* x2, int ldx2,
               "bn_apply: dropout needs the keep mask, 0 <= p < 1 and a single source");
   int grid = lane_grid(npix, c, out_stats != nullptr ? 4 : 8);
   size_t smem = out_stats != nullptr ? 2 * (size_t)c * sizeof(float) : 0;
+  if (dt == B2U_F16 && g_b2u_bn_async && out_stats == nullptr && p_drop == 0.f) {          // the cp.async version
+    B2U_LAUNCH(bn_apply_async_kernel, grid, kThreads, (size_t)kAD * kThreads * sizeof(uint4), stream, (const __half*)x, ldx,
+               (__half*)y, ldy, c, npix, scale, shift, (const __half*)x2, ldx2, split);
+    return B2U_OK;
+  }
   DISPATCH_T(dt, B2U_LAUNCH(bn_apply_kernel<T>, grid, kThreads, smem, stream, (const T*)x, ldx, (T*)y, ldy, c, npix,
                             scale, shift, out_stats, out_sq_off, (const T*)x2, ldx2, split, (const uint8_t*)drop_bits,
                             p_drop));
@@ -1341,6 +1500,22 @@ int b2u_bn_bwd_apply_cs(int dt, const void* dy, int lddy, const void* x, int ldx
   B2U_REQUIRE(p_drop == 0.f || (drop_bits != nullptr && p_drop > 0.f && p_drop < 1.f && split == c),
               "bn_bwd_apply: dropout needs the keep mask, 0 <= p < 1 and a single tensor");
   int grid = lane_grid(npix, c);
+  // fp16, one tensor, no dropout, activation mask (if any) = the BN input itself: the cp.async version
+  if (dt == B2U_F16 && g_b2u_bn_async && p_drop == 0.f && aligned16(dy) && aligned16(x) && aligned16(dx) &&
+      (mask == nullptr || (mask == x && ldmask == ldx && split == c))) {
+    const size_t ring_bytes = (size_t)kAD * 2 * kThreads * sizeof(uint4);
+    const int ma = mask != nullptr ? mask_act : B2U_ACT_NONE;
+    if (colsum != nullptr) {
+      B2U_LAUNCH(bn_bwd_apply_async_kernel<true>, grid, kThreads, ring_bytes + c * sizeof(float), stream, (const __half*)dy,
+                 lddy, (const __half*)x, ldx, (__half*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums, dgamma,
+                 dbeta, ma, colsum, (const __half*)x2, ldx2, (__half*)dx2, lddx2, split);
+    } else {
+      B2U_LAUNCH(bn_bwd_apply_async_kernel<false>, grid, kThreads, ring_bytes, stream, (const __half*)dy, lddy,
+                 (const __half*)x, ldx, (__half*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums, dgamma, dbeta, ma,
+                 colsum, (const __half*)x2, ldx2, (__half*)dx2, lddx2, split);
+    }
+    return B2U_OK;
+  }
   if (colsum != nullptr) {
     DISPATCH_T(dt, B2U_LAUNCH((bn_bwd_apply_kernel<T, true, true>), grid, kThreads, c * sizeof(float), stream, (const T*)dy,
                               lddy, (const T*)x, ldx, (T*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums,

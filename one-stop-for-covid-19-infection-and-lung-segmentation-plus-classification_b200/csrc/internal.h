@@ -27,6 +27,7 @@ extern int g_b2u_tc_halo;
 extern int g_b2u_tc_bgroup;
 extern int g_b2u_tc_max_ctas;
 extern int g_b2u_tc_mcast;
+extern int g_b2u_bn_async;
 extern int g_b2u_wgrad_halo;
 extern int g_b2u_wgrad_dhm;
 extern int g_b2u_convt_jt;

@@ -12,7 +12,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from gpu_harness import LIB, P  # noqa: E402
 
 lib = LIB.lib()
-n, h, w, c = 8, 512, 512, 32
+for f in sys.argv[1:]:                            # opt:name=value -> b2u_set_option
+    if f.startswith("opt:"):
+        lib.b2u_set_option(f[4:].split("=")[0].encode(), int(f.split("=")[1]))
+n, h, w, c = 8, 512, 512, int(os.environ.get("PROBE_C", "32"))
 npix = n * h * w
 dt = P.F16
 ws = torch.empty(int(lib.b2u_ws_bytes()), dtype=torch.uint8, device="cuda")
