@@ -412,7 +412,9 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_async_kernel(const __hal
                                                                      __half* __restrict__ y, int ldy, int C, long long npix,
                                                                      const float* __restrict__ scale,
                                                                      const float* __restrict__ shift,
-                                                                     const __half* __restrict__ x2, int ldx2, int split) {
+                                                                     const __half* __restrict__ x2, int ldx2, int split,
+                                                                     const uint8_t* __restrict__ drop_bits, float p_drop) {
+  // (drop_bits, p_drop): the input is dropout(x) of an unmaterialised Dropout layer (keep bits stored by the statistics pass)
   B2U_PDL_PROLOGUE();
   extern __shared__ __align__(16) uint4 ring[];            // [kAD][kThreads]
   const int cg = C >> 3;
@@ -424,6 +426,7 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_async_kernel(const __hal
   for (int k = 0; k < 8; ++k) { sc[k] = scale[g * 8 + k]; sh[k] = shift[g * 8 + k]; }
   const __half* src = g * 8 < split ? x + g * 8 : x2 + (g * 8 - split);
   const long long lds = g * 8 < split ? ldx : ldx2;
+  const float dsc = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   const long long stride = (long long)gridDim.x * lanes;
   uint4* my = ring + threadIdx.x;
   long long pl = (long long)blockIdx.x * lanes + lane_;
@@ -442,6 +445,12 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_async_kernel(const __hal
     pl += stride;
     float v[8];
     unpack8h(ux, v);
+    if (p_drop > 0.f) {
+      float f[8];
+      bits_factors(drop_bits[((uint64_t)p * C + g * 8) >> 3], dsc, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= f[k];
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
     store8<__half>(y + p * ldy + g * 8, v);
@@ -457,8 +466,9 @@ __global__ void __launch_bounds__(kThreads, kColsum ? 3 : 4) bn_bwd_apply_async_
     long long npix, long long count, const float* __restrict__ gamma, const float* __restrict__ mean,
     const float* __restrict__ invstd, const double* __restrict__ sums, float* __restrict__ dgamma,
     float* __restrict__ dbeta, int mask_act, float* __restrict__ colsum, const __half* __restrict__ x2, int ldx2,
-    __half* __restrict__ dx2, int lddx2, int split) {
+    __half* __restrict__ dx2, int lddx2, int split, const uint8_t* __restrict__ drop_bits, float p_drop) {
   // (x2, dx2, split): channels [split, C) of the BN input / its gradient live in a second tensor (split concatenate)
+  // (drop_bits, p_drop): the BN input is dropout(x) of an unmaterialised Dropout layer (see bn_bwd_apply_kernel)
   B2U_PDL_PROLOGUE();
   extern __shared__ __align__(16) uint4 ring[];            // [kAD][2][kThreads], then [C] floats of column-sum partials
   float* scs = reinterpret_cast<float*>(ring + kAD * 2 * kThreads);
@@ -500,6 +510,7 @@ __global__ void __launch_bounds__(kThreads, kColsum ? 3 : 4) bn_bwd_apply_async_
   const __half* xs = first ? x + g * 8 : x2 + (g * 8 - split);       // this thread's channel group: source / destination
   __half* ds = first ? dx + g * 8 : dx2 + (g * 8 - split);
   const long long lxs = first ? ldx : ldx2, lds = first ? lddx : lddx2;
+  const float dsc = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   long long pl = (long long)blockIdx.x * lanes + lane_;     // next pixel to load
 #pragma unroll
   for (int d = 0; d < kAD; ++d) {
@@ -523,8 +534,15 @@ __global__ void __launch_bounds__(kThreads, kColsum ? 3 : 4) bn_bwd_apply_async_
     float d[8], xv[8], o[8];
     unpack8h(ud, d);
     unpack8h(ux, xv);
+    if (p_drop > 0.f) {
+      float f[8];
+      bits_factors(drop_bits[((uint64_t)p * C + g * 8) >> 3], dsc, f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = fmaf(ca[k], d[k], fmaf(cb[k], xv[k], cc[k]));
+      for (int k = 0; k < 8; ++k) o[k] = f[k] * fmaf(ca[k], d[k], fmaf(cb[k], xv[k] * f[k], cc[k]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(ca[k], d[k], fmaf(cb[k], xv[k], cc[k]));
+    }
     if (mask_act != B2U_ACT_NONE) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] *= act_bwd_from_y(xv[k], mask_act);
@@ -631,6 +649,103 @@ __global__ void __launch_bounds__(kThreads) bn_apply_pool_kernel(const T* __rest
     if (threadIdx.x / (C >> 3) < kThreads / (C >> 3)) {
       group_add8(sst, o1, C >> 3, threadIdx.x % (C >> 3));
       group_add8(sst + C, o2, C >> 3, threadIdx.x % (C >> 3));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      atomicAdd(&out_stats[i], (double)sst[i]);
+      atomicAdd(&out_stats[out_sq_off + i], (double)sst[C + i]);
+    }
+  }
+}
+
+// fp16 cp.async version (see bn_bwd_apply_async_kernel): the four window loads of kPD output pixels in flight per thread
+constexpr int kPD = 4;
+__global__ void __launch_bounds__(kThreads, 2) bn_apply_pool_async_kernel(
+    const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int C, int N, int H, int W,
+    const float* __restrict__ scale, const float* __restrict__ shift, double* __restrict__ out_stats, int out_sq_off,
+    __half* __restrict__ yp, int ldp, float p_drop, int op_id, const b2u_step_state* __restrict__ st) {
+  B2U_PDL_PROLOGUE();
+  extern __shared__ __align__(16) uint4 ring[];            // [kPD][4][kThreads], then [2*C] floats of statistics partials
+  float* sst = reinterpret_cast<float*>(ring + kPD * 4 * kThreads);
+  float o1[8], o2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { o1[k] = 0.f; o2[k] = 0.f; }
+  if (out_stats != nullptr) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sst[i] = 0.f;
+    __syncthreads();
+  }
+  const int cg = C >> 3;
+  const int lanes = kThreads / cg;
+  const int g = threadIdx.x % cg, lane_ = threadIdx.x / cg;
+  if (lane_ < lanes) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = scale[g * 8 + k]; sh[k] = shift[g * 8 + k]; }
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long long nopix = (long long)N * Ho * Wo;
+    const long long stride = (long long)gridDim.x * lanes;
+    uint4* my = ring + threadIdx.x;
+    auto in_pix = [&](long long op) {                      // first input pixel of output pixel op's window
+      const unsigned opu = (unsigned)op;
+      const int wo = (int)(opu % (unsigned)Wo);
+      const unsigned t = opu / (unsigned)Wo;
+      const int ho = (int)(t % (unsigned)Ho);
+      const int n = (int)(t / (unsigned)Ho);
+      return ((long long)n * H + 2 * ho) * W + 2 * wo;
+    };
+    auto issue = [&](int slot, long long op) {
+      const long long ip = in_pix(op);
+      const __half* b = x + ip * ldx + g * 8;
+      cp_async16(my + (slot * 4 + 0) * kThreads, b);
+      cp_async16(my + (slot * 4 + 1) * kThreads, b + ldx);
+      cp_async16(my + (slot * 4 + 2) * kThreads, b + (long long)W * ldx);
+      cp_async16(my + (slot * 4 + 3) * kThreads, b + (long long)W * ldx + ldx);
+    };
+    long long pl = (long long)blockIdx.x * lanes + lane_;
+#pragma unroll
+    for (int d = 0; d < kPD; ++d) {
+      if (pl < nopix) issue(d, pl);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      pl += stride;
+    }
+    int slot = 0;
+    for (long long p = (long long)blockIdx.x * lanes + lane_; p < nopix; p += stride) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kPD - 1) : "memory");
+      uint4 u[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) u[q] = my[(slot * 4 + q) * kThreads];
+      if (pl < nopix) issue(slot, pl);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      pl += stride;
+      const long long ip = in_pix(p);
+      float m[8];
+#pragma unroll
+      for (int pos = 0; pos < 4; ++pos) {
+        float v[8];
+        unpack8h(u[pos], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v[k] = round_to<__half>(fmaf(v[k], sc[k], sh[k]));        // the value as stored
+          m[k] = pos == 0 ? v[k] : fmaxf(m[k], v[k]);
+          o1[k] += v[k];
+          o2[k] = fmaf(v[k], v[k], o2[k]);
+        }
+        store8<__half>(y + (ip + (pos >> 1) * (long long)W + (pos & 1)) * ldy + g * 8, v);
+      }
+      if (p_drop > 0.f) {
+        float f[8];
+        keep_factors(p_drop, (uint64_t)p * C + g * 8, st, op_id, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] *= f[k];
+      }
+      store8<__half>(yp + p * ldp + g * 8, m);
+      if (++slot == kPD) slot = 0;
+    }
+  }
+  if (out_stats != nullptr) {
+    if (lane_ < lanes) {
+      group_add8(sst, o1, cg, g);
+      group_add8(sst + C, o2, cg, g);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -776,6 +891,143 @@ __global__ void __launch_bounds__(kThreads, 2) maxpool_bwd_kernel(const T* __res
       }
       group_add8(sbn, t1, C >> 3, threadIdx.x % (C >> 3));
       group_add8(sbn + C, t2, C >> 3, threadIdx.x % (C >> 3));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&bn_sums[i], (double)sbn[i]);
+  }
+}
+
+// fp16 cp.async version: the nine 16-byte loads of an output pixel (four window values, the pooled gradient, the four
+// gradients accumulated into) for kMD output pixels in flight per thread
+constexpr int kMD = 2;
+__global__ void __launch_bounds__(kThreads, 2) maxpool_bwd_async_kernel(
+    const __half* __restrict__ x, int ldx, const __half* __restrict__ dy, int lddy, __half* __restrict__ dx, int lddx, int C,
+    int N, int H, int W, float p_drop, int op_id, const b2u_step_state* __restrict__ st, int accumulate,
+    double* __restrict__ bn_sums, const float* __restrict__ bn_gamma, const float* __restrict__ bn_beta) {
+  B2U_PDL_PROLOGUE();
+  extern __shared__ __align__(16) uint4 ring[];            // [kMD][9][kThreads], then [2*C] floats of BN-statistics partials
+  float* sbn = reinterpret_cast<float*>(ring + kMD * 9 * kThreads);
+  float t1[8], t2[8], bt[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { t1[k] = 0.f; t2[k] = 0.f; bt[k] = 0.f; }
+  const int cg = C >> 3;
+  const int lanes = kThreads / cg;
+  const int g = threadIdx.x % cg, lane_ = threadIdx.x / cg;
+  if (bn_sums != nullptr) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sbn[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bt[k] = bn_beta[g * 8 + k];
+    __syncthreads();
+  }
+  if (lane_ < lanes) {
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long long nopix = (long long)N * Ho * Wo;
+    const long long stride = (long long)gridDim.x * lanes;
+    uint4* my = ring + threadIdx.x;
+    auto in_pix = [&](long long op) {
+      const unsigned opu = (unsigned)op;
+      const int wo = (int)(opu % (unsigned)Wo);
+      const unsigned t = opu / (unsigned)Wo;
+      const int ho = (int)(t % (unsigned)Ho);
+      const int n = (int)(t / (unsigned)Ho);
+      return ((long long)n * H + 2 * ho) * W + 2 * wo;
+    };
+    auto issue = [&](int slot, long long op) {
+      const long long ip = in_pix(op);
+      const __half* b = x + ip * ldx + g * 8;
+      uint4* s0 = my + (slot * 9) * kThreads;
+      cp_async16(s0 + 0 * kThreads, b);
+      cp_async16(s0 + 1 * kThreads, b + ldx);
+      cp_async16(s0 + 2 * kThreads, b + (long long)W * ldx);
+      cp_async16(s0 + 3 * kThreads, b + (long long)W * ldx + ldx);
+      cp_async16(s0 + 4 * kThreads, dy + op * lddy + g * 8);
+      if (accumulate) {
+        const __half* e = dx + ip * lddx + g * 8;
+        cp_async16(s0 + 5 * kThreads, e);
+        cp_async16(s0 + 6 * kThreads, e + lddx);
+        cp_async16(s0 + 7 * kThreads, e + (long long)W * lddx);
+        cp_async16(s0 + 8 * kThreads, e + (long long)W * lddx + lddx);
+      }
+    };
+    long long pl = (long long)blockIdx.x * lanes + lane_;
+#pragma unroll
+    for (int d = 0; d < kMD; ++d) {
+      if (pl < nopix) issue(d, pl);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      pl += stride;
+    }
+    int slot = 0;
+    for (long long p = (long long)blockIdx.x * lanes + lane_; p < nopix; p += stride) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kMD - 1) : "memory");
+      uint4 xw[4], ew[4], gp;
+      const uint4* s0 = my + (slot * 9) * kThreads;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) xw[q] = s0[q * kThreads];
+      gp = s0[4 * kThreads];
+      if (accumulate) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ew[q] = s0[(5 + q) * kThreads];
+      }
+      if (pl < nopix) issue(slot, pl);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      pl += stride;
+      const long long ip = in_pix(p);
+      __half* ob_ = dx + ip * lddx + g * 8;
+      float gy[8];
+      unpack8h(gp, gy);
+      if (p_drop > 0.f) {
+        float f[8];
+        keep_factors(p_drop, (uint64_t)p * C + g * 8, st, op_id, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gy[k] *= f[k];
+      }
+      // first maximum in window order (0,0),(0,1),(1,0),(1,1) takes the gradient (TF/torch tie rule)
+      int sel[8];
+      {
+        float a[8], b[8], m[8];
+        unpack8h(xw[0], a);
+        unpack8h(xw[1], b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sel[k] = b[k] > a[k] ? 1 : 0; m[k] = fmaxf(a[k], b[k]); }
+        unpack8h(xw[2], a);
+        unpack8h(xw[3], b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (a[k] > m[k]) { sel[k] = 2; m[k] = a[k]; }
+          if (b[k] > m[k]) { sel[k] = 3; }
+        }
+      }
+#pragma unroll
+      for (int pos = 0; pos < 4; ++pos) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = sel[k] == pos ? gy[k] : 0.f;
+        if (accumulate) {
+          float e[8];
+          unpack8h(ew[pos], e);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] += e[k];
+        }
+        store8<__half>(ob_ + (pos >> 1) * (long long)W * lddx + (pos & 1) * lddx, o);
+        if (bn_sums != nullptr) {
+          float xv[8];
+          unpack8h(xw[pos], xv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { t1[k] += o[k]; t2[k] = fmaf(o[k], xv[k] - bt[k], t2[k]); }
+        }
+      }
+      if (++slot == kMD) slot = 0;
+    }
+  }
+  if (bn_sums != nullptr) {
+    if (lane_ < lanes) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float gm = bn_gamma[g * 8 + k];
+        t2[k] *= fabsf(gm) > 1e-12f ? 1.f / gm : 0.f;
+      }
+      group_add8(sbn, t1, cg, g);
+      group_add8(sbn + C, t2, cg, g);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&bn_sums[i], (double)sbn[i]);
@@ -1399,9 +1651,9 @@ int b2u_bn_apply_split(int dt, const void* x, int ldx, const void* x2, int ldx2,
               "bn_apply: dropout needs the keep mask, 0 <= p < 1 and a single source");
   int grid = lane_grid(npix, c, out_stats != nullptr ? 4 : 8);
   size_t smem = out_stats != nullptr ? 2 * (size_t)c * sizeof(float) : 0;
-  if (dt == B2U_F16 && g_b2u_bn_async && out_stats == nullptr && p_drop == 0.f) {          // the cp.async version
+  if (dt == B2U_F16 && g_b2u_bn_async && out_stats == nullptr) {                           // the cp.async version
     B2U_LAUNCH(bn_apply_async_kernel, grid, kThreads, (size_t)kAD * kThreads * sizeof(uint4), stream, (const __half*)x, ldx,
-               (__half*)y, ldy, c, npix, scale, shift, (const __half*)x2, ldx2, split);
+               (__half*)y, ldy, c, npix, scale, shift, (const __half*)x2, ldx2, split, (const uint8_t*)drop_bits, p_drop);
     return B2U_OK;
   }
   DISPATCH_T(dt, B2U_LAUNCH(bn_apply_kernel<T>, grid, kThreads, smem, stream, (const T*)x, ldx, (T*)y, ldy, c, npix,
@@ -1437,6 +1689,17 @@ extern "C" int b2u_bn_apply_pool(int dt, const void* x, int ldx, void* y, int ld
   B2U_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "bn_apply_pool: bad dropout rate");
   int grid = lane_grid((long long)n * (h / 2) * (wd / 2), c, out_stats != nullptr ? 4 : 8);
   size_t smem = out_stats != nullptr ? 2 * (size_t)c * sizeof(float) : 0;
+  if (dt == B2U_F16 && g_b2u_bn_async) {                    // the cp.async version (64 KB ring + statistics partials)
+    static bool attr = false;
+    if (!attr) {
+      B2U_CHECK_CUDA(cudaFuncSetAttribute(bn_apply_pool_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr = true;
+    }
+    B2U_LAUNCH(bn_apply_pool_async_kernel, grid, kThreads, (size_t)kPD * 4 * kThreads * sizeof(uint4) + 2 * (size_t)c * sizeof(float),
+               stream, (const __half*)x, ldx, (__half*)y, ldy, c, n, h, wd, scale, shift, out_stats, out_sq_off, (__half*)yp, ldp,
+               p_drop, op_id, d_state);
+    return B2U_OK;
+  }
   DISPATCH_T(dt, B2U_LAUNCH(bn_apply_pool_kernel<T>, grid, kThreads, smem, stream, (const T*)x, ldx, (T*)y, ldy, c, n, h,
                             wd, scale, shift, out_stats, out_sq_off, (T*)yp, ldp, p_drop, op_id, d_state));
   return B2U_OK;
@@ -1501,18 +1764,18 @@ int b2u_bn_bwd_apply_cs(int dt, const void* dy, int lddy, const void* x, int ldx
               "bn_bwd_apply: dropout needs the keep mask, 0 <= p < 1 and a single tensor");
   int grid = lane_grid(npix, c);
   // fp16, one tensor, no dropout, activation mask (if any) = the BN input itself: the cp.async version
-  if (dt == B2U_F16 && g_b2u_bn_async && p_drop == 0.f && aligned16(dy) && aligned16(x) && aligned16(dx) &&
+  if (dt == B2U_F16 && g_b2u_bn_async && aligned16(dy) && aligned16(x) && aligned16(dx) &&
       (mask == nullptr || (mask == x && ldmask == ldx && split == c))) {
     const size_t ring_bytes = (size_t)kAD * 2 * kThreads * sizeof(uint4);
     const int ma = mask != nullptr ? mask_act : B2U_ACT_NONE;
     if (colsum != nullptr) {
       B2U_LAUNCH(bn_bwd_apply_async_kernel<true>, grid, kThreads, ring_bytes + c * sizeof(float), stream, (const __half*)dy,
                  lddy, (const __half*)x, ldx, (__half*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums, dgamma,
-                 dbeta, ma, colsum, (const __half*)x2, ldx2, (__half*)dx2, lddx2, split);
+                 dbeta, ma, colsum, (const __half*)x2, ldx2, (__half*)dx2, lddx2, split, (const uint8_t*)drop_bits, p_drop);
     } else {
       B2U_LAUNCH(bn_bwd_apply_async_kernel<false>, grid, kThreads, ring_bytes, stream, (const __half*)dy, lddy,
                  (const __half*)x, ldx, (__half*)dx, lddx, c, npix, count, gamma, save_mean, save_invstd, sums, dgamma, dbeta, ma,
-                 colsum, (const __half*)x2, ldx2, (__half*)dx2, lddx2, split);
+                 colsum, (const __half*)x2, ldx2, (__half*)dx2, lddx2, split, (const uint8_t*)drop_bits, p_drop);
     }
     return B2U_OK;
   }
@@ -1560,6 +1823,17 @@ extern "C" int b2u_maxpool_bwd(int dt, const void* x, int ldx, const void* dy, i
   B2U_REQUIRE(bn_sums == nullptr || (bn_gamma != nullptr && bn_beta != nullptr), "maxpool_bwd: fused BN statistics need gamma/beta");
   if (bn_sums != nullptr && grid > 4 * B2U_NUM_SMS) grid = 4 * B2U_NUM_SMS;     // fewer block epilogues
   size_t smem = bn_sums != nullptr ? 2 * (size_t)c * sizeof(float) : 0;
+  if (dt == B2U_F16 && g_b2u_bn_async && aligned16(x) && aligned16(dy) && aligned16(dx)) {   // the cp.async version (72 KB ring)
+    static bool attr = false;
+    if (!attr) {
+      B2U_CHECK_CUDA(cudaFuncSetAttribute(maxpool_bwd_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr = true;
+    }
+    B2U_LAUNCH(maxpool_bwd_async_kernel, grid, kThreads, (size_t)kMD * 9 * kThreads * sizeof(uint4) + 2 * (size_t)c * sizeof(float),
+               stream, (const __half*)x, ldx, (const __half*)dy, lddy, (__half*)dx, lddx, c, n, h, wd, p_drop, op_id, d_state,
+               accumulate, bn_sums, bn_gamma, bn_beta);
+    return B2U_OK;
+  }
   DISPATCH_T(dt, B2U_LAUNCH(maxpool_bwd_kernel<T>, grid, kThreads, smem, stream, (const T*)x, ldx, (const T*)dy, lddy,
                             (T*)dx, lddx, c, n, h, wd, p_drop, op_id, d_state, accumulate, bn_sums, bn_gamma, bn_beta));
   return B2U_OK;
