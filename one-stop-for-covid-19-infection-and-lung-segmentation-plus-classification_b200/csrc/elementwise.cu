@@ -407,7 +407,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                : "memory");
 }
-// BN apply, same scheme (one 16-byte copy per pixel group in flight kAD deep); channels [split, C) from a second tensor
+// BN apply, same scheme; it has ONE input stream, so the ring is kAA = 8 deep for the same 128 KB in flight per SM;
+// channels [split, C) from a second tensor
+constexpr int kAA = 8;
 __global__ void __launch_bounds__(kThreads, 4) bn_apply_async_kernel(const __half* __restrict__ x, int ldx,
                                                                      __half* __restrict__ y, int ldy, int C, long long npix,
                                                                      const float* __restrict__ scale,
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_async_kernel(const __hal
                                                                      const uint8_t* __restrict__ drop_bits, float p_drop) {
   // (drop_bits, p_drop): the input is dropout(x) of an unmaterialised Dropout layer (keep bits stored by the statistics pass)
   B2U_PDL_PROLOGUE();
-  extern __shared__ __align__(16) uint4 ring[];            // [kAD][kThreads]
+  extern __shared__ __align__(16) uint4 ring[];            // [kAA][kThreads]
   const int cg = C >> 3;
   const int lanes = kThreads / cg;
   const int g = threadIdx.x % cg, lane_ = threadIdx.x / cg;
@@ -431,14 +433,14 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_async_kernel(const __hal
   uint4* my = ring + threadIdx.x;
   long long pl = (long long)blockIdx.x * lanes + lane_;
 #pragma unroll
-  for (int d = 0; d < kAD; ++d) {
+  for (int d = 0; d < kAA; ++d) {
     if (pl < npix) cp_async16(my + d * kThreads, src + pl * lds);
     asm volatile("cp.async.commit_group;" ::: "memory");
     pl += stride;
   }
   int slot = 0;
   for (long long p = (long long)blockIdx.x * lanes + lane_; p < npix; p += stride) {
-    asm volatile("cp.async.wait_group %0;" ::"n"(kAD - 1) : "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(kAA - 1) : "memory");
     const uint4 ux = my[slot * kThreads];
     if (pl < npix) cp_async16(my + slot * kThreads, src + pl * lds);
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -454,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_async_kernel(const __hal
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
     store8<__half>(y + p * ldy + g * 8, v);
-    if (++slot == kAD) slot = 0;
+    if (++slot == kAA) slot = 0;
   }
 }
 
@@ -1652,7 +1654,7 @@ int b2u_bn_apply_split(int dt, const void* x, int ldx, const void* x2, int ldx2,
   int grid = lane_grid(npix, c, out_stats != nullptr ? 4 : 8);
   size_t smem = out_stats != nullptr ? 2 * (size_t)c * sizeof(float) : 0;
   if (dt == B2U_F16 && g_b2u_bn_async && out_stats == nullptr) {                           // the cp.async version
-    B2U_LAUNCH(bn_apply_async_kernel, grid, kThreads, (size_t)kAD * kThreads * sizeof(uint4), stream, (const __half*)x, ldx,
+    B2U_LAUNCH(bn_apply_async_kernel, grid, kThreads, (size_t)kAA * kThreads * sizeof(uint4), stream, (const __half*)x, ldx,
                (__half*)y, ldy, c, npix, scale, shift, (const __half*)x2, ldx2, split, (const uint8_t*)drop_bits, p_drop);
     return B2U_OK;
   }
