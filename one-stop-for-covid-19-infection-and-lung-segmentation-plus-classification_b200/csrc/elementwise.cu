@@ -1106,6 +1106,56 @@ __global__ void __launch_bounds__(kThreads) copy_slice_kernel(const T* __restric
   }
 }
 
+// fp16 cp.async version (the multi-consumer concat copies of U-Net++): source (and, accumulating, destination) vectors kAA
+// deep in flight per thread, as in bn_apply_async_kernel
+__global__ void __launch_bounds__(kThreads, 4) copy_slice_async_kernel(const __half* __restrict__ s, int lds,
+                                                                       __half* __restrict__ d, int ldd, int C, long long npix,
+                                                                       int accumulate) {
+  B2U_PDL_PROLOGUE();
+  extern __shared__ __align__(16) uint4 ring[];            // [kAA / 2][2][kThreads]
+  constexpr int kD = kAA / 2;
+  const int cg = C >> 3;
+  const int lanes = kThreads / cg;
+  const int g = threadIdx.x % cg, lane_ = threadIdx.x / cg;
+  if (lane_ >= lanes) return;
+  const long long stride = (long long)gridDim.x * lanes;
+  uint4* my = ring + threadIdx.x;
+  long long pl = (long long)blockIdx.x * lanes + lane_;
+#pragma unroll
+  for (int q = 0; q < kD; ++q) {
+    if (pl < npix) {
+      cp_async16(my + (q * 2 + 0) * kThreads, s + pl * lds + g * 8);
+      if (accumulate) cp_async16(my + (q * 2 + 1) * kThreads, d + pl * ldd + g * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pl += stride;
+  }
+  int slot = 0;
+  for (long long p = (long long)blockIdx.x * lanes + lane_; p < npix; p += stride) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kD - 1) : "memory");
+    const uint4 us = my[(slot * 2 + 0) * kThreads];
+    uint4 ue = make_uint4(0u, 0u, 0u, 0u);
+    if (accumulate) ue = my[(slot * 2 + 1) * kThreads];
+    if (pl < npix) {
+      cp_async16(my + (slot * 2 + 0) * kThreads, s + pl * lds + g * 8);
+      if (accumulate) cp_async16(my + (slot * 2 + 1) * kThreads, d + pl * ldd + g * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pl += stride;
+    if (accumulate) {
+      float v[8], e[8];
+      unpack8h(us, v);
+      unpack8h(ue, e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += e[k];
+      store8<__half>(d + p * ldd + g * 8, v);
+    } else {
+      *reinterpret_cast<uint4*>(d + p * ldd + g * 8) = us;
+    }
+    if (++slot == kD) slot = 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // output head: 1x1 conv (Cin -> 1) + sigmoid, BCE+Dice sums, and their backward
 // ------------------------------------------------------------------------------------------
@@ -1870,6 +1920,11 @@ extern "C" int b2u_copy_slice(int dt, const void* src, int ldsrc, void* dst, int
   B2U_REQUIRE(ldsrc % 8 == 0 && lddst % 8 == 0, "copy_slice: ld%%8==0 required");
   B2U_REQUIRE(c <= 2048, "copy_slice: c <= 2048");
   int grid = lane_grid(npix, c);
+  if (dt == B2U_F16 && g_b2u_bn_async && aligned16(src) && aligned16(dst)) {
+    B2U_LAUNCH(copy_slice_async_kernel, grid, kThreads, (size_t)kAA * kThreads * sizeof(uint4), stream, (const __half*)src, ldsrc,
+               (__half*)dst, lddst, c, npix, accumulate);
+    return B2U_OK;
+  }
   DISPATCH_T(dt, B2U_LAUNCH(copy_slice_kernel<T>, grid, kThreads, 0, stream, (const T*)src, ldsrc, (T*)dst, lddst, c,
                             npix, accumulate));
   return B2U_OK;
